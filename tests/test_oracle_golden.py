@@ -1,0 +1,177 @@
+"""CPU: the oracle restatement must reproduce the unmodified reference (golden fixtures)."""
+import torch
+
+import oracle
+from conftest import load_golden, rel_err, grads_close
+from synth import randn, synth_state_dict
+
+TOL = 2e-5   # fp32 vs fp32, different op order
+
+
+def _leaf(d):
+    return {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in d.items()}
+
+
+def test_pinv():
+    g = load_golden("pinv")
+    x = g["x"].clone().requires_grad_()
+    z = oracle.nystrom.pinv_iter(x, g["iters"])
+    assert rel_err(z, g["z"]) < TOL
+    z.backward(g["gz"])
+    assert rel_err(x.grad, g["gx"]) < 1e-4
+
+
+def test_nystrom_attention():
+    for c in load_golden("nystrom"):
+        p = _leaf(c["state"])
+        x = c["x"].clone().requires_grad_()
+        cfg = c["cfg"]
+        y, parts = oracle.nystrom.nystrom_attention(x, p, heads=cfg["heads"], num_landmarks=cfg["num_landmarks"],
+                                                    pinv_iterations=cfg["pinv_iterations"], return_parts=True)
+        assert rel_err(y, c["y"]) < TOL
+        y.backward(c["gy"])
+        assert rel_err(x.grad, c["gx"]) < 1e-4
+        grads_close({k: p[k].grad for k in c["gparams"]}, c["gparams"], 1e-4)
+        n = x.shape[1]; m = cfg["num_landmarks"]
+        npad = n + parts["pad"]
+        assert torch.equal(parts["landmark_ids"], torch.arange(npad) // (npad // m))
+
+
+def test_translayer_ppeg():
+    g = load_golden("translayer_ppeg")
+    p = _leaf(g["tl_state"]); x = g["x"].clone().requires_grad_()
+    y = oracle.nystrom.trans_layer(x, p, "", dim=64)
+    assert rel_err(y, g["y"]) < TOL
+    y.backward(g["gy"])
+    assert rel_err(x.grad, g["gx"]) < 1e-4
+    p = _leaf(g["pp_state"]); x = g["px"].clone().requires_grad_()
+    y = oracle.nystrom.ppeg(x, p, "", 6, 6)
+    assert rel_err(y, g["py"]) < TOL
+    y.backward(g["pgy"])
+    assert rel_err(x.grad, g["pgx"]) < 1e-4
+    grads_close({k: p[k].grad for k in g["pp_gparams"]}, g["pp_gparams"], 1e-4)
+
+
+def test_transmil():
+    g = load_golden("transmil")
+    p = _leaf(synth_state_dict(g["shapes"], g["seed"]))
+    x = randn(g["x_shape"], g["x_seed"])
+    enc, logits = oracle.nystrom.transmil(x, p)
+    assert rel_err(logits, g["logits"]) < 1e-4
+    assert rel_err(enc, g["enc"]) < 1e-4
+    loss = (logits * randn(logits.shape, g["glogits_seed"])).sum() + (enc * randn(enc.shape, g["genc_seed"])).sum()
+    loss.backward()
+    grads_close({k: p[k].grad for k in g["gparams"]}, g["gparams"], 1e-3)
+    for k, nv in g["gnorms"].items():
+        assert abs(float(p[k].grad.norm()) - nv) <= 1e-3 * nv + 1e-6, k
+
+
+def test_deform1d():
+    g = load_golden("deform1d")
+    p = _leaf(g["state"])
+    x1 = g["x1"].clone().requires_grad_(); x2 = g["x2"].clone().requires_grad_()
+    y, parts = oracle.deform.deform_attn_1d(x1, x2, p, return_parts=True)
+    assert rel_err(y, g["y"]) < TOL
+    assert rel_err(parts["vgrid"], g["vgrid"]) < TOL
+    y.backward(g["gy"])
+    assert rel_err(x1.grad, g["gx1"]) < 1e-4
+    assert rel_err(x2.grad, g["gx2"]) < 1e-4
+    grads_close({k: p[k].grad for k in g["gparams"]}, g["gparams"], 1e-4)
+    # chunked evaluation is the same function
+    y2 = oracle.deform.deform_attn_1d(g["x1"], g["x2"], g["state"], q_chunk=7)
+    assert rel_err(y2, g["y"]) < TOL
+    # F5: only the middle token of x2 matters in the reference pad order
+    x2b = g["x2"].clone(); x2b[:, :, :20] = 7.0; x2b[:, :, 21:] = -3.0
+    y3 = oracle.deform.deform_attn_1d(g["x1"], x2b, g["state"])
+    assert rel_err(y3, g["y"]) < TOL
+
+
+def test_deform1d_upstream_taps_match_grid_sample():
+    """The non-default pad order equals F.grid_sample on the transposed axes; taps are integer-exact."""
+    import torch.nn.functional as F
+    feat = randn((3, 5, 23, 1), 7)
+    gy = randn((3, 11), 8).clamp(-1.3, 1.3)
+    out, (x0, y0) = oracle.deform.bilinear_sample(feat, torch.zeros_like(gy), gy)
+    grid = torch.stack([torch.zeros_like(gy), gy], -1).view(3, 11, 1, 2)
+    ref = F.grid_sample(feat, grid, mode="bilinear", padding_mode="zeros", align_corners=False)[..., 0]
+    assert rel_err(out, ref) < 1e-6
+    assert torch.equal(y0, torch.floor(((gy + 1) * 23 - 1) / 2).long())
+
+
+def test_deform2d():
+    g = load_golden("deform2d")
+    p = _leaf(g["state"])
+    x1 = randn((1, 128, 2500), g["x1_seed"]).requires_grad_(); x2 = randn((1, 128, 2500), g["x2_seed"]).requires_grad_()
+    y, vgrid = oracle.deform.deform_attn_2d(x1, x2, p, side=50, q_chunk=500)
+    assert rel_err(y, g["y"]) < TOL
+    assert rel_err(vgrid, g["vgrid"]) < TOL
+    y.backward(randn(y.shape, g["gy_seed"]))
+    assert rel_err(x1.grad[:, :, ::7], g["gx1"]) < 1e-4
+    assert rel_err(x2.grad[:, :, ::7], g["gx2"]) < 1e-4
+    grads_close({k: p[k].grad for k in g["gparams"]}, g["gparams"], 1e-4)
+
+
+def test_deform_cross_transmil():
+    for ad in (2, 1):
+        g = load_golden(f"deformtransmil_ad{ad}")
+        st = synth_state_dict(g["shapes"], g["seed"])
+        for k in st:
+            if k.endswith("to_offsets.2.weight"):
+                st[k] = st[k] * g["offw_scale"]
+        p = _leaf(st)
+        path = randn((1, 2500, 1024), 83).requires_grad_(); omic = randn((1, 128), 84).abs().requires_grad_()
+        o = oracle.deform.deform_cross_transmil(path, omic, p, attn_dim=ad, q_chunk=500)
+        assert rel_err(o["logits"], g["logits"]) < 1e-4
+        assert rel_err(o["encoded"], g["enc"]) < 1e-4
+        loss = (o["logits"] * randn(o["logits"].shape, 85)).sum() + (o["encoded"] * randn(o["encoded"].shape, 86)).sum()
+        if ad == 2:
+            assert rel_err(o["vgrid"], g["vgrid"]) < 1e-4
+            loss = loss + (o["vgrid"] * randn(o["vgrid"].shape, 87)).sum() * 0.01
+        loss.backward()
+        assert rel_err(omic.grad, g["gomic"]) < 1e-3
+        assert rel_err(path.grad[:, ::50, ::16], g["gpath_sub"]) < 1e-3
+        for k, nv in g["gnorms"].items():
+            assert abs(float(p[k].grad.norm()) - nv) <= 2e-3 * nv + 1e-6, k
+
+
+def test_mha():
+    g = load_golden("mha")
+    p = _leaf(g["state"])
+    q = g["q"].clone().requires_grad_(); kv = g["kv"].clone().requires_grad_()
+    o, raw = oracle.heads.mha_coattn(q, kv, kv, p, 1)
+    assert rel_err(o, g["out"]) < TOL and rel_err(raw, g["raw"]) < TOL
+    (o * g["go"]).sum().backward()
+    assert rel_err(q.grad, g["gq"]) < 1e-4 and rel_err(kv.grad, g["gkv"]) < 1e-4
+    grads_close({k: p[k].grad for k in g["gparams"]}, g["gparams"], 1e-4)
+    o4, raw4 = oracle.heads.mha_coattn(g["kv"], g["q"], g["q"], g["state"], 4)
+    assert rel_err(o4, g["out4"]) < TOL and rel_err(raw4, g["raw4"]) < TOL
+
+
+def test_bilinear_fusion():
+    g = load_golden("bilinear_fusion")
+    p = _leaf(synth_state_dict(g["shapes"], g["seed"]))
+    ye = oracle.heads.bilinear_fusion(g["v1"], g["v2"], p, training_bn=False)
+    assert rel_err(ye, g["y_eval"]) < 1e-4
+    v1 = g["v1"].clone().requires_grad_(); v2 = g["v2"].clone().requires_grad_()
+    yt = oracle.heads.bilinear_fusion(v1, v2, p, training_bn=True)
+    assert rel_err(yt, g["y_train"]) < 1e-4
+    yt.backward(g["gy"])
+    assert rel_err(v1.grad, g["gv1"]) < 1e-3 and rel_err(v2.grad, g["gv2"]) < 1e-3
+
+
+def test_losses():
+    g = load_golden("losses")
+    om = g["omic"].clone().requires_grad_(); vg = g["vgrid"].clone().requires_grad_()
+    bl = oracle.loss.batch_loss(om, vg, om.shape[0])
+    assert rel_err(bl, g["batch_loss"]) < TOL
+    bl.backward(g["gbl"])
+    assert rel_err(om.grad, g["gomic"]) < 1e-4 and rel_err(vg.grad, g["gvgrid"]) < 1e-4
+    ts = [g[k].clone().requires_grad_() for k in ("P", "Ph", "G", "Gh")]
+    ol = oracle.loss.orthogonal_loss(*ts)
+    assert rel_err(ol, g["orth"]) < TOL
+    ol.sum().backward()
+    for t, k in zip(ts, ("gP", "gPh", "gG", "gGh")):
+        assert rel_err(t.grad, g[k]) < 1e-4
+    mean, inv_std, unb = oracle.loss.sync_bn_stats([g["bn_x"][:4], g["bn_x"][4:]])
+    assert rel_err(mean, g["bn_mean"]) < TOL and rel_err(inv_std, g["bn_inv_std"]) < TOL
+    assert rel_err(0.9 * torch.ones(8) + 0.1 * unb, g["bn_running_var"]) < TOL
