@@ -1,0 +1,131 @@
+/* sml_b200.h — C-ABI of libsml_b200.so: the B200 (sm_100a) kernels behind the
+ * Subspace-Multimodal-Learning multiple-instance fusion hot path.
+ *
+ * The reference is pure Python (no FFI of its own); each entry point below is
+ * the unit a reference-side binding replaces, cited as /root/reference file:line.
+ * Conventions:
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller owns all memory (inputs, outputs, workspaces); nothing is allocated
+ *     or freed behind the ABI and no call synchronises the device;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = ok, non-zero = error, message via sml_last_error()
+ *     (thread-local); no exceptions cross the boundary;
+ *   - entries are re-entrant (forward runs on the caller thread, backward on the
+ *     autograd thread).
+ */
+#ifndef SML_B200_H
+#define SML_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* sml_last_error(void);
+int sml_version(void);
+/* number of kernels launched through this library by the calling process (bench `gpu_launches`) */
+int64_t sml_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense contractions.  One descriptor drives both engines:
+ *   sml_gemm_f32 : SIMT fp32 FFMA path (exact-fp32 reference path on the device; any strides)
+ *   sml_gemm_tc  : tcgen05.mma + TMEM accumulators + TMA-fed smem operands (bf16 operands,
+ *                  fp32 accumulate; optional bf16x3 split operands for fp32-grade results)
+ * C[b1,b2] = alpha * A[b1,b2] (MxK) * B[b1,b2] (KxN) + beta * C + diag * I  (+ bias[n]) (relu)
+ * Replaces every torch matmul / einsum / nn.Linear / 1x1 conv on the path:
+ *   models/NystromAttention.py:89,122-125,140,150 ; :20-35 (pinv chain, `diag`)
+ *   models/DeformableAttention1D.py:175,199,211,230,233 ; models/DeformableAttention2D.py:246,279,292,311,314
+ *   models/DeformCrossTransMIL.py:83,35-37 ; models/MultiheadAttention.py:125-182,282,303-306 ; models/mil.py:214,219
+ * ------------------------------------------------------------------------------------- */
+typedef struct sml_gemm_desc {
+  int32_t M, N, K;
+  int32_t nb1, nb2;                 /* two-level batch (e.g. slides x heads) */
+  const void* A;  int64_t sa_m, sa_k, sa_b1, sa_b2;   /* element strides; A is [M,K] */
+  const void* B;  int64_t sb_k, sb_n, sb_b1, sb_b2;   /* B is [K,N] */
+  void*       C;  int64_t sc_m, sc_n, sc_b1, sc_b2;   /* fp32 output (may be NULL for tc if Cb given) */
+  float alpha, beta, diag;
+  const float* bias;                /* [N] or NULL */
+  int32_t relu;
+  /* tensor-core engine only: */
+  const void* A_lo; const void* B_lo;  /* bf16 low parts for the bf16x3 split (NULL = single pass) */
+  void* Cb_hi; void* Cb_lo;            /* optional bf16 copies of the result (same strides as C) */
+} sml_gemm_desc;
+
+int sml_gemm_f32(const sml_gemm_desc* d, void* stream);
+int sml_gemm_tc(const sml_gemm_desc* d, void* stream);
+/* fp32 -> bf16 hi (and lo = bf16(x - hi) when lo != NULL), n elements */
+int sml_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row-wise kernels shared by the path.
+ * ------------------------------------------------------------------------------------- */
+/* LayerNorm over the last dim D of x[R,D] -> y rows written with row stride y_ld; saves mean/rstd.
+ * (models/mil.py:186, models/DeformCrossTransMIL.py:66,127, nn.LayerNorm eps=1e-5) */
+/* row r of x ([R,D], R = batches*n) is written to row (r/n)*npad + pad + r%n of y (front-padded layout of
+ * models/NystromAttention.py:79-82; pass n=R, npad=R, pad=0 for a plain LayerNorm) */
+int sml_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                      int64_t R, int32_t D, float eps, int64_t n, int64_t npad, int64_t pad, void* stream);
+/* dx = LN'(dy); dw_part/db_part are [nblk,D] partial sums (nblk = sml_layernorm_bwd_blocks(R)) */
+int sml_layernorm_bwd_blocks(int64_t R);
+int sml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                      float* dx, float* dw_part, float* db_part, int64_t R, int32_t D, int64_t n, int64_t npad,
+                      int64_t pad, void* stream);   /* dy is read in the padded layout, dx written dense */
+/* y[r,:] = softmax(x[r,:]) in place over C columns (models/NystromAttention.py:137) */
+int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* stream);
+/* in place on dA: dS = A * (dA - sum(dA*A)) */
+int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* stream);
+/* y = x + dropout(u, p) with a counter-based generator (seed, offset); p == 0 -> plain add.
+ * Same call with grad tensors regenerates the mask in backward (models/mil.py:183 dropout=0.1) */
+int sml_dropout_add(const float* x, const float* u, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
+                    void* stream);
+int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* stream);   /* y = a*x + b*y */
+/* out = a*x + dg*I over nmat square m x m matrices (identity terms of models/NystromAttention.py:33) */
+int sml_diag_axpby(float* out, const float* x, float a, float dg, int64_t nmat, int32_t m, void* stream);
+/* dx = dy where y > 0 else 0 (ReLU of models/mil.py:214, models/DeformCrossTransMIL.py:83) */
+int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+/* 1 if any tcgen05 kernel hit its bounded mbarrier wait (protocol error); reads a device flag (synchronises) */
+int sml_tc_timeout_flag(void);
+/* out[c] = sum_r x[r,c] + beta*out[c]; part is a [sml_colsum_parts(R), C] workspace */
+int sml_colsum_parts(int64_t R);
+int sml_colsum(const float* x, float* out, float* part, int64_t R, int64_t C, float beta, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Nystrom attention pieces (models/NystromAttention.py:74-157, :20-35).
+ * qkv layout: [B, n', 3, h, d] fp32 (row = token, q|k|v chunks, head-major inside a chunk).
+ * ------------------------------------------------------------------------------------- */
+/* landmark segment means of q and k: ql, kl [B,h,m,d]; landmark id of token t is t / l (:102-118) */
+int sml_nystrom_landmarks_fwd(const float* qkv, float* ql, float* kl, int32_t B, int32_t npad, int32_t h, int32_t d,
+                              int32_t m, void* stream);
+/* dqkv[q,k chunks][t] += d{ql,kl}[t / l] / l */
+int sml_nystrom_landmarks_bwd(float* dqkv, const float* dql, const float* dkl, int32_t B, int32_t npad, int32_t h,
+                              int32_t d, int32_t m, void* stream);
+/* integer landmark ids (bit-exact contract): ids[t] = t / (npad / m) */
+int sml_nystrom_landmark_ids(int32_t* ids, int32_t npad, int32_t m, void* stream);
+/* scal[0] = max over all (b,h,i) of sum_j |x|, scal[1] = max over all (b,h,j) of sum_i |x| (global, F8);
+ * arg[0] = flat (bh*m + i) of the row max, arg[1] = flat (bh*m + j) of the column max.  x [BH,m,m] (:22-26) */
+int sml_pinv_scale(const float* x, float* scal, int32_t* arg, void* packed_ws /*16 B*/, int32_t BH, int32_t m,
+                   void* stream);
+/* z0 = x^T / (scal[0]*scal[1]) (:26) */
+int sml_pinv_init(const float* x, const float* scal, float* z0, int32_t BH, int32_t m, void* stream);
+/* backward of pinv_init: dx += dz0^T / s ; then the scalar path d s -> row/col max positions */
+int sml_pinv_init_bwd(const float* x, const float* scal, const int32_t* arg, const float* dz0, float* dx,
+                      float* tmp /*4 B*/, int32_t BH, int32_t m, void* stream);
+/* depthwise conv along tokens on the v chunk, per head, shared over d: out[B,n',h*d] += conv(v) (:144-145) */
+int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
+                            int32_t d, int32_t ksize, void* stream);
+/* dqkv[v chunk] += conv^T(dout); dw[h,k] = sum dout*v (dw_part [nblk,h,k]; nblk returned by ..._blocks) */
+int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad);
+int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
+                            int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* stream);
+/* PPEG: identity + depthwise 7x7 + 5x5 + 3x3 folded into one 7x7 stencil, token-major [B,1+H*W,C];
+ * the cls row is copied through (models/mil.py:192-206).  w7 [49,C] folded tap-major weights, bias [C] folded.
+ * Backward: dw_part [nblk,49,C], db_part [nblk,C]. */
+int sml_ppeg_fwd(const float* x, const float* w7, const float* bias, float* y, int32_t B, int32_t H, int32_t W,
+                 int32_t C, void* stream);
+int sml_ppeg_bwd_blocks(int32_t B, int32_t H, int32_t W);
+int sml_ppeg_bwd(const float* x, const float* w7, const float* dy, float* dx, float* dw_part, float* db_part,
+                 int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,8 @@
+"""sml_b200 — B200-native (sm_100a) kernels behind the Subspace-Multimodal-Learning module signatures.
+
+The package directory is ``subspace-multimodal-learning_b200`` (not an importable identifier); import it
+through the repo-root shim ``sml_b200`` or ``__graft_entry__.load_package()``.
+"""
+from . import _lib, ops, functional, nystrom  # noqa: F401
+from .models.NystromAttention import NystromAttention, moore_penrose_iter_pinv  # noqa: F401
+from .models.mil import TransLayer, PPEG, TransMIL  # noqa: F401

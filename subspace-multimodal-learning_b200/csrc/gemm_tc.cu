@@ -1,0 +1,464 @@
+// gemm_tc.cu — tcgen05 / TMEM / TMA batched GEMM for sm_100a.
+//
+//   C[b1,b2] = epilogue( alpha * A[b1,b2] (MxK, bf16) * B[b1,b2] (KxN, bf16) ),  fp32 accumulation in TMEM.
+//
+// * operands are staged global -> shared by TMA (cp.async.bulk.tensor.4d, SWIZZLE_128B, zero OOB fill so
+//   M/N/K tails need no special casing) into a STAGES-deep mbarrier ring;
+// * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) on shared-memory
+//   descriptors; both K-major and MN-major operands are supported (4 layout combinations), so every
+//   forward and backward contraction of the path runs without a transposed copy;
+// * optional bf16x3 split (A_hi*B_hi + A_hi*B_lo + A_lo*B_hi) gives fp32-grade products (~2^-16) for the
+//   fp32 parity mode and the Moore-Penrose chain;
+// * 4 epilogue warps read the accumulator with tcgen05.ld (one TMEM lane = one output row per thread) and
+//   apply alpha / beta*C / diag*I / bias / ReLU or a fused row softmax (row fits one tile: the three
+//   Nystrom similarity softmaxes over m landmarks), writing fp32 and/or bf16 (hi, lo) results.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace sml {
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ unsigned int g_tc_timeout_flag = 0;
+// bounded wait: a protocol bug must never hang the GPU box; on timeout raise a flag the host can read and go on
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((it & 1023u) == 1023u && *((volatile unsigned int*)&g_tc_timeout_flag) != 0u) return false;
+  }
+  atomicExch(&g_tc_timeout_flag, 1u);
+  return false;
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (sm100 "version 1"), SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;   // descriptor version (Blackwell)
+  d |= 2ull << 61;   // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D=f32, A=B=bf16
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct EpiParams {
+  int M, N, K, nb2;
+  float* C; int64_t sc_m, sc_n, sc_b1, sc_b2;
+  __nv_bfloat16* Cb_hi; __nv_bfloat16* Cb_lo;
+  float alpha, beta, diag;
+  const float* bias;
+  int relu, softmax;
+};
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+
+template <int BN, bool SPLIT, int STAGES>
+struct TcSmem {
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = (TC_A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ void store_row_chunk(const EpiParams& ep, float* crow, __nv_bfloat16* hrow,
+                                                __nv_bfloat16* lrow, int gm, int gn0, const float (&v)[32]) {
+  // one thread owns 32 consecutive columns of one output row
+  const bool vec = (ep.sc_n == 1) && (gn0 + 32 <= ep.N);
+  if (crow) {
+    if (vec && ((reinterpret_cast<uintptr_t>(crow + gn0) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(crow + gn0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (gn0 + j < ep.N) crow[(int64_t)(gn0 + j) * ep.sc_n] = v[j];
+    }
+  }
+  if (hrow) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (gn0 + j < ep.N) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+        hrow[(int64_t)(gn0 + j) * ep.sc_n] = hi;
+        if (lrow) lrow[(int64_t)(gn0 + j) * ep.sc_n] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+      }
+    }
+  }
+  (void)gm;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl, const EpiParams ep) {
+  using S = TcSmem<BN, SPLIT, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+  const int b1 = blockIdx.z / ep.nb2, b2 = blockIdx.z % ep.nb2;
+  const int nkb = (ep.K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation: BN fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1u)) break;
+        mbar_expect_tx(&full_bar[s], (uint32_t)S::STAGE_BYTES);
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + TC_A_BYTES * (SPLIT ? 2 : 1);
+        const int k0 = kb * TC_BK;
+#pragma unroll
+        for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+          const CUtensorMap* ta = part ? &tmAl : &tmA;
+          const CUtensorMap* tb = part ? &tmBl : &tmB;
+          uint8_t* ad = a_dst + part * TC_A_BYTES;
+          uint8_t* bd = b_dst + part * S::B_BYTES;
+          if (!A_MN) tma_load_4d(ad, ta, &full_bar[s], k0, m0, b2, b1);
+          else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / 64; ++c) tma_load_4d(ad + c * 8192, ta, &full_bar[s], m0 + c * 64, k0, b2, b1);
+          }
+          if (!B_MN) tma_load_4d(bd, tb, &full_bar[s], k0, n0, b2, b1);
+          else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_4d(bd + c * 8192, tb, &full_bar[s], n0 + c * 64, k0, b2, b1);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, A_MN, B_MN);
+      // K-major: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major: 64-element chunks 8 KB apart (LBO),
+      // 8-k-row groups 1024 B apart (SBO).
+      constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
+      constexpr uint32_t a_kstep = A_MN ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;   // bytes per UMMA_K = 16
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        if (!mbar_wait(&full_bar[s], ph)) break;
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + TC_A_BYTES * (SPLIT ? 2 : 1);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024u);
+          const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024u);
+          tc_mma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (SPLIT) {
+            const uint64_t dal = make_smem_desc(a_addr + TC_A_BYTES + k * a_kstep, a_lbo, 1024u);
+            const uint64_t dbl = make_smem_desc(b_addr + S::B_BYTES + k * b_kstep, b_lbo, 1024u);
+            tc_mma_bf16(tmem_base, da, dbl, idesc, 1u);
+            tc_mma_bf16(tmem_base, dal, db, idesc, 1u);
+          }
+        }
+        tc_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+      }
+      tc_commit(tmem_full);         // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int gm = m0 + row;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool row_ok = gm < ep.M;
+    const int64_t coff = (int64_t)b1 * ep.sc_b1 + (int64_t)b2 * ep.sc_b2 + (int64_t)gm * ep.sc_m;
+    float* crow = ep.C ? ep.C + coff : nullptr;
+    __nv_bfloat16* hrow = ep.Cb_hi ? ep.Cb_hi + coff : nullptr;
+    __nv_bfloat16* lrow = ep.Cb_lo ? ep.Cb_lo + coff : nullptr;
+    uint32_t r[32];
+    if (ep.softmax) {
+      // the whole row lives in this thread's TMEM lane: max / sum / normalise without any cross-thread traffic
+      float mx = -INFINITY;
+      for (int c = 0; c < BN; c += 32) {
+        tc_ld32(trow + c, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < ep.N) mx = fmaxf(mx, ep.alpha * __uint_as_float(r[j]));
+      }
+      float sum = 0.f;
+      for (int c = 0; c < BN; c += 32) {
+        tc_ld32(trow + c, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < ep.N) sum += __expf(ep.alpha * __uint_as_float(r[j]) - mx);
+      }
+      const float inv = 1.f / sum;
+      for (int c = 0; c < BN; c += 32) {
+        tc_ld32(trow + c, r);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __expf(ep.alpha * __uint_as_float(r[j]) - mx) * inv;
+        if (row_ok && n0 + c < ep.N) store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
+      }
+    } else {
+      for (int c = 0; c < BN; c += 32) {
+        tc_ld32(trow + c, r);
+        if (!(row_ok && n0 + c < ep.N)) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int gn = n0 + c + j;
+          float x = ep.alpha * __uint_as_float(r[j]);
+          if (gn < ep.N) {
+            if (ep.beta != 0.f) x = fmaf(ep.beta, crow[(int64_t)gn * ep.sc_n], x);
+            if (gn == gm) x += ep.diag;
+            if (ep.bias) x += __ldg(ep.bias + gn);
+            if (ep.relu) x = fmaxf(x, 0.f);
+          }
+          v[j] = x;
+        }
+        store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// operand viewed as [rows, inner] bf16 with `inner` contiguous, row stride ld, plus two batch dims
+static int make_map(CUtensorMap* tm, const void* base, int64_t inner, int64_t rows, int64_t ld, int nb2, int64_t sb2,
+                    int nb1, int64_t sb1, int box_inner, int box_rows, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  SML_CHECK(enc, "sml_gemm_tc: cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  SML_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "sml_gemm_tc: %s base not 16-byte aligned", what);
+  SML_CHECK((ld * 2) % 16 == 0, "sml_gemm_tc: %s row stride %lld not a multiple of 8 elements", what, (long long)ld);
+  int64_t s2 = sb2, s1 = sb1;
+  cuuint64_t d2 = (cuuint64_t)nb2, d1 = (cuuint64_t)nb1;
+  if (nb2 <= 1 || s2 == 0) { d2 = 1; s2 = rows * ld; }     // broadcast / absent batch dim: size 1, any legal stride
+  if (nb1 <= 1 || s1 == 0) { d1 = 1; s1 = rows * ld; }
+  if (s2 <= 0) s2 = 8;
+  if (s1 <= 0) s1 = 8;
+  SML_CHECK((s2 * 2) % 16 == 0 && (s1 * 2) % 16 == 0, "sml_gemm_tc: %s batch strides must be multiples of 8 elements", what);
+  cuuint64_t gdim[4] = {(cuuint64_t)inner, (cuuint64_t)rows, d2, d1};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s2 * 2, (cuuint64_t)s1 * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SML_CHECK(r == CUDA_SUCCESS, "sml_gemm_tc: cuTensorMapEncodeTiled(%s) failed with %d (inner=%lld rows=%lld ld=%lld)", what,
+            (int)r, (long long)inner, (long long)rows, (long long)ld);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES>
+static int launch_tc(const CUtensorMap* tms, const EpiParams& ep, dim3 grid, cudaStream_t st) {
+  using S = TcSmem<BN, SPLIT, STAGES>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, SPLIT, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    SML_CHECK(e == cudaSuccess, "sml_gemm_tc: cudaFuncSetAttribute(%d B) failed: %s", S::TOTAL, cudaGetErrorString(e));
+    attr = true;
+  }
+  kern<<<grid, TC_THREADS, S::TOTAL, st>>>(tms[0], tms[1], tms[2], tms[3], ep);
+  SML_LAUNCH_OK("sml_gemm_tc");
+  return 0;
+}
+
+template <int BN, bool SPLIT, int STAGES>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tms, const EpiParams& ep, dim3 grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, SPLIT, STAGES>(tms, ep, grid, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, SPLIT, STAGES>(tms, ep, grid, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false, SPLIT, STAGES>(tms, ep, grid, st);
+  return launch_tc<BN, true, true, SPLIT, STAGES>(tms, ep, grid, st);
+}
+
+}  // namespace sml
+
+using namespace sml;
+
+extern "C" int sml_tc_timeout_flag(void) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_tc_timeout_flag, sizeof(v));
+  return (int)v;
+}
+
+extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
+  SML_CHECK(d && d->A && d->B && (d->C || d->Cb_hi), "sml_gemm_tc: null pointer");
+  SML_CHECK(d->M > 0 && d->N > 0 && d->K > 0 && d->nb1 > 0 && d->nb2 > 0, "sml_gemm_tc: bad sizes");
+  const bool split = d->A_lo != nullptr || d->B_lo != nullptr;
+  SML_CHECK(!split || (d->A_lo && d->B_lo), "sml_gemm_tc: bf16x3 split needs both A_lo and B_lo");
+  // operand majors: A is [M,K]; K-major if sa_k == 1, M-major if sa_m == 1.  B is [K,N]; K-major if sb_k == 1.
+  bool a_mn, b_mn;
+  if (d->sa_k == 1 && (d->sa_m != 1 || d->K == 1)) a_mn = false;
+  else if (d->sa_m == 1) a_mn = true;
+  else { set_error("sml_gemm_tc: A needs unit stride along M or K (sa_m=%lld sa_k=%lld)", (long long)d->sa_m, (long long)d->sa_k); return 1; }
+  if (d->sb_k == 1 && (d->sb_n != 1 || d->K == 1)) b_mn = false;
+  else if (d->sb_n == 1) b_mn = true;
+  else { set_error("sml_gemm_tc: B needs unit stride along N or K (sb_k=%lld sb_n=%lld)", (long long)d->sb_k, (long long)d->sb_n); return 1; }
+  // when both strides are 1 (degenerate dim) prefer K-major
+  if (d->sa_k == 1 && d->sa_m == 1) a_mn = (d->M > 1 && d->K == 1);
+  if (d->sb_k == 1 && d->sb_n == 1) b_mn = (d->N > 1 && d->K == 1);
+
+  const int softmax = (d->relu & 2) ? 1 : 0;
+  int BN = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
+  if (split && BN == 256) BN = 128;
+  SML_CHECK(!softmax || d->N <= BN, "sml_gemm_tc: fused row softmax needs N <= %d (N=%d)", BN, d->N);
+
+  CUtensorMap tms[4];
+  const int64_t lda = a_mn ? d->sa_k : d->sa_m, ldb = b_mn ? d->sb_k : d->sb_n;
+  for (int part = 0; part < (split ? 2 : 1); ++part) {
+    const void* A = part ? d->A_lo : d->A;
+    const void* B = part ? d->B_lo : d->B;
+    int rc;
+    if (!a_mn) rc = make_map(&tms[part], A, d->K, d->M, lda, d->nb2, d->sa_b2, d->nb1, d->sa_b1, 64, TC_BM, "A");
+    else rc = make_map(&tms[part], A, d->M, d->K, lda, d->nb2, d->sa_b2, d->nb1, d->sa_b1, 64, 64, "A");
+    if (rc) return rc;
+    if (!b_mn) rc = make_map(&tms[2 + part], B, d->K, d->N, ldb, d->nb2, d->sb_b2, d->nb1, d->sb_b1, 64, BN, "B");
+    else rc = make_map(&tms[2 + part], B, d->N, d->K, ldb, d->nb2, d->sb_b2, d->nb1, d->sb_b1, 64, 64, "B");
+    if (rc) return rc;
+  }
+  if (!split) { tms[1] = tms[0]; tms[3] = tms[2]; }
+
+  EpiParams ep;
+  ep.M = d->M; ep.N = d->N; ep.K = d->K; ep.nb2 = d->nb2;
+  ep.C = (float*)d->C; ep.sc_m = d->sc_m; ep.sc_n = d->sc_n; ep.sc_b1 = d->sc_b1; ep.sc_b2 = d->sc_b2;
+  ep.Cb_hi = (__nv_bfloat16*)d->Cb_hi; ep.Cb_lo = (__nv_bfloat16*)d->Cb_lo;
+  ep.alpha = d->alpha; ep.beta = d->beta; ep.diag = d->diag; ep.bias = d->bias;
+  ep.relu = d->relu & 1; ep.softmax = softmax;
+  SML_CHECK(!(ep.beta != 0.f) || ep.C, "sml_gemm_tc: beta needs an fp32 C");
+
+  const long long nbz = (long long)d->nb1 * d->nb2;
+  SML_CHECK(nbz <= 65535, "sml_gemm_tc: batch %lld > 65535", nbz);
+  dim3 grid((d->N + BN - 1) / BN, (d->M + TC_BM - 1) / TC_BM, (unsigned)nbz);
+  SML_CHECK(grid.y <= 65535, "sml_gemm_tc: M too large for grid.y");
+  cudaStream_t st = as_stream(stream);
+  const bool deep = d->K > 2 * TC_BK;
+  if (!split) {
+    if (BN == 256) return deep ? dispatch_major<256, false, 4>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<256, false, 2>(a_mn, b_mn, tms, ep, grid, st);
+    if (BN == 128) return deep ? dispatch_major<128, false, 6>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<128, false, 2>(a_mn, b_mn, tms, ep, grid, st);
+    return deep ? dispatch_major<64, false, 8>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<64, false, 2>(a_mn, b_mn, tms, ep, grid, st);
+  } else {
+    if (BN == 128) return deep ? dispatch_major<128, true, 3>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<128, true, 2>(a_mn, b_mn, tms, ep, grid, st);
+    return deep ? dispatch_major<64, true, 4>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<64, true, 2>(a_mn, b_mn, tms, ep, grid, st);
+  }
+}
+
+namespace sml {
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+}  // namespace sml
+
+extern "C" int sml_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  int64_t g = (n + 255) / 256;
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  split_bf16_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  SML_LAUNCH_OK("sml_split_bf16");
+  return 0;
+}

@@ -1,0 +1,376 @@
+// nystrom.cu — the non-GEMM pieces of Nystrom attention (models/NystromAttention.py:20-35, :74-157)
+// and the PPEG stencil of TransMIL (models/mil.py:192-206).  All HBM-bound; layouts are token-major so
+// that the channel axis (h*d or C) is the coalesced one.
+#include "common.cuh"
+
+namespace sml {
+
+// ------------------------------------------------------------------ landmarks
+// grid (m, B); block = h*d threads (<= 1024).  qkv [B, npad, 3, h, d]
+__global__ void landmarks_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ql, float* __restrict__ kl,
+                                     int npad, int h, int d, int m) {
+  const int j = blockIdx.x, b = blockIdx.y, c = threadIdx.x;   // c = head*d + dd
+  const int hd = h * d, l = npad / m;
+  const float* base = qkv + ((int64_t)b * npad + (int64_t)j * l) * 3 * hd;
+  float sq = 0.f, sk = 0.f;
+  for (int t = 0; t < l; ++t) {
+    sq += base[(int64_t)t * 3 * hd + c];
+    sk += base[(int64_t)t * 3 * hd + hd + c];
+  }
+  const int head = c / d, dd = c % d;
+  const int64_t o = (((int64_t)b * h + head) * m + j) * d + dd;
+  ql[o] = sq / (float)l;
+  kl[o] = sk / (float)l;
+}
+__global__ void landmarks_bwd_kernel(float* __restrict__ dqkv, const float* __restrict__ dql,
+                                     const float* __restrict__ dkl, int npad, int h, int d, int m) {
+  const int j = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+  const int hd = h * d, l = npad / m;
+  const int head = c / d, dd = c % d;
+  const int64_t o = (((int64_t)b * h + head) * m + j) * d + dd;
+  const float gq = dql[o] / (float)l, gk = dkl[o] / (float)l;
+  float* base = dqkv + ((int64_t)b * npad + (int64_t)j * l) * 3 * hd;
+  for (int t = 0; t < l; ++t) {
+    base[(int64_t)t * 3 * hd + c] += gq;
+    base[(int64_t)t * 3 * hd + hd + c] += gk;
+  }
+}
+__global__ void landmark_ids_kernel(int32_t* ids, int npad, int l) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < npad) ids[t] = t / l;
+}
+
+// ------------------------------------------------------------------ pinv scale (global max of row / column sums)
+// grid BH blocks, 256 threads.  packed[0] / packed[1]: (float bits << 32) | (0xFFFFFFFF - flat index)
+__global__ void __launch_bounds__(256) pinv_scale_kernel(const float* __restrict__ x, unsigned long long* packed, int m) {
+  __shared__ float red[32];
+  __shared__ unsigned long long best[2];
+  const int bh = blockIdx.x;
+  const float* X = x + (int64_t)bh * m * m;
+  if (threadIdx.x < 2) best[threadIdx.x] = 0ull;
+  __syncthreads();
+  // column sums: thread per column, coalesced across threads
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < m; ++i) s += fabsf(X[(int64_t)i * m + j]);
+    const unsigned long long p = ((unsigned long long)__float_as_uint(s) << 32) | (0xFFFFFFFFu - (unsigned)(bh * m + j));
+    atomicMax(&best[1], p);
+  }
+  // row sums: warp per row
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = wid; i < m; i += nw) {
+    float s = 0.f;
+    for (int j = lane; j < m; j += 32) s += fabsf(X[(int64_t)i * m + j]);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const unsigned long long p = ((unsigned long long)__float_as_uint(s) << 32) | (0xFFFFFFFFu - (unsigned)(bh * m + i));
+      atomicMax(&best[0], p);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) atomicMax(&packed[threadIdx.x], best[threadIdx.x]);
+  (void)red;
+}
+__global__ void pinv_scale_final_kernel(const unsigned long long* packed, float* scal, int32_t* arg) {
+  const int t = threadIdx.x;
+  if (t < 2) {
+    scal[t] = __uint_as_float((unsigned)(packed[t] >> 32));
+    arg[t] = (int32_t)(0xFFFFFFFFu - (unsigned)(packed[t] & 0xFFFFFFFFull));
+  }
+}
+// z0 = x^T / (scal0*scal1): 32x32 smem-tiled transpose. grid (m/32, m/32, BH), block (32,8)
+__global__ void pinv_init_kernel(const float* __restrict__ x, const float* __restrict__ scal, float* __restrict__ z0, int m) {
+  __shared__ float tile[32][33];
+  const float inv = 1.f / (scal[0] * scal[1]);
+  const int64_t off = (int64_t)blockIdx.z * m * m;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = by + r, j = bx + threadIdx.x;
+    tile[r][threadIdx.x] = (i < m && j < m) ? x[off + (int64_t)i * m + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = bx + r, j = by + threadIdx.x;     // z0[i,j] = x[j,i]
+    if (i < m && j < m) z0[off + (int64_t)i * m + j] = tile[threadIdx.x][r] * inv;
+  }
+}
+// dx[j,i] += dz0[i,j]/s ; acc += sum dz0[i,j]*x[j,i]
+__global__ void pinv_init_bwd_kernel(const float* __restrict__ x, const float* __restrict__ scal,
+                                     const float* __restrict__ dz0, float* __restrict__ dx, float* __restrict__ acc, int m) {
+  __shared__ float tile[32][33];
+  __shared__ float red[32];
+  const float inv = 1.f / (scal[0] * scal[1]);
+  const int64_t off = (int64_t)blockIdx.z * m * m;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = by + r, j = bx + threadIdx.x;
+    tile[r][threadIdx.x] = (i < m && j < m) ? dz0[off + (int64_t)i * m + j] : 0.f;
+  }
+  __syncthreads();
+  float part = 0.f;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int jj = bx + r, ii = by + threadIdx.x;   // x[jj, ii] pairs with dz0[ii, jj]
+    if (ii < m && jj < m) {
+      const float g = tile[threadIdx.x][r];
+      const int64_t o = off + (int64_t)jj * m + ii;
+      part += g * x[o];
+      dx[o] += g * inv;
+    }
+  }
+  // block reduce (256 threads laid out 32x8)
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  part = warp_sum(part);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(acc, s);
+  }
+}
+// scalar path: s = c*r, ds = -acc / s^2 ; dc = ds*r -> row arg[0] ; dr = ds*c -> column arg[1]
+__global__ void pinv_init_bwd_scalar_kernel(const float* __restrict__ x, const float* __restrict__ scal,
+                                            const int32_t* __restrict__ arg, const float* __restrict__ acc,
+                                            float* __restrict__ dx, int m) {
+  const float c = scal[0], r = scal[1];
+  const float s = c * r;
+  const float ds = -acc[0] / (s * s);
+  const float dc = ds * r, dr = ds * c;
+  const int64_t rowbase = (int64_t)arg[0] * m;                          // flat (bh*m + i) * m
+  const int64_t colbh = (int64_t)(arg[1] / m) * m * m, colj = arg[1] % m;
+  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+    const float xv = x[rowbase + t];
+    atomicAdd(&dx[rowbase + t], dc * (xv > 0.f ? 1.f : (xv < 0.f ? -1.f : 0.f)));
+    const int64_t o = colbh + (int64_t)t * m + colj;
+    const float xc = x[o];
+    atomicAdd(&dx[o], dr * (xc > 0.f ? 1.f : (xc < 0.f ? -1.f : 0.f)));
+  }
+}
+
+// ------------------------------------------------------------------ residual depthwise conv along tokens
+// src rows have stride src_ld, channel c; dst rows stride dst_ld.  dst[t,c] += sum_k w[c/d][k'] src[t + k - half, c]
+// with k' = k (fwd) or K-1-k (flip, used for the transposed conv in backward).  Each thread owns TT tokens.
+constexpr int RC_TT = 8;
+template <bool FLIP>
+__global__ void __launch_bounds__(512) resconv_kernel(const float* __restrict__ src, int64_t src_ld,
+                                                      const float* __restrict__ w, float* __restrict__ dst,
+                                                      int64_t dst_ld, int npad, int hd, int d, int K) {
+  extern __shared__ float sw[];   // [h*K]
+  const int h = hd / d;
+  for (int i = threadIdx.x; i < h * K; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * RC_TT;
+  const int half = K / 2;
+  for (int c = threadIdx.x; c < hd; c += blockDim.x) {
+    const float* wp = sw + (c / d) * K;
+    const float* s = src + (int64_t)b * npad * src_ld + c;
+    float acc[RC_TT];
+#pragma unroll
+    for (int i = 0; i < RC_TT; ++i) acc[i] = 0.f;
+    for (int u = -half; u < RC_TT + half; ++u) {       // source token t0+u contributes to outputs i = u-k+half
+      const int ts = t0 + u;
+      if (ts < 0 || ts >= npad) continue;
+      const float v = s[(int64_t)ts * src_ld];
+#pragma unroll
+      for (int i = 0; i < RC_TT; ++i) {
+        const int k = u - i + half;
+        if (k >= 0 && k < K) acc[i] = fmaf(wp[FLIP ? (K - 1 - k) : k], v, acc[i]);
+      }
+    }
+    float* o = dst + (int64_t)b * npad * dst_ld + c;
+#pragma unroll
+    for (int i = 0; i < RC_TT; ++i)
+      if (t0 + i < npad) o[(int64_t)(t0 + i) * dst_ld] += acc[i];
+  }
+}
+// dw_part[blk, head, k] = sum over the block's tokens and the head's d channels of dout[t,c] * v[t+k-half, c]
+constexpr int RCB_TOK = 64;
+__global__ void __launch_bounds__(512) resconv_dw_kernel(const float* __restrict__ v, int64_t v_ld,
+                                                         const float* __restrict__ dout, int64_t o_ld,
+                                                         float* __restrict__ dw_part, int npad, int hd, int d, int K) {
+  extern __shared__ float sdw[];   // [h*K]
+  const int h = hd / d;
+  for (int i = threadIdx.x; i < h * K; i += blockDim.x) sdw[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.y, t0 = blockIdx.x * RCB_TOK, half = K / 2;
+  const int t1 = min(npad, t0 + RCB_TOK);
+  for (int c = threadIdx.x; c < hd; c += blockDim.x) {
+    const float* vp = v + (int64_t)b * npad * v_ld + c;
+    const float* gp = dout + (int64_t)b * npad * o_ld + c;
+    for (int k = 0; k < K; ++k) {
+      float s = 0.f;
+      for (int t = t0; t < t1; ++t) {
+        const int ts = t + k - half;
+        if (ts >= 0 && ts < npad) s = fmaf(gp[(int64_t)t * o_ld], vp[(int64_t)ts * v_ld], s);
+      }
+      if ((d & 31) == 0) {
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[(c / d) * K + k], s);
+      } else {
+        atomicAdd(&sdw[(c / d) * K + k], s);
+      }
+    }
+  }
+  __syncthreads();
+  float* o = dw_part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * h * K;
+  for (int i = threadIdx.x; i < h * K; i += blockDim.x) o[i] = sdw[i];
+}
+
+// ------------------------------------------------------------------ PPEG 7x7 folded stencil, token-major
+// x,y [B, 1+H*W, C]; w7 [49, C] (tap-major so channel reads coalesce); bias [C].
+template <bool FLIP>
+__global__ void __launch_bounds__(256) ppeg_kernel(const float* __restrict__ x, const float* __restrict__ w7,
+                                                   const float* __restrict__ bias, float* __restrict__ y, int H, int W,
+                                                   int C) {
+  const int b = blockIdx.z;
+  const int tok = blockIdx.y;            // 0 .. H*W  (0 = cls row)
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int64_t base = (int64_t)b * (1 + H * W) * C;
+  if (tok == 0) { y[base + c] = x[base + c]; return; }
+  const int p = tok - 1, i = p / W, j = p % W;
+  float acc = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+  for (int di = 0; di < 7; ++di) {
+    const int ii = i + di - 3;
+    if (ii < 0 || ii >= H) continue;
+#pragma unroll
+    for (int dj = 0; dj < 7; ++dj) {
+      const int jj = j + dj - 3;
+      if (jj < 0 || jj >= W) continue;
+      const int tap = FLIP ? (48 - (di * 7 + dj)) : (di * 7 + dj);
+      acc = fmaf(__ldg(w7 + tap * C + c), x[base + (int64_t)(1 + ii * W + jj) * C + c], acc);
+    }
+  }
+  y[base + (int64_t)tok * C + c] = acc;
+}
+constexpr int PPB_TOK = 64;
+// dw_part[blk, tap, c], db_part[blk, c]; grid (ceil(HW/PPB_TOK), B), block C threads (loops if C > blockDim)
+__global__ void __launch_bounds__(512) ppeg_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                      float* __restrict__ dw_part, float* __restrict__ db_part, int H,
+                                                      int W, int C) {
+  const int b = blockIdx.y, p0 = blockIdx.x * PPB_TOK, p1 = min(H * W, p0 + PPB_TOK);
+  const int64_t base = (int64_t)b * (1 + H * W) * C;
+  const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[49];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) acc[t] = 0.f;
+    float ab = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const int i = p / W, j = p % W;
+      const float g = dy[base + (int64_t)(1 + p) * C + c];
+      ab += g;
+#pragma unroll
+      for (int di = 0; di < 7; ++di) {
+        const int ii = i + di - 3;
+#pragma unroll
+        for (int dj = 0; dj < 7; ++dj) {
+          const int jj = j + dj - 3;
+          if (ii >= 0 && ii < H && jj >= 0 && jj < W)
+            acc[di * 7 + dj] = fmaf(g, x[base + (int64_t)(1 + ii * W + jj) * C + c], acc[di * 7 + dj]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 49; ++t) dw_part[(blk * 49 + t) * C + c] = acc[t];
+    db_part[blk * C + c] = ab;
+  }
+}
+
+}  // namespace sml
+
+using namespace sml;
+
+extern "C" int sml_nystrom_landmarks_fwd(const float* qkv, float* ql, float* kl, int32_t B, int32_t npad, int32_t h,
+                                         int32_t d, int32_t m, void* stream) {
+  SML_CHECK(h * d <= 1024 && npad % m == 0, "sml_nystrom_landmarks_fwd: need h*d<=1024 and npad %% m == 0 (npad=%d m=%d)", npad, m);
+  landmarks_fwd_kernel<<<dim3(m, B), h * d, 0, as_stream(stream)>>>(qkv, ql, kl, npad, h, d, m);
+  SML_LAUNCH_OK("sml_nystrom_landmarks_fwd");
+  return 0;
+}
+extern "C" int sml_nystrom_landmarks_bwd(float* dqkv, const float* dql, const float* dkl, int32_t B, int32_t npad,
+                                         int32_t h, int32_t d, int32_t m, void* stream) {
+  SML_CHECK(h * d <= 1024 && npad % m == 0, "sml_nystrom_landmarks_bwd: bad sizes");
+  landmarks_bwd_kernel<<<dim3(m, B), h * d, 0, as_stream(stream)>>>(dqkv, dql, dkl, npad, h, d, m);
+  SML_LAUNCH_OK("sml_nystrom_landmarks_bwd");
+  return 0;
+}
+extern "C" int sml_nystrom_landmark_ids(int32_t* ids, int32_t npad, int32_t m, void* stream) {
+  SML_CHECK(m > 0 && npad % m == 0, "sml_nystrom_landmark_ids: npad %% m != 0");
+  landmark_ids_kernel<<<(npad + 255) / 256, 256, 0, as_stream(stream)>>>(ids, npad, npad / m);
+  SML_LAUNCH_OK("sml_nystrom_landmark_ids");
+  return 0;
+}
+extern "C" int sml_pinv_scale(const float* x, float* scal, int32_t* arg, void* packed_ws, int32_t BH, int32_t m,
+                              void* stream) {
+  cudaStream_t s = as_stream(stream);
+  SML_CHECK(cudaMemsetAsync(packed_ws, 0, 16, s) == cudaSuccess, "sml_pinv_scale: memset failed");
+  pinv_scale_kernel<<<BH, 256, 0, s>>>(x, (unsigned long long*)packed_ws, m);
+  SML_LAUNCH_OK("sml_pinv_scale");
+  pinv_scale_final_kernel<<<1, 32, 0, s>>>((const unsigned long long*)packed_ws, scal, arg);
+  SML_LAUNCH_OK("sml_pinv_scale_final");
+  return 0;
+}
+extern "C" int sml_pinv_init(const float* x, const float* scal, float* z0, int32_t BH, int32_t m, void* stream) {
+  pinv_init_kernel<<<dim3((m + 31) / 32, (m + 31) / 32, BH), dim3(32, 8), 0, as_stream(stream)>>>(x, scal, z0, m);
+  SML_LAUNCH_OK("sml_pinv_init");
+  return 0;
+}
+extern "C" int sml_pinv_init_bwd(const float* x, const float* scal, const int32_t* arg, const float* dz0, float* dx,
+                                 float* tmp, int32_t BH, int32_t m, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  SML_CHECK(cudaMemsetAsync(tmp, 0, 4, s) == cudaSuccess, "sml_pinv_init_bwd: memset failed");
+  pinv_init_bwd_kernel<<<dim3((m + 31) / 32, (m + 31) / 32, BH), dim3(32, 8), 0, s>>>(x, scal, dz0, dx, tmp, m);
+  SML_LAUNCH_OK("sml_pinv_init_bwd");
+  pinv_init_bwd_scalar_kernel<<<1, 256, 0, s>>>(x, scal, arg, tmp, dx, m);
+  SML_LAUNCH_OK("sml_pinv_init_bwd_scalar");
+  return 0;
+}
+extern "C" int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
+                                       int32_t d, int32_t ksize, void* stream) {
+  const int hd = h * d;
+  SML_CHECK(ksize % 2 == 1, "sml_nystrom_resconv_fwd: kernel size must be odd");
+  dim3 grid((npad + RC_TT - 1) / RC_TT, B);
+  resconv_kernel<false><<<grid, hd < 512 ? hd : 512, h * ksize * sizeof(float), as_stream(stream)>>>(
+      qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, ksize);
+  SML_LAUNCH_OK("sml_nystrom_resconv_fwd");
+  return 0;
+}
+extern "C" int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad) { return B * ((npad + RCB_TOK - 1) / RCB_TOK); }
+extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
+                                       int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* stream) {
+  const int hd = h * d;
+  cudaStream_t s = as_stream(stream);
+  dim3 grid((npad + RC_TT - 1) / RC_TT, B);
+  resconv_kernel<true><<<grid, hd < 512 ? hd : 512, h * ksize * sizeof(float), s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd,
+                                                                                   npad, hd, d, ksize);
+  SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
+  dim3 grid2((npad + RCB_TOK - 1) / RCB_TOK, B);
+  resconv_dw_kernel<<<grid2, hd < 512 ? hd : 512, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part,
+                                                                                 npad, hd, d, ksize);
+  SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dw)");
+  return 0;
+}
+extern "C" int sml_ppeg_fwd(const float* x, const float* w7, const float* bias, float* y, int32_t B, int32_t H, int32_t W,
+                            int32_t C, void* stream) {
+  dim3 grid((C + 255) / 256, 1 + H * W, B);
+  SML_CHECK(1 + H * W <= 65535 * 2 && grid.y <= 65535, "sml_ppeg_fwd: H*W too large for grid.y (%d)", H * W);
+  ppeg_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, w7, bias, y, H, W, C);
+  SML_LAUNCH_OK("sml_ppeg_fwd");
+  return 0;
+}
+extern "C" int sml_ppeg_bwd_blocks(int32_t B, int32_t H, int32_t W) { return B * ((H * W + PPB_TOK - 1) / PPB_TOK); }
+extern "C" int sml_ppeg_bwd(const float* x, const float* w7, const float* dy, float* dx, float* dw_part, float* db_part,
+                            int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  dim3 grid((C + 255) / 256, 1 + H * W, B);
+  SML_CHECK(grid.y <= 65535, "sml_ppeg_bwd: H*W too large for grid.y (%d)", H * W);
+  ppeg_kernel<true><<<grid, 256, 0, s>>>(dy, w7, nullptr, dx, H, W, C);     // transposed stencil = flipped taps
+  SML_LAUNCH_OK("sml_ppeg_bwd(dx)");
+  dim3 grid2((H * W + PPB_TOK - 1) / PPB_TOK, B);
+  ppeg_dw_kernel<<<grid2, C < 512 ? C : 512, 0, s>>>(x, dy, dw_part, db_part, H, W, C);
+  SML_LAUNCH_OK("sml_ppeg_bwd(dw)");
+  return 0;
+}

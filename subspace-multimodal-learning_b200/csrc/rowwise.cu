@@ -1,0 +1,372 @@
+// rowwise.cu — HBM-bound row kernels: LayerNorm fwd/bwd, softmax fwd/bwd, dropout+add, axpby, column sums.
+#include "common.cuh"
+
+namespace sml {
+
+// ------------------------------------------------------------------ LayerNorm
+// one warp per row; D % 4 == 0 (float4 I/O), D <= 1024
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, float* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd,
+                                                            int64_t R, int D, float eps, int64_t n, int64_t npad,
+                                                            int64_t pad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int64_t yrow = (row / n) * npad + pad + (row % n);   // destination row in the front-padded layout
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  const int nv = D >> 2;
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) { v[i] = xr[c]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  }
+  const float mu = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float a = v[i].x - mu, bb = v[i].y - mu, cc = v[i].z - mu, dd = v[i].w - mu;
+      q += a * a + bb * bb + cc * cc + dd * dd;
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  float4* yr = reinterpret_cast<float4*>(y + yrow * D);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float4 ww = __ldg(w4 + c), bb = __ldg(b4 + c);
+      float4 o;
+      o.x = (v[i].x - mu) * rs * ww.x + bb.x;
+      o.y = (v[i].y - mu) * rs * ww.y + bb.y;
+      o.z = (v[i].z - mu) * rs * ww.z + bb.z;
+      o.w = (v[i].w - mu) * rs * ww.w + bb.w;
+      yr[c] = o;
+    }
+  }
+}
+
+// Each block owns a contiguous slab of rows; a warp handles rows, accumulating dw/db partials in registers,
+// then the block reduces them through shared memory into dw_part[blk], db_part[blk].
+constexpr int LNB_WARPS = 8;
+__global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
+    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+    const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
+    float* __restrict__ dw_part, float* __restrict__ db_part, int64_t R, int D, int64_t rows_per_block, int64_t n,
+    int64_t npad, int64_t pad) {
+  extern __shared__ float sm[];   // [LNB_WARPS][2][D]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nv = D >> 2;
+  float4 aw[8], ab[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(R, r0 + rows_per_block);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  for (int64_t row = r0 + wid; row < r1; row += LNB_WARPS) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const float4* gr = reinterpret_cast<const float4*>(dy + ((row / n) * npad + pad + (row % n)) * D);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[8], g[8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        const float4 xv = xr[c], gv = gr[c], ww = __ldg(w4 + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        ab[i].x += gv.x; ab[i].y += gv.y; ab[i].z += gv.z; ab[i].w += gv.w;
+        aw[i].x += gv.x * xh[i].x; aw[i].y += gv.y * xh[i].y; aw[i].z += gv.z * xh[i].z; aw[i].w += gv.w * xh[i].w;
+        g[i] = make_float4(gv.x * ww.x, gv.y * ww.y, gv.z * ww.z, gv.w * ww.w);
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+      }
+    }
+    s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
+    float4* dr = reinterpret_cast<float4*>(dx + row * D);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+        dr[c] = o;
+      }
+    }
+  }
+  float4* sw = reinterpret_cast<float4*>(sm) + (size_t)wid * 2 * nv;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) { sw[c] = aw[i]; sw[nv + c] = ab[i]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < LNB_WARPS; ++wv) s += sm[(size_t)wv * 2 * D + c];
+    if (c < D) dw_part[(size_t)blockIdx.x * D + c] = s;
+    else db_part[(size_t)blockIdx.x * D + (c - D)] = s;
+  }
+}
+
+// ------------------------------------------------------------------ softmax
+// short rows (C <= 1024): one warp per row, row kept in registers
+template <int VPT>
+__global__ void __launch_bounds__(256) softmax_fwd_warp_kernel(float* __restrict__ x, int64_t R, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  float* xr = x + row * C;
+  float v[VPT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (c < C) ? xr[c] : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) { v[i] = __expf(v[i] - mx); s += v[i]; }
+  const float inv = 1.f / warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) xr[c] = v[i] * inv;
+  }
+}
+// long rows: one block per row, three passes through L2-resident data
+__global__ void __launch_bounds__(1024) softmax_fwd_block_kernel(float* __restrict__ x, int64_t C) {
+  __shared__ float red[32];
+  float* xr = x + (int64_t)blockIdx.x * C;
+  float mx = -INFINITY;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, xr[c]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) { const float e = __expf(xr[c] - mx); xr[c] = e; s += e; }
+  s = block_sum(s, red);
+  const float inv = 1.f / s;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) xr[c] *= inv;
+}
+template <int VPT>
+__global__ void __launch_bounds__(256) softmax_bwd_warp_kernel(const float* __restrict__ A, float* __restrict__ dA,
+                                                               int64_t R, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float* ar = A + row * C;
+  float* gr = dA + row * C;
+  float a[VPT], g[VPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    a[i] = (c < C) ? ar[c] : 0.f;
+    g[i] = (c < C) ? gr[c] : 0.f;
+    s += a[i] * g[i];
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) gr[c] = a[i] * (g[i] - s);
+  }
+}
+__global__ void __launch_bounds__(1024) softmax_bwd_block_kernel(const float* __restrict__ A, float* __restrict__ dA,
+                                                                 int64_t C) {
+  __shared__ float red[32];
+  const float* ar = A + (int64_t)blockIdx.x * C;
+  float* gr = dA + (int64_t)blockIdx.x * C;
+  float s = 0.f;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) s += ar[c] * gr[c];
+  s = block_sum(s, red);
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) gr[c] = ar[c] * (gr[c] - s);
+}
+
+// ------------------------------------------------------------------ dropout + add (counter-based RNG)
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {   // splitmix64 finaliser -> 32 bits
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 16);
+}
+__global__ void __launch_bounds__(256) dropout_add_kernel(const float* __restrict__ x, const float* __restrict__ u,
+                                                          float* __restrict__ y, int64_t n, float p, uint64_t seed,
+                                                          uint64_t offset) {
+  const float scale = 1.f / (1.f - p);
+  const uint32_t thresh = (uint32_t)(p * 4294967296.0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float uv = u[i];
+    if (p > 0.f) {
+      const uint32_t r = mix32(seed * 0xD1342543DE82EF95ull + offset + (uint64_t)i);
+      uv = (r >= thresh) ? uv * scale : 0.f;
+    }
+    y[i] = (x ? x[i] : 0.f) + uv;
+  }
+}
+__global__ void __launch_bounds__(256) axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b,
+                                                    int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a * x[i] + (b != 0.f ? b * y[i] : 0.f);
+}
+__global__ void __launch_bounds__(256) diag_axpby_kernel(float* __restrict__ out, const float* __restrict__ x, float a,
+                                                         float dg, int64_t total, int m) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i % ((int64_t)m * m);
+    const int r = (int)(e / m), c = (int)(e % m);
+    out[i] = a * x[i] + (r == c ? dg : 0.f);
+  }
+}
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                       float* __restrict__ dx, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+// out[c] = sum_r x[r,c] (+ beta*out).  grid.x covers columns in chunks of 32, 32x8 threads, rows strided by 8*gridDim.y
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ part, int64_t R,
+                                                     int64_t C) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < C)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < R; r += (int64_t)gridDim.y * 8) s += x[r * C + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][tx];
+    part[(int64_t)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int64_t C,
+                                    float beta) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * C + c];
+  out[c] = s + (beta != 0.f ? beta * out[c] : 0.f);
+}
+
+}  // namespace sml
+
+using namespace sml;
+
+extern "C" int sml_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
+                                 int64_t R, int32_t D, float eps, int64_t n, int64_t npad, int64_t pad, void* stream) {
+  SML_CHECK(n > 0 && npad >= n + pad && R % n == 0, "sml_layernorm_fwd: bad row mapping n=%lld npad=%lld pad=%lld",
+            (long long)n, (long long)npad, (long long)pad);
+  SML_CHECK(D % 4 == 0 && D <= 1024, "sml_layernorm_fwd: D=%d must be a multiple of 4 and <= 1024", D);
+  if (R == 0) return 0;
+  const int wpb = 8;
+  layernorm_fwd_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(x, w, b, y, mean, rstd, R, D, eps, n, npad, pad);
+  SML_LAUNCH_OK("sml_layernorm_fwd");
+  return 0;
+}
+extern "C" int sml_layernorm_bwd_blocks(int64_t R) {
+  int64_t nb = (R + 63) / 64;
+  if (nb > 2 * kNumSMs) nb = 2 * kNumSMs;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+extern "C" int sml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                                 float* dx, float* dw_part, float* db_part, int64_t R, int32_t D, int64_t n, int64_t npad,
+                                 int64_t pad, void* stream) {
+  SML_CHECK(D % 4 == 0 && D <= 1024, "sml_layernorm_bwd: D=%d must be a multiple of 4 and <= 1024", D);
+  const int nb = sml_layernorm_bwd_blocks(R);
+  const int64_t rpb = (R + nb - 1) / nb;
+  const size_t smem = (size_t)LNB_WARPS * 2 * D * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  layernorm_bwd_kernel<<<nb, LNB_WARPS * 32, smem, as_stream(stream)>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
+  SML_LAUNCH_OK("sml_layernorm_bwd");
+  return 0;
+}
+extern "C" int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* stream) {
+  if (R == 0 || C == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  const unsigned gw = (unsigned)((R + 7) / 8);
+  if (C <= 128) softmax_fwd_warp_kernel<4><<<gw, 256, 0, s>>>(x, R, (int)C);
+  else if (C <= 256) softmax_fwd_warp_kernel<8><<<gw, 256, 0, s>>>(x, R, (int)C);
+  else if (C <= 512) softmax_fwd_warp_kernel<16><<<gw, 256, 0, s>>>(x, R, (int)C);
+  else {
+    SML_CHECK(R <= 2147483647LL, "sml_softmax_fwd: too many rows");
+    softmax_fwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(x, C);
+  }
+  SML_LAUNCH_OK("sml_softmax_fwd");
+  return 0;
+}
+extern "C" int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* stream) {
+  if (R == 0 || C == 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  const unsigned gw = (unsigned)((R + 7) / 8);
+  if (C <= 128) softmax_bwd_warp_kernel<4><<<gw, 256, 0, s>>>(A, dA, R, (int)C);
+  else if (C <= 256) softmax_bwd_warp_kernel<8><<<gw, 256, 0, s>>>(A, dA, R, (int)C);
+  else if (C <= 512) softmax_bwd_warp_kernel<16><<<gw, 256, 0, s>>>(A, dA, R, (int)C);
+  else softmax_bwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(A, dA, C);
+  SML_LAUNCH_OK("sml_softmax_bwd");
+  return 0;
+}
+static inline unsigned ew_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+extern "C" int sml_dropout_add(const float* x, const float* u, float* y, int64_t n, float p, uint64_t seed,
+                               uint64_t offset, void* stream) {
+  SML_CHECK(p >= 0.f && p < 1.f, "sml_dropout_add: p=%f out of range", p);
+  if (n == 0) return 0;
+  dropout_add_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, u, y, n, p, seed, offset);
+  SML_LAUNCH_OK("sml_dropout_add");
+  return 0;
+}
+extern "C" int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  axpby_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, x, a, b, n);
+  SML_LAUNCH_OK("sml_axpby");
+  return 0;
+}
+extern "C" int sml_colsum_parts(int64_t R) {
+  int64_t p = (R + 255) / 256;
+  return (int)(p < 1 ? 1 : (p > 64 ? 64 : p));
+}
+extern "C" int sml_colsum(const float* x, float* out, float* part, int64_t R, int64_t C, float beta, void* stream) {
+  const int np = sml_colsum_parts(R);
+  dim3 grid((unsigned)((C + 31) / 32), np);
+  colsum_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, part, R, C);
+  SML_LAUNCH_OK("sml_colsum");
+  colsum_final_kernel<<<(unsigned)((C + 255) / 256), 256, 0, as_stream(stream)>>>(part, out, np, C, beta);
+  SML_LAUNCH_OK("sml_colsum_final");
+  return 0;
+}
+
+extern "C" int sml_diag_axpby(float* out, const float* x, float a, float dg, int64_t nmat, int32_t m, void* stream) {
+  const int64_t total = nmat * m * m;
+  if (total == 0) return 0;
+  diag_axpby_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(out, x, a, dg, total, m);
+  SML_LAUNCH_OK("sml_diag_axpby");
+  return 0;
+}
+extern "C" int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream) {
+  if (n == 0) return 0;
+  relu_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, dy, dx, n);
+  SML_LAUNCH_OK("sml_relu_bwd");
+  return 0;
+}

@@ -1,0 +1,150 @@
+"""Autograd functions for the glue ops of the path (Linear(+ReLU), LayerNorm, PPEG, dropout+residual).
+
+Every forward/backward is a C-ABI kernel call; there is no torch-eager arithmetic fallback.
+"""
+import torch
+
+from . import ops
+from ._lib import c_i32, check, lib, ptr, stream
+from .ops import F32, gemm, to_bf16
+
+_seed_state = {"seed": 0x5EED, "offset": 0}
+
+
+def manual_seed(seed):
+    _seed_state["seed"] = int(seed) & 0xFFFFFFFFFFFF
+    _seed_state["offset"] = 0
+
+
+def _next_offset(n):
+    o = _seed_state["offset"]
+    _seed_state["offset"] = o + int(n)
+    return o
+
+
+def _prep(t, mode):
+    return t if mode == "fp32" else to_bf16(t.contiguous(), split=(mode == "bf16x3"))
+
+
+def _T(op):
+    return op.transpose(-1, -2)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b, optional fused ReLU.  x [..., K] -> [..., N]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu, mode):
+        ops.require_cuda(x, w, b)
+        shp = x.shape
+        x2 = x.contiguous().view(-1, shp[-1])
+        y = gemm(_prep(x2, mode), _T(_prep(w.detach().contiguous(), mode)), bias=None if b is None else b.detach(), relu=relu)
+        ctx.save_for_backward(x2, w, y if relu else None)
+        ctx.cfg = (relu, mode, shp, b is not None)
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        relu, mode, shp, has_b = ctx.cfg
+        x2, w, y = ctx.saved_tensors
+        dy2 = dy.contiguous().view(-1, w.shape[0])
+        if relu:
+            g = torch.empty_like(dy2)
+            check(lib.sml_relu_bwd(ptr(y), ptr(dy2), ptr(g), ops.c_i64(g.numel()), stream()), "relu_bwd")
+            dy2 = g
+        dy_op = _prep(dy2, mode)
+        dx = gemm(dy_op, _prep(w.detach().contiguous(), mode)).view(shp) if ctx.needs_input_grad[0] else None
+        dw = gemm(_T(dy_op), _prep(x2, mode))
+        db = ops.colsum(dy2) if has_b else None
+        return dx, dw, db, None, None
+
+
+def linear(x, w, b=None, relu=False, mode="fp32"):
+    return LinearFn.apply(x, w, b, relu, mode)
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        ops.require_cuda(x, w, b)
+        shp = x.shape
+        x2 = x.contiguous().view(-1, shp[-1])
+        y = torch.empty_like(x2)
+        R = x2.shape[0]
+        mean, rstd = ops.layernorm_fwd(x2, w.detach(), b.detach(), y, R, R, 0, eps)
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.shp = shp
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        R = x2.shape[0]
+        dx, dw, db = ops.layernorm_bwd(dy.contiguous().view(R, -1), x2, w.detach(), mean, rstd, R, R, 0)
+        return dx.view(ctx.shp), dw, db, None
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+class DropoutAddFn(torch.autograd.Function):
+    """y = x + dropout(u, p)  (x may be None).  The mask is regenerated from (seed, offset) in backward."""
+
+    @staticmethod
+    def forward(ctx, x, u, p, seed, offset):
+        ops.require_cuda(u)
+        y = ops.dropout_add(None if x is None else x.contiguous(), u.contiguous(), p, seed, offset)
+        ctx.cfg = (p, seed, offset, x is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, offset, has_x = ctx.cfg
+        dy = dy.contiguous()
+        du = ops.dropout_add(None, dy, p, seed, offset) if p > 0 else dy
+        return (dy if has_x else None), du, None, None, None
+
+
+def dropout_add(x, u, p, training):
+    p = float(p) if training else 0.0
+    if p == 0.0 and x is None:
+        return u
+    off = _next_offset(u.numel()) if p > 0 else 0
+    return DropoutAddFn.apply(x, u, p, _seed_state["seed"], off)
+
+
+class PPEGFn(torch.autograd.Function):
+    """x [B,1+H*W,C] -> cls row copied, tokens get the folded 7x7 depthwise stencil (mil.py:192-206).
+    w7 [49,C] (tap-major) and bias [C] are the folded parameters (see models/mil.py:PPEG.folded)."""
+
+    @staticmethod
+    def forward(ctx, x, w7, bias, H, W):
+        ops.require_cuda(x, w7, bias)
+        x = x.contiguous()
+        B, T, C = x.shape
+        assert T == 1 + H * W
+        y = torch.empty_like(x)
+        w7c = w7.detach().contiguous()
+        check(lib.sml_ppeg_fwd(ptr(x), ptr(w7c), ptr(bias.detach()), ptr(y), c_i32(B), c_i32(H), c_i32(W), c_i32(C), stream()),
+              "ppeg_fwd")
+        ctx.save_for_backward(x, w7c)
+        ctx.cfg = (B, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C = ctx.cfg
+        x, w7 = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        nb = lib.sml_ppeg_bwd_blocks(c_i32(B), c_i32(H), c_i32(W))
+        dwp = torch.empty(nb, 49 * C, device=x.device, dtype=F32)
+        dbp = torch.empty(nb, C, device=x.device, dtype=F32)
+        check(lib.sml_ppeg_bwd(ptr(x), ptr(w7), ptr(dy), ptr(dx), ptr(dwp), ptr(dbp), c_i32(B), c_i32(H), c_i32(W), c_i32(C),
+                               stream()), "ppeg_bwd")
+        return dx, ops.colsum(dwp).view(49, C), ops.colsum(dbp), None, None
+
+
+def ppeg(x, w7, bias, H, W):
+    return PPEGFn.apply(x, w7, bias, H, W)

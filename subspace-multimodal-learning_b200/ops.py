@@ -1,0 +1,177 @@
+"""Thin Python wrappers over the C-ABI primitives: tensors in, tensors out, current stream, no fallback."""
+import ctypes
+
+import torch
+
+from ._lib import GemmDesc, c_f32, c_i32, c_i64, c_u64, c_vp, check, lib, ptr, require_cuda, stream
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+class Split:
+    """bf16 operand for the tensor-core engine: ``hi`` (+ optional ``lo`` residual for the bf16x3 split).
+    ``map(f)`` applies the same view function to both parts."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+    def map(self, f):
+        return Split(f(self.hi), None if self.lo is None else f(self.lo))
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def transpose(self, a, b):
+        return self.map(lambda t: t.transpose(a, b))
+
+
+def to_bf16(x, split=False):
+    """fp32 -> Split(bf16 hi[, lo]) with one pass of the split kernel (x must be contiguous)."""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    hi = torch.empty_like(x, dtype=BF16)
+    lo = torch.empty_like(x, dtype=BF16) if split else None
+    check(lib.sml_split_bf16(ptr(x), ptr(hi), ptr(lo), c_i64(x.numel()), stream()), "split_bf16")
+    return Split(hi, lo)
+
+
+def _batch_strides(t, nb):
+    """t has shape [*batch, r, c] with len(batch) <= 2; returns (s_b1, s_b2) honouring broadcast (size-1) dims."""
+    bs = t.shape[:-2]
+    st = t.stride()[:-2]
+    pads = 2 - len(bs)
+    bs = (1,) * pads + tuple(bs)
+    st = (0,) * pads + tuple(st)
+    out = []
+    for want, have, s in zip(nb, bs, st):
+        assert have == want or have == 1, "batch dims %s do not broadcast to %s" % (bs, nb)
+        out.append(0 if have == 1 else s)
+    return out
+
+
+def gemm(A, B, out=None, *, alpha=1.0, beta=0.0, diag=0.0, bias=None, relu=False, softmax=False,
+         out_bf16=None, out_bf16_lo=None, want_f32=True):
+    """out[..., M, N] = epi(alpha * A[..., M, K] @ B[..., K, N]).
+
+    fp32 tensors -> SIMT fp32 engine (sml_gemm_f32); ``Split`` operands -> tcgen05 engine (sml_gemm_tc).
+    Any strides / transposed views are passed through as strides (no copies).  ``softmax`` (row softmax
+    over N fused in the epilogue) is only available on the tensor-core engine with N <= 256.
+    """
+    tc = isinstance(A, Split)
+    assert tc == isinstance(B, Split), "both operands must use the same engine"
+    a, b = (A.hi, B.hi) if tc else (A, B)
+    require_cuda(a, b, out)
+    M, K = a.shape[-2:]
+    K2, N = b.shape[-2:]
+    assert K == K2, "inner dims differ: %s @ %s" % (tuple(a.shape), tuple(b.shape))
+    ba, bb = a.shape[:-2], b.shape[:-2]
+    nbs = torch.broadcast_shapes(ba, bb)
+    assert len(nbs) <= 2
+    nb = (1,) * (2 - len(nbs)) + tuple(nbs)
+    if out is None and (want_f32 or not tc):
+        out = torch.empty(tuple(nbs) + (M, N), device=a.device, dtype=F32)
+        assert beta == 0.0
+    d = GemmDesc()
+    d.M, d.N, d.K, d.nb1, d.nb2 = M, N, K, nb[0], nb[1]
+    d.A = a.data_ptr(); d.sa_m, d.sa_k = a.stride(-2), a.stride(-1)
+    d.sa_b1, d.sa_b2 = _batch_strides(a, nb)
+    d.B = b.data_ptr(); d.sb_k, d.sb_n = b.stride(-2), b.stride(-1)
+    d.sb_b1, d.sb_b2 = _batch_strides(b, nb)
+    ref = out if out is not None else out_bf16
+    assert ref is not None and tuple(ref.shape[-2:]) == (M, N)
+    d.C = out.data_ptr() if out is not None else None
+    d.sc_m, d.sc_n = ref.stride(-2), ref.stride(-1)
+    d.sc_b1, d.sc_b2 = _batch_strides(ref, nb)
+    d.alpha, d.beta, d.diag = alpha, beta, diag
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.relu = (1 if relu else 0) | (2 if softmax else 0)
+    if tc:
+        assert a.dtype == BF16 and b.dtype == BF16
+        if (A.lo is None) != (B.lo is None):     # mixed: give the single-precision side a zero residual? no: drop to single pass
+            A, B = Split(A.hi), Split(B.hi)
+        d.A_lo = A.lo.data_ptr() if A.lo is not None else None
+        d.B_lo = B.lo.data_ptr() if B.lo is not None else None
+        if A.lo is not None:
+            assert A.lo.stride() == a.stride() and B.lo.stride() == b.stride()
+        for ob in (out_bf16, out_bf16_lo):
+            if ob is not None:
+                assert ob.dtype == BF16 and ob.stride() == ref.stride()
+        d.Cb_hi = out_bf16.data_ptr() if out_bf16 is not None else None
+        d.Cb_lo = out_bf16_lo.data_ptr() if out_bf16_lo is not None else None
+        check(lib.sml_gemm_tc(ctypes.byref(d), stream()), "gemm_tc")
+    else:
+        assert a.dtype == F32 and b.dtype == F32 and not softmax and out_bf16 is None
+        check(lib.sml_gemm_f32(ctypes.byref(d), stream()), "gemm_f32")
+    return out
+
+
+def layernorm_fwd(x2d, w, b, y, n, npad, pad, eps=1e-5):
+    R, D = x2d.shape
+    mean = torch.empty(R, device=x2d.device, dtype=F32)
+    rstd = torch.empty(R, device=x2d.device, dtype=F32)
+    check(lib.sml_layernorm_fwd(ptr(x2d), ptr(w), ptr(b), ptr(y), ptr(mean), ptr(rstd), c_i64(R), c_i32(D), c_f32(eps),
+                                c_i64(n), c_i64(npad), c_i64(pad), stream()), "layernorm_fwd")
+    return mean, rstd
+
+
+def layernorm_bwd(dy, x2d, w, mean, rstd, n, npad, pad):
+    R, D = x2d.shape
+    nb = lib.sml_layernorm_bwd_blocks(c_i64(R))
+    dx = torch.empty_like(x2d)
+    dwp = torch.empty(nb, D, device=x2d.device, dtype=F32)
+    dbp = torch.empty(nb, D, device=x2d.device, dtype=F32)
+    check(lib.sml_layernorm_bwd(ptr(dy), ptr(x2d), ptr(w), ptr(mean), ptr(rstd), ptr(dx), ptr(dwp), ptr(dbp), c_i64(R),
+                                c_i32(D), c_i64(n), c_i64(npad), c_i64(pad), stream()), "layernorm_bwd")
+    return dx, colsum(dwp), colsum(dbp)
+
+
+def colsum(x2d, out=None, beta=0.0):
+    R, C = x2d.shape
+    if out is None:
+        out = torch.empty(C, device=x2d.device, dtype=F32)
+    part = torch.empty(lib.sml_colsum_parts(c_i64(R)), C, device=x2d.device, dtype=F32)
+    check(lib.sml_colsum(ptr(x2d), ptr(out), ptr(part), c_i64(R), c_i64(C), c_f32(beta), stream()), "colsum")
+    return out
+
+
+def softmax_(x2d):
+    R, C = x2d.shape
+    assert x2d.is_contiguous()
+    check(lib.sml_softmax_fwd(ptr(x2d), c_i64(R), c_i64(C), stream()), "softmax_fwd")
+    return x2d
+
+
+def softmax_bwd_(A2d, dA2d):
+    R, C = A2d.shape
+    assert A2d.is_contiguous() and dA2d.is_contiguous()
+    check(lib.sml_softmax_bwd(ptr(A2d), ptr(dA2d), c_i64(R), c_i64(C), stream()), "softmax_bwd")
+    return dA2d
+
+
+def dropout_add(x, u, p, seed, offset=0, out=None):
+    """out = x + dropout(u, p) (x may be None).  Same (seed, offset) regenerates the mask (used for backward)."""
+    assert u.is_contiguous() and (x is None or x.is_contiguous())
+    if out is None:
+        out = torch.empty_like(u)
+    check(lib.sml_dropout_add(ptr(x), ptr(u), ptr(out), c_i64(u.numel()), c_f32(p), c_u64(seed), c_u64(offset), stream()),
+          "dropout_add")
+    return out
+
+
+def axpby_(y, x, a, b):
+    assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
+    check(lib.sml_axpby(ptr(y), ptr(x), c_f32(a), c_f32(b), c_i64(y.numel()), stream()), "axpby")
+    return y
+
+
+def diag_axpby(x, a, dg, out=None):
+    """out = a*x + dg*I for a batch of square matrices."""
+    m = x.shape[-1]
+    assert x.is_contiguous() and x.shape[-2] == m
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.sml_diag_axpby(ptr(out), ptr(x), c_f32(a), c_f32(dg), c_i64(x.numel() // (m * m)), c_i32(m), stream()),
+          "diag_axpby")
+    return out

@@ -1,0 +1,55 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sml_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "sml_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sml_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    import sml_b200  # builds the library if needed
+    lib = ctypes.CDLL(os.path.join(ROOT, "subspace-multimodal-learning_b200", "libsml_b200.so"))
+    names = _declared()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sml_b200._lib.lib.sml_version() >= 100
+
+
+def test_gemm_desc_layout_matches_header():
+    """ctypes mirror of sml_gemm_desc: field order / count follow the header."""
+    import sml_b200
+    src = open(os.path.join(ROOT, "include", "sml_b200.h")).read()
+    body = re.search(r"typedef struct sml_gemm_desc \{(.*?)\} sml_gemm_desc;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = re.sub(r"^(const\s+)?(void|float|int32_t|int64_t)\s*\*?", "", decl)
+        fields += [n.strip().lstrip("*").strip() for n in names.split(",")]
+    assert fields == [f[0] for f in sml_b200._lib.GemmDesc._fields_]
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    import sml_b200
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        sml_b200.NystromAttention(dim=64, dim_head=8, heads=8, num_landmarks=16)(torch.randn(1, 20, 64))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "subspace-multimodal-learning_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)

@@ -1,0 +1,128 @@
+"""GPU parity: Nystrom attention / TransLayer / PPEG / TransMIL on libsml_b200 vs the CPU oracle and the
+golden fixtures made from the unmodified reference.  Tolerances are BASELINE.json's: 1e-4 relative in the
+fp32 modes ("fp32" SIMT and "bf16x3" tensor-core split), 2e-2 in bf16; landmark ids bit-exact."""
+import pytest
+import torch
+
+import oracle
+from conftest import grads_close, load_golden, rel_err
+from synth import randn, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16x3": 1e-4, "bf16": 2e-2}
+MODES = ["fp32", "bf16x3", "bf16"]
+
+
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_pinv_golden(mode):
+    import sml_b200
+    from sml_b200.nystrom import pinv_fwd, pinv_bwd
+    g = load_golden("pinv")
+    x = g["x"].cuda()
+    z, saved = pinv_fwd(x, g["iters"], mode)
+    assert rel_err(z, g["z"]) < 1e-4
+    gx = pinv_bwd(x, saved, g["gz"].cuda(), mode)
+    assert rel_err(gx, g["gx"]) < 1e-3
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_nystrom_golden(mode):
+    import sml_b200
+    for c in load_golden("nystrom"):
+        cfg = c["cfg"]
+        mod = sml_b200.NystromAttention(dim=cfg["dim"], dim_head=cfg["dim_head"], heads=cfg["heads"],
+                                        num_landmarks=cfg["num_landmarks"], pinv_iterations=cfg["pinv_iterations"],
+                                        dropout=0.1).cuda().eval()
+        mod.load_state_dict(c["state"])
+        mod.precision = mode
+        x = c["x"].cuda().requires_grad_()
+        y = mod(x)
+        assert rel_err(y, c["y"]) < TOL[mode], cfg
+        y.backward(c["gy"].cuda())
+        assert rel_err(x.grad, c["gx"]) < 10 * TOL[mode], cfg
+        grads_close({k: p.grad for k, p in mod.named_parameters()}, c["gparams"], 10 * TOL[mode], what=str(cfg))
+        n, m = x.shape[1], cfg["num_landmarks"]
+        ids = mod.landmark_ids(n).cpu().long()
+        npad = n + (m - n % m) % m
+        assert torch.equal(ids, oracle.nystrom.landmark_ids(npad, m))        # bit-exact index contract
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_nystrom_vs_oracle_mid_size(mode):
+    """dim 512 / 8 heads / d 64 / m 256 (the TransMIL configuration) on a 1 000-token bag, fwd + bwd."""
+    import sml_b200
+    torch.manual_seed(0)
+    mod = sml_b200.NystromAttention(dim=512, dim_head=64, heads=8, num_landmarks=256, pinv_iterations=6).cuda().eval()
+    mod.precision = mode
+    p = {k: v.detach().cpu().clone().requires_grad_() for k, v in mod.state_dict().items()}
+    xc = randn((2, 1001, 512), 5).requires_grad_()
+    gy = randn((2, 1001, 512), 6)
+    yo = oracle.nystrom.nystrom_attention(xc, p, heads=8, num_landmarks=256, pinv_iterations=6)
+    yo.backward(gy)
+    x = xc.detach().cuda().requires_grad_()
+    y = mod(x)
+    assert rel_err(y, yo) < TOL[mode]
+    y.backward(gy.cuda())
+    assert rel_err(x.grad, xc.grad) < 10 * TOL[mode]
+    grads_close({k: q.grad for k, q in mod.named_parameters()}, {k: v.grad for k, v in p.items()}, 10 * TOL[mode])
+
+
+def test_translayer_ppeg_golden():
+    import sml_b200
+    g = load_golden("translayer_ppeg")
+    tl = sml_b200.TransLayer(dim=64).cuda().eval()
+    tl.load_state_dict(g["tl_state"])
+    x = g["x"].cuda().requires_grad_()
+    y = tl(x)
+    assert rel_err(y, g["y"]) < 1e-4
+    y.backward(g["gy"].cuda())
+    assert rel_err(x.grad, g["gx"]) < 1e-3
+    grads_close({k: p.grad for k, p in tl.named_parameters()}, g["tl_gparams"], 1e-3)
+    pp = sml_b200.PPEG(dim=64).cuda().eval()
+    pp.load_state_dict(g["pp_state"])
+    x = g["px"].cuda().requires_grad_()
+    y = pp(x, 6, 6)
+    assert rel_err(y, g["py"]) < 1e-5
+    y.backward(g["pgy"].cuda())
+    assert rel_err(x.grad, g["pgx"]) < 1e-5
+    grads_close({k: p.grad for k, p in pp.named_parameters()}, g["pp_gparams"], 1e-4)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_transmil_golden(mode):
+    import sml_b200
+    from argparse import Namespace
+    g = load_golden("transmil")
+    tm = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).cuda().eval()
+    tm.load_state_dict(synth_state_dict(g["shapes"], g["seed"]))
+    tm.set_precision(mode)
+    x = randn(g["x_shape"], g["x_seed"]).cuda()
+    enc, logits, _ = tm(x)
+    assert rel_err(logits, g["logits"]) < TOL[mode]
+    assert rel_err(enc, g["enc"]) < TOL[mode]
+    loss = (logits * randn(logits.shape, g["glogits_seed"]).cuda()).sum() + (enc * randn(enc.shape, g["genc_seed"]).cuda()).sum()
+    loss.backward()
+    gp = {k: p.grad for k, p in tm.named_parameters()}
+    grads_close({k: gp[k] for k in g["gparams"]}, g["gparams"], 20 * TOL[mode])
+    for k, nv in g["gnorms"].items():
+        if gp[k] is None:
+            continue
+        assert abs(float(gp[k].norm()) - nv) <= 20 * TOL[mode] * nv + 1e-5, (k, float(gp[k].norm()), nv)
+
+
+def test_dropout_statistics():
+    import sml_b200
+    from sml_b200 import functional as Fn
+    Fn.manual_seed(1)
+    u = torch.ones(1 << 20, device="cuda", requires_grad=True)
+    y = Fn.dropout_add(None, u, 0.1, True)
+    keep = (y != 0).float().mean().item()
+    assert abs(keep - 0.9) < 2e-3
+    assert abs(y.mean().item() - 1.0) < 5e-3
+    y.sum().backward()
+    assert torch.equal(u.grad != 0, y != 0)          # same mask regenerated in backward
