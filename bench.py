@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py — train slides/sec on 16k-patch bags (BASELINE.json metric), one process per GPU.
+
+Workload (BASELINE.json configs[1]): Nystrom-attention TransMIL (dim 512, 8 heads x 64, 256 landmarks, 6 pinv
+iterations, PPEG, 2 layers) on synthetic bags of 16 384 x 1024-d patch embeddings; one "step" = forward + CE loss +
+backward + Adam step on `--batch` slides per GPU (data parallel over slides, gradient all-reduce over NCCL).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+import torch  # noqa: E402
+
+METRIC = "train slides/sec at 16k-patch bags"
+UNIT = "slides/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SML_PRECISION", "bf16"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--batch", type=int, default=2, help="slides per step per GPU")
+    ap.add_argument("--patches", type=int, default=16384)
+    ap.add_argument("--cpu-sample", type=int, default=1, help="slides in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
+
+
+def synth_bag(batch, patches, seed, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn(batch, patches, 1024, generator=g, device=device)
+    y = torch.randint(0, 4, (batch,), generator=g, device=device)
+    return x, y
+
+
+# ------------------------------------------------------------------------------------------- reference arm / CPU
+def cpu_port_step_fn(patches, threads):
+    """The reference algorithm (oracle restatement of models/mil.py:209-259 + NystromAttention) on host cores."""
+    import oracle
+    from argparse import Namespace
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    import sml_b200
+    shapes = {k: tuple(v.shape) for k, v in sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).state_dict().items()}
+    from synth import synth_state_dict
+    params = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in synth_state_dict(shapes, 7).items()}
+    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-3, weight_decay=0.1)
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        _, logits = oracle.nystrom.transmil(x, params)
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    step = cpu_port_step_fn(args.patches, threads)
+    x, y = synth_bag(1, args.patches, 42, "cpu")
+    for _ in range(min(args.warmup, 1)):
+        step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(x, y)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TransMIL(Nystrom m=256, 6 pinv iters) fwd+loss+bwd+Adam, %d-patch bags, 1 slide/step"
+                                   % args.patches, "arm": "oracle port of the reference algorithm on host cores"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d steps x 1 slide of %d patches, fp32, %d of %d host threads"
+                                       % (args.steps, args.patches, torch.get_num_threads(), threads)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from argparse import Namespace
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import sml_b200
+    from sml_b200 import functional as Fn
+    from sml_b200 import ops
+
+    torch.manual_seed(42)
+    model = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev).train()
+    model.set_precision(args.precision)
+    Fn.manual_seed(42 + rank)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                        broadcast_buffers=False, gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
+    B, N = args.batch, args.patches
+    x_dev, y_dev = synth_bag(B, N, 42 + rank, dev)
+    x_host = x_dev.cpu().pin_memory()
+    y_host = y_dev.cpu().pin_memory()
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        _, logits, _ = net(x)
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = sml_b200._lib.launch_count()
+    ms = timed(lambda: step(x_dev, y_dev), args.steps)
+    launches = sml_b200._lib.launch_count() - l0
+    sampler.stop_flag = True
+
+    def e2e_step():
+        x = x_host.to(dev, non_blocking=True)
+        y = y_host.to(dev, non_blocking=True)
+        return float(step(x, y).detach())          # D2H read of the loss
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- per-kernel roofline: instrumented pass (CUDA events around every GEMM launch on the launch stream)
+    ops.PROFILE = []
+    step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg = {}
+    for eng, flops, e0, e1 in prof:
+        a = agg.setdefault(eng, [0.0, 0.0, 0])
+        a[0] += flops; a[1] += e0.elapsed_time(e1) * 1e-3; a[2] += 1
+    pk, pk_src = peaks()
+    roof = None
+    if "tc" in agg and agg["tc"][1] > 0:
+        f, t, n = agg["tc"]
+        ach = f / t / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"kernel": "gemm_tc_kernel (tcgen05, all %d launches of one step)" % n, "bound": "tensor", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " (sustained)",
+                "share_of_step": t / (ms * 1e-3 / args.steps),
+                "note": "bf16x3 launches count 1x algorithmic FLOPs (3 MMA passes executed)"}
+    elif "simt" in agg:
+        f, t, n = agg["simt"]
+        roof = {"kernel": "gemm_f32_kernel (SIMT fp32, %d launches)" % n, "bound": "tensor", "achieved": f / t / 1e12,
+                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": f / t / 1e12 / pk["bf16_tflops_sustained"],
+                "traffic": None, "peak_source": pk_src}
+
+    if rank == 0:
+        total = B * world * args.steps
+        line = {"metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "f32 (bf16x3 split)", "fp32": "f32"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags"
+                                       % N, "slides_per_step_per_gpu": B, "global_batch": B * world, "precision": args.precision,
+                           "parallelism": "dp%d" % world, "l2": "inputs (%d MB/step) and activations exceed the 126 MB L2"
+                                                              % (B * N * 1024 * 4 // 2 ** 20)},
+                "gpu_launches": int(launches),
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
+                        "d2h_bytes_per_step": 4},
+                "clocks": sampler.summary(), "roofline": roof}
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            cstep = cpu_port_step_fn(N, threads)
+            xs, ys = synth_bag(1, N, 42, "cpu")
+            t0 = time.perf_counter()
+            for _ in range(args.cpu_sample):
+                cstep(xs, ys)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "%d slide(s) of %d patches, fwd+CE+bwd+Adam, fp32 oracle port, %d host threads"
+                                              % (args.cpu_sample, N, torch.get_num_threads())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
 
 struct EpiParams {
   int M, N, K, nb2;
+  int a_c1, a_c2, b_c1, b_c2;   // 0 when that batch dim is broadcast for the operand (TMA coordinate stays 0)
   float* C; int64_t sc_m, sc_n, sc_b1, sc_b2;
   __nv_bfloat16* Cb_hi; __nv_bfloat16* Cb_lo;
   float alpha, beta, diag;
@@ -193,15 +194,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const CUtensorMap* tb = part ? &tmBl : &tmB;
           uint8_t* ad = a_dst + part * TC_A_BYTES;
           uint8_t* bd = b_dst + part * S::B_BYTES;
-          if (!A_MN) tma_load_4d(ad, ta, &full_bar[s], k0, m0, b2, b1);
+          const int ab1 = b1 * ep.a_c1, ab2 = b2 * ep.a_c2, bb1 = b1 * ep.b_c1, bb2 = b2 * ep.b_c2;
+          if (!A_MN) tma_load_4d(ad, ta, &full_bar[s], k0, m0, ab2, ab1);
           else {
 #pragma unroll
-            for (int c = 0; c < TC_BM / 64; ++c) tma_load_4d(ad + c * 8192, ta, &full_bar[s], m0 + c * 64, k0, b2, b1);
+            for (int c = 0; c < TC_BM / 64; ++c) tma_load_4d(ad + c * 8192, ta, &full_bar[s], m0 + c * 64, k0, ab2, ab1);
           }
-          if (!B_MN) tma_load_4d(bd, tb, &full_bar[s], k0, n0, b2, b1);
+          if (!B_MN) tma_load_4d(bd, tb, &full_bar[s], k0, n0, bb2, bb1);
           else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_4d(bd + c * 8192, tb, &full_bar[s], n0 + c * 64, k0, b2, b1);
+            for (int c = 0; c < BN / 64; ++c) tma_load_4d(bd + c * 8192, tb, &full_bar[s], n0 + c * 64, k0, bb2, bb1);
           }
         }
       }
@@ -400,7 +402,7 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
 
   const int softmax = (d->relu & 2) ? 1 : 0;
   int BN = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
-  if (split && BN == 256) BN = 128;
+  if (split && BN == 256 && !softmax) BN = 128;   // split keeps 128-wide tiles (smem) unless a fused softmax needs the row
   SML_CHECK(!softmax || d->N <= BN, "sml_gemm_tc: fused row softmax needs N <= %d (N=%d)", BN, d->N);
 
   CUtensorMap tms[4];
@@ -420,6 +422,8 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
 
   EpiParams ep;
   ep.M = d->M; ep.N = d->N; ep.K = d->K; ep.nb2 = d->nb2;
+  ep.a_c1 = (d->nb1 > 1 && d->sa_b1 != 0) ? 1 : 0; ep.a_c2 = (d->nb2 > 1 && d->sa_b2 != 0) ? 1 : 0;
+  ep.b_c1 = (d->nb1 > 1 && d->sb_b1 != 0) ? 1 : 0; ep.b_c2 = (d->nb2 > 1 && d->sb_b2 != 0) ? 1 : 0;
   ep.C = (float*)d->C; ep.sc_m = d->sc_m; ep.sc_n = d->sc_n; ep.sc_b1 = d->sc_b1; ep.sc_b2 = d->sc_b2;
   ep.Cb_hi = (__nv_bfloat16*)d->Cb_hi; ep.Cb_lo = (__nv_bfloat16*)d->Cb_lo;
   ep.alpha = d->alpha; ep.beta = d->beta; ep.diag = d->diag; ep.bias = d->bias;
@@ -437,6 +441,7 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
     if (BN == 128) return deep ? dispatch_major<128, false, 6>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<128, false, 2>(a_mn, b_mn, tms, ep, grid, st);
     return deep ? dispatch_major<64, false, 8>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<64, false, 2>(a_mn, b_mn, tms, ep, grid, st);
   } else {
+    if (BN == 256) return dispatch_major<256, true, 2>(a_mn, b_mn, tms, ep, grid, st);
     if (BN == 128) return deep ? dispatch_major<128, true, 3>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<128, true, 2>(a_mn, b_mn, tms, ep, grid, st);
     return deep ? dispatch_major<64, true, 4>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<64, true, 2>(a_mn, b_mn, tms, ep, grid, st);
   }

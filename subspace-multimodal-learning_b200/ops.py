@@ -7,6 +7,9 @@ from ._lib import GemmDesc, c_f32, c_i32, c_i64, c_u64, c_vp, check, lib, ptr, r
 
 F32, BF16 = torch.float32, torch.bfloat16
 
+# bench instrumentation: when a list, every gemm() appends (engine, algorithmic flops, start event, end event)
+PROFILE = None
+
 
 class Split:
     """bf16 operand for the tensor-core engine: ``hi`` (+ optional ``lo`` residual for the bf16x3 split).
@@ -100,10 +103,18 @@ def gemm(A, B, out=None, *, alpha=1.0, beta=0.0, diag=0.0, bias=None, relu=False
                 assert ob.dtype == BF16 and ob.stride() == ref.stride()
         d.Cb_hi = out_bf16.data_ptr() if out_bf16 is not None else None
         d.Cb_lo = out_bf16_lo.data_ptr() if out_bf16_lo is not None else None
-        check(lib.sml_gemm_tc(ctypes.byref(d), stream()), "gemm_tc")
+        fn, eng = lib.sml_gemm_tc, "tc"
     else:
         assert a.dtype == F32 and b.dtype == F32 and not softmax and out_bf16 is None
-        check(lib.sml_gemm_f32(ctypes.byref(d), stream()), "gemm_f32")
+        fn, eng = lib.sml_gemm_f32, "simt"
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(ctypes.byref(d), stream()), "gemm_" + eng)
+        e1.record()
+        PROFILE.append((eng, 2.0 * M * N * K * nb[0] * nb[1], e0, e1))
+    else:
+        check(fn(ctypes.byref(d), stream()), "gemm_" + eng)
     return out
 
 

@@ -27,7 +27,16 @@ def test_pinv_golden(mode):
     z, saved = pinv_fwd(x, g["iters"], mode)
     assert rel_err(z, g["z"]) < 1e-4
     gx = pinv_bwd(x, saved, g["gz"].cuda(), mode)
-    assert rel_err(gx, g["gx"]) < 1e-3
+    # The init scale is max(row sums) * max(col sums) of a softmax output: every row sum is 1 up to an ulp, so
+    # WHICH row is the arg-max (and receives the scalar's gradient as a row-constant shift) is decided by
+    # rounding — the reference's own fp32 gradient differs from an fp64 evaluation by 5e-2 here.  On the path x
+    # is always a softmax output and a row-constant shift of dx is annihilated by the softmax backward, so
+    # parity is stated on the gradient w.r.t. the logits: ds = x * (dx - sum(dx * x)).
+    def through_softmax(gxx):
+        xx = g["x"].double()
+        gxx = gxx.detach().double().cpu()
+        return xx * (gxx - (gxx * xx).sum(-1, keepdim=True))
+    assert rel_err(through_softmax(gx), through_softmax(g["gx"])) < 1e-3
 
 
 @pytest.mark.parametrize("mode", MODES)
