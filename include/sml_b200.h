@@ -82,6 +82,12 @@ int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* strea
 int sml_diag_axpby(float* out, const float* x, float a, float dg, int64_t nmat, int32_t m, void* stream);
 /* dx = dy where y > 0 else 0 (ReLU of models/mil.py:214, models/DeformCrossTransMIL.py:83) */
 int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+/* y[b,t,:] = (x ? x[b,t,:] : 0) + a*vec[b,:]  — the rank-1 half of FusionNet (models/DeformCrossTransMIL.py:104,33-38:
+ * the repeated omic vector is never materialised) and the backward of the token mean (Pooler :193) */
+int sml_add_rowvec(float* y, const float* x, const float* vec, float a, int64_t B, int64_t T, int32_t C, void* stream);
+/* pointwise heads: op 0 tanh (Pooler :200), 1 sigmoid, 2 relu (fusion.py:38-50), 3 elu (model.py:150) */
+int sml_unary_fwd(int32_t op, const float* x, float* y, int64_t n, void* stream);
+int sml_unary_bwd(int32_t op, const float* x, const float* y, const float* dy, float* dx, int64_t n, void* stream);
 /* 1 if any tcgen05 kernel hit its bounded mbarrier wait (protocol error); reads a device flag (synchronises) */
 int sml_tc_timeout_flag(void);
 /* out[c] = sum_r x[r,c] + beta*out[c]; part is a [sml_colsum_parts(R), C] workspace */
@@ -113,7 +119,7 @@ int sml_pinv_init_bwd(const float* x, const float* scal, const int32_t* arg, con
 int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
                             int32_t d, int32_t ksize, void* stream);
 /* dqkv[v chunk] += conv^T(dout); dw[h,k] = sum dout*v (dw_part [nblk,h,k]; nblk returned by ..._blocks) */
-int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad);
+int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad, int32_t hd);
 int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
                             int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* stream);
 /* PPEG: identity + depthwise 7x7 + 5x5 + 3x3 folded into one 7x7 stencil, token-major [B,1+H*W,C];
@@ -124,6 +130,42 @@ int sml_ppeg_fwd(const float* x, const float* w7, const float* bias, float* y, i
 int sml_ppeg_bwd_blocks(int32_t B, int32_t H, int32_t W);
 int sml_ppeg_bwd(const float* x, const float* w7, const float* dy, float* dx, float* dw_part, float* db_part,
                  int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------
+ * Deformable cross-attention 1-D / 2-D (models/DeformableAttention1D.py:156-240,
+ * models/DeformableAttention2D.py:223-325).  Token-major tensors: q/k/v/out [b, tokens, heads*64],
+ * x2/kv [b, tokens, C].  A 1-D sequence is the 2-D case with H = 1 (offset net) / W = 1 (sampling, F5).
+ * ------------------------------------------------------------------------------------- */
+/* cfg13 = {B, G, gd, inner, H, W, KH, KW, SH, SW, PH, PW, OC}: depthwise conv(k,s,p) -> GELU -> 1x1 (gd->OC) -> tanh
+ * -> *scale -> + grid -> normalise (1D.py:139-146,182-188; 2D.py:207-213,255-265).
+ * off [(b g), nkv, OC], vgrid [(b g), OC, HK, WK] (returned to the caller as in the reference), vs [(b g), nkv, OC] */
+int sml_deform_offsets_fwd(const int32_t* cfg13, float scale, const float* q, const float* wc, const float* bc,
+                           const float* w2, float* off, float* vgrid, float* vs, void* stream);
+int sml_deform_offsets_bwd_blocks(const int32_t* cfg13);
+/* dvs [(b g), nkv, OC] and optional dvgrid (grad of the returned vgrid); dpre [(b g), nkv, gd] workspace;
+ * part [nblk, gd*KH*KW + gd + OC*gd] partial parameter grads; dq [b, H*W, inner] is accumulated (+=) atomic-free */
+int sml_deform_offsets_bwd(const int32_t* cfg13, float scale, const float* q, const float* wc, const float* bc,
+                           const float* w2, const float* off, const float* dvs, const float* dvgrid, float* dpre,
+                           float* part, float* dq, void* stream);
+/* cfg8 = {B, G, cg, H, W, nkv, CD, mode}: bilinear grid_sample, zeros padding, align_corners=False
+ * (1D.py:36-43 with mode 0 = the reference's (x=vgrid, y=0) pad order on an [n,1] image, mode 1 = upstream order;
+ * 2D.py:268-271).  taps (optional) [(b g), nkv, 2] int32 = floor of the pixel coordinate (x0, y0): bit-exact contract */
+int sml_deform_gather_fwd(const int32_t* cfg8, const float* x2, const float* vs, float* kv, int32_t* taps, void* stream);
+/* dx2 must be zeroed by the caller; dvs_out = dvs_in (may be NULL) + sampling-path gradient */
+int sml_deform_gather_bwd(const int32_t* cfg8, const float* x2, const float* vs, const float* dkv, float* dx2,
+                          const float* dvs_in, float* dvs_out, void* stream);
+/* cfg8 = {B, heads, n, nkv, G, CD, W, 64}: out = softmax(q k^T + CPB(q_pos - k_pos)) v with the bias MLP evaluated per
+ * pair on the fly (1D.py:60-102,211-231; 2D.py:120-157,292-312); q pre-scaled; dropout on the probabilities with a
+ * counter-based mask (seed); cpb = packed [W1 32*CD][b1 32][W2 32*32][b2 32][W3 OUT*32][b3 OUT]; lse [b, heads, n] */
+int sml_deform_attn_fwd(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
+                        const float* vs, const float* cpb, float* out, float* lse, void* stream);
+int sml_deform_attn_bwd_blocks(const int32_t* cfg8);
+int sml_deform_cpb_nparams(int32_t CD, int32_t OUT);
+/* dk, dv, dvs zero-initialised by the caller; part [nblk, nparams] CPB partial grads */
+int sml_deform_attn_bwd(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
+                        const float* vs, const float* cpb, const float* out, const float* lse, const float* dout,
+                        float* dq, float* dk, float* dv, float* dvs, float* part, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,6 +3,9 @@
 The package directory is ``subspace-multimodal-learning_b200`` (not an importable identifier); import it
 through the repo-root shim ``sml_b200`` or ``__graft_entry__.load_package()``.
 """
-from . import _lib, ops, functional, nystrom  # noqa: F401
+from . import _lib, ops, functional, nystrom, deform  # noqa: F401
 from .models.NystromAttention import NystromAttention, moore_penrose_iter_pinv  # noqa: F401
 from .models.mil import TransLayer, PPEG, TransMIL  # noqa: F401
+from .models.DeformableAttention1D import DeformCrossAttention1D  # noqa: F401
+from .models.DeformableAttention2D import DeformCrossAttention2D  # noqa: F401
+from .models.DeformCrossTransMIL import DeformCrossTransMIL, FusionNet, DeformCrossTransLayer, Pooler  # noqa: F401

@@ -43,7 +43,6 @@ __global__ void landmark_ids_kernel(int32_t* ids, int npad, int l) {
 // ------------------------------------------------------------------ pinv scale (global max of row / column sums)
 // grid BH blocks, 256 threads.  packed[0] / packed[1]: (float bits << 32) | (0xFFFFFFFF - flat index)
 __global__ void __launch_bounds__(256) pinv_scale_kernel(const float* __restrict__ x, unsigned long long* packed, int m) {
-  __shared__ float red[32];
   __shared__ unsigned long long best[2];
   const int bh = blockIdx.x;
   const float* X = x + (int64_t)bh * m * m;
@@ -69,7 +68,6 @@ __global__ void __launch_bounds__(256) pinv_scale_kernel(const float* __restrict
   }
   __syncthreads();
   if (threadIdx.x < 2) atomicMax(&packed[threadIdx.x], best[threadIdx.x]);
-  (void)red;
 }
 __global__ void pinv_scale_final_kernel(const unsigned long long* packed, float* scal, int32_t* arg) {
   const int t = threadIdx.x;
@@ -149,53 +147,116 @@ __global__ void pinv_init_bwd_scalar_kernel(const float* __restrict__ x, const f
 
 // ------------------------------------------------------------------ residual depthwise conv along tokens
 // src rows have stride src_ld, channel c; dst rows stride dst_ld.  dst[t,c] += sum_k w[c/d][k'] src[t + k - half, c]
-// with k' = k (fwd) or K-1-k (flip, used for the transposed conv in backward).  Each thread owns TT tokens.
-constexpr int RC_TT = 8;
-template <bool FLIP>
-__global__ void __launch_bounds__(512) resconv_kernel(const float* __restrict__ src, int64_t src_ld,
+// with k' = k (fwd) or K-1-k (FLIP: the transposed conv of the backward).  Each thread owns TT consecutive tokens of
+// one channel: the K taps live in registers and every (tap, output) pair is resolved at compile time.
+constexpr int RC_TT = 16;
+template <bool FLIP, int K>
+__global__ void __launch_bounds__(256) resconv_kernel(const float* __restrict__ src, int64_t src_ld,
                                                       const float* __restrict__ w, float* __restrict__ dst,
-                                                      int64_t dst_ld, int npad, int hd, int d, int K) {
-  extern __shared__ float sw[];   // [h*K]
-  const int h = hd / d;
-  for (int i = threadIdx.x; i < h * K; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int b = blockIdx.y;
+                                                      int64_t dst_ld, int npad, int hd, int d) {
+  constexpr int HALF = K / 2;
+  const int b = blockIdx.z;
   const int t0 = blockIdx.x * RC_TT;
-  const int half = K / 2;
-  for (int c = threadIdx.x; c < hd; c += blockDim.x) {
-    const float* wp = sw + (c / d) * K;
-    const float* s = src + (int64_t)b * npad * src_ld + c;
-    float acc[RC_TT];
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= hd) return;
+  float wr[K];
 #pragma unroll
-    for (int i = 0; i < RC_TT; ++i) acc[i] = 0.f;
-    for (int u = -half; u < RC_TT + half; ++u) {       // source token t0+u contributes to outputs i = u-k+half
-      const int ts = t0 + u;
-      if (ts < 0 || ts >= npad) continue;
-      const float v = s[(int64_t)ts * src_ld];
+  for (int k = 0; k < K; ++k) wr[k] = __ldg(w + (c / d) * K + (FLIP ? (K - 1 - k) : k));
+  const float* s = src + (int64_t)b * npad * src_ld + c;
+  float acc[RC_TT];
 #pragma unroll
-      for (int i = 0; i < RC_TT; ++i) {
-        const int k = u - i + half;
-        if (k >= 0 && k < K) acc[i] = fmaf(wp[FLIP ? (K - 1 - k) : k], v, acc[i]);
-      }
+  for (int i = 0; i < RC_TT; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int u = -HALF; u < RC_TT + HALF; ++u) {       // source token t0+u feeds output i through tap k = u - i + HALF
+    const int ts = t0 + u;
+    const float v = (ts >= 0 && ts < npad) ? s[(int64_t)ts * src_ld] : 0.f;
+#pragma unroll
+    for (int i = 0; i < RC_TT; ++i) {
+      const int k = u - i + HALF;
+      if (k >= 0 && k < K) acc[i] = fmaf(wr[k], v, acc[i]);
     }
-    float* o = dst + (int64_t)b * npad * dst_ld + c;
-#pragma unroll
-    for (int i = 0; i < RC_TT; ++i)
-      if (t0 + i < npad) o[(int64_t)(t0 + i) * dst_ld] += acc[i];
   }
+  float* o = dst + (int64_t)b * npad * dst_ld + c;
+#pragma unroll
+  for (int i = 0; i < RC_TT; ++i)
+    if (t0 + i < npad) o[(int64_t)(t0 + i) * dst_ld] += acc[i];
 }
-// dw_part[blk, head, k] = sum over the block's tokens and the head's d channels of dout[t,c] * v[t+k-half, c]
-constexpr int RCB_TOK = 64;
-__global__ void __launch_bounds__(512) resconv_dw_kernel(const float* __restrict__ v, int64_t v_ld,
+// dw_part[blk, head, k] = sum over the block's token strip and the head's d channels of dout[t,c] * v[t+k-half, c].
+// Thread = one channel; it walks its strip in chunks of 16 tokens with a (16 + K - 1)-wide register window of v.
+constexpr int RCB_TOK = 256;
+template <int K>
+__global__ void __launch_bounds__(256) resconv_dw_kernel(const float* __restrict__ v, int64_t v_ld,
                                                          const float* __restrict__ dout, int64_t o_ld,
-                                                         float* __restrict__ dw_part, int npad, int hd, int d, int K) {
+                                                         float* __restrict__ dw_part, int npad, int hd, int d) {
+  constexpr int HALF = K / 2, CH = 16;
   extern __shared__ float sdw[];   // [h*K]
   const int h = hd / d;
   for (int i = threadIdx.x; i < h * K; i += blockDim.x) sdw[i] = 0.f;
   __syncthreads();
-  const int b = blockIdx.y, t0 = blockIdx.x * RCB_TOK, half = K / 2;
+  const int b = blockIdx.z, t0 = blockIdx.x * RCB_TOK;
   const int t1 = min(npad, t0 + RCB_TOK);
-  for (int c = threadIdx.x; c < hd; c += blockDim.x) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c < hd) {
+    const float* vp = v + (int64_t)b * npad * v_ld + c;
+    const float* gp = dout + (int64_t)b * npad * o_ld + c;
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
+    for (int tc = t0; tc < t1; tc += CH) {
+      float win[CH + K - 1], g[CH];
+#pragma unroll
+      for (int u = 0; u < CH + K - 1; ++u) {
+        const int ts = tc + u - HALF;
+        win[u] = (ts >= 0 && ts < npad) ? vp[(int64_t)ts * v_ld] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < CH; ++i) g[i] = (tc + i < t1) ? gp[(int64_t)(tc + i) * o_ld] : 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < CH; ++i) acc[k] = fmaf(g[i], win[i + k], acc[k]);
+    }
+    const bool whole_warp_one_head = (d & 31) == 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (whole_warp_one_head) {
+        const float s = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[(c / d) * K + k], s);
+      } else {
+        atomicAdd(&sdw[(c / d) * K + k], acc[k]);
+      }
+    }
+  }
+  __syncthreads();
+  float* o = dw_part + (((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * h * K;
+  for (int i = threadIdx.x; i < h * K; i += blockDim.x) o[i] = sdw[i];
+}
+// generic-K fallbacks (any odd kernel size; the reference path uses 33)
+template <bool FLIP>
+__global__ void __launch_bounds__(256) resconv_generic_kernel(const float* __restrict__ src, int64_t src_ld,
+                                                              const float* __restrict__ w, float* __restrict__ dst,
+                                                              int64_t dst_ld, int npad, int hd, int d, int K) {
+  const int b = blockIdx.z, t = blockIdx.x, half = K / 2;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= hd) return;
+  const float* s = src + (int64_t)b * npad * src_ld + c;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int ts = t + k - half;
+    if (ts >= 0 && ts < npad) acc = fmaf(__ldg(w + (c / d) * K + (FLIP ? K - 1 - k : k)), s[(int64_t)ts * src_ld], acc);
+  }
+  dst[((int64_t)b * npad + t) * dst_ld + c] += acc;
+}
+__global__ void __launch_bounds__(256) resconv_dw_generic_kernel(const float* __restrict__ v, int64_t v_ld,
+                                                                 const float* __restrict__ dout, int64_t o_ld,
+                                                                 float* __restrict__ dw_part, int npad, int hd, int d, int K) {
+  extern __shared__ float sdw[];
+  const int h = hd / d, half = K / 2;
+  for (int i = threadIdx.x; i < h * K; i += blockDim.x) sdw[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.z, t0 = blockIdx.x * RCB_TOK, t1 = min(npad, t0 + RCB_TOK);
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c < hd) {
     const float* vp = v + (int64_t)b * npad * v_ld + c;
     const float* gp = dout + (int64_t)b * npad * o_ld + c;
     for (int k = 0; k < K; ++k) {
@@ -204,78 +265,104 @@ __global__ void __launch_bounds__(512) resconv_dw_kernel(const float* __restrict
         const int ts = t + k - half;
         if (ts >= 0 && ts < npad) s = fmaf(gp[(int64_t)t * o_ld], vp[(int64_t)ts * v_ld], s);
       }
-      if ((d & 31) == 0) {
-        s = warp_sum(s);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[(c / d) * K + k], s);
-      } else {
-        atomicAdd(&sdw[(c / d) * K + k], s);
-      }
+      atomicAdd(&sdw[(c / d) * K + k], s);
     }
   }
   __syncthreads();
-  float* o = dw_part + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * h * K;
+  float* o = dw_part + (((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * h * K;
   for (int i = threadIdx.x; i < h * K; i += blockDim.x) o[i] = sdw[i];
 }
 
 // ------------------------------------------------------------------ PPEG 7x7 folded stencil, token-major
-// x,y [B, 1+H*W, C]; w7 [49, C] (tap-major so channel reads coalesce); bias [C].
+// x,y [B, 1+H*W, C]; w7 [49, C] (tap-major); bias [C].  Block = 16x8 spatial tile x 32 channels staged in shared
+// memory with a 3-pixel halo; thread = (channel, tile row) sliding along the row with its 49 taps in registers.
+constexpr int PT_W = 16, PT_H = 8, PT_C = 32;
 template <bool FLIP>
 __global__ void __launch_bounds__(256) ppeg_kernel(const float* __restrict__ x, const float* __restrict__ w7,
                                                    const float* __restrict__ bias, float* __restrict__ y, int H, int W,
-                                                   int C) {
+                                                   int C, int tiles_x) {
+  __shared__ float tile[PT_H + 6][PT_W + 6][PT_C + 1];
   const int b = blockIdx.z;
-  const int tok = blockIdx.y;            // 0 .. H*W  (0 = cls row)
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c0 = blockIdx.y * PT_C;
+  const int ty0 = (blockIdx.x / tiles_x) * PT_H, tx0 = (blockIdx.x % tiles_x) * PT_W;
   const int64_t base = (int64_t)b * (1 + H * W) * C;
-  if (tok == 0) { y[base + c] = x[base + c]; return; }
-  const int p = tok - 1, i = p / W, j = p % W;
-  float acc = bias ? __ldg(bias + c) : 0.f;
-#pragma unroll
-  for (int di = 0; di < 7; ++di) {
-    const int ii = i + di - 3;
-    if (ii < 0 || ii >= H) continue;
-#pragma unroll
-    for (int dj = 0; dj < 7; ++dj) {
-      const int jj = j + dj - 3;
-      if (jj < 0 || jj >= W) continue;
-      const int tap = FLIP ? (48 - (di * 7 + dj)) : (di * 7 + dj);
-      acc = fmaf(__ldg(w7 + tap * C + c), x[base + (int64_t)(1 + ii * W + jj) * C + c], acc);
-    }
+  const int lc = threadIdx.x & 31, lr = threadIdx.x >> 5;     // channel lane, 8 row groups
+  const int c = c0 + lc;
+  if (blockIdx.x == 0 && lr == 0 && c < C) y[base + c] = x[base + c];      // cls row passes through (mil.py:201-205)
+  for (int e = lr; e < (PT_H + 6) * (PT_W + 6); e += 8) {
+    const int ry = e / (PT_W + 6), rx = e % (PT_W + 6);
+    const int gy = ty0 + ry - 3, gx = tx0 + rx - 3;
+    tile[ry][rx][lc] = (gy >= 0 && gy < H && gx >= 0 && gx < W && c < C) ? x[base + (int64_t)(1 + gy * W + gx) * C + c] : 0.f;
   }
-  y[base + (int64_t)tok * C + c] = acc;
+  __syncthreads();
+  if (c >= C) return;
+  float wr[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) wr[t] = __ldg(w7 + (FLIP ? 48 - t : t) * C + c);
+  const float bv = bias ? __ldg(bias + c) : 0.f;
+  const int oy = ty0 + lr;
+  if (oy >= H) return;
+  for (int ox = 0; ox < PT_W; ++ox) {
+    if (tx0 + ox >= W) break;
+    float acc = bv;
+#pragma unroll
+    for (int di = 0; di < 7; ++di)
+#pragma unroll
+      for (int dj = 0; dj < 7; ++dj) acc = fmaf(wr[di * 7 + dj], tile[lr + di][ox + dj][lc], acc);
+    y[base + (int64_t)(1 + oy * W + tx0 + ox) * C + c] = acc;
+  }
 }
-constexpr int PPB_TOK = 64;
-// dw_part[blk, tap, c], db_part[blk, c]; grid (ceil(HW/PPB_TOK), B), block C threads (loops if C > blockDim)
-__global__ void __launch_bounds__(512) ppeg_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+// dw_part[grp, tap, c], db_part[grp, c]: grid (C/32, groups, B); a block walks its share of spatial tiles
+constexpr int PPB_GROUPS = 32;
+__global__ void __launch_bounds__(256) ppeg_dw_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                       float* __restrict__ dw_part, float* __restrict__ db_part, int H,
-                                                      int W, int C) {
-  const int b = blockIdx.y, p0 = blockIdx.x * PPB_TOK, p1 = min(H * W, p0 + PPB_TOK);
+                                                      int W, int C, int tiles_x, int ntiles) {
+  __shared__ float tile[PT_H + 6][PT_W + 6][PT_C + 1];
+  __shared__ float red[50][PT_C + 1];
+  const int b = blockIdx.z, c0 = blockIdx.x * PT_C;
+  const int lc = threadIdx.x & 31, lr = threadIdx.x >> 5;
+  const int c = c0 + lc;
   const int64_t base = (int64_t)b * (1 + H * W) * C;
-  const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc[49];
+  float acc[49];
 #pragma unroll
-    for (int t = 0; t < 49; ++t) acc[t] = 0.f;
-    float ab = 0.f;
-    for (int p = p0; p < p1; ++p) {
-      const int i = p / W, j = p % W;
-      const float g = dy[base + (int64_t)(1 + p) * C + c];
-      ab += g;
+  for (int t = 0; t < 49; ++t) acc[t] = 0.f;
+  float ab = 0.f;
+  for (int tl = blockIdx.y; tl < ntiles; tl += gridDim.y) {
+    const int ty0 = (tl / tiles_x) * PT_H, tx0 = (tl % tiles_x) * PT_W;
+    __syncthreads();
+    for (int e = lr; e < (PT_H + 6) * (PT_W + 6); e += 8) {
+      const int ry = e / (PT_W + 6), rx = e % (PT_W + 6);
+      const int gy = ty0 + ry - 3, gx = tx0 + rx - 3;
+      tile[ry][rx][lc] = (gy >= 0 && gy < H && gx >= 0 && gx < W && c < C) ? x[base + (int64_t)(1 + gy * W + gx) * C + c] : 0.f;
+    }
+    __syncthreads();
+    const int oy = ty0 + lr;
+    if (c < C && oy < H) {
+      for (int ox = 0; ox < PT_W; ++ox) {
+        if (tx0 + ox >= W) break;
+        const float g = dy[base + (int64_t)(1 + oy * W + tx0 + ox) * C + c];
+        ab += g;
 #pragma unroll
-      for (int di = 0; di < 7; ++di) {
-        const int ii = i + di - 3;
+        for (int di = 0; di < 7; ++di)
 #pragma unroll
-        for (int dj = 0; dj < 7; ++dj) {
-          const int jj = j + dj - 3;
-          if (ii >= 0 && ii < H && jj >= 0 && jj < W)
-            acc[di * 7 + dj] = fmaf(g, x[base + (int64_t)(1 + ii * W + jj) * C + c], acc[di * 7 + dj]);
-        }
+          for (int dj = 0; dj < 7; ++dj) acc[di * 7 + dj] = fmaf(g, tile[lr + di][ox + dj][lc], acc[di * 7 + dj]);
       }
     }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 50 * (PT_C + 1); e += blockDim.x) (&red[0][0])[e] = 0.f;
+  __syncthreads();
 #pragma unroll
-    for (int t = 0; t < 49; ++t) dw_part[(blk * 49 + t) * C + c] = acc[t];
-    db_part[blk * C + c] = ab;
+  for (int t = 0; t < 49; ++t) atomicAdd(&red[t][lc], acc[t]);
+  atomicAdd(&red[49][lc], ab);
+  __syncthreads();
+  const int64_t grp = (int64_t)blockIdx.z * gridDim.y + blockIdx.y;
+  for (int e = threadIdx.x; e < 50 * PT_C; e += blockDim.x) {
+    const int t = e / PT_C, l = e % PT_C;
+    if (c0 + l >= C) continue;
+    const float s = red[t][l];
+    if (t < 49) dw_part[(grp * 49 + t) * C + c0 + l] = s;
+    else db_part[grp * C + c0 + l] = s;
   }
 }
 
@@ -328,49 +415,58 @@ extern "C" int sml_pinv_init_bwd(const float* x, const float* scal, const int32_
   SML_LAUNCH_OK("sml_pinv_init_bwd_scalar");
   return 0;
 }
+static inline dim3 rc_grid(int npad, int hd, int B, int tok) { return dim3((npad + tok - 1) / tok, (hd + 255) / 256, B); }
 extern "C" int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
                                        int32_t d, int32_t ksize, void* stream) {
   const int hd = h * d;
   SML_CHECK(ksize % 2 == 1, "sml_nystrom_resconv_fwd: kernel size must be odd");
-  dim3 grid((npad + RC_TT - 1) / RC_TT, B);
-  resconv_kernel<false><<<grid, hd < 512 ? hd : 512, h * ksize * sizeof(float), as_stream(stream)>>>(
-      qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, ksize);
+  if (ksize == 33)
+    resconv_kernel<false, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d);
+  else
+    resconv_generic_kernel<false><<<rc_grid(npad, hd, B, 1), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, ksize);
   SML_LAUNCH_OK("sml_nystrom_resconv_fwd");
   return 0;
 }
-extern "C" int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad) { return B * ((npad + RCB_TOK - 1) / RCB_TOK); }
+extern "C" int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad, int32_t hd) {
+  return B * ((hd + 255) / 256) * ((npad + RCB_TOK - 1) / RCB_TOK);
+}
 extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
                                        int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* stream) {
   const int hd = h * d;
   cudaStream_t s = as_stream(stream);
-  dim3 grid((npad + RC_TT - 1) / RC_TT, B);
-  resconv_kernel<true><<<grid, hd < 512 ? hd : 512, h * ksize * sizeof(float), s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd,
-                                                                                   npad, hd, d, ksize);
-  SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
-  dim3 grid2((npad + RCB_TOK - 1) / RCB_TOK, B);
-  resconv_dw_kernel<<<grid2, hd < 512 ? hd : 512, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part,
-                                                                                 npad, hd, d, ksize);
+  if (ksize == 33) {
+    resconv_kernel<true, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d);
+    SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
+    resconv_dw_kernel<33><<<rc_grid(npad, hd, B, RCB_TOK), 256, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
+  } else {
+    resconv_generic_kernel<true><<<rc_grid(npad, hd, B, 1), 256, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d, ksize);
+    SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
+    resconv_dw_generic_kernel<<<rc_grid(npad, hd, B, RCB_TOK), 256, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d, ksize);
+  }
   SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dw)");
   return 0;
 }
 extern "C" int sml_ppeg_fwd(const float* x, const float* w7, const float* bias, float* y, int32_t B, int32_t H, int32_t W,
                             int32_t C, void* stream) {
-  dim3 grid((C + 255) / 256, 1 + H * W, B);
-  SML_CHECK(1 + H * W <= 65535 * 2 && grid.y <= 65535, "sml_ppeg_fwd: H*W too large for grid.y (%d)", H * W);
-  ppeg_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, w7, bias, y, H, W, C);
+  const int tx = (W + PT_W - 1) / PT_W, tyc = (H + PT_H - 1) / PT_H;
+  dim3 grid(tx * tyc, (C + PT_C - 1) / PT_C, B);
+  ppeg_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, w7, bias, y, H, W, C, tx);
   SML_LAUNCH_OK("sml_ppeg_fwd");
   return 0;
 }
-extern "C" int sml_ppeg_bwd_blocks(int32_t B, int32_t H, int32_t W) { return B * ((H * W + PPB_TOK - 1) / PPB_TOK); }
+extern "C" int sml_ppeg_bwd_blocks(int32_t B, int32_t H, int32_t W) {
+  const int nt = ((W + PT_W - 1) / PT_W) * ((H + PT_H - 1) / PT_H);
+  return B * (nt < PPB_GROUPS ? nt : PPB_GROUPS);
+}
 extern "C" int sml_ppeg_bwd(const float* x, const float* w7, const float* dy, float* dx, float* dw_part, float* db_part,
                             int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
   cudaStream_t s = as_stream(stream);
-  dim3 grid((C + 255) / 256, 1 + H * W, B);
-  SML_CHECK(grid.y <= 65535, "sml_ppeg_bwd: H*W too large for grid.y (%d)", H * W);
-  ppeg_kernel<true><<<grid, 256, 0, s>>>(dy, w7, nullptr, dx, H, W, C);     // transposed stencil = flipped taps
+  const int tx = (W + PT_W - 1) / PT_W, tyc = (H + PT_H - 1) / PT_H, nt = tx * tyc;
+  dim3 grid(nt, (C + PT_C - 1) / PT_C, B);
+  ppeg_kernel<true><<<grid, 256, 0, s>>>(dy, w7, nullptr, dx, H, W, C, tx);     // transposed stencil = flipped taps
   SML_LAUNCH_OK("sml_ppeg_bwd(dx)");
-  dim3 grid2((H * W + PPB_TOK - 1) / PPB_TOK, B);
-  ppeg_dw_kernel<<<grid2, C < 512 ? C : 512, 0, s>>>(x, dy, dw_part, db_part, H, W, C);
+  dim3 grid2((C + PT_C - 1) / PT_C, nt < PPB_GROUPS ? nt : PPB_GROUPS, B);
+  ppeg_dw_kernel<<<grid2, 256, 0, s>>>(x, dy, dw_part, db_part, H, W, C, tx, nt);
   SML_LAUNCH_OK("sml_ppeg_bwd(dw)");
   return 0;
 }

@@ -235,6 +235,41 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dx[i] = y[i] > 0.f ? dy[i] : 0.f;
 }
+// y[b,t,:] = (x ? x[b,t,:] : 0) + a * vec[b,:]
+__global__ void __launch_bounds__(256) add_rowvec_kernel(float* __restrict__ y, const float* __restrict__ x,
+                                                         const float* __restrict__ vec, float a, int64_t total, int64_t TC,
+                                                         int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / TC;
+    const int c = (int)(i % C);
+    y[i] = (x ? x[i] : 0.f) + a * vec[b * C + c];
+  }
+}
+// unary ops: 0 tanh, 1 sigmoid, 2 relu, 3 elu(alpha=1)
+__device__ __forceinline__ float unary_f(int op, float x) {
+  switch (op) {
+    case 0: return tanhf(x);
+    case 1: return 1.f / (1.f + expf(-x));
+    case 2: return fmaxf(x, 0.f);
+    default: return x > 0.f ? x : expm1f(x);
+  }
+}
+__device__ __forceinline__ float unary_g(int op, float x, float y) {
+  switch (op) {
+    case 0: return 1.f - y * y;
+    case 1: return y * (1.f - y);
+    case 2: return x > 0.f ? 1.f : 0.f;
+    default: return x > 0.f ? 1.f : y + 1.f;
+  }
+}
+__global__ void __launch_bounds__(256) unary_fwd_kernel(int op, const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = unary_f(op, x[i]);
+}
+__global__ void __launch_bounds__(256) unary_bwd_kernel(int op, const float* __restrict__ x, const float* __restrict__ y,
+                                                        const float* __restrict__ dy, float* __restrict__ dx, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * unary_g(op, x[i], y[i]);
+}
 // out[c] = sum_r x[r,c] (+ beta*out).  grid.x covers columns in chunks of 32, 32x8 threads, rows strided by 8*gridDim.y
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ part, int64_t R,
                                                      int64_t C) {
@@ -368,5 +403,27 @@ extern "C" int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t 
   if (n == 0) return 0;
   relu_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, dy, dx, n);
   SML_LAUNCH_OK("sml_relu_bwd");
+  return 0;
+}
+
+extern "C" int sml_add_rowvec(float* y, const float* x, const float* vec, float a, int64_t B, int64_t T, int32_t C, void* stream) {
+  const int64_t total = B * T * C;
+  if (total == 0) return 0;
+  add_rowvec_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(y, x, vec, a, total, T * C, C);
+  SML_LAUNCH_OK("sml_add_rowvec");
+  return 0;
+}
+extern "C" int sml_unary_fwd(int32_t op, const float* x, float* y, int64_t n, void* stream) {
+  SML_CHECK(op >= 0 && op <= 3, "sml_unary_fwd: unknown op %d", op);
+  if (n == 0) return 0;
+  unary_fwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(op, x, y, n);
+  SML_LAUNCH_OK("sml_unary_fwd");
+  return 0;
+}
+extern "C" int sml_unary_bwd(int32_t op, const float* x, const float* y, const float* dy, float* dx, int64_t n, void* stream) {
+  SML_CHECK(op >= 0 && op <= 3, "sml_unary_bwd: unknown op %d", op);
+  if (n == 0) return 0;
+  unary_bwd_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(op, x, y, dy, dx, n);
+  SML_LAUNCH_OK("sml_unary_bwd");
   return 0;
 }

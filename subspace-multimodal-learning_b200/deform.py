@@ -1,0 +1,184 @@
+"""Deformable cross-attention (1-D / 2-D) forward/backward on the C-ABI kernels.
+
+Implements /root/reference/models/DeformableAttention1D.py:156-240 and
+models/DeformableAttention2D.py:223-325 on token-major tensors; the bias MLP (CPB) is never materialised.
+"""
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
+from .ops import F32, gemm
+
+
+def _cfg(*vals):
+    return (c_i32 * len(vals))(*[int(v) for v in vals])
+
+
+def gconv(x, w2d, G, out=None):
+    """grouped 1x1 conv on token-major x [b,T,Cin]: w2d [Cout, Cin/G] -> [b,T,Cout]."""
+    b, T, Cin = x.shape
+    Cout = w2d.shape[0]
+    if out is None:
+        out = torch.empty(b, T, Cout, device=x.device, dtype=F32)
+    if G == 1:
+        gemm(x, w2d.t(), out=out)
+    else:
+        ci, co = Cin // G, Cout // G
+        gemm(x.view(b, T, G, ci).permute(0, 2, 1, 3), w2d.view(1, G, co, ci).transpose(-1, -2),
+             out=out.view(b, T, G, co).permute(0, 2, 1, 3))
+    return out
+
+
+def gconv_bwd(x, w2d, G, dy, need_dx=True, dx_out=None, dx_beta=0.0):
+    """returns (dx [b,T,Cin] or None, dw [Cout, Cin/G])."""
+    b, T, Cin = x.shape
+    Cout = w2d.shape[0]
+    dx = None
+    if G == 1:
+        dw = gemm(dy.reshape(b * T, Cout).t(), x.reshape(b * T, Cin))
+        if need_dx:
+            dx = dx_out if dx_out is not None else torch.empty_like(x)
+            gemm(dy, w2d, out=dx, beta=dx_beta)
+    else:
+        ci, co = Cin // G, Cout // G
+        # dw_g = sum_b dy_g^T x_g : fold the batch into the contraction by looping b with beta accumulation
+        dw = torch.empty(G, co, ci, device=x.device, dtype=F32)
+        xg = x.view(b, T, G, ci).permute(0, 2, 1, 3)            # [b,G,T,ci]
+        dyg = dy.view(b, T, G, co).permute(0, 2, 1, 3)          # [b,G,T,co]
+        for bi in range(b):
+            gemm(dyg[bi].transpose(-1, -2), xg[bi], out=dw, beta=0.0 if bi == 0 else 1.0)
+        dw = dw.view(Cout, ci)
+        if need_dx:
+            dx = dx_out if dx_out is not None else torch.empty_like(x)
+            gemm(dyg, w2d.view(1, G, co, ci), out=dx.view(b, T, G, ci).permute(0, 2, 1, 3), beta=dx_beta)
+    return dx, dw
+
+
+class DeformAttnFn(torch.autograd.Function):
+    """(x1t, x2t) [b,T,C] token-major -> (y [b,T,C], vgrid).  cfg: dict(dim2d, side, heads, groups, ds, ksize, scale,
+    gq, gkv, p_drop, seed, mode, want_taps)."""
+
+    @staticmethod
+    def forward(ctx, x1t, x2t, wq, wk, wv, wout, bout, wc, bc, w2, cw1, cb1, cw2, cb2, cw3, cb3, cfg):
+        ops.require_cuda(x1t, x2t)
+        x1t, x2t = x1t.contiguous(), x2t.contiguous()
+        b, T, C = x1t.shape
+        heads, G, ds, ks = cfg["heads"], cfg["groups"], cfg["ds"], cfg["ksize"]
+        inner = heads * 64
+        gd = inner // G
+        two_d = cfg["dim2d"]
+        dev = x1t.device
+        gq = G if cfg["gq"] else 1
+        gkv = G if cfg["gkv"] else 1
+        wq2, wk2, wv2 = (w.detach().reshape(w.shape[0], -1).contiguous() for w in (wq, wk, wv))
+        wo2 = wout.detach().reshape(wout.shape[0], -1).contiguous()
+        q = gconv(x1t, wq2, gq)                                                  # 1D.py:175 / 2D.py:246
+        pad = (ks - ds) // 2
+        if two_d:
+            side = cfg["side"]
+            assert side * side == T
+            ocfg = _cfg(b, G, gd, inner, side, side, ks, ks, ds, ds, pad, pad, 2)
+            hk = (side + 2 * pad - ks) // ds + 1
+            nkv, OC = hk * hk, 2
+            vshape = (b * G, 2, hk, hk)
+            gcfg = _cfg(b, G, C // G, side, side, nkv, 2, 0)
+        else:
+            ocfg = _cfg(b, G, gd, inner, 1, T, 1, ks, 1, ds, 0, pad, 1)
+            nkv, OC = (T + 2 * pad - ks) // ds + 1, 1
+            vshape = (b * G, nkv)
+            gcfg = (_cfg(b, G, C // G, T, 1, nkv, 1, 0) if cfg["mode"] == 0 else _cfg(b, G, C // G, T, 1, nkv, 1, 1))
+        wc2 = wc.detach().reshape(gd, -1).contiguous()
+        w22 = w2.detach().reshape(OC, gd).contiguous()
+        off = torch.empty(b * G, nkv, OC, device=dev, dtype=F32)
+        vgrid = torch.empty(vshape, device=dev, dtype=F32)
+        vs = torch.empty(b * G, nkv, OC, device=dev, dtype=F32)
+        check(lib.sml_deform_offsets_fwd(ocfg, c_f32(cfg["scale"]), ptr(q), ptr(wc2), ptr(bc.detach()), ptr(w22), ptr(off),
+                                         ptr(vgrid), ptr(vs), stream()), "deform_offsets_fwd")
+        kv = torch.empty(b, nkv, C, device=dev, dtype=F32)
+        taps = torch.empty(b * G, nkv, 2, device=dev, dtype=torch.int32) if cfg.get("want_taps") else None
+        check(lib.sml_deform_gather_fwd(gcfg, ptr(x2t), ptr(vs), ptr(kv), ptr(taps), stream()), "deform_gather_fwd")
+        k = gconv(kv, wk2, gkv)                                                  # 1D.py:199 / 2D.py:279
+        v = gconv(kv, wv2, gkv)
+        qs = torch.empty_like(q)
+        ops.axpby_(qs, q, 64 ** -0.5, 0.0)                                       # q * scale after the offsets (1D.py:203)
+        cpb = torch.cat([t.detach().reshape(-1) for t in (cw1, cb1, cw2, cb2, cw3, cb3)]).contiguous()
+        acfg = _cfg(b, heads, T, nkv, G, OC, cfg["side"] if two_d else 1, 64)
+        out = torch.empty(b, T, inner, device=dev, dtype=F32)
+        lse = torch.empty(b, heads, T, device=dev, dtype=F32)
+        check(lib.sml_deform_attn_fwd(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
+                                      ptr(out), ptr(lse), stream()), "deform_attn_fwd")
+        y = torch.empty(b, T, C, device=dev, dtype=F32)
+        gemm(out.view(b * T, inner), wo2.t(), out=y.view(b * T, C), bias=bout.detach())       # 1D.py:233 / 2D.py:314
+        ctx.save_for_backward(x1t, x2t, wq2, wk2, wv2, wo2, wc2, bc, w22, q, qs, off, vs, kv, k, v, cpb, out, lse)
+        ctx.cfg = dict(cfg, ocfg=ocfg, gcfg=gcfg, acfg=acfg, nkv=nkv, OC=OC, gd=gd, gq=gq, gkv=gkv, inner=inner,
+                       shapes=[t.shape for t in (wq, wk, wv, wout, wc, w2, cw1, cb1, cw2, cb2, cw3, cb3)])
+        ctx.taps = taps
+        ctx.mark_non_differentiable(*([] if taps is None else []))
+        return y, vgrid
+
+    @staticmethod
+    def backward(ctx, dy, dvgrid):
+        cfg = ctx.cfg
+        (x1t, x2t, wq2, wk2, wv2, wo2, wc2, bc, w22, q, qs, off, vs, kv, k, v, cpb, out, lse) = ctx.saved_tensors
+        b, T, C = x1t.shape
+        G, heads, inner, nkv, OC, gd = cfg["groups"], cfg["heads"], cfg["inner"], cfg["nkv"], cfg["OC"], cfg["gd"]
+        dev = x1t.device
+        dy = dy.contiguous()
+        dy2 = dy.view(b * T, C)
+        db_out = ops.colsum(dy2)
+        dw_out = gemm(dy2.t(), out.view(b * T, inner))
+        dout = gemm(dy2, wo2).view(b, T, inner)
+        dqs = torch.empty_like(q)
+        dk = torch.zeros_like(k)
+        dv = torch.zeros_like(v)
+        dvs_b = torch.zeros_like(vs)
+        nblk = lib.sml_deform_attn_bwd_blocks(cfg["acfg"])
+        npar = lib.sml_deform_cpb_nparams(c_i32(OC), c_i32(heads // G))
+        part = torch.empty(nblk, npar, device=dev, dtype=F32)
+        check(lib.sml_deform_attn_bwd(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
+                                      ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b), ptr(part),
+                                      stream()), "deform_attn_bwd")
+        dcpb = ops.colsum(part)
+        # k, v projections
+        dkv, dwk = gconv_bwd(kv, wk2, cfg["gkv"], dk)
+        _, dwv = gconv_bwd(kv, wv2, cfg["gkv"], dv, dx_out=dkv, dx_beta=1.0)
+        # sampling
+        dx2t = torch.zeros_like(x2t)
+        dvs = torch.empty_like(vs)
+        check(lib.sml_deform_gather_bwd(cfg["gcfg"], ptr(x2t), ptr(vs), ptr(dkv), ptr(dx2t), ptr(dvs_b), ptr(dvs), stream()),
+              "deform_gather_bwd")
+        # offsets network: dq = scale * dqs (+ offset path, accumulated in place)
+        dq = torch.empty_like(q)
+        ops.axpby_(dq, dqs, 64 ** -0.5, 0.0)
+        nb = lib.sml_deform_offsets_bwd_blocks(cfg["ocfg"])
+        KK = wc2.shape[1]
+        nacc = gd * KK + gd + OC * gd
+        dpre = torch.empty(b * G, nkv, gd, device=dev, dtype=F32)
+        opart = torch.empty(nb, nacc, device=dev, dtype=F32)
+        dvg = dvgrid.contiguous() if dvgrid is not None else None
+        check(lib.sml_deform_offsets_bwd(cfg["ocfg"], c_f32(cfg["scale"]), ptr(q), ptr(wc2), ptr(bc.detach()), ptr(w22), ptr(off),
+                                         ptr(dvs), ptr(dvg), ptr(dpre), ptr(opart), ptr(dq), stream()), "deform_offsets_bwd")
+        osum = ops.colsum(opart)
+        dwc, dbc, dw2 = osum[:gd * KK], osum[gd * KK:gd * KK + gd], osum[gd * KK + gd:]
+        dx1t, dwq = gconv_bwd(x1t, wq2, cfg["gq"], dq)
+        sh = cfg["shapes"]
+        sizes = [int(torch.Size(s).numel()) for s in sh[6:]]
+        dc = torch.split(dcpb, sizes)
+        return (dx1t, dx2t, dwq.reshape(sh[0]), dwk.reshape(sh[1]), dwv.reshape(sh[2]), dw_out.reshape(sh[3]), db_out,
+                dwc.reshape(sh[4]), dbc.clone(), dw2.reshape(sh[5]), *[g.reshape(s) for g, s in zip(dc, sh[6:])], None)
+
+
+def gather_with_taps(x2t, vs, G, H, W, mode=0):
+    """Forward bilinear gather alone (test / inspection entry): x2t [b, H*W, C], vs [(b G), nkv, CD]
+    -> (kv [b, nkv, C], taps int32 [(b G), nkv, 2] = (x0, y0) top-left tap of every sample)."""
+    ops.require_cuda(x2t, vs)
+    x2t, vs = x2t.contiguous(), vs.contiguous()
+    b, T, C = x2t.shape
+    nkv, CD = vs.shape[1], vs.shape[2]
+    kv = torch.empty(b, nkv, C, device=x2t.device, dtype=F32)
+    taps = torch.empty(b * G, nkv, 2, device=x2t.device, dtype=torch.int32)
+    check(lib.sml_deform_gather_fwd(_cfg(b, G, C // G, H, W, nkv, CD, mode), ptr(x2t), ptr(vs), ptr(kv), ptr(taps), stream()),
+          "deform_gather_fwd")
+    return kv, taps

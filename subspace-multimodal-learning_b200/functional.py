@@ -148,3 +148,84 @@ class PPEGFn(torch.autograd.Function):
 
 def ppeg(x, w7, bias, H, W):
     return PPEGFn.apply(x, w7, bias, H, W)
+
+
+class AddRowVecFn(torch.autograd.Function):
+    """y[b,t,:] = x[b,t,:] + vec[b,:]  (x [B,T,C], vec [B,C])."""
+
+    @staticmethod
+    def forward(ctx, x, vec):
+        ops.require_cuda(x, vec)
+        x, vec = x.contiguous(), vec.contiguous()
+        B, T, C = x.shape
+        y = torch.empty_like(x)
+        check(lib.sml_add_rowvec(ptr(y), ptr(x), ptr(vec), ops.c_f32(1.0), ops.c_i64(B), ops.c_i64(T), c_i32(C), stream()), "add_rowvec")
+        ctx.shape = (B, T, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, C = ctx.shape
+        dy = dy.contiguous()
+        dvec = torch.empty(B, C, device=dy.device, dtype=F32)
+        for b in range(B):
+            ops.colsum(dy[b], out=dvec[b])
+        return dy, dvec
+
+
+def add_rowvec(x, vec):
+    return AddRowVecFn.apply(x, vec)
+
+
+class MeanTokensFn(torch.autograd.Function):
+    """x [B,T,C] -> mean over T [B,C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ops.require_cuda(x)
+        x = x.contiguous()
+        B, T, C = x.shape
+        y = torch.empty(B, C, device=x.device, dtype=F32)
+        for b in range(B):
+            ops.colsum(x[b], out=y[b])
+        ops.axpby_(y, y.clone(), 1.0 / T, 0.0)
+        ctx.shape = (B, T, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, C = ctx.shape
+        dx = torch.empty(B, T, C, device=dy.device, dtype=F32)
+        check(lib.sml_add_rowvec(ptr(dx), None, ptr(dy.contiguous()), ops.c_f32(1.0 / T), ops.c_i64(B), ops.c_i64(T), c_i32(C),
+                                 stream()), "add_rowvec")
+        return dx
+
+
+def mean_tokens(x):
+    return MeanTokensFn.apply(x)
+
+
+_UNARY = {"tanh": 0, "sigmoid": 1, "relu": 2, "elu": 3}
+
+
+class UnaryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, op):
+        ops.require_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.sml_unary_fwd(c_i32(op), ptr(x), ptr(y), ops.c_i64(x.numel()), stream()), "unary_fwd")
+        ctx.save_for_backward(x, y)
+        ctx.op = op
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        check(lib.sml_unary_bwd(c_i32(ctx.op), ptr(x), ptr(y), ptr(dy.contiguous()), ptr(dx), ops.c_i64(x.numel()), stream()), "unary_bwd")
+        return dx, None
+
+
+def unary(x, name):
+    return UnaryFn.apply(x, _UNARY[name])

@@ -212,7 +212,7 @@ class NystromAttentionFn(torch.autograd.Function):
         da3v_op = _prep(da3v, mode)
         da3 = gemm(da3v_op, _T(v_op))                                                        # [b,h,m,npad]
         gemm(_T(a3_op), da3v_op, out=dv)                                                     # dv = A3^T dA3V
-        dwc_part = torch.empty(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad)), h * ksize, device=dev, dtype=F32)
+        dwc_part = torch.empty(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad), c_i32(h * d)), h * ksize, device=dev, dtype=F32)
         check(lib.sml_nystrom_resconv_bwd(ptr(qkv), ptr(wc), ptr(dmerged), ptr(dqkv), ptr(dwc_part), c_i32(b), c_i32(npad),
                                           c_i32(h), c_i32(d), c_i32(ksize), stream()), "resconv_bwd")   # dv += conv^T
         dw_conv = ops.colsum(dwc_part).view(h, 1, ksize, 1)

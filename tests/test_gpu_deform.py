@@ -1,0 +1,153 @@
+"""GPU parity: deformable cross-attention 1-D / 2-D and DeformCrossTransMIL on libsml_b200 vs the golden
+fixtures of the unmodified reference (N = 2500) and the CPU oracle (other N).  fp32: 1e-4 relative on outputs,
+1e-3 on gradients (atomics / different summation order); tap indices bit-exact for identical coordinates."""
+from argparse import Namespace
+
+import pytest
+import torch
+
+import oracle
+from conftest import grads_close, load_golden, rel_err
+from synth import randn, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def test_deform1d_golden():
+    import sml_b200
+    g = load_golden("deform1d")
+    mod = sml_b200.DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6).cuda().eval()
+    mod.load_state_dict(g["state"])
+    x1 = g["x1"].cuda().requires_grad_(); x2 = g["x2"].cuda().requires_grad_()
+    y, vg = mod(x1, x2, return_vgrid=True)
+    assert rel_err(vg, g["vgrid"]) < 1e-5
+    assert rel_err(y, g["y"]) < 1e-4
+    y.backward(g["gy"].cuda())
+    assert rel_err(x1.grad, g["gx1"]) < 1e-3
+    assert rel_err(x2.grad, g["gx2"]) < 1e-3
+    grads_close({k: p.grad for k, p in mod.named_parameters()}, g["gparams"], 1e-3)
+
+
+def test_deform1d_upstream_order_vs_oracle():
+    import sml_b200
+    g = load_golden("deform1d")
+    mod = sml_b200.DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6,
+                                          pad_order="upstream").cuda().eval()
+    mod.load_state_dict(g["state"])
+    p = {k: v.clone().requires_grad_() for k, v in g["state"].items()}
+    x1c = g["x1"].clone().requires_grad_(); x2c = g["x2"].clone().requires_grad_()
+    yo = oracle.deform.deform_attn_1d(x1c, x2c, p, pad_order="upstream")
+    yo.backward(g["gy"])
+    x1 = g["x1"].cuda().requires_grad_(); x2 = g["x2"].cuda().requires_grad_()
+    y = mod(x1, x2)
+    assert rel_err(y, yo) < 1e-4
+    y.backward(g["gy"].cuda())
+    assert rel_err(x1.grad, x1c.grad) < 1e-3 and rel_err(x2.grad, x2c.grad) < 1e-3
+    grads_close({k: q.grad for k, q in mod.named_parameters()}, {k: v.grad for k, v in p.items()}, 1e-3)
+
+
+def test_gather_taps_bit_exact():
+    """Same normalised coordinates in -> identical integer tap indices and values as the oracle sampler."""
+    from sml_b200.deform import gather_with_taps
+    b, G, H, W, cg, nkv = 2, 8, 50, 50, 16, 144
+    x2 = randn((b, H * W, G * cg), 1)
+    vs = (randn((b * G, nkv, 2), 2) * 0.7).clamp(-1.4, 1.4)
+    feat = x2.view(b, H, W, G, cg).permute(0, 3, 4, 1, 2).reshape(b * G, cg, H, W)
+    want, (x0, y0) = oracle.deform.bilinear_sample(feat, vs[..., 0], vs[..., 1])
+    kv, taps = gather_with_taps(x2.cuda(), vs.cuda(), G, H, W)
+    assert torch.equal(taps[..., 0].cpu().long(), x0) and torch.equal(taps[..., 1].cpu().long(), y0)
+    got = kv.view(b, nkv, G, cg).permute(0, 2, 3, 1).reshape(b * G, cg, nkv)
+    assert rel_err(got, want) < 1e-6
+    # 1-D, both pad orders (H = n, W = 1)
+    n = 41
+    x1d = randn((b, n, 4 * 32), 3)
+    v1 = (randn((b * 4, 10, 1), 4)).clamp(-1.9, 1.9)
+    f1 = x1d.view(b, n, 4, 32).permute(0, 2, 3, 1).reshape(b * 4, 32, n, 1)
+    for mode in (0, 1):
+        z = torch.zeros_like(v1[..., 0])
+        want, (x0, y0) = oracle.deform.bilinear_sample(f1, v1[..., 0] if mode == 0 else z, z if mode == 0 else v1[..., 0])
+        kv, taps = gather_with_taps(x1d.cuda(), v1.cuda(), 4, n, 1, mode=mode)
+        assert torch.equal(taps[..., 0].cpu().long(), x0) and torch.equal(taps[..., 1].cpu().long(), y0)
+        assert rel_err(kv.view(b, 10, 4, 32).permute(0, 2, 3, 1).reshape(b * 4, 32, 10), want) < 1e-6
+
+
+def test_deform2d_golden():
+    import sml_b200
+    g = load_golden("deform2d")
+    mod = sml_b200.DeformCrossAttention2D(dim=128, dim_head=64, heads=8, dropout=0.1, downsample_factor=4, offset_scale=4,
+                                          offset_groups=8, offset_kernel_size=6).cuda().eval()
+    mod.load_state_dict(g["state"])
+    x1 = randn((1, 128, 2500), g["x1_seed"]).cuda().requires_grad_(); x2 = randn((1, 128, 2500), g["x2_seed"]).cuda().requires_grad_()
+    y, vg = mod(x1, x2, return_vgrid=True)
+    assert rel_err(vg, g["vgrid"]) < 1e-5
+    assert rel_err(y, g["y"]) < 1e-4
+    y.backward(randn(y.shape, g["gy_seed"]).cuda())
+    assert rel_err(x1.grad[:, :, ::7], g["gx1"]) < 1e-3
+    assert rel_err(x2.grad[:, :, ::7], g["gx2"]) < 1e-3
+    grads_close({k: p.grad for k, p in mod.named_parameters()}, g["gparams"], 1e-3)
+
+
+def test_deform2d_vs_oracle_64x64_batch2():
+    import sml_b200
+    torch.manual_seed(3)
+    mod = sml_b200.DeformCrossAttention2D(dim=128).cuda().eval()
+    sd = mod.state_dict()
+    sd["to_offsets.2.weight"] = sd["to_offsets.2.weight"] * 8.0
+    mod.load_state_dict(sd)
+    p = {k: v.detach().cpu().clone().requires_grad_() for k, v in mod.state_dict().items()}
+    x1c = randn((2, 128, 4096), 11).requires_grad_(); x2c = randn((2, 128, 4096), 12).requires_grad_()
+    gy = randn((2, 128, 4096), 13); gv = randn((16, 2, 16, 16), 14)
+    yo, vo = oracle.deform.deform_attn_2d(x1c, x2c, p, side=64, q_chunk=1024)
+    (yo * gy).sum().add((vo * gv).sum()).backward()
+    x1 = x1c.detach().cuda().requires_grad_(); x2 = x2c.detach().cuda().requires_grad_()
+    y, v = mod(x1, x2, return_vgrid=True)
+    assert rel_err(y, yo) < 1e-4 and rel_err(v, vo) < 1e-5
+    (y * gy.cuda()).sum().add((v * gv.cuda()).sum()).backward()
+    assert rel_err(x1.grad, x1c.grad) < 1e-3 and rel_err(x2.grad, x2c.grad) < 1e-3
+    grads_close({k: q.grad for k, q in mod.named_parameters()}, {k: t.grad for k, t in p.items()}, 1e-3)
+
+
+@pytest.mark.parametrize("ad", [2, 1])
+def test_deform_cross_transmil_golden(ad):
+    import sml_b200
+    g = load_golden(f"deformtransmil_ad{ad}")
+    net = sml_b200.DeformCrossTransMIL(Namespace(path_dim=128, attn_dim=ad, return_vgrid=(ad == 2))).cuda().eval()
+    st = synth_state_dict(g["shapes"], g["seed"])
+    for k in st:
+        if k.endswith("to_offsets.2.weight"):
+            st[k] = st[k] * g["offw_scale"]
+    net.load_state_dict(st)
+    path = randn((1, 2500, 1024), 83).cuda().requires_grad_(); omic = randn((1, 128), 84).abs().cuda().requires_grad_()
+    outs = net(path, omic)
+    enc, logits = outs[0], outs[1]
+    assert rel_err(logits, g["logits"]) < 1e-4 and rel_err(enc, g["enc"]) < 1e-4
+    loss = (logits * randn(logits.shape, 85).cuda()).sum() + (enc * randn(enc.shape, 86).cuda()).sum()
+    if ad == 2:
+        assert rel_err(outs[4], g["vgrid"]) < 1e-4
+        assert outs[3].shape == (1, 2500, 128) and torch.equal(outs[3][0, 17], omic.detach()[0])
+        loss = loss + (outs[4] * randn(outs[4].shape, 87).cuda()).sum() * 0.01
+    loss.backward()
+    assert rel_err(omic.grad, g["gomic"]) < 1e-3
+    assert rel_err(path.grad[:, ::50, ::16], g["gpath_sub"]) < 1e-3
+    gp = {k: p.grad for k, p in net.named_parameters()}
+    grads_close({k: gp[k] for k in g["gparams"] if gp[k] is not None}, {k: v for k, v in g["gparams"].items() if gp[k] is not None}, 2e-3)
+    for k, nv in g["gnorms"].items():
+        if gp[k] is None:
+            assert nv == 0.0 or "attn1d" in k or "attn2d" in k or k in ("cls_token",) or "pooler" in k, k
+            continue
+        assert abs(float(gp[k].norm()) - nv) <= 2e-3 * nv + 1e-5, (k, float(gp[k].norm()), nv)
+
+
+def test_deform_attention_dropout_is_unbiased():
+    import sml_b200
+    from sml_b200 import functional as Fn
+    torch.manual_seed(5)
+    mod = sml_b200.DeformCrossAttention2D(dim=128, dropout=0.1).cuda()
+    x1 = randn((1, 128, 1024), 21).cuda(); x2 = randn((1, 128, 1024), 22).cuda()
+    mod.eval(); y0 = mod(x1, x2)
+    mod.train(); Fn.manual_seed(3)
+    acc = torch.zeros_like(y0)
+    for _ in range(16):
+        acc += mod(x1, x2).detach()
+    assert rel_err(acc / 16, y0) < 0.1                   # dropout(p) / (1-p) keeps the expectation
+    assert rel_err(mod(x1, x2), y0) > 1e-3               # and it is really applied in training mode
