@@ -167,6 +167,30 @@ int sml_deform_attn_bwd(const int32_t* cfg8, float p_drop, uint64_t seed, const 
                         const float* vs, const float* cpb, const float* out, const float* lse, const float* dout,
                         float* dq, float* dk, float* dv, float* dvs, float* part, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Fusion heads, subspace losses and the batch-norm statistics the ranks exchange.
+ * ------------------------------------------------------------------------------------- */
+int sml_mul(const float* a, const float* b, float* y, int64_t n, void* stream);     /* gates of models/fusion.py:43,50 */
+/* sums [2C] = (sum x, sum x^2) over the R local rows: the message of utils/sync_batchnorm/batchnorm.py:104-133
+ * and torch.nn.SyncBatchNorm (main.py:118); all-reduced by the caller, then normalised with the global mean/invstd */
+int sml_bn_stats(const float* x, float* sums, int32_t R, int32_t C, void* stream);
+int sml_bn_fwd(const float* x, const float* mean, const float* invstd, const float* w, const float* b, float* y, int32_t R,
+               int32_t C, void* stream);
+int sml_bn_bwd_stats(const float* dy, const float* x, const float* mean, const float* invstd, float* sums, int32_t R, int32_t C,
+                     void* stream);                                              /* (sum dy, sum dy*xhat) */
+int sml_bn_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* w, const float* sums,
+               float inv_n, float* dx, int32_t R, int32_t C, void* stream);
+/* BatchLoss epilogue on Gram matrices (utils/loss.py:26-38): S [N,N] = omic Gram, T [NS,N,N] = vgrid slab Grams;
+ * loss [N,N] = (rownorm(S) - mean_s rownorm(T_s))^2 / N; rn [(1+NS),N] saved row norms */
+int sml_batchloss_fwd(const float* S, const float* T, float* loss, float* rn, int32_t N, int32_t NS, void* stream);
+int sml_batchloss_bwd(const float* S, const float* T, const float* rn, const float* dloss, float* dS, float* dT, int32_t N,
+                      int32_t NS, void* stream);
+/* OrthogonalLoss (models/cmta_utils.py:1217-1228): loss [B]; stats [B,9] saved; barred operands are detached */
+int sml_orthogonal_loss_fwd(const float* P, const float* Ph, const float* G, const float* Gh, float gamma, float* loss,
+                            float* stats, int32_t B, int32_t D, void* stream);
+int sml_orthogonal_loss_bwd(const float* P, const float* Ph, const float* G, const float* Gh, float gamma, const float* stats,
+                            const float* dloss, float* dP, float* dPh, float* dG, float* dGh, int32_t B, int32_t D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,3 +229,90 @@ class UnaryFn(torch.autograd.Function):
 
 def unary(x, name):
     return UnaryFn.apply(x, _UNARY[name])
+
+
+class MatmulFn(torch.autograd.Function):
+    """C = A @ B on strided fp32 views ([..., M, K] @ [..., K, N], <= 2 equal batch dims)."""
+
+    @staticmethod
+    def forward(ctx, A, B, alpha):
+        ops.require_cuda(A, B)
+        assert A.shape[:-2] == B.shape[:-2], "MatmulFn needs equal batch dims"
+        ctx.save_for_backward(A, B)
+        ctx.alpha = alpha
+        return gemm(A, B, alpha=alpha)
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B = ctx.saved_tensors
+        dC = dC.contiguous()
+        dA = gemm(dC, B.transpose(-1, -2), alpha=ctx.alpha) if ctx.needs_input_grad[0] else None
+        dB = gemm(A.transpose(-1, -2), dC, alpha=ctx.alpha) if ctx.needs_input_grad[1] else None
+        return dA, dB, None
+
+
+def matmul(A, B, alpha=1.0):
+    return MatmulFn.apply(A, B, alpha)
+
+
+class SoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ops.require_cuda(x)
+        y = x.contiguous().clone()
+        ops.softmax_(y.view(-1, y.shape[-1]))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        g = dy.contiguous().clone()
+        ops.softmax_bwd_(y.view(-1, y.shape[-1]), g.view(-1, y.shape[-1]))
+        return g
+
+
+def softmax_lastdim(x):
+    return SoftmaxFn.apply(x)
+
+
+class MulFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ops.require_cuda(a, b)
+        a, b = a.contiguous(), b.contiguous()
+        ctx.save_for_backward(a, b)
+        return _mul(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b = ctx.saved_tensors
+        dy = dy.contiguous()
+        return _mul(dy, b), _mul(dy, a)
+
+
+def _mul(a, b):
+    y = torch.empty_like(a)
+    check(lib.sml_mul(ptr(a), ptr(b), ptr(y), ops.c_i64(a.numel()), stream()), "mul")
+    return y
+
+
+def mul(a, b):
+    return MulFn.apply(a, b)
+
+
+class ScaleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, a):
+        ctx.a = a
+        x = x.contiguous()
+        return ops.axpby_(torch.empty_like(x), x, a, 0.0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        return ops.axpby_(torch.empty_like(dy), dy, ctx.a, 0.0), None
+
+
+def scale(x, a):
+    return ScaleFn.apply(x, float(a))

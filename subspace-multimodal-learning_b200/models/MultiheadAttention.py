@@ -1,0 +1,71 @@
+"""Drop-in for /root/reference/models/MultiheadAttention.py:333-489 (+ multi_head_attention_forward :7-321; identical
+copy at models/cmta_utils.py:354-847): same constructor, forward signature, parameter names; the second output is
+the RAW pre-softmax score tensor [B, heads, L, S] (need_raw=True, :299-312).  CUDA only.
+
+Only the paths the reference call sites use are implemented (MCAT model.py:587,627; CMTA model.py:748-750,809-818):
+packed in-projection with bias, no masks, no bias_kv / zero_attn, same embedding dim for q/k/v."""
+import torch
+from torch import nn
+from torch.nn.init import constant_, xavier_uniform_
+
+from .. import functional as Fn
+
+
+class MultiheadAttention(nn.Module):
+    def __init__(self, embed_dim, num_heads, dropout=0., bias=True, add_bias_kv=False, add_zero_attn=False, kdim=None, vdim=None):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.kdim = kdim if kdim is not None else embed_dim
+        self.vdim = vdim if vdim is not None else embed_dim
+        self._qkv_same_embed_dim = self.kdim == embed_dim and self.vdim == embed_dim
+        if not self._qkv_same_embed_dim or add_bias_kv or add_zero_attn:
+            raise NotImplementedError("sml_b200 MultiheadAttention: kdim/vdim/add_bias_kv/add_zero_attn are not used by the reference")
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == self.embed_dim, "embed_dim must be divisible by num_heads"
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.register_parameter('q_proj_weight', None)
+        self.register_parameter('k_proj_weight', None)
+        self.register_parameter('v_proj_weight', None)
+        if bias:
+            self.in_proj_bias = nn.Parameter(torch.empty(3 * embed_dim))
+        else:
+            self.register_parameter('in_proj_bias', None)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+        self.bias_k = self.bias_v = None
+        self.add_zero_attn = add_zero_attn
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        xavier_uniform_(self.in_proj_weight)
+        if self.in_proj_bias is not None:
+            constant_(self.in_proj_bias, 0.)
+            constant_(self.out_proj.bias, 0.)
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=True, need_raw=True, attn_mask=None):
+        if key_padding_mask is not None or attn_mask is not None:
+            raise NotImplementedError("sml_b200 MultiheadAttention: masks are never passed by the reference call sites")
+        L, B, E = query.shape
+        S = key.shape[0]
+        h, hd = self.num_heads, self.head_dim
+        assert key.shape == value.shape and E == self.embed_dim
+        w, bias = self.in_proj_weight, self.in_proj_bias
+        bq, bk, bv = (None, None, None) if bias is None else (bias[:E], bias[E:2 * E], bias[2 * E:])
+        q = Fn.scale(Fn.linear(query.float(), w[:E], bq), float(hd) ** -0.5)            # :125-205
+        k = Fn.linear(key.float(), w[E:2 * E], bk)
+        v = k if False else Fn.linear(value.float(), w[2 * E:], bv)
+        qh = q.view(L, B, h, hd).permute(1, 2, 0, 3)                                    # [B,h,L,hd] views (:245-249)
+        kh = k.view(S, B, h, hd).permute(1, 2, 0, 3)
+        vh = v.view(S, B, h, hd).permute(1, 2, 0, 3)
+        raw = Fn.matmul(qh, kh.transpose(-1, -2))                                       # [B,h,L,S]  :282
+        attn = Fn.softmax_lastdim(raw)                                                  # :300
+        attn = Fn.dropout_add(None, attn, self.dropout, self.training)                  # :301
+        o = Fn.matmul(attn, vh)                                                         # [B,h,L,hd] :303
+        o = o.permute(2, 0, 1, 3).reshape(L, B, E)                                      # :305
+        out = Fn.linear(o, self.out_proj.weight, self.out_proj.bias)                    # :306
+        if need_weights:
+            if need_raw:
+                return out, raw                                                         # :308-312
+            return out, Fn.scale(attn.sum(dim=1), 1.0 / h)
+        return out, None

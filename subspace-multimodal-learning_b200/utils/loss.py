@@ -1,0 +1,94 @@
+"""Drop-in for BatchLoss of /root/reference/utils/loss.py:7-40 (same constructor / forward).  CUDA only.
+
+Schedule differences (same result): the Gram of the token-repeated omic tensor [Ng, N*128] is evaluated on the
+[Ng,128] base vectors when DeformCrossTransMIL tagged them (row normalisation cancels the factor N);
+omic base and vgrid travel in ONE packed all_gather instead of two (C3/C4); the row-norm / mean / squared-difference
+epilogue is one kernel."""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._lib import c_i32, check, lib, ptr, stream
+from ..ops import F32, gemm
+from .gather import PackedGather
+
+
+class _BatchLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, O, V):
+        """O [Ng,F], V [NS,Ng,Fv] -> loss [Ng,Ng]"""
+        ops.require_cuda(O, V)
+        O, V = O.contiguous(), V.contiguous()
+        Ng, NS = O.shape[0], V.shape[0]
+        S = gemm(O, O.t())
+        T = gemm(V, V.transpose(-1, -2))
+        loss = torch.empty(Ng, Ng, device=O.device, dtype=F32)
+        rn = torch.empty(1 + NS, Ng, device=O.device, dtype=F32)
+        check(lib.sml_batchloss_fwd(ptr(S), ptr(T), ptr(loss), ptr(rn), c_i32(Ng), c_i32(NS), stream()), "batchloss_fwd")
+        ctx.save_for_backward(O, V, S, T, rn)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        O, V, S, T, rn = ctx.saved_tensors
+        Ng, NS = O.shape[0], V.shape[0]
+        dS, dT = torch.empty_like(S), torch.empty_like(T)
+        check(lib.sml_batchloss_bwd(ptr(S), ptr(T), ptr(rn), ptr(dloss.contiguous()), ptr(dS), ptr(dT), c_i32(Ng), c_i32(NS), stream()),
+              "batchloss_bwd")
+        dO = gemm(dS, O)
+        gemm(dS.t(), O, out=dO, beta=1.0)
+        dV = gemm(dT, V)
+        gemm(dT.transpose(-1, -2), V, out=dV, beta=1.0)
+        return dO, dV
+
+
+class BatchLoss(nn.Module):
+    def __init__(self, batch_size, world_size):
+        super().__init__()
+        self.batch_size = batch_size
+        self.world_size = world_size
+
+    def forward(self, omic, vgrid):
+        N = self.batch_size * self.world_size
+        base = getattr(omic, "_sml_base", None)          # [B,128] base of the token-repeated omic (DeformCrossTransMIL)
+        o = base if base is not None else omic.reshape(omic.shape[0], -1)
+        if self.world_size > 1:
+            o, vgrid = PackedGather.apply(o.float(), vgrid.float())
+        o = o.reshape(N, -1).float()
+        v = vgrid.reshape(8, N, -1).float()              # raw reinterpretation of the (rank, b, g)-major buffer (loss.py:24)
+        return _BatchLossFn.apply(o, v)
+
+
+class _OrthFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, P, Ph, G, Gh, gamma):
+        ops.require_cuda(P, Ph, G, Gh)
+        P, Ph, G, Gh = (t.contiguous().float() for t in (P, Ph, G, Gh))
+        B, D = P.shape
+        loss = torch.empty(B, device=P.device, dtype=F32)
+        stats = torch.empty(B, 9, device=P.device, dtype=F32)
+        check(lib.sml_orthogonal_loss_fwd(ptr(P), ptr(Ph), ptr(G), ptr(Gh), ops.c_f32(gamma), ptr(loss), ptr(stats), c_i32(B), c_i32(D),
+                                          stream()), "orthogonal_loss_fwd")
+        ctx.save_for_backward(P, Ph, G, Gh, stats)
+        ctx.gamma = gamma
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        P, Ph, G, Gh, stats = ctx.saved_tensors
+        B, D = P.shape
+        gs = [torch.empty_like(P) for _ in range(4)]
+        check(lib.sml_orthogonal_loss_bwd(ptr(P), ptr(Ph), ptr(G), ptr(Gh), ops.c_f32(ctx.gamma), ptr(stats), ptr(dloss.contiguous()),
+                                          *[ptr(g) for g in gs], c_i32(B), c_i32(D), stream()), "orthogonal_loss_bwd")
+        return gs[0], gs[1], gs[2], gs[3], None
+
+
+class OrthogonalLoss(nn.Module):
+    """Drop-in for /root/reference/models/cmta_utils.py:1212-1228."""
+
+    def __init__(self, gamma=0.5):
+        super().__init__()
+        self.gamma = gamma
+
+    def forward(self, P, P_hat, G, G_hat):
+        return _OrthFn.apply(P, P_hat, G, G_hat, float(self.gamma))

@@ -1,0 +1,88 @@
+"""GPU parity: co-attention, fusion heads and subspace losses vs golden fixtures of the unmodified reference."""
+import pytest
+import torch
+
+import oracle
+from conftest import grads_close, load_golden, rel_err
+from synth import randn, synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mha_golden():
+    import sml_b200
+    g = load_golden("mha")
+    mha = sml_b200.MultiheadAttention(256, 1).cuda().eval()
+    mha.load_state_dict(g["state"])
+    q = g["q"].cuda().requires_grad_(); kv = g["kv"].cuda().requires_grad_()
+    o, raw = mha(q, kv, kv)
+    assert o.shape == (6, 2, 256) and raw.shape == (2, 1, 6, 70)
+    assert rel_err(o, g["out"]) < 1e-4 and rel_err(raw, g["raw"]) < 1e-4
+    (o * g["go"].cuda()).sum().backward()
+    assert rel_err(q.grad, g["gq"]) < 1e-3 and rel_err(kv.grad, g["gkv"]) < 1e-3
+    grads_close({k: p.grad for k, p in mha.named_parameters()}, g["gparams"], 1e-3)
+    mha4 = sml_b200.MultiheadAttention(256, 4).cuda().eval()           # CMTA direction: N queries x G keys, 4 heads
+    mha4.load_state_dict(g["state"])
+    o4, raw4 = mha4(g["kv"].cuda(), g["q"].cuda(), g["q"].cuda())
+    assert rel_err(o4, g["out4"]) < 1e-4 and rel_err(raw4, g["raw4"]) < 1e-4
+
+
+def test_bilinear_fusion_golden():
+    import sml_b200
+    g = load_golden("bilinear_fusion")
+    bf = sml_b200.BilinearFusion(skip=0, use_bilinear=1, gate1=1, gate2=1, dim1=32, dim2=32, scale_dim1=1, scale_dim2=1,
+                                 mmhid=64, dropout_rate=0.0).cuda()
+    bf.load_state_dict(synth_state_dict(g["shapes"], g["seed"]))
+    bf.eval()
+    assert rel_err(bf(g["v1"].cuda(), g["v2"].cuda()), g["y_eval"]) < 1e-4
+    bf.train()
+    v1 = g["v1"].cuda().requires_grad_(); v2 = g["v2"].cuda().requires_grad_()
+    y = bf(v1, v2)
+    assert rel_err(y, g["y_train"]) < 1e-4
+    y.backward(g["gy"].cuda())
+    assert rel_err(v1.grad, g["gv1"]) < 1e-3 and rel_err(v2.grad, g["gv2"]) < 1e-3
+    gp = {k: p.grad for k, p in bf.named_parameters()}
+    grads_close({k: gp[k] for k in g["gparams"]}, g["gparams"], 1e-3)
+
+
+def test_losses_golden():
+    import sml_b200
+    g = load_golden("losses")
+    om = g["omic"].cuda().requires_grad_(); vg = g["vgrid"].cuda().requires_grad_()
+    bl = sml_b200.BatchLoss(om.shape[0], 1)(om, vg)
+    assert rel_err(bl, g["batch_loss"]) < 1e-4
+    bl.backward(g["gbl"].cuda())
+    assert rel_err(om.grad, g["gomic"]) < 1e-3 and rel_err(vg.grad, g["gvgrid"]) < 1e-3
+    ts = [g[k].cuda().requires_grad_() for k in ("P", "Ph", "G", "Gh")]
+    ol = sml_b200.OrthogonalLoss(gamma=0.5)(*ts)
+    assert rel_err(ol, g["orth"]) < 1e-5
+    ol.sum().backward()
+    for t, k in zip(ts, ("gP", "gPh", "gG", "gGh")):
+        assert rel_err(t.grad, g[k]) < 1e-4
+    bn = sml_b200.SynchronizedBatchNorm1d(8).cuda().train()
+    y = bn(g["bn_x"].cuda())
+    want = (g["bn_x"] - g["bn_mean"]) * g["bn_inv_std"]
+    assert rel_err(y, want) < 1e-5
+    assert rel_err(bn.running_var, g["bn_running_var"]) < 1e-5
+
+
+def test_batchloss_collapsed_gram_equals_repeated():
+    """omic repeated over N tokens (DeformCrossTransMIL.py:104) vs the tagged [B,128] base: same loss and gradients."""
+    import sml_b200
+    B, N = 6, 400
+    base = randn((B, 128), 1).abs()
+    vg = randn((8 * B, 2, 5, 5), 2)
+    bc = base.clone().requires_grad_(); vc = vg.clone().requires_grad_()
+    want = oracle.loss.batch_loss(bc.unsqueeze(1).repeat(1, N, 1), vc, B)
+    gl = randn(want.shape, 3)
+    want.backward(gl)
+    b1 = base.cuda().requires_grad_(); v1 = vg.cuda().requires_grad_()
+    rep = b1.unsqueeze(1).repeat(1, N, 1)
+    rep._sml_base = b1
+    got = sml_b200.BatchLoss(B, 1)(rep, v1)
+    assert rel_err(got, want) < 1e-4
+    got.backward(gl.cuda())
+    assert rel_err(b1.grad, bc.grad) < 1e-3 and rel_err(v1.grad, vc.grad) < 1e-3
+    b2 = base.cuda().requires_grad_()
+    got2 = sml_b200.BatchLoss(B, 1)(b2.unsqueeze(1).repeat(1, N, 1), vg.cuda())     # untagged: generic [Ng, N*128] Gram
+    assert rel_err(got2, want) < 1e-4
