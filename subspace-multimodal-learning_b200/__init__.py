@@ -14,3 +14,4 @@ from .models.fusion import BilinearFusion  # noqa: F401
 from .utils.loss import BatchLoss, OrthogonalLoss  # noqa: F401
 from .utils.gather import GatherLayer, PackedGather  # noqa: F401
 from .utils.sync_batchnorm import SyncBatchNorm1d, SynchronizedBatchNorm1d, convert_model  # noqa: F401
+from .install import install  # noqa: F401
