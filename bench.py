@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--patches", type=int, default=16384)
     ap.add_argument("--cpu-sample", type=int, default=1, help="slides in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prof-out", default=None, help="write the per-shape GEMM timing table of the instrumented pass here")
     return ap.parse_args()
 
 
@@ -216,9 +217,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     agg = {}
-    for eng, flops, e0, e1 in prof:
+    shapes = {}
+    for eng, flops, e0, e1, tag in prof:
+        dt = e0.elapsed_time(e1) * 1e-3
         a = agg.setdefault(eng, [0.0, 0.0, 0])
-        a[0] += flops; a[1] += e0.elapsed_time(e1) * 1e-3; a[2] += 1
+        a[0] += flops; a[1] += dt; a[2] += 1
+        sh = shapes.setdefault((eng,) + tag, [0.0, 0.0, 0])
+        sh[0] += flops; sh[1] += dt; sh[2] += 1
+    if args.prof_out and rank == 0:
+        with open(args.prof_out, "w") as f:
+            f.write("# eng M N K batch A_MNmajor B_MNmajor split relu|2softmax C Cb_hi Cb_lo beta : launches total_us avg_us TFLOP/s\n")
+            for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                f.write("%s : %d %.1f %.1f %.1f\n" % (" ".join(str(x) for x in k), v[2], v[1] * 1e6, v[1] * 1e6 / v[2], v[0] / v[1] / 1e12))
     pk, pk_src = peaks()
     roof = None
     if "tc" in agg and agg["tc"][1] > 0:

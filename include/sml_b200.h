@@ -63,23 +63,24 @@ int sml_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 /* row r of x ([R,D], R = batches*n) is written to row (r/n)*npad + pad + r%n of y (front-padded layout of
  * models/NystromAttention.py:79-82; pass n=R, npad=R, pad=0 for a plain LayerNorm) */
 int sml_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
-                      int64_t R, int32_t D, float eps, int64_t n, int64_t npad, int64_t pad, void* stream);
+                      int64_t R, int32_t D, float eps, int64_t n, int64_t npad, int64_t pad, void* y_hi, void* y_lo,
+                      void* stream);   /* y_hi/y_lo: optional bf16 (hi, residual) copies of y for the tcgen05 engine */
 /* dx = LN'(dy); dw_part/db_part are [nblk,D] partial sums (nblk = sml_layernorm_bwd_blocks(R)) */
 int sml_layernorm_bwd_blocks(int64_t R);
 int sml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                       float* dx, float* dw_part, float* db_part, int64_t R, int32_t D, int64_t n, int64_t npad,
                       int64_t pad, void* stream);   /* dy is read in the padded layout, dx written dense */
 /* y[r,:] = softmax(x[r,:]) in place over C columns (models/NystromAttention.py:137) */
-int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* stream);
+int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi, void* lo, void* stream);   /* hi/lo: optional bf16 copies */
 /* in place on dA: dS = A * (dA - sum(dA*A)) */
-int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* stream);
+int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* hi, void* lo, void* stream);
 /* y = x + dropout(u, p) with a counter-based generator (seed, offset); p == 0 -> plain add.
  * Same call with grad tensors regenerates the mask in backward (models/mil.py:183 dropout=0.1) */
 int sml_dropout_add(const float* x, const float* u, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,
                     void* stream);
-int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* stream);   /* y = a*x + b*y */
+int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* hi, void* lo, void* stream);   /* y = a*x + b*y */
 /* out = a*x + dg*I over nmat square m x m matrices (identity terms of models/NystromAttention.py:33) */
-int sml_diag_axpby(float* out, const float* x, float a, float dg, int64_t nmat, int32_t m, void* stream);
+int sml_diag_axpby(float* out, const float* x, float a, float dg, int64_t nmat, int32_t m, void* hi, void* lo, void* stream);
 /* dx = dy where y > 0 else 0 (ReLU of models/mil.py:214, models/DeformCrossTransMIL.py:83) */
 int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* stream);
 /* y[b,t,:] = (x ? x[b,t,:] : 0) + a*vec[b,:]  — the rank-1 half of FusionNet (models/DeformCrossTransMIL.py:104,33-38:
@@ -103,7 +104,7 @@ int sml_nystrom_landmarks_fwd(const float* qkv, float* ql, float* kl, int32_t B,
                               int32_t m, void* stream);
 /* dqkv[q,k chunks][t] += d{ql,kl}[t / l] / l */
 int sml_nystrom_landmarks_bwd(float* dqkv, const float* dql, const float* dkl, int32_t B, int32_t npad, int32_t h,
-                              int32_t d, int32_t m, void* stream);
+                              int32_t d, int32_t m, void* dqkv_hi, void* dqkv_lo, void* stream);
 /* integer landmark ids (bit-exact contract): ids[t] = t / (npad / m) */
 int sml_nystrom_landmark_ids(int32_t* ids, int32_t npad, int32_t m, void* stream);
 /* scal[0] = max over all (b,h,i) of sum_j |x|, scal[1] = max over all (b,h,j) of sum_i |x| (global, F8);
@@ -117,11 +118,12 @@ int sml_pinv_init_bwd(const float* x, const float* scal, const int32_t* arg, con
                       float* tmp /*4 B*/, int32_t BH, int32_t m, void* stream);
 /* depthwise conv along tokens on the v chunk, per head, shared over d: out[B,n',h*d] += conv(v) (:144-145) */
 int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
-                            int32_t d, int32_t ksize, void* stream);
+                            int32_t d, int32_t ksize, void* out_hi, void* out_lo, void* stream);
 /* dqkv[v chunk] += conv^T(dout); dw[h,k] = sum dout*v (dw_part [nblk,h,k]; nblk returned by ..._blocks) */
 int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad, int32_t hd);
 int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
-                            int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* stream);
+                            int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* dqkv_hi, void* dqkv_lo,
+                            void* stream);
 /* PPEG: identity + depthwise 7x7 + 5x5 + 3x3 folded into one 7x7 stencil, token-major [B,1+H*W,C];
  * the cls row is copied through (models/mil.py:192-206).  w7 [49,C] folded tap-major weights, bias [C] folded.
  * Backward: dw_part [nblk,49,C], db_part [nblk,C]. */

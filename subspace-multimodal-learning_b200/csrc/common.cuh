@@ -65,4 +65,13 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 constexpr int kNumSMs = 148;
 
+// optional bf16 copies of a value written by a kernel: hi = bf16(v), lo = bf16(v - hi) (operands of the tcgen05 engine)
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i, float v) {
+  if (hi) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
 }  // namespace sml

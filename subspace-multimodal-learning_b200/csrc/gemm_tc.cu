@@ -106,6 +106,8 @@ struct EpiParams {
   float alpha, beta, diag;
   const float* bias;
   int relu, softmax;
+  int ksplit, kb_per_split;     // split-K: blockIdx.z = batch*ksplit + ks; partial sums are red.add'ed into a zeroed C
+  int staged_ok;                // rows 16-byte aligned, unit column stride: coalesced stores through shared memory
 };
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
@@ -115,6 +117,8 @@ template <int BN, bool SPLIT, int STAGES>
 struct TcSmem {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = (TC_A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int STAGING = 4 * 32 * 36 * 4;   // epilogue staging tile (aliases operand stage 0 once the MMAs are done)
+  static_assert(STAGING <= STAGE_BYTES, "staging tile must fit in one operand stage");
   static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
@@ -146,6 +150,41 @@ __device__ __forceinline__ void store_row_chunk(const EpiParams& ep, float* crow
   (void)gm;
 }
 
+
+// Coalesced variant: the warp's 32 rows x 32 columns go through a padded shared-memory tile so that every store
+// instruction writes 4 complete 128-byte row segments (instead of 32 scattered 16-byte pieces).
+__device__ __forceinline__ void store_chunk_staged(const EpiParams& ep, float* stg, int lane, int row0, int64_t batch_off,
+                                                   int gn0, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, col = (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rr;
+    const int grow = row0 + r;
+    if (grow < ep.M) {
+      const float4 val = *reinterpret_cast<const float4*>(stg + r * 36 + col);
+      const int64_t off = batch_off + (int64_t)grow * ep.sc_m + gn0 + col;
+      if (ep.C) *reinterpret_cast<float4*>(ep.C + off) = val;
+      if (ep.Cb_hi) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(val.x, val.y), h1 = __floats2bfloat162_rn(val.z, val.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(ep.Cb_hi + off) = pk;
+        if (ep.Cb_lo) {
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          const __nv_bfloat162 l0 = __floats2bfloat162_rn(val.x - f0.x, val.y - f0.y), l1 = __floats2bfloat162_rn(val.z - f1.x, val.w - f1.y);
+          pk.x = *reinterpret_cast<const uint32_t*>(&l0); pk.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(ep.Cb_lo + off) = pk;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
@@ -157,11 +196,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* staging = reinterpret_cast<float*>(smem);   // valid after tmem_full: every TMA load has landed and been consumed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
-  const int b1 = blockIdx.z / ep.nb2, b2 = blockIdx.z % ep.nb2;
-  const int nkb = (ep.K + TC_BK - 1) / TC_BK;
+  const int bz = blockIdx.z / ep.ksplit, ks = blockIdx.z % ep.ksplit;
+  const int b1 = bz / ep.nb2, b2 = bz % ep.nb2;
+  const int nkb_all = (ep.K + TC_BK - 1) / TC_BK;
+  const int kb_lo = ks * ep.kb_per_split;
+  const int nkb = min(nkb_all, kb_lo + ep.kb_per_split) - kb_lo;      // k-blocks of this CTA (>= 1 by construction)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -187,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(&full_bar[s], (uint32_t)S::STAGE_BYTES);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + TC_A_BYTES * (SPLIT ? 2 : 1);
-        const int k0 = kb * TC_BK;
+        const int k0 = (kb_lo + kb) * TC_BK;
 #pragma unroll
         for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
           const CUtensorMap* ta = part ? &tmAl : &tmA;
@@ -253,7 +296,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __nv_bfloat16* hrow = ep.Cb_hi ? ep.Cb_hi + coff : nullptr;
     __nv_bfloat16* lrow = ep.Cb_lo ? ep.Cb_lo + coff : nullptr;
     uint32_t r[32];
-    if (ep.softmax) {
+    float* stg = staging + (warp - 2) * 32 * 36;
+    const int64_t batch_off = (int64_t)b1 * ep.sc_b1 + (int64_t)b2 * ep.sc_b2;
+    const int row0 = m0 + q * 32;
+    if (ep.ksplit > 1) {
+      // split-K partial: alpha * acc (+ bias / diag on split 0) accumulated with red.global.add into the zeroed C
+      for (int c = 0; c < BN; c += 32) {
+        tc_ld32(trow + c, r);
+        if (!(row_ok && n0 + c < ep.N)) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int gn = n0 + c + j;
+          if (gn < ep.N) {
+            float x = ep.alpha * __uint_as_float(r[j]);
+            if (ks == 0) { if (gn == gm) x += ep.diag; if (ep.bias) x += __ldg(ep.bias + gn); }
+            atomicAdd(crow + (int64_t)gn * ep.sc_n, x);
+          }
+        }
+      }
+    } else if (ep.softmax) {
       // the whole row lives in this thread's TMEM lane: max / sum / normalise without any cross-thread traffic
       float mx = -INFINITY;
       for (int c = 0; c < BN; c += 32) {
@@ -275,12 +336,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __expf(ep.alpha * __uint_as_float(r[j]) - mx) * inv;
-        if (row_ok && n0 + c < ep.N) store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
+        if (ep.staged_ok && n0 + c + 32 <= ep.N) store_chunk_staged(ep, stg, lane, row0, batch_off, n0 + c, v);
+        else if (row_ok && n0 + c < ep.N) store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
       }
     } else {
+      const bool staged = ep.staged_ok && ep.beta == 0.f;
       for (int c = 0; c < BN; c += 32) {
         tc_ld32(trow + c, r);
-        if (!(row_ok && n0 + c < ep.N)) continue;
+        const bool st_chunk = staged && n0 + c + 32 <= ep.N;         // warp-uniform
+        if (!st_chunk && !(row_ok && n0 + c < ep.N)) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -294,7 +358,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           v[j] = x;
         }
-        store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
+        if (st_chunk) store_chunk_staged(ep, stg, lane, row0, batch_off, n0 + c, v);
+        else store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
       }
     }
   }
@@ -430,12 +495,36 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
   ep.relu = d->relu & 1; ep.softmax = softmax;
   SML_CHECK(!(ep.beta != 0.f) || ep.C, "sml_gemm_tc: beta needs an fp32 C");
 
-  const long long nbz = (long long)d->nb1 * d->nb2;
+  long long nbz = (long long)d->nb1 * d->nb2;
+  const int tiles_mn = ((d->N + BN - 1) / BN) * ((d->M + TC_BM - 1) / TC_BM);
+  const int nkb_all = (d->K + TC_BK - 1) / TC_BK;
+  ep.ksplit = 1; ep.kb_per_split = nkb_all;
+  // split-K when the output has too few tiles to fill the 148 SMs and K is long (weight gradients: K = B*n')
+  if (tiles_mn * nbz < 74 && nkb_all >= 32 && ep.C && !ep.Cb_hi && !ep.relu && !softmax && ep.beta == 0.f) {
+    int want = (int)((2 * kNumSMs + tiles_mn * nbz - 1) / (tiles_mn * nbz));
+    if (want > nkb_all / 8) want = nkb_all / 8;
+    if (want > 1) {
+      ep.kb_per_split = (nkb_all + want - 1) / want;
+      ep.ksplit = (nkb_all + ep.kb_per_split - 1) / ep.kb_per_split;
+      // zero C (strided views: row by row through cudaMemset2DAsync)
+      for (long long bz = 0; bz < nbz; ++bz) {
+        float* cb = ep.C + (bz / d->nb2) * ep.sc_b1 + (bz % d->nb2) * ep.sc_b2;
+        SML_CHECK(ep.sc_n == 1, "sml_gemm_tc: split-K needs unit column stride");
+        cudaError_t e = cudaMemset2DAsync(cb, (size_t)ep.sc_m * 4, 0, (size_t)d->N * 4, (size_t)d->M, as_stream(stream));
+        SML_CHECK(e == cudaSuccess, "sml_gemm_tc: split-K memset failed: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  ep.staged_ok = (ep.sc_n == 1 && (ep.sc_m % 4) == 0 && (ep.sc_b1 % 4) == 0 && (ep.sc_b2 % 4) == 0 &&
+                  (!ep.C || (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
+                  (!ep.Cb_hi || (reinterpret_cast<uintptr_t>(ep.Cb_hi) & 7) == 0) &&
+                  (!ep.Cb_lo || (reinterpret_cast<uintptr_t>(ep.Cb_lo) & 7) == 0)) ? 1 : 0;
+  nbz *= ep.ksplit;
   SML_CHECK(nbz <= 65535, "sml_gemm_tc: batch %lld > 65535", nbz);
   dim3 grid((d->N + BN - 1) / BN, (d->M + TC_BM - 1) / TC_BM, (unsigned)nbz);
   SML_CHECK(grid.y <= 65535, "sml_gemm_tc: M too large for grid.y");
   cudaStream_t st = as_stream(stream);
-  const bool deep = d->K > 2 * TC_BK;
+  const bool deep = ep.kb_per_split > 2;
   if (!split) {
     if (BN == 256) return deep ? dispatch_major<256, false, 4>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<256, false, 2>(a_mn, b_mn, tms, ep, grid, st);
     if (BN == 128) return deep ? dispatch_major<128, false, 6>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<128, false, 2>(a_mn, b_mn, tms, ep, grid, st);

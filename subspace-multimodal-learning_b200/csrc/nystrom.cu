@@ -23,16 +23,21 @@ __global__ void landmarks_fwd_kernel(const float* __restrict__ qkv, float* __res
   kl[o] = sk / (float)l;
 }
 __global__ void landmarks_bwd_kernel(float* __restrict__ dqkv, const float* __restrict__ dql,
-                                     const float* __restrict__ dkl, int npad, int h, int d, int m) {
+                                     const float* __restrict__ dkl, int npad, int h, int d, int m,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int j = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
   const int hd = h * d, l = npad / m;
   const int head = c / d, dd = c % d;
   const int64_t o = (((int64_t)b * h + head) * m + j) * d + dd;
   const float gq = dql[o] / (float)l, gk = dkl[o] / (float)l;
   float* base = dqkv + ((int64_t)b * npad + (int64_t)j * l) * 3 * hd;
+  const int64_t boff = ((int64_t)b * npad + (int64_t)j * l) * 3 * hd;
   for (int t = 0; t < l; ++t) {
-    base[(int64_t)t * 3 * hd + c] += gq;
-    base[(int64_t)t * 3 * hd + hd + c] += gk;
+    const float vq = base[(int64_t)t * 3 * hd + c] + gq, vk = base[(int64_t)t * 3 * hd + hd + c] + gk;
+    base[(int64_t)t * 3 * hd + c] = vq;
+    base[(int64_t)t * 3 * hd + hd + c] = vk;
+    store_split(hi, lo, boff + (int64_t)t * 3 * hd + c, vq);
+    store_split(hi, lo, boff + (int64_t)t * 3 * hd + hd + c, vk);
   }
 }
 __global__ void landmark_ids_kernel(int32_t* ids, int npad, int l) {
@@ -153,7 +158,8 @@ constexpr int RC_TT = 16;
 template <bool FLIP, int K>
 __global__ void __launch_bounds__(256) resconv_kernel(const float* __restrict__ src, int64_t src_ld,
                                                       const float* __restrict__ w, float* __restrict__ dst,
-                                                      int64_t dst_ld, int npad, int hd, int d) {
+                                                      int64_t dst_ld, int npad, int hd, int d,
+                                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   constexpr int HALF = K / 2;
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * RC_TT;
@@ -177,9 +183,14 @@ __global__ void __launch_bounds__(256) resconv_kernel(const float* __restrict__ 
     }
   }
   float* o = dst + (int64_t)b * npad * dst_ld + c;
+  const int64_t ooff = (int64_t)b * npad * dst_ld + c;   // same offset inside the (already chunk-shifted) bf16 buffers
 #pragma unroll
   for (int i = 0; i < RC_TT; ++i)
-    if (t0 + i < npad) o[(int64_t)(t0 + i) * dst_ld] += acc[i];
+    if (t0 + i < npad) {
+      const float v = o[(int64_t)(t0 + i) * dst_ld] + acc[i];
+      o[(int64_t)(t0 + i) * dst_ld] = v;
+      store_split(hi, lo, ooff + (int64_t)(t0 + i) * dst_ld, v);
+    }
 }
 // dw_part[blk, head, k] = sum over the block's token strip and the head's d channels of dout[t,c] * v[t+k-half, c].
 // Thread = one channel; it walks its strip in chunks of 16 tokens with a (16 + K - 1)-wide register window of v.
@@ -378,9 +389,9 @@ extern "C" int sml_nystrom_landmarks_fwd(const float* qkv, float* ql, float* kl,
   return 0;
 }
 extern "C" int sml_nystrom_landmarks_bwd(float* dqkv, const float* dql, const float* dkl, int32_t B, int32_t npad,
-                                         int32_t h, int32_t d, int32_t m, void* stream) {
+                                         int32_t h, int32_t d, int32_t m, void* hi, void* lo, void* stream) {
   SML_CHECK(h * d <= 1024 && npad % m == 0, "sml_nystrom_landmarks_bwd: bad sizes");
-  landmarks_bwd_kernel<<<dim3(m, B), h * d, 0, as_stream(stream)>>>(dqkv, dql, dkl, npad, h, d, m);
+  landmarks_bwd_kernel<<<dim3(m, B), h * d, 0, as_stream(stream)>>>(dqkv, dql, dkl, npad, h, d, m, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   SML_LAUNCH_OK("sml_nystrom_landmarks_bwd");
   return 0;
 }
@@ -417,11 +428,11 @@ extern "C" int sml_pinv_init_bwd(const float* x, const float* scal, const int32_
 }
 static inline dim3 rc_grid(int npad, int hd, int B, int tok) { return dim3((npad + tok - 1) / tok, (hd + 255) / 256, B); }
 extern "C" int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
-                                       int32_t d, int32_t ksize, void* stream) {
+                                       int32_t d, int32_t ksize, void* out_hi, void* out_lo, void* stream) {
   const int hd = h * d;
   SML_CHECK(ksize % 2 == 1, "sml_nystrom_resconv_fwd: kernel size must be odd");
   if (ksize == 33)
-    resconv_kernel<false, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d);
+    resconv_kernel<false, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
   else
     resconv_generic_kernel<false><<<rc_grid(npad, hd, B, 1), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, ksize);
   SML_LAUNCH_OK("sml_nystrom_resconv_fwd");
@@ -431,11 +442,13 @@ extern "C" int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad, int32_t h
   return B * ((hd + 255) / 256) * ((npad + RCB_TOK - 1) / RCB_TOK);
 }
 extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
-                                       int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* stream) {
+                                       int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* dqkv_hi, void* dqkv_lo,
+                                       void* stream) {
   const int hd = h * d;
   cudaStream_t s = as_stream(stream);
   if (ksize == 33) {
-    resconv_kernel<true, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d);
+    resconv_kernel<true, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d,
+        dqkv_hi ? (__nv_bfloat16*)dqkv_hi + 2 * hd : nullptr, dqkv_lo ? (__nv_bfloat16*)dqkv_lo + 2 * hd : nullptr);
     SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
     resconv_dw_kernel<33><<<rc_grid(npad, hd, B, RCB_TOK), 256, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
   } else {

@@ -9,7 +9,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ b, float* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
                                                             int64_t R, int D, float eps, int64_t n, int64_t npad,
-                                                            int64_t pad) {
+                                                            int64_t pad, __nv_bfloat16* __restrict__ yhi,
+                                                            __nv_bfloat16* __restrict__ ylo) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -49,6 +50,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
       o.z = (v[i].z - mu) * rs * ww.z + bb.z;
       o.w = (v[i].w - mu) * rs * ww.w + bb.w;
       yr[c] = o;
+      if (yhi) {
+        const int64_t e = yrow * D + 4 * c;
+        store_split(yhi, ylo, e, o.x); store_split(yhi, ylo, e + 1, o.y);
+        store_split(yhi, ylo, e + 2, o.z); store_split(yhi, ylo, e + 3, o.w);
+      }
     }
   }
 }
@@ -123,7 +129,8 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
 // ------------------------------------------------------------------ softmax
 // short rows (C <= 1024): one warp per row, row kept in registers
 template <int VPT>
-__global__ void __launch_bounds__(256) softmax_fwd_warp_kernel(float* __restrict__ x, int64_t R, int C) {
+__global__ void __launch_bounds__(256) softmax_fwd_warp_kernel(float* __restrict__ x, int64_t R, int C,
+                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -144,11 +151,12 @@ __global__ void __launch_bounds__(256) softmax_fwd_warp_kernel(float* __restrict
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = lane + i * 32;
-    if (c < C) xr[c] = v[i] * inv;
+    if (c < C) { xr[c] = v[i] * inv; store_split(hi, lo, row * C + c, v[i] * inv); }
   }
 }
 // long rows: one block per row, three passes through L2-resident data
-__global__ void __launch_bounds__(1024) softmax_fwd_block_kernel(float* __restrict__ x, int64_t C) {
+__global__ void __launch_bounds__(1024) softmax_fwd_block_kernel(float* __restrict__ x, int64_t C,
+                                                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float red[32];
   float* xr = x + (int64_t)blockIdx.x * C;
   float mx = -INFINITY;
@@ -158,11 +166,16 @@ __global__ void __launch_bounds__(1024) softmax_fwd_block_kernel(float* __restri
   for (int64_t c = threadIdx.x; c < C; c += blockDim.x) { const float e = __expf(xr[c] - mx); xr[c] = e; s += e; }
   s = block_sum(s, red);
   const float inv = 1.f / s;
-  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) xr[c] *= inv;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
+    const float pv = xr[c] * inv;
+    xr[c] = pv;
+    store_split(hi, lo, (int64_t)blockIdx.x * C + c, pv);
+  }
 }
 template <int VPT>
 __global__ void __launch_bounds__(256) softmax_bwd_warp_kernel(const float* __restrict__ A, float* __restrict__ dA,
-                                                               int64_t R, int C) {
+                                                               int64_t R, int C, __nv_bfloat16* __restrict__ hi,
+                                                               __nv_bfloat16* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -181,18 +194,23 @@ __global__ void __launch_bounds__(256) softmax_bwd_warp_kernel(const float* __re
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = lane + i * 32;
-    if (c < C) gr[c] = a[i] * (g[i] - s);
+    if (c < C) { const float dsv = a[i] * (g[i] - s); gr[c] = dsv; store_split(hi, lo, row * C + c, dsv); }
   }
 }
 __global__ void __launch_bounds__(1024) softmax_bwd_block_kernel(const float* __restrict__ A, float* __restrict__ dA,
-                                                                 int64_t C) {
+                                                                 int64_t C, __nv_bfloat16* __restrict__ hi,
+                                                                 __nv_bfloat16* __restrict__ lo) {
   __shared__ float red[32];
   const float* ar = A + (int64_t)blockIdx.x * C;
   float* gr = dA + (int64_t)blockIdx.x * C;
   float s = 0.f;
   for (int64_t c = threadIdx.x; c < C; c += blockDim.x) s += ar[c] * gr[c];
   s = block_sum(s, red);
-  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) gr[c] = ar[c] * (gr[c] - s);
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
+    const float dsv = ar[c] * (gr[c] - s);
+    gr[c] = dsv;
+    store_split(hi, lo, (int64_t)blockIdx.x * C + c, dsv);
+  }
 }
 
 // ------------------------------------------------------------------ dropout + add (counter-based RNG)
@@ -218,16 +236,22 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const float* __restric
   }
 }
 __global__ void __launch_bounds__(256) axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b,
-                                                    int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    y[i] = a * x[i] + (b != 0.f ? b * y[i] : 0.f);
+                                                    int64_t n, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = a * x[i] + (b != 0.f ? b * y[i] : 0.f);
+    y[i] = v;
+    store_split(hi, lo, i, v);
+  }
 }
 __global__ void __launch_bounds__(256) diag_axpby_kernel(float* __restrict__ out, const float* __restrict__ x, float a,
-                                                         float dg, int64_t total, int m) {
+                                                         float dg, int64_t total, int m, __nv_bfloat16* __restrict__ hi,
+                                                         __nv_bfloat16* __restrict__ lo) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = i % ((int64_t)m * m);
     const int r = (int)(e / m), c = (int)(e % m);
-    out[i] = a * x[i] + (r == c ? dg : 0.f);
+    const float v = a * x[i] + (r == c ? dg : 0.f);
+    out[i] = v;
+    store_split(hi, lo, i, v);
   }
 }
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
@@ -302,13 +326,14 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 using namespace sml;
 
 extern "C" int sml_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean, float* rstd,
-                                 int64_t R, int32_t D, float eps, int64_t n, int64_t npad, int64_t pad, void* stream) {
+                                 int64_t R, int32_t D, float eps, int64_t n, int64_t npad, int64_t pad, void* y_hi,
+                                 void* y_lo, void* stream) {
   SML_CHECK(n > 0 && npad >= n + pad && R % n == 0, "sml_layernorm_fwd: bad row mapping n=%lld npad=%lld pad=%lld",
             (long long)n, (long long)npad, (long long)pad);
   SML_CHECK(D % 4 == 0 && D <= 1024, "sml_layernorm_fwd: D=%d must be a multiple of 4 and <= 1024", D);
   if (R == 0) return 0;
   const int wpb = 8;
-  layernorm_fwd_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(x, w, b, y, mean, rstd, R, D, eps, n, npad, pad);
+  layernorm_fwd_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(x, w, b, y, mean, rstd, R, D, eps, n, npad, pad, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo);
   SML_LAUNCH_OK("sml_layernorm_fwd");
   return 0;
 }
@@ -334,28 +359,30 @@ extern "C" int sml_layernorm_bwd(const float* dy, const float* x, const float* w
   SML_LAUNCH_OK("sml_layernorm_bwd");
   return 0;
 }
-extern "C" int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* stream) {
+extern "C" int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi_, void* lo_, void* stream) {
+  __nv_bfloat16* hi = (__nv_bfloat16*)hi_; __nv_bfloat16* lo = (__nv_bfloat16*)lo_;
   if (R == 0 || C == 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned gw = (unsigned)((R + 7) / 8);
-  if (C <= 128) softmax_fwd_warp_kernel<4><<<gw, 256, 0, s>>>(x, R, (int)C);
-  else if (C <= 256) softmax_fwd_warp_kernel<8><<<gw, 256, 0, s>>>(x, R, (int)C);
-  else if (C <= 512) softmax_fwd_warp_kernel<16><<<gw, 256, 0, s>>>(x, R, (int)C);
+  if (C <= 128) softmax_fwd_warp_kernel<4><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo);
+  else if (C <= 256) softmax_fwd_warp_kernel<8><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo);
+  else if (C <= 512) softmax_fwd_warp_kernel<16><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo);
   else {
     SML_CHECK(R <= 2147483647LL, "sml_softmax_fwd: too many rows");
-    softmax_fwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(x, C);
+    softmax_fwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(x, C, hi, lo);
   }
   SML_LAUNCH_OK("sml_softmax_fwd");
   return 0;
 }
-extern "C" int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* stream) {
+extern "C" int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* hi_, void* lo_, void* stream) {
+  __nv_bfloat16* hi = (__nv_bfloat16*)hi_; __nv_bfloat16* lo = (__nv_bfloat16*)lo_;
   if (R == 0 || C == 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned gw = (unsigned)((R + 7) / 8);
-  if (C <= 128) softmax_bwd_warp_kernel<4><<<gw, 256, 0, s>>>(A, dA, R, (int)C);
-  else if (C <= 256) softmax_bwd_warp_kernel<8><<<gw, 256, 0, s>>>(A, dA, R, (int)C);
-  else if (C <= 512) softmax_bwd_warp_kernel<16><<<gw, 256, 0, s>>>(A, dA, R, (int)C);
-  else softmax_bwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(A, dA, C);
+  if (C <= 128) softmax_bwd_warp_kernel<4><<<gw, 256, 0, s>>>(A, dA, R, (int)C, hi, lo);
+  else if (C <= 256) softmax_bwd_warp_kernel<8><<<gw, 256, 0, s>>>(A, dA, R, (int)C, hi, lo);
+  else if (C <= 512) softmax_bwd_warp_kernel<16><<<gw, 256, 0, s>>>(A, dA, R, (int)C, hi, lo);
+  else softmax_bwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(A, dA, C, hi, lo);
   SML_LAUNCH_OK("sml_softmax_bwd");
   return 0;
 }
@@ -372,9 +399,9 @@ extern "C" int sml_dropout_add(const float* x, const float* u, float* y, int64_t
   SML_LAUNCH_OK("sml_dropout_add");
   return 0;
 }
-extern "C" int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* stream) {
+extern "C" int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* hi, void* lo, void* stream) {
   if (n == 0) return 0;
-  axpby_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, x, a, b, n);
+  axpby_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(y, x, a, b, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   SML_LAUNCH_OK("sml_axpby");
   return 0;
 }
@@ -392,10 +419,11 @@ extern "C" int sml_colsum(const float* x, float* out, float* part, int64_t R, in
   return 0;
 }
 
-extern "C" int sml_diag_axpby(float* out, const float* x, float a, float dg, int64_t nmat, int32_t m, void* stream) {
+extern "C" int sml_diag_axpby(float* out, const float* x, float a, float dg, int64_t nmat, int32_t m, void* hi, void* lo,
+                              void* stream) {
   const int64_t total = nmat * m * m;
   if (total == 0) return 0;
-  diag_axpby_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(out, x, a, dg, total, m);
+  diag_axpby_kernel<<<ew_grid(total), 256, 0, as_stream(stream)>>>(out, x, a, dg, total, m, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   SML_LAUNCH_OK("sml_diag_axpby");
   return 0;
 }

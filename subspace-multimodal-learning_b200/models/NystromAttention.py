@@ -16,7 +16,7 @@ DEFAULT_PRECISION = "fp32"
 def moore_penrose_iter_pinv(x, iters=6, precision=None):
     """NystromAttention.py:20-35 on the device kernels (forward only helper)."""
     from ..nystrom import pinv_fwd
-    return pinv_fwd(x.contiguous(), iters, precision or DEFAULT_PRECISION)[0]
+    return pinv_fwd(x.contiguous(), iters, precision or DEFAULT_PRECISION)[0].f
 
 
 class NystromAttention(nn.Module):

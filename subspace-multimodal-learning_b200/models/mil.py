@@ -18,11 +18,13 @@ class TransLayer(nn.Module):
 
     def forward(self, x):
         a = self.attn
-        xn = Fn.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         from ..nystrom import nystrom_attention
         from . import NystromAttention as NA
-        y = nystrom_attention(xn, a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias, a.res_conv.weight, a.heads,
-                              a.num_landmarks, a.pinv_iterations, a.precision or NA.DEFAULT_PRECISION)
+        # LayerNorm fused into the attention function: it writes the normalised rows (and their bf16 copy) straight
+        # into the front-padded buffer the qkv GEMM reads
+        y = nystrom_attention(x.float(), a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias, a.res_conv.weight, a.heads,
+                              a.num_landmarks, a.pinv_iterations, a.precision or NA.DEFAULT_PRECISION,
+                              pre_norm=(self.norm.weight, self.norm.bias, self.norm.eps))
         return Fn.dropout_add(x, y, a.to_out[1].p, self.training)      # x + dropout(attn(norm(x)))
 
 

@@ -4,8 +4,10 @@ Implements /root/reference/models/NystromAttention.py:74-157 (+ pinv :20-35) wit
 Differences in *schedule* only (results match the reference within the tolerances in tests/):
   * q-scale folded into the q rows of W_qkv (exact for dim_head = 64: scale = 2^-3);
   * (A1 @ Z) @ (A3 @ V) is evaluated as A1 @ (Z @ (A3 @ V))  (4x fewer FLOPs, SURVEY K14);
-  * the three similarity softmaxes over the landmark axis are fused into the GEMM epilogue on the
-    tensor-core engine; identity terms of the pinv iteration are GEMM-epilogue diagonals.
+  * the similarity softmaxes over the landmark axis are fused into the GEMM epilogue on the tensor-core engine;
+    identity terms of the pinv iteration are GEMM-epilogue diagonals;
+  * every producer (GEMM epilogue, softmax, LayerNorm, conv, landmark backward) also emits the bf16 (hi[, lo]) copy its
+    consumer contraction needs, so there are no stand-alone conversion passes over the big tensors.
 
 Precision modes (``precision`` argument):
   "fp32"   — SIMT fp32 FFMA engine everywhere (device-side exact-fp32 path);
@@ -15,25 +17,10 @@ Precision modes (``precision`` argument):
 import torch
 
 from . import ops
-from ._lib import c_i32, c_vp, check, lib, ptr, stream
-from .ops import F32, Split, gemm, to_bf16
+from ._lib import c_i32, check, lib, ptr, stream
+from .ops import F32, TB, mm
 
 PRECISIONS = ("fp32", "bf16x3", "bf16")
-
-
-def _prep(t, mode, hi_precision=False):
-    """contiguous fp32 tensor -> GEMM operand for `mode`."""
-    if mode == "fp32":
-        return t
-    return to_bf16(t.contiguous(), split=(mode == "bf16x3" or hi_precision))
-
-
-def _view(op, f):
-    return op.map(f) if isinstance(op, Split) else f(op)
-
-
-def _T(op):
-    return _view(op, lambda t: t.transpose(-1, -2))
 
 
 def landmarks_fwd(qkv, b, npad, h, d, m):
@@ -50,73 +37,80 @@ def landmark_ids(npad, m, device):
     return ids
 
 
-def pinv_fwd(a2, iters, mode):
-    """Moore-Penrose iteration (NystromAttention.py:20-35).  Returns z and what backward needs."""
+def _new_like(t, mode):
+    """bundle for a pinv-chain matrix batch: fp32 + (hi, lo) in tensor-core modes (the chain is always bf16x3)."""
+    return TB.new(t.shape, t.device, mode, hp=True)
+
+
+def _pinv_step(pa2, z, mode, need_t=False):
+    """one Moore-Penrose iteration on bundles: returns (xz, t1, t2, t3) bundles"""
+    xz = mm(pa2, z, _new_like(z.f, mode))                                        # x z
+    t1 = _new_like(z.f, mode)
+    ops.diag_axpby(xz.f, -1.0, 7.0, out=t1.f, hi=t1.hi, lo=t1.lo)                # 7I - xz
+    t2 = mm(xz, t1, _new_like(z.f, mode), alpha=-1.0, diag=15.0)                 # 15I - xz t1
+    t3 = mm(xz, t2, _new_like(z.f, mode), alpha=-1.0, diag=13.0)                 # 13I - xz t2
+    return xz, t1, t2, t3
+
+
+def pinv_fwd(a2, iters, mode, a2_bundle=None):
+    """Moore-Penrose iteration (NystromAttention.py:20-35).  Returns z (fp32) and what backward needs."""
     bh, m = a2.numel() // (a2.shape[-1] ** 2), a2.shape[-1]
     dev = a2.device
     scal = torch.empty(2, device=dev, dtype=F32)
     arg = torch.empty(2, device=dev, dtype=torch.int32)
     ws = torch.empty(2, device=dev, dtype=torch.int64)
     check(lib.sml_pinv_scale(ptr(a2), ptr(scal), ptr(arg), ptr(ws), c_i32(bh), c_i32(m), stream()), "pinv_scale")
-    z = torch.empty_like(a2)
-    check(lib.sml_pinv_init(ptr(a2), ptr(scal), ptr(z), c_i32(bh), c_i32(m), stream()), "pinv_init")
-    zs = [z]
-    hp = mode != "fp32"
-    pa2 = _prep(a2, mode, True)
+    z0 = torch.empty_like(a2)
+    check(lib.sml_pinv_init(ptr(a2), ptr(scal), ptr(z0), c_i32(bh), c_i32(m), stream()), "pinv_init")
+    pa2 = a2_bundle if (a2_bundle is not None and (mode == "fp32" or a2_bundle.lo is not None)) else TB.of(a2, mode, hp=True)
+    z = TB.of(z0, mode, hp=True)
+    zs = [z.f]
     for _ in range(iters):
-        z = zs[-1]
-        z_op = _prep(z, mode, True)
-        xz = gemm(pa2, z_op)                                        # x z
-        xz_op = _prep(xz, mode, True)
-        t1 = ops.diag_axpby(xz, -1.0, 7.0)                          # 7I - xz
-        t2 = gemm(xz_op, _prep(t1, mode, True), alpha=-1.0, diag=15.0)   # 15I - xz t1
-        t3 = gemm(xz_op, _prep(t2, mode, True), alpha=-1.0, diag=13.0)   # 13I - xz t2
-        zs.append(gemm(z_op, _prep(t3, mode, True), alpha=0.25))    # z <- 1/4 z t3
-    del hp
-    return zs[-1], (zs[:-1], scal, arg)
+        _, _, _, t3 = _pinv_step(pa2, z, mode)
+        z = mm(z, t3, _new_like(z.f, mode), alpha=0.25)                          # z <- 1/4 z t3
+        zs.append(z.f)
+    return z, (zs[:-1], scal, arg)
 
 
 def pinv_bwd(a2, saved, dz, mode):
     """d a2 given d z_final; recomputes xz, t1..t3 per iteration from the saved z_k."""
     zs, scal, arg = saved
     bh, m = a2.numel() // (a2.shape[-1] ** 2), a2.shape[-1]
-    pa2 = _prep(a2, mode, True)
+    pa2 = TB.of(a2, mode, hp=True)
     da2 = torch.zeros_like(a2)
-    g = dz
-    for z in reversed(zs):
-        z_op = _prep(z, mode, True)
-        xz = gemm(pa2, z_op)
-        xz_op = _prep(xz, mode, True)
-        t1 = ops.diag_axpby(xz, -1.0, 7.0)
-        t1_op = _prep(t1, mode, True)
-        t2 = gemm(xz_op, t1_op, alpha=-1.0, diag=15.0)
-        t2_op = _prep(t2, mode, True)
-        t3 = gemm(xz_op, t2_op, alpha=-1.0, diag=13.0)
-        g_op = _prep(g, mode, True)
-        dzk = gemm(g_op, _T(_prep(t3, mode, True)), alpha=0.25)             # 1/4 G t3^T
-        dt3 = gemm(_T(z_op), g_op, alpha=0.25)                              # 1/4 z^T G
-        dt3_op = _prep(dt3, mode, True)
-        dxz = gemm(dt3_op, _T(t2_op), alpha=-1.0)                           # -dt3 t2^T
-        dt2 = gemm(_T(xz_op), dt3_op, alpha=-1.0)                           # -xz^T dt3
-        dt2_op = _prep(dt2, mode, True)
-        gemm(dt2_op, _T(t1_op), out=dxz, alpha=-1.0, beta=1.0)              # -dt2 t1^T
-        dt1 = gemm(_T(xz_op), dt2_op, alpha=-1.0)                           # -xz^T dt2
-        ops.axpby_(dxz, dt1, -1.0, 1.0)                                     # t1 = 7I - xz
-        dxz_op = _prep(dxz, mode, True)
-        gemm(dxz_op, _T(z_op), out=da2, beta=1.0)                           # dx += dxz z^T
-        gemm(_T(pa2), dxz_op, out=dzk, beta=1.0)                            # dz += x^T dxz
-        g = dzk
+    g = TB.of(dz.contiguous(), mode, hp=True)
+    for zk in reversed(zs):
+        z = TB.of(zk, mode, hp=True)
+        xz, t1, t2, t3 = _pinv_step(pa2, z, mode)
+        dzk = mm(g, t3.T(), _new_like(zk, mode), alpha=0.25)                     # 1/4 G t3^T
+        dt3 = mm(z.T(), g, _new_like(zk, mode), alpha=0.25)                      # 1/4 z^T G
+        dxz = TB(torch.empty_like(zk))
+        mm(dt3, t2.T(), dxz, alpha=-1.0)                                         # -dt3 t2^T
+        dt2 = mm(xz.T(), dt3, _new_like(zk, mode), alpha=-1.0)                   # -xz^T dt3
+        mm(dt2, t1.T(), dxz, alpha=-1.0, beta=1.0)                               # -dt2 t1^T
+        dt1 = mm(xz.T(), dt2, TB(torch.empty_like(zk)), alpha=-1.0)              # -xz^T dt2
+        dxz_b = _new_like(zk, mode)
+        dxz_b.f = dxz.f
+        ops.axpby_(dxz.f, dt1.f, -1.0, 1.0, hi=dxz_b.hi, lo=dxz_b.lo)            # t1 = 7I - xz  ->  dxz -= dt1
+        mm(dxz_b, z.T(), TB(da2), beta=1.0)                                      # dx += dxz z^T
+        dzk2 = _new_like(zk, mode)
+        dzk2.f = dzk.f
+        mm(pa2.T(), dxz_b, dzk2, beta=1.0)                                       # dz += x^T dxz  (re-emits hi/lo of the sum)
+        g = dzk2
     tmp = torch.empty(1, device=a2.device, dtype=F32)
-    check(lib.sml_pinv_init_bwd(ptr(a2), ptr(scal), ptr(arg), ptr(g), ptr(da2), ptr(tmp), c_i32(bh), c_i32(m), stream()),
+    check(lib.sml_pinv_init_bwd(ptr(a2), ptr(scal), ptr(arg), ptr(g.f), ptr(da2), ptr(tmp), c_i32(bh), c_i32(m), stream()),
           "pinv_init_bwd")
     return da2
 
 
 class NystromAttentionFn(torch.autograd.Function):
-    """y = NystromAttention(x) without the trailing dropout.  x [b,n,D] fp32 CUDA."""
+    """y = NystromAttention(x) without the trailing dropout.  x [b,n,D] fp32 CUDA.
+
+    ``pre_norm`` = (ln_weight, ln_bias, eps) fuses the TransLayer LayerNorm (mil.py:186): the normalised rows are
+    written straight into the front-padded buffer (and its bf16 copy)."""
 
     @staticmethod
-    def forward(ctx, x, w_qkv, w_out, b_out, w_conv, heads, m, iters, mode):
+    def forward(ctx, x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, m, iters, mode, ln_eps):
         assert mode in PRECISIONS
         ops.require_cuda(x, w_qkv, w_out, b_out, w_conv)
         b, n, D = x.shape
@@ -126,61 +120,86 @@ class NystromAttentionFn(torch.autograd.Function):
         npad = n + pad
         dev = x.device
         x = x.contiguous()
+        tc = mode != "fp32"
+        hv = lambda t, i: t[:, :, i].permute(0, 2, 1, 3)                             # [b,h,npad,d] view of a qkv chunk
+        # ---- (LayerNorm +) front pad (:79-82)
+        xp = TB.new((b, npad, D), dev, mode)
         if pad:
-            xp = torch.zeros(b, npad, D, device=dev, dtype=F32)        # front pad (:79-82)
-            xp[:, pad:] = x
+            for t in (xp.f, xp.hi, xp.lo):
+                if t is not None:
+                    t[:, :pad].zero_()
+        ln_saved = None
+        if ln_w is not None:
+            mean, rstd = ops.layernorm_fwd(x.view(b * n, D), ln_w.detach(), ln_b.detach(), xp.f, n, npad, pad, ln_eps,
+                                           y_hi=xp.hi, y_lo=xp.lo)
+            ln_saved = (mean, rstd)
         else:
-            xp = x
+            xp.f[:, pad:] = x
+            if tc:
+                s = ops.to_bf16(xp.f, split=(mode == "bf16x3"))
+                xp.hi, xp.lo = s.hi, s.lo
+        xp2 = xp.map(lambda t: t.view(b * npad, D))
         weff = w_qkv.detach().clone()
         ops.axpby_(weff[:inner], w_qkv.detach()[:inner].contiguous(), d ** -0.5, 0.0)    # fold q * scale (:98)
-        tc = mode != "fp32"
-        xp_op = _prep(xp.view(b * npad, D), mode)
-        weff_op = _prep(weff, mode)
-        qkv = torch.empty(b, npad, 3, h, d, device=dev, dtype=F32)
-        gemm(xp_op, _T(weff_op), out=qkv.view(b * npad, 3 * inner))                  # :89
-        ql, kl = landmarks_fwd(qkv, b, npad, h, d, m)                                # :102-118
-        qkv_op = _prep(qkv, mode)
-        hv = lambda t, i: t[:, :, i].permute(0, 2, 1, 3)                             # [b,h,npad,d] view
-        q_op, k_op, v_op = (_view(qkv_op, lambda t, i=i: hv(t, i)) for i in range(3))
-        ql_op, kl_op = _prep(ql, mode), _prep(kl, mode)
-        a1 = torch.empty(b, h, npad, m, device=dev, dtype=F32)
-        a2 = torch.empty(b, h, m, m, device=dev, dtype=F32)
-        a3 = torch.empty(b, h, m, npad, device=dev, dtype=F32)
+        weff_b = TB.of(weff, mode)
+        # ---- qkv projection (:89), fp32 + bf16 copy from the same epilogue
+        qkv = TB.new((b, npad, 3, h, d), dev, mode)
+        mm(xp2, weff_b.T(), qkv.map(lambda t: t.view(b * npad, 3 * inner)))
+        ql, kl = landmarks_fwd(qkv.f, b, npad, h, d, m)                              # :102-118
+        ql_b, kl_b = TB.of(ql, mode), TB.of(kl, mode)
+        q_b, k_b, v_b = (qkv.map(lambda t, i=i: hv(t, i)) for i in range(3))
+        # ---- similarities + softmaxes (:122-137)
+        a1 = TB.new((b, h, npad, m), dev, mode)
+        a2 = TB.new((b, h, m, m), dev, mode, hp=True)
+        a3 = TB.new((b, h, m, npad), dev, mode)
         fuse = tc and m <= 256
-        gemm(q_op, _T(kl_op), out=a1, softmax=fuse)                                  # sim1 (+softmax)
-        gemm(ql_op, _T(kl_op), out=a2, softmax=fuse)                                 # sim2
-        gemm(ql_op, _T(k_op), out=a3)                                                # sim3
+        mm(q_b, kl_b.T(), a1, softmax=fuse)
+        mm(ql_b, kl_b.T(), a2, softmax=fuse)
+        mm(ql_b, k_b.T(), TB(a3.f))
         if not fuse:
-            ops.softmax_(a1.view(-1, m))
-            ops.softmax_(a2.view(-1, m))
-        ops.softmax_(a3.view(-1, npad))                                              # softmax over tokens
-        z, pinv_saved = pinv_fwd(a2, iters, mode)                                    # :138
-        a3_op = _prep(a3, mode)
-        a3v = gemm(a3_op, v_op)                                                      # [b,h,m,d]
-        wm = gemm(_prep(z, mode), _prep(a3v, mode))                                  # Z (A3 V)
-        merged = torch.empty(b, npad, inner, device=dev, dtype=F32)
-        mview = merged.view(b, npad, h, d).permute(0, 2, 1, 3)
-        a1_op = _prep(a1, mode)
-        gemm(a1_op, _prep(wm, mode), out=mview)                                      # A1 (Z A3 V)  :140
+            ops.softmax_(a1.f.view(-1, m), a1.hi, a1.lo)
+            ops.softmax_(a2.f.view(-1, m), a2.hi, a2.lo)
+        ops.softmax_(a3.f.view(-1, npad), a3.hi, a3.lo)                              # softmax over tokens
+        z, pinv_saved = pinv_fwd(a2.f, iters, mode, a2)                              # :138
+        a3v = mm(a3, v_b, TB.new((b, h, m, d), dev, mode))                           # [b,h,m,d]
+        z_op = z if mode != "bf16" else TB(z.f, z.hi, None)
+        wm = mm(z_op, a3v, TB.new((b, h, m, d), dev, mode))                          # Z (A3 V)
+        merged = TB.new((b, npad, inner), dev, mode)
+        mm(a1, wm, TB(merged.f.view(b, npad, h, d).permute(0, 2, 1, 3)))             # A1 (Z A3 V)  :140
         ksize = w_conv.shape[2]
         wc = w_conv.detach().reshape(h, ksize).contiguous()
-        check(lib.sml_nystrom_resconv_fwd(ptr(qkv), ptr(wc), ptr(merged), c_i32(b), c_i32(npad), c_i32(h), c_i32(d),
-                                          c_i32(ksize), stream()), "resconv_fwd")   # :144-145
+        fused_cvt = ksize == 33
+        check(lib.sml_nystrom_resconv_fwd(ptr(qkv.f), ptr(wc), ptr(merged.f), c_i32(b), c_i32(npad), c_i32(h), c_i32(d),
+                                          c_i32(ksize), ptr(merged.hi) if fused_cvt else None,
+                                          ptr(merged.lo) if fused_cvt else None, stream()), "resconv_fwd")   # :144-145
+        if tc and not fused_cvt:
+            s = ops.to_bf16(merged.f, split=(mode == "bf16x3"))
+            merged.hi, merged.lo = s.hi, s.lo
         y = torch.empty(b, n, D, device=dev, dtype=F32)
-        m_op = _prep(merged, mode)
-        gemm(_view(m_op, lambda t: t[:, pad:]), _T(_prep(w_out.detach().contiguous(), mode)), out=y, bias=b_out.detach())  # :150-151
-        ctx.save_for_backward(xp, weff, w_out, qkv, ql, kl, a1, a2, a3, z, a3v, wm, merged, wc, *pinv_saved[0],
-                              pinv_saved[1], pinv_saved[2])
-        ctx.cfg = (b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode)
+        wout_b = TB.of(w_out.detach().contiguous(), mode)
+        mm(merged.map(lambda t: t[:, pad:]), wout_b.T(), TB(y), bias=b_out.detach())  # :150-151
+        ctx.save_for_backward(x, ln_w, ln_b, xp.f, xp.hi, xp.lo, weff, w_out, qkv.f, qkv.hi, qkv.lo, ql, kl, a1.f, a1.hi, a1.lo,
+                              a2.f, a3.f, a3.hi, a3.lo, z.f, a3v.f, wm.f, merged.f, merged.hi, merged.lo, wc,
+                              *(ln_saved or ()), *pinv_saved[0], pinv_saved[1], pinv_saved[2])
+        ctx.cfg = (b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode, ln_w is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode = ctx.cfg
-        sv = ctx.saved_tensors
-        xp, weff, w_out, qkv, ql, kl, a1, a2, a3, z, a3v, wm, merged, wc = sv[:14]
-        zs, scal, arg = list(sv[14:14 + iters]), sv[14 + iters], sv[15 + iters]
+        b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode, has_ln = ctx.cfg
+        sv = list(ctx.saved_tensors)
+        (x, ln_w, ln_b, xp_f, xp_hi, xp_lo, weff, w_out, qkv_f, qkv_hi, qkv_lo, ql, kl, a1_f, a1_hi, a1_lo, a2_f, a3_f, a3_hi,
+         a3_lo, z_f, a3v_f, wm_f, mg_f, mg_hi, mg_lo, wc) = sv[:27]
+        rest = sv[27:]
+        if has_ln:
+            mean, rstd = rest[0], rest[1]
+            rest = rest[2:]
+        zs, scal, arg = list(rest[:iters]), rest[iters], rest[iters + 1]
         dev = dy.device
+        tc = mode != "fp32"
+        hv = lambda t, i: t[:, :, i].permute(0, 2, 1, 3)
+        xp = TB(xp_f, xp_hi, xp_lo); qkv = TB(qkv_f, qkv_hi, qkv_lo); a1 = TB(a1_f, a1_hi, a1_lo); a3 = TB(a3_f, a3_hi, a3_lo)
+        merged = TB(mg_f, mg_hi, mg_lo)
         dy = dy.contiguous()
         if pad:
             dyp = torch.zeros(b, npad, D, device=dev, dtype=F32)
@@ -188,58 +207,67 @@ class NystromAttentionFn(torch.autograd.Function):
         else:
             dyp = dy
         dyp2 = dyp.view(b * npad, D)
-        dy_op = _prep(dyp2, mode)
-        hv = lambda t, i: t[:, :, i].permute(0, 2, 1, 3)
+        dy_b = TB.of(dyp2, mode)
         # ---- to_out
         db_out = ops.colsum(dyp2)
-        dw_out = gemm(_T(dy_op), _prep(merged.view(b * npad, inner), mode))                  # [D, inner]
-        dmerged = gemm(dy_op, _prep(w_out.detach().contiguous(), mode)).view(b, npad, inner)
-        dout_h = dmerged.view(b, npad, h, d).permute(0, 2, 1, 3)
-        dm_op = _prep(dmerged, mode)
-        dout_op = _view(dm_op, lambda t: t.view(b, npad, h, d).permute(0, 2, 1, 3))
-        qkv_op = _prep(qkv, mode)
-        q_op, k_op, v_op = (_view(qkv_op, lambda t, i=i: hv(t, i)) for i in range(3))
-        ql_op, kl_op = _prep(ql, mode), _prep(kl, mode)
-        dqkv = torch.empty_like(qkv)
-        dq, dk, dv = (hv(dqkv, i) for i in range(3))
+        dw_out = mm(dy_b.T(), merged.map(lambda t: t.view(b * npad, inner))).f                  # [D, inner]
+        dmerged = TB.new((b, npad, inner), dev, mode)
+        mm(dy_b, TB.of(w_out.detach().contiguous(), mode), dmerged.map(lambda t: t.view(b * npad, inner)))
+        dout_b = dmerged.map(lambda t: t.view(b, npad, h, d).permute(0, 2, 1, 3))
+        q_b, k_b, v_b = (qkv.map(lambda t, i=i: hv(t, i)) for i in range(3))
+        ql_b, kl_b = TB.of(ql, mode), TB.of(kl, mode)
+        dqkv = TB.new((b, npad, 3, h, d), dev, mode)
+        dq, dk, dv = (hv(dqkv.f, i) for i in range(3))
         # ---- out = A1 Wm ; Wm = Z A3V ; A3V = A3 V
-        a1_op, a3_op = _prep(a1, mode), _prep(a3, mode)
-        da1 = gemm(dout_op, _T(_prep(wm, mode)))                                             # [b,h,npad,m]
-        dwm = gemm(_T(a1_op), dout_op)                                                       # [b,h,m,d]
-        dwm_op = _prep(dwm, mode)
-        dz = gemm(dwm_op, _T(_prep(a3v, mode)))                                              # [b,h,m,m]
-        da3v = gemm(_T(_prep(z, mode)), dwm_op)                                              # [b,h,m,d]
-        da3v_op = _prep(da3v, mode)
-        da3 = gemm(da3v_op, _T(v_op))                                                        # [b,h,m,npad]
-        gemm(_T(a3_op), da3v_op, out=dv)                                                     # dv = A3^T dA3V
-        dwc_part = torch.empty(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad), c_i32(h * d)), h * ksize, device=dev, dtype=F32)
-        check(lib.sml_nystrom_resconv_bwd(ptr(qkv), ptr(wc), ptr(dmerged), ptr(dqkv), ptr(dwc_part), c_i32(b), c_i32(npad),
-                                          c_i32(h), c_i32(d), c_i32(ksize), stream()), "resconv_bwd")   # dv += conv^T
+        da1 = mm(dout_b, TB.of(wm_f, mode).T(), TB(torch.empty(b, h, npad, m, device=dev, dtype=F32)))
+        dwm = mm(a1.T(), dout_b, TB.new((b, h, m, d), dev, mode))                               # [b,h,m,d]
+        dz = mm(dwm, TB.of(a3v_f, mode).T()).f                                                  # [b,h,m,m]
+        da3v = mm(TB.of(z_f, mode).T(), dwm, TB.new((b, h, m, d), dev, mode))                   # [b,h,m,d]
+        da3 = mm(da3v, v_b.T(), TB(torch.empty(b, h, m, npad, device=dev, dtype=F32)))
+        mm(a3.T(), da3v, TB(dv))                                                                # dv = A3^T dA3V
+        dwc_part = torch.empty(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad), c_i32(h * d)), h * ksize, device=dev,
+                               dtype=F32)
+        fused_cvt = ksize == 33
+        check(lib.sml_nystrom_resconv_bwd(ptr(qkv.f), ptr(wc), ptr(dmerged.f), ptr(dqkv.f), ptr(dwc_part), c_i32(b), c_i32(npad),
+                                          c_i32(h), c_i32(d), c_i32(ksize), ptr(dqkv.hi) if fused_cvt else None,
+                                          ptr(dqkv.lo) if fused_cvt else None, stream()), "resconv_bwd")   # dv += conv^T
         dw_conv = ops.colsum(dwc_part).view(h, 1, ksize, 1)
-        # ---- pinv + softmaxes
-        da2 = pinv_bwd(a2, (zs, scal, arg), dz, mode)
-        ds1 = ops.softmax_bwd_(a1.view(-1, m), da1.view(-1, m)).view(b, h, npad, m)
-        ds2 = ops.softmax_bwd_(a2.view(-1, m), da2.view(-1, m)).view(b, h, m, m)
-        ds3 = ops.softmax_bwd_(a3.view(-1, npad), da3.view(-1, npad)).view(b, h, m, npad)
-        ds1_op, ds2_op, ds3_op = _prep(ds1, mode), _prep(ds2, mode), _prep(ds3, mode)
+        # ---- pinv + softmaxes (dS emitted with its bf16 copy by the softmax-backward kernel)
+        da2 = pinv_bwd(a2_f, (zs, scal, arg), dz, mode)
+        ds1 = TB.new((b, h, npad, m), dev, mode, f32=False); ds1.f = da1.f
+        ds3 = TB.new((b, h, m, npad), dev, mode, f32=False); ds3.f = da3.f
+        ops.softmax_bwd_(a1.f.view(-1, m), ds1.f.view(-1, m), ds1.hi, ds1.lo)
+        ops.softmax_bwd_(a2_f.view(-1, m), da2.view(-1, m))
+        ops.softmax_bwd_(a3.f.view(-1, npad), ds3.f.view(-1, npad), ds3.hi, ds3.lo)
+        ds2 = TB.of(da2, mode)
         # ---- similarities
-        gemm(ds1_op, kl_op, out=dq)                                                          # dq = dS1 kl
-        dkl = gemm(_T(ds1_op), q_op)                                                         # dkl = dS1^T q
-        dql = gemm(ds2_op, kl_op)
-        gemm(_T(ds2_op), ql_op, out=dkl, beta=1.0)
-        gemm(ds3_op, k_op, out=dql, beta=1.0)
-        gemm(_T(ds3_op), ql_op, out=dk)                                                      # dk = dS3^T ql
-        check(lib.sml_nystrom_landmarks_bwd(ptr(dqkv), ptr(dql), ptr(dkl), c_i32(b), c_i32(npad), c_i32(h), c_i32(d),
-                                            c_i32(m), stream()), "landmarks_bwd")
+        mm(ds1, kl_b, TB(dq))                                                                   # dq = dS1 kl
+        dkl = mm(ds1.T(), q_b)                                                                  # dkl = dS1^T q
+        dql = mm(ds2, kl_b)
+        mm(ds2.T(), ql_b, dkl, beta=1.0)
+        mm(ds3, k_b, dql, beta=1.0)
+        mm(ds3.T(), ql_b, TB(dk))                                                               # dk = dS3^T ql
+        check(lib.sml_nystrom_landmarks_bwd(ptr(dqkv.f), ptr(dql.f), ptr(dkl.f), c_i32(b), c_i32(npad), c_i32(h), c_i32(d),
+                                            c_i32(m), ptr(dqkv.hi), ptr(dqkv.lo), stream()), "landmarks_bwd")
+        if tc and not fused_cvt:
+            s = ops.to_bf16(dqkv.f, split=(mode == "bf16x3"))
+            dqkv.hi, dqkv.lo = s.hi, s.lo
         # ---- qkv projection
-        dqkv2 = dqkv.view(b * npad, 3 * inner)
-        dqkv_op = _prep(dqkv2, mode)
-        dxp = gemm(dqkv_op, _prep(weff, mode)).view(b, npad, D)
-        dw_qkv = gemm(_T(dqkv_op), _prep(xp.view(b * npad, D), mode))                        # [3 inner, D]
+        dqkv2 = dqkv.map(lambda t: t.view(b * npad, 3 * inner))
+        dxp = mm(dqkv2, TB.of(weff, mode)).f.view(b, npad, D)
+        dw_qkv = mm(dqkv2.T(), xp.map(lambda t: t.view(b * npad, D))).f                         # [3 inner, D]
         ops.axpby_(dw_qkv[:inner], dw_qkv[:inner].clone(), d ** -0.5, 0.0)
-        dx = dxp[:, pad:]
-        return dx, dw_qkv, dw_out, db_out, dw_conv, None, None, None, None
+        dln_w = dln_b = None
+        if has_ln:
+            dx2, dln_w, dln_b = ops.layernorm_bwd(dxp.view(b * npad, D), x.view(b * n, D), ln_w.detach(), mean, rstd, n, npad, pad)
+            dx = dx2.view(b, n, D)
+        else:
+            dx = dxp[:, pad:]
+        return dx, dw_qkv, dw_out, db_out, dw_conv, dln_w, dln_b, None, None, None, None, None
 
 
-def nystrom_attention(x, w_qkv, w_out, b_out, w_conv, heads, num_landmarks, pinv_iterations, precision="fp32"):
-    return NystromAttentionFn.apply(x, w_qkv, w_out, b_out, w_conv, heads, num_landmarks, pinv_iterations, precision)
+def nystrom_attention(x, w_qkv, w_out, b_out, w_conv, heads, num_landmarks, pinv_iterations, precision="fp32",
+                      pre_norm=None):
+    ln_w, ln_b, eps = pre_norm if pre_norm is not None else (None, None, 1e-5)
+    return NystromAttentionFn.apply(x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, num_landmarks, pinv_iterations,
+                                    precision, eps)

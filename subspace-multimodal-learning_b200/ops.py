@@ -30,6 +30,63 @@ class Split:
         return self.map(lambda t: t.transpose(a, b))
 
 
+class TB:
+    """Tensor bundle: fp32 tensor ``f`` (may be None) plus optional bf16 copies ``hi`` / ``lo`` that producers fill in
+    the same pass (GEMM epilogues, softmax, LayerNorm, ...), so no separate conversion pass is needed before a
+    tensor-core contraction.  ``map(fn)`` applies one view function to every part."""
+    __slots__ = ("f", "hi", "lo")
+
+    def __init__(self, f=None, hi=None, lo=None):
+        self.f, self.hi, self.lo = f, hi, lo
+
+    @staticmethod
+    def new(shape, device, mode, hp=False, f32=True):
+        """mode "fp32": fp32 only; "bf16": + hi (and lo when ``hp``); "bf16x3": + hi, lo."""
+        f = torch.empty(shape, device=device, dtype=F32) if (f32 or mode == "fp32") else None
+        hi = lo = None
+        if mode != "fp32":
+            hi = torch.empty(shape, device=device, dtype=BF16)
+            if mode == "bf16x3" or hp:
+                lo = torch.empty(shape, device=device, dtype=BF16)
+        return TB(f, hi, lo)
+
+    @staticmethod
+    def of(x, mode, hp=False):
+        """wrap an existing contiguous fp32 tensor, converting with one split pass if the mode needs bf16."""
+        if mode == "fp32":
+            return TB(x)
+        s = to_bf16(x.contiguous(), split=(mode == "bf16x3" or hp))
+        return TB(x, s.hi, s.lo)
+
+    def map(self, fn):
+        return TB(None if self.f is None else fn(self.f), None if self.hi is None else fn(self.hi),
+                  None if self.lo is None else fn(self.lo))
+
+    def T(self):
+        return self.map(lambda t: t.transpose(-1, -2))
+
+    def operand(self):
+        return self.f if self.hi is None else Split(self.hi, self.lo)
+
+    def ptrs(self):
+        return ptr(self.hi), ptr(self.lo)
+
+
+def mm(A, B, out=None, **kw):
+    """gemm on bundles: operands pick the engine (bf16 parts present -> tcgen05); ``out`` bundle receives fp32 and/or
+    bf16 hi/lo straight from the epilogue."""
+    a, b = A.operand(), B.operand()
+    if isinstance(a, Split) != isinstance(b, Split):
+        raise RuntimeError("mm: operands prepared for different engines")
+    if out is None:
+        return TB(gemm(a, b, **kw))
+    if isinstance(a, Split):
+        gemm(a, b, out=out.f, out_bf16=out.hi, out_bf16_lo=out.lo, want_f32=False, **kw)
+    else:
+        gemm(a, b, out=out.f, **kw)
+    return out
+
+
 def to_bf16(x, split=False):
     """fp32 -> Split(bf16 hi[, lo]) with one pass of the split kernel (x must be contiguous)."""
     require_cuda(x)
@@ -112,18 +169,19 @@ def gemm(A, B, out=None, *, alpha=1.0, beta=0.0, diag=0.0, bias=None, relu=False
         e0.record()
         check(fn(ctypes.byref(d), stream()), "gemm_" + eng)
         e1.record()
-        PROFILE.append((eng, 2.0 * M * N * K * nb[0] * nb[1], e0, e1))
+        tag = (M, N, K, nb[0] * nb[1], int(d.sa_k != 1), int(d.sb_k != 1), int(bool(d.A_lo)), d.relu, int(bool(d.C)), int(bool(d.Cb_hi)), int(bool(d.Cb_lo)), float(beta))
+        PROFILE.append((eng, 2.0 * M * N * K * nb[0] * nb[1], e0, e1, tag))
     else:
         check(fn(ctypes.byref(d), stream()), "gemm_" + eng)
     return out
 
 
-def layernorm_fwd(x2d, w, b, y, n, npad, pad, eps=1e-5):
+def layernorm_fwd(x2d, w, b, y, n, npad, pad, eps=1e-5, y_hi=None, y_lo=None):
     R, D = x2d.shape
     mean = torch.empty(R, device=x2d.device, dtype=F32)
     rstd = torch.empty(R, device=x2d.device, dtype=F32)
     check(lib.sml_layernorm_fwd(ptr(x2d), ptr(w), ptr(b), ptr(y), ptr(mean), ptr(rstd), c_i64(R), c_i32(D), c_f32(eps),
-                                c_i64(n), c_i64(npad), c_i64(pad), stream()), "layernorm_fwd")
+                                c_i64(n), c_i64(npad), c_i64(pad), ptr(y_hi), ptr(y_lo), stream()), "layernorm_fwd")
     return mean, rstd
 
 
@@ -147,17 +205,17 @@ def colsum(x2d, out=None, beta=0.0):
     return out
 
 
-def softmax_(x2d):
+def softmax_(x2d, hi=None, lo=None):
     R, C = x2d.shape
     assert x2d.is_contiguous()
-    check(lib.sml_softmax_fwd(ptr(x2d), c_i64(R), c_i64(C), stream()), "softmax_fwd")
+    check(lib.sml_softmax_fwd(ptr(x2d), c_i64(R), c_i64(C), ptr(hi), ptr(lo), stream()), "softmax_fwd")
     return x2d
 
 
-def softmax_bwd_(A2d, dA2d):
+def softmax_bwd_(A2d, dA2d, hi=None, lo=None):
     R, C = A2d.shape
     assert A2d.is_contiguous() and dA2d.is_contiguous()
-    check(lib.sml_softmax_bwd(ptr(A2d), ptr(dA2d), c_i64(R), c_i64(C), stream()), "softmax_bwd")
+    check(lib.sml_softmax_bwd(ptr(A2d), ptr(dA2d), c_i64(R), c_i64(C), ptr(hi), ptr(lo), stream()), "softmax_bwd")
     return dA2d
 
 
@@ -171,18 +229,18 @@ def dropout_add(x, u, p, seed, offset=0, out=None):
     return out
 
 
-def axpby_(y, x, a, b):
+def axpby_(y, x, a, b, hi=None, lo=None):
     assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
-    check(lib.sml_axpby(ptr(y), ptr(x), c_f32(a), c_f32(b), c_i64(y.numel()), stream()), "axpby")
+    check(lib.sml_axpby(ptr(y), ptr(x), c_f32(a), c_f32(b), c_i64(y.numel()), ptr(hi), ptr(lo), stream()), "axpby")
     return y
 
 
-def diag_axpby(x, a, dg, out=None):
+def diag_axpby(x, a, dg, out=None, hi=None, lo=None):
     """out = a*x + dg*I for a batch of square matrices."""
     m = x.shape[-1]
     assert x.is_contiguous() and x.shape[-2] == m
     if out is None:
         out = torch.empty_like(x)
-    check(lib.sml_diag_axpby(ptr(out), ptr(x), c_f32(a), c_f32(dg), c_i64(x.numel() // (m * m)), c_i32(m), stream()),
+    check(lib.sml_diag_axpby(ptr(out), ptr(x), c_f32(a), c_f32(dg), c_i64(x.numel() // (m * m)), c_i32(m), ptr(hi), ptr(lo), stream()),
           "diag_axpby")
     return out

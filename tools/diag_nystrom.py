@@ -20,7 +20,7 @@ print("pinv golden(fp32 ref) vs fp64 oracle: z %.2e gx %.2e" % (rel(g["z"], z64)
 for mode in ("fp32", "bf16x3", "bf16"):
     z, saved = pinv_fwd(g["x"].cuda(), 6, mode)
     gx = pinv_bwd(g["x"].cuda(), saved, g["gz"].cuda(), mode)
-    print("pinv %-6s vs fp64: z %.2e gx %.2e | scal %s arg %s" % (mode, rel(z, z64), rel(gx, x64.grad), saved[1].tolist(), saved[2].tolist()))
+    print("pinv %-6s vs fp64: z %.2e gx %.2e | scal %s arg %s" % (mode, rel(z.f, z64), rel(gx, x64.grad), saved[1].tolist(), saved[2].tolist()))
 ax = g["x"].abs(); print("   oracle scal", float(ax.sum(-1).max()), float(ax.sum(-2).max()))
 
 for (dim, dh, hh, m, n, b) in [(64, 8, 8, 16, 37, 2), (512, 64, 8, 256, 1001, 2)]:
