@@ -33,11 +33,11 @@ UNIT = "slides/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SML_PRECISION", "bf16"), choices=["fp32", "bf16x3", "bf16"])
-    ap.add_argument("--batch", type=int, default=2, help="slides per step per GPU")
+    ap.add_argument("--batch", type=int, default=8, help="slides per step per GPU (config_mine.yaml batch_size: 8)")
     ap.add_argument("--patches", type=int, default=16384)
     ap.add_argument("--cpu-sample", type=int, default=1, help="slides in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
         if not self.samples:
@@ -195,14 +195,13 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    sampler = ClockSampler(local)
+    sampler.start()                      # samples from the last warm-up steps through the timed and e2e regions (all under load)
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = sml_b200._lib.launch_count()
     ms = timed(lambda: step(x_dev, y_dev), args.steps)
     launches = sml_b200._lib.launch_count() - l0
-    sampler.stop_flag = True
 
     def e2e_step():
         x = x_host.to(dev, non_blocking=True)
@@ -210,6 +209,7 @@ def run_ours(args):
         return float(step(x, y).detach())          # D2H read of the loss
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    sampler.stop_flag = True
 
     # ---- per-kernel roofline: instrumented pass (CUDA events around every GEMM launch on the launch stream)
     ops.PROFILE = []

@@ -13,7 +13,8 @@
 //   apply alpha / beta*C / diag*I / bias / ReLU or a fused row softmax (row fits one tile: the three
 //   Nystrom similarity softmaxes over m landmarks), writing fp32 and/or bf16 (hi, lo) results.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (two warps per TMEM lane quarter, each taking half of the tile's columns).
 #include "common.cuh"
 #include <cuda.h>
 
@@ -107,19 +108,17 @@ struct EpiParams {
   const float* bias;
   int relu, softmax;
   int ksplit, kb_per_split;     // split-K: blockIdx.z = batch*ksplit + ks; partial sums are red.add'ed into a zeroed C
-  int staged_ok;                // rows 16-byte aligned, unit column stride: coalesced stores through shared memory
+  int vec_ok;                   // rows 16-byte aligned, unit column stride: 128-bit epilogue loads / stores
 };
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 
 template <int BN, bool SPLIT, int STAGES>
 struct TcSmem {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = (TC_A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
-  static constexpr int STAGING = 4 * 32 * 36 * 4;   // epilogue staging tile (aliases operand stage 0 once the MMAs are done)
-  static_assert(STAGING <= STAGE_BYTES, "staging tile must fit in one operand stage");
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ void store_row_chunk(const EpiParams& ep, float* crow, __nv_bfloat16* hrow,
@@ -151,40 +150,6 @@ __device__ __forceinline__ void store_row_chunk(const EpiParams& ep, float* crow
 }
 
 
-// Coalesced variant: the warp's 32 rows x 32 columns go through a padded shared-memory tile so that every store
-// instruction writes 4 complete 128-byte row segments (instead of 32 scattered 16-byte pieces).
-__device__ __forceinline__ void store_chunk_staged(const EpiParams& ep, float* stg, int lane, int row0, int64_t batch_off,
-                                                   int gn0, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(stg + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  __syncwarp();
-  const int rr = lane >> 3, col = (lane & 7) * 4;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rr;
-    const int grow = row0 + r;
-    if (grow < ep.M) {
-      const float4 val = *reinterpret_cast<const float4*>(stg + r * 36 + col);
-      const int64_t off = batch_off + (int64_t)grow * ep.sc_m + gn0 + col;
-      if (ep.C) *reinterpret_cast<float4*>(ep.C + off) = val;
-      if (ep.Cb_hi) {
-        const __nv_bfloat162 h0 = __floats2bfloat162_rn(val.x, val.y), h1 = __floats2bfloat162_rn(val.z, val.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(ep.Cb_hi + off) = pk;
-        if (ep.Cb_lo) {
-          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-          const __nv_bfloat162 l0 = __floats2bfloat162_rn(val.x - f0.x, val.y - f0.y), l1 = __floats2bfloat162_rn(val.z - f1.x, val.w - f1.y);
-          pk.x = *reinterpret_cast<const uint32_t*>(&l0); pk.y = *reinterpret_cast<const uint32_t*>(&l1);
-          *reinterpret_cast<uint2*>(ep.Cb_lo + off) = pk;
-        }
-      }
-    }
-  }
-  __syncwarp();
-}
-
 template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
@@ -196,7 +161,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* staging = reinterpret_cast<float*>(smem);   // valid after tmem_full: every TMA load has landed and been consumed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
@@ -285,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp handles
     const int row = q * 32 + lane;
     const int gm = m0 + row;
     mbar_wait(tmem_full, 0);
@@ -296,12 +261,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __nv_bfloat16* hrow = ep.Cb_hi ? ep.Cb_hi + coff : nullptr;
     __nv_bfloat16* lrow = ep.Cb_lo ? ep.Cb_lo + coff : nullptr;
     uint32_t r[32];
-    float* stg = staging + (warp - 2) * 32 * 36;
-    const int64_t batch_off = (int64_t)b1 * ep.sc_b1 + (int64_t)b2 * ep.sc_b2;
-    const int row0 = m0 + q * 32;
+    constexpr int CH = BN / 2;                    // columns per epilogue warp
+    const int cbeg = half * CH;
     if (ep.ksplit > 1) {
       // split-K partial: alpha * acc (+ bias / diag on split 0) accumulated with red.global.add into the zeroed C
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = cbeg; c < cbeg + CH; c += 32) {
         tc_ld32(trow + c, r);
         if (!(row_ok && n0 + c < ep.N)) continue;
 #pragma unroll
@@ -314,52 +278,111 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-    } else if (ep.softmax) {
-      // the whole row lives in this thread's TMEM lane: max / sum / normalise without any cross-thread traffic
-      float mx = -INFINITY;
-      for (int c = 0; c < BN; c += 32) {
-        tc_ld32(trow + c, r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c + j < ep.N) mx = fmaxf(mx, ep.alpha * __uint_as_float(r[j]));
-      }
-      float sum = 0.f;
-      for (int c = 0; c < BN; c += 32) {
-        tc_ld32(trow + c, r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c + j < ep.N) sum += __expf(ep.alpha * __uint_as_float(r[j]) - mx);
-      }
-      const float inv = 1.f / sum;
-      for (int c = 0; c < BN; c += 32) {
-        tc_ld32(trow + c, r);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __expf(ep.alpha * __uint_as_float(r[j]) - mx) * inv;
-        if (ep.staged_ok && n0 + c + 32 <= ep.N) store_chunk_staged(ep, stg, lane, row0, batch_off, n0 + c, v);
-        else if (row_ok && n0 + c < ep.N) store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
-      }
     } else {
-      const bool staged = ep.staged_ok && ep.beta == 0.f;
-      for (int c = 0; c < BN; c += 32) {
-        tc_ld32(trow + c, r);
-        const bool st_chunk = staged && n0 + c + 32 <= ep.N;         // warp-uniform
-        if (!st_chunk && !(row_ok && n0 + c < ep.N)) continue;
-        float v[32];
+      float mx = -INFINITY, inv = 1.f;
+      if (ep.softmax) {
+        // the whole row lives in ONE TMEM lane: each of the two warps sharing the lane quarter reduces all BN columns
+        // itself (TMEM reads are cheap), so max / sum need no cross-thread traffic
+        for (int c = 0; c < BN; c += 32) {
+          tc_ld32(trow + c, r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int gn = n0 + c + j;
-          float x = ep.alpha * __uint_as_float(r[j]);
-          if (gn < ep.N) {
-            if (ep.beta != 0.f) x = fmaf(ep.beta, crow[(int64_t)gn * ep.sc_n], x);
-            if (gn == gm) x += ep.diag;
-            if (ep.bias) x += __ldg(ep.bias + gn);
-            if (ep.relu) x = fmaxf(x, 0.f);
-          }
-          v[j] = x;
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c + j < ep.N) mx = fmaxf(mx, ep.alpha * __uint_as_float(r[j]));
         }
-        if (st_chunk) store_chunk_staged(ep, stg, lane, row0, batch_off, n0 + c, v);
-        else store_row_chunk(ep, crow, hrow, lrow, gm, n0 + c, v);
+        float sum = 0.f;
+        for (int c = 0; c < BN; c += 32) {
+          tc_ld32(trow + c, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c + j < ep.N) sum += __expf(ep.alpha * __uint_as_float(r[j]) - mx);
+        }
+        inv = 1.f / sum;
+      }
+      for (int c = cbeg; c < cbeg + CH; c += 32) {
+        tc_ld32(trow + c, r);
+        const int gn0 = n0 + c;
+        if (gn0 >= ep.N) break;
+        float v[32];
+        if (ep.vec_ok && gn0 + 32 <= ep.N) {
+          // ---- lean path: full 32-column chunk, 16-byte aligned rows, unit column stride
+          if (ep.softmax) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __expf(ep.alpha * __uint_as_float(r[j]) - mx) * inv;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ep.alpha * __uint_as_float(r[j]);
+            if (ep.beta != 0.f && row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 cv = *reinterpret_cast<const float4*>(crow + gn0 + j);
+                v[j] = fmaf(ep.beta, cv.x, v[j]); v[j + 1] = fmaf(ep.beta, cv.y, v[j + 1]);
+                v[j + 2] = fmaf(ep.beta, cv.z, v[j + 2]); v[j + 3] = fmaf(ep.beta, cv.w, v[j + 3]);
+              }
+            }
+            if (ep.diag != 0.f) {
+              const int dj = gm - gn0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += (j == dj) ? ep.diag : 0.f;
+            }
+            if (ep.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gn0 + j));
+                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              }
+            }
+            if (ep.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+          }
+          if (row_ok) {
+            if (crow) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + gn0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (hrow) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 h[4];
+                uint4 pk;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h[0]); pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                pk.z = *reinterpret_cast<uint32_t*>(&h[2]); pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                *reinterpret_cast<uint4*>(hrow + gn0 + j) = pk;
+                if (lrow) {
+                  __nv_bfloat162 l[4];
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const float2 f = __bfloat1622float2(h[t]);
+                    l[t] = __floats2bfloat162_rn(v[j + 2 * t] - f.x, v[j + 2 * t + 1] - f.y);
+                  }
+                  pk.x = *reinterpret_cast<uint32_t*>(&l[0]); pk.y = *reinterpret_cast<uint32_t*>(&l[1]);
+                  pk.z = *reinterpret_cast<uint32_t*>(&l[2]); pk.w = *reinterpret_cast<uint32_t*>(&l[3]);
+                  *reinterpret_cast<uint4*>(lrow + gn0 + j) = pk;
+                }
+              }
+            }
+          }
+        } else {
+          // ---- general path (N tail, odd strides)
+          if (!row_ok) continue;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gn = gn0 + j;
+            float x = ep.alpha * __uint_as_float(r[j]);
+            if (ep.softmax) x = __expf(x - mx) * inv;
+            else if (gn < ep.N) {
+              if (ep.beta != 0.f) x = fmaf(ep.beta, crow[(int64_t)gn * ep.sc_n], x);
+              if (gn == gm) x += ep.diag;
+              if (ep.bias) x += __ldg(ep.bias + gn);
+              if (ep.relu) x = fmaxf(x, 0.f);
+            }
+            v[j] = x;
+          }
+          store_row_chunk(ep, crow, hrow, lrow, gm, gn0, v);
+        }
       }
     }
   }
@@ -515,24 +538,26 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
       }
     }
   }
-  ep.staged_ok = (ep.sc_n == 1 && (ep.sc_m % 4) == 0 && (ep.sc_b1 % 4) == 0 && (ep.sc_b2 % 4) == 0 &&
+  ep.vec_ok = (ep.sc_n == 1 && (ep.sc_m % 4) == 0 && (ep.sc_b1 % 4) == 0 && (ep.sc_b2 % 4) == 0 &&
                   (!ep.C || (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
-                  (!ep.Cb_hi || (reinterpret_cast<uintptr_t>(ep.Cb_hi) & 7) == 0) &&
-                  (!ep.Cb_lo || (reinterpret_cast<uintptr_t>(ep.Cb_lo) & 7) == 0)) ? 1 : 0;
+                  (!ep.Cb_hi || ((reinterpret_cast<uintptr_t>(ep.Cb_hi) & 15) == 0 && ep.sc_m % 8 == 0 && ep.sc_b1 % 8 == 0 && ep.sc_b2 % 8 == 0)) &&
+               (!ep.Cb_lo || (reinterpret_cast<uintptr_t>(ep.Cb_lo) & 15) == 0) &&
+               (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0)) ? 1 : 0;
   nbz *= ep.ksplit;
   SML_CHECK(nbz <= 65535, "sml_gemm_tc: batch %lld > 65535", nbz);
   dim3 grid((d->N + BN - 1) / BN, (d->M + TC_BM - 1) / TC_BM, (unsigned)nbz);
   SML_CHECK(grid.y <= 65535, "sml_gemm_tc: M too large for grid.y");
   cudaStream_t st = as_stream(stream);
-  const bool deep = ep.kb_per_split > 2;
+  // ring depths sized so that two CTAs share an SM (<= ~100 KB each): one CTA's epilogue overlaps the other's
+  // TMA + MMA main loop.  The bf16x3 variants carry twice the operand bytes per stage.
   if (!split) {
-    if (BN == 256) return deep ? dispatch_major<256, false, 4>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<256, false, 2>(a_mn, b_mn, tms, ep, grid, st);
-    if (BN == 128) return deep ? dispatch_major<128, false, 6>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<128, false, 2>(a_mn, b_mn, tms, ep, grid, st);
-    return deep ? dispatch_major<64, false, 8>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<64, false, 2>(a_mn, b_mn, tms, ep, grid, st);
+    if (BN == 256) return dispatch_major<256, false, 2>(a_mn, b_mn, tms, ep, grid, st);
+    if (BN == 128) return dispatch_major<128, false, 3>(a_mn, b_mn, tms, ep, grid, st);
+    return dispatch_major<64, false, 4>(a_mn, b_mn, tms, ep, grid, st);
   } else {
     if (BN == 256) return dispatch_major<256, true, 2>(a_mn, b_mn, tms, ep, grid, st);
-    if (BN == 128) return deep ? dispatch_major<128, true, 3>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<128, true, 2>(a_mn, b_mn, tms, ep, grid, st);
-    return deep ? dispatch_major<64, true, 4>(a_mn, b_mn, tms, ep, grid, st) : dispatch_major<64, true, 2>(a_mn, b_mn, tms, ep, grid, st);
+    if (BN == 128) return dispatch_major<128, true, 3>(a_mn, b_mn, tms, ep, grid, st);
+    return dispatch_major<64, true, 2>(a_mn, b_mn, tms, ep, grid, st);
   }
 }
 
