@@ -48,6 +48,9 @@ typedef struct sml_gemm_desc {
   /* tensor-core engine only: */
   const void* A_lo; const void* B_lo;  /* bf16 low parts for the bf16x3 split (NULL = single pass) */
   void* Cb_hi; void* Cb_lo;            /* optional bf16 copies of the result (same strides as C) */
+  /* optional row-segment broadcast term added in the epilogue: + rowtab_scale * rowtab[b1,b2][m / rowdiv][n]
+   * (the landmark-mean backward dq[t] += dq_landmark[t / l] / l of models/NystromAttention.py:102-118, fused) */
+  const float* rowtab; int64_t rt_m, rt_b1, rt_b2; int32_t rowdiv; float rowtab_scale;
 } sml_gemm_desc;
 
 int sml_gemm_f32(const sml_gemm_desc* d, void* stream);

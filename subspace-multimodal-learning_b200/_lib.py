@@ -23,6 +23,7 @@ class GemmDesc(ctypes.Structure):
         ("alpha", c_f32), ("beta", c_f32), ("diag", c_f32),
         ("bias", c_vp), ("relu", c_i32),
         ("A_lo", c_vp), ("B_lo", c_vp), ("Cb_hi", c_vp), ("Cb_lo", c_vp),
+        ("rowtab", c_vp), ("rt_m", c_i64), ("rt_b1", c_i64), ("rt_b2", c_i64), ("rowdiv", c_i32), ("rowtab_scale", c_f32),
     ]
 
 

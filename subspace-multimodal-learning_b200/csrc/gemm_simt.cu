@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_f32_kernel(const sml_gemm_desc d, 
       if (beta != 0.f) v = fmaf(beta, *p, v);
       if (gm == gn) v += diag;
       if (d.bias) v += __ldg(d.bias + gn);
+      if (d.rowtab) v = fmaf(d.rowtab_scale, __ldg(d.rowtab + b1 * d.rt_b1 + b2 * d.rt_b2 + (int64_t)(gm / d.rowdiv) * d.rt_m + gn), v);
       if (d.relu) v = fmaxf(v, 0.f);
       *p = v;
     }

@@ -108,6 +108,7 @@ struct EpiParams {
   const float* bias;
   int relu, softmax;
   int ksplit, kb_per_split;     // split-K: blockIdx.z = batch*ksplit + ks; partial sums are red.add'ed into a zeroed C
+  const float* rowtab; int64_t rt_m, rt_b1, rt_b2; int rowdiv; float rowtab_scale;
   int vec_ok;                   // rows 16-byte aligned, unit column stride: 128-bit epilogue loads / stores
 };
 
@@ -281,22 +282,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
       float mx = -INFINITY, inv = 1.f;
       if (ep.softmax) {
-        // the whole row lives in ONE TMEM lane: each of the two warps sharing the lane quarter reduces all BN columns
-        // itself (TMEM reads are cheap), so max / sum need no cross-thread traffic
-        for (int c = 0; c < BN; c += 32) {
+        // Row softmax fused in the epilogue.  A row lives in one TMEM lane; the two warps sharing a lane quarter each
+        // scan their own half of the columns ONCE with an online (max, sum) update and swap the pair through shared
+        // memory (operand stage 0 is free once tmem_full has fired), so statistics cost one TMEM pass, not two full ones.
+        float m_ = -INFINITY, l_ = 0.f;
+        for (int c = cbeg; c < cbeg + CH; c += 32) {
+          if (n0 + c >= ep.N) break;
           tc_ld32(trow + c, r);
+          float cm = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + c + j < ep.N) mx = fmaxf(mx, ep.alpha * __uint_as_float(r[j]));
-        }
-        float sum = 0.f;
-        for (int c = 0; c < BN; c += 32) {
-          tc_ld32(trow + c, r);
+            if (n0 + c + j < ep.N) cm = fmaxf(cm, ep.alpha * __uint_as_float(r[j]));
+          const float mn = fmaxf(m_, cm);
+          float acc = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + c + j < ep.N) sum += __expf(ep.alpha * __uint_as_float(r[j]) - mx);
+            if (n0 + c + j < ep.N) acc += __expf(ep.alpha * __uint_as_float(r[j]) - mn);
+          l_ = l_ * __expf(m_ - mn) + acc;            // exp(-inf) = 0 on the first chunk
+          m_ = mn;
         }
-        inv = 1.f / sum;
+        float2* stats = reinterpret_cast<float2*>(smem);          // [2 halves][128 rows]
+        stats[half * TC_BM + row] = make_float2(m_, l_);
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
+        const float2 o = stats[(half ^ 1) * TC_BM + row];
+        mx = fmaxf(m_, o.x);
+        const float lsum = (m_ == -INFINITY ? 0.f : l_ * __expf(m_ - mx)) + (o.x == -INFINITY ? 0.f : o.y * __expf(o.x - mx));
+        inv = 1.f / lsum;
       }
       for (int c = cbeg; c < cbeg + CH; c += 32) {
         tc_ld32(trow + c, r);
@@ -329,6 +340,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 32; j += 4) {
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gn0 + j));
                 v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              }
+            }
+            if (ep.rowtab) {
+              const float* tr = ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 tv = __ldg(reinterpret_cast<const float4*>(tr + j));
+                v[j] = fmaf(ep.rowtab_scale, tv.x, v[j]); v[j + 1] = fmaf(ep.rowtab_scale, tv.y, v[j + 1]);
+                v[j + 2] = fmaf(ep.rowtab_scale, tv.z, v[j + 2]); v[j + 3] = fmaf(ep.rowtab_scale, tv.w, v[j + 3]);
               }
             }
             if (ep.relu) {
@@ -377,6 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (ep.beta != 0.f) x = fmaf(ep.beta, crow[(int64_t)gn * ep.sc_n], x);
               if (gn == gm) x += ep.diag;
               if (ep.bias) x += __ldg(ep.bias + gn);
+              if (ep.rowtab) x = fmaf(ep.rowtab_scale, __ldg(ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn), x);
               if (ep.relu) x = fmaxf(x, 0.f);
             }
             v[j] = x;
@@ -490,7 +511,6 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
 
   const int softmax = (d->relu & 2) ? 1 : 0;
   int BN = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
-  if (split && BN == 256 && !softmax) BN = 128;   // split keeps 128-wide tiles (smem) unless a fused softmax needs the row
   SML_CHECK(!softmax || d->N <= BN, "sml_gemm_tc: fused row softmax needs N <= %d (N=%d)", BN, d->N);
 
   CUtensorMap tms[4];
@@ -516,6 +536,8 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
   ep.Cb_hi = (__nv_bfloat16*)d->Cb_hi; ep.Cb_lo = (__nv_bfloat16*)d->Cb_lo;
   ep.alpha = d->alpha; ep.beta = d->beta; ep.diag = d->diag; ep.bias = d->bias;
   ep.relu = d->relu & 1; ep.softmax = softmax;
+  ep.rowtab = d->rowtab; ep.rt_m = d->rt_m; ep.rt_b1 = d->rt_b1; ep.rt_b2 = d->rt_b2; ep.rowdiv = d->rowdiv > 0 ? d->rowdiv : 1;
+  ep.rowtab_scale = d->rowtab_scale;
   SML_CHECK(!(ep.beta != 0.f) || ep.C, "sml_gemm_tc: beta needs an fp32 C");
 
   long long nbz = (long long)d->nb1 * d->nb2;
@@ -523,7 +545,7 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
   const int nkb_all = (d->K + TC_BK - 1) / TC_BK;
   ep.ksplit = 1; ep.kb_per_split = nkb_all;
   // split-K when the output has too few tiles to fill the 148 SMs and K is long (weight gradients: K = B*n')
-  if (tiles_mn * nbz < 74 && nkb_all >= 32 && ep.C && !ep.Cb_hi && !ep.relu && !softmax && ep.beta == 0.f) {
+  if (tiles_mn * nbz < 74 && nkb_all >= 32 && ep.C && !ep.Cb_hi && !ep.relu && !softmax && ep.beta == 0.f && !ep.rowtab) {
     int want = (int)((2 * kNumSMs + tiles_mn * nbz - 1) / (tiles_mn * nbz));
     if (want > nkb_all / 8) want = nkb_all / 8;
     if (want > 1) {
@@ -542,7 +564,8 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
                   (!ep.C || (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
                   (!ep.Cb_hi || ((reinterpret_cast<uintptr_t>(ep.Cb_hi) & 15) == 0 && ep.sc_m % 8 == 0 && ep.sc_b1 % 8 == 0 && ep.sc_b2 % 8 == 0)) &&
                (!ep.Cb_lo || (reinterpret_cast<uintptr_t>(ep.Cb_lo) & 15) == 0) &&
-               (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0)) ? 1 : 0;
+               (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
+               (!ep.rowtab || ((reinterpret_cast<uintptr_t>(ep.rowtab) & 15) == 0 && ep.rt_m % 4 == 0 && ep.rt_b1 % 4 == 0 && ep.rt_b2 % 4 == 0))) ? 1 : 0;
   nbz *= ep.ksplit;
   SML_CHECK(nbz <= 65535, "sml_gemm_tc: batch %lld > 65535", nbz);
   dim3 grid((d->N + BN - 1) / BN, (d->M + TC_BM - 1) / TC_BM, (unsigned)nbz);

@@ -313,15 +313,22 @@ __global__ void __launch_bounds__(256) ppeg_kernel(const float* __restrict__ x, 
   const float bv = bias ? __ldg(bias + c) : 0.f;
   const int oy = ty0 + lr;
   if (oy >= H) return;
-  for (int ox = 0; ox < PT_W; ++ox) {
-    if (tx0 + ox >= W) break;
-    float acc = bv;
+  float acc[PT_W];
 #pragma unroll
-    for (int di = 0; di < 7; ++di)
+  for (int ox = 0; ox < PT_W; ++ox) acc[ox] = bv;
 #pragma unroll
-      for (int dj = 0; dj < 7; ++dj) acc = fmaf(wr[di * 7 + dj], tile[lr + di][ox + dj][lc], acc);
-    y[base + (int64_t)(1 + oy * W + tx0 + ox) * C + c] = acc;
+  for (int di = 0; di < 7; ++di) {
+    float rowv[PT_W + 6];                                   // one halo row of the tile, reused by 7 taps x 16 outputs
+#pragma unroll
+    for (int u = 0; u < PT_W + 6; ++u) rowv[u] = tile[lr + di][u][lc];
+#pragma unroll
+    for (int ox = 0; ox < PT_W; ++ox)
+#pragma unroll
+      for (int dj = 0; dj < 7; ++dj) acc[ox] = fmaf(wr[di * 7 + dj], rowv[ox + dj], acc[ox]);
   }
+#pragma unroll
+  for (int ox = 0; ox < PT_W; ++ox)
+    if (tx0 + ox < W) y[base + (int64_t)(1 + oy * W + tx0 + ox) * C + c] = acc[ox];
 }
 // dw_part[grp, tap, c], db_part[grp, c]: grid (C/32, groups, B); a block walks its share of spatial tiles
 constexpr int PPB_GROUPS = 32;
@@ -349,14 +356,21 @@ __global__ void __launch_bounds__(256) ppeg_dw_kernel(const float* __restrict__ 
     __syncthreads();
     const int oy = ty0 + lr;
     if (c < C && oy < H) {
+      float g[PT_W];
+#pragma unroll
       for (int ox = 0; ox < PT_W; ++ox) {
-        if (tx0 + ox >= W) break;
-        const float g = dy[base + (int64_t)(1 + oy * W + tx0 + ox) * C + c];
-        ab += g;
+        g[ox] = (tx0 + ox < W) ? dy[base + (int64_t)(1 + oy * W + tx0 + ox) * C + c] : 0.f;
+        ab += g[ox];
+      }
 #pragma unroll
-        for (int di = 0; di < 7; ++di)
+      for (int di = 0; di < 7; ++di) {
+        float rowv[PT_W + 6];
 #pragma unroll
-          for (int dj = 0; dj < 7; ++dj) acc[di * 7 + dj] = fmaf(g, tile[lr + di][ox + dj][lc], acc[di * 7 + dj]);
+        for (int u = 0; u < PT_W + 6; ++u) rowv[u] = tile[lr + di][u][lc];
+#pragma unroll
+        for (int dj = 0; dj < 7; ++dj)
+#pragma unroll
+          for (int ox = 0; ox < PT_W; ++ox) acc[di * 7 + dj] = fmaf(g[ox], rowv[ox + dj], acc[di * 7 + dj]);
       }
     }
   }

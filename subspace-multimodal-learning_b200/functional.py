@@ -316,3 +316,52 @@ class ScaleFn(torch.autograd.Function):
 
 def scale(x, a):
     return ScaleFn.apply(x, float(a))
+
+
+class Fc1ClsFn(torch.autograd.Function):
+    """TransMIL front end in one pass (mil.py:227-240): h = [cls | relu(x W^T + b) | first `add` rows again].
+    The GEMM writes straight into the [B, 1+n+add, D] buffer through a strided output view (no torch.cat copy)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, cls, add, mode):
+        ops.require_cuda(x, w, b, cls)
+        B, n, K = x.shape
+        D = w.shape[0]
+        x = x.contiguous()
+        h = torch.empty(B, 1 + n + add, D, device=x.device, dtype=F32)
+        xo = _prep(x.view(B * n, K), mode)
+        wo = _prep(w.detach().contiguous(), mode)
+        xo3 = xo if mode == "fp32" else xo.map(lambda t: t.view(B, n, K))
+        gemm(xo3 if mode != "fp32" else x, _T(wo), out=h[:, 1:1 + n], bias=b.detach(), relu=True)
+        h[:, 0] = cls.detach().reshape(1, D)
+        if add:
+            h[:, 1 + n:] = h[:, 1:1 + add]
+        ctx.save_for_backward(x, w, h)
+        ctx.cfg = (B, n, K, D, add, mode, xo if mode != "fp32" else None)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        B, n, K, D, add, mode, xo = ctx.cfg
+        x, w, h = ctx.saved_tensors
+        dh = dh.contiguous()
+        dcls = dh[:, 0].sum(0).reshape(1, 1, D)
+        dmain = dh[:, 1:1 + n]
+        if add:
+            dmain = dmain.clone()
+            dmain[:, :add] += dh[:, 1 + n:]
+        g = torch.empty(B, n, D, device=dh.device, dtype=F32)
+        for bi in range(B):
+            hb, db_ = h[bi, 1:1 + n], dmain[bi]
+            check(lib.sml_relu_bwd(ptr(hb), ptr(db_.contiguous()), ptr(g[bi]), ops.c_i64(n * D), stream()), "relu_bwd")
+        g2 = g.view(B * n, D)
+        g_op = _prep(g2, mode)
+        x_op = xo if xo is not None else x.view(B * n, K)
+        dw = gemm(_T(g_op), x_op)
+        db = ops.colsum(g2)
+        dx = gemm(g_op, _prep(w.detach().contiguous(), mode)).view(B, n, K) if ctx.needs_input_grad[0] else None
+        return dx, dw, db, dcls, None, None
+
+
+def fc1_cls(x, w, b, cls, add, mode="fp32"):
+    return Fc1ClsFn.apply(x, w, b, cls, add, mode)

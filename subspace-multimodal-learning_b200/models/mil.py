@@ -74,12 +74,11 @@ class TransMIL(nn.Module):
     def forward(self, x):
         from . import NystromAttention as NA
         mode = self.precision or NA.DEFAULT_PRECISION
-        h = Fn.linear(x.float(), self._fc1[0].weight, self._fc1[0].bias, relu=True, mode=mode)   # [B,n,512]
-        n = h.shape[1]
+        n = x.shape[1]
         side = int(math.ceil(math.sqrt(n)))
         add = side * side - n
-        B = h.shape[0]
-        h = torch.cat([self.cls_token.expand(B, -1, -1), h, h[:, :add]], dim=1)                  # mil.py:232-240
+        # _fc1 + ReLU, pad-to-square and cls token in one pass: the GEMM writes into the [B, 1+n+add, 512] buffer
+        h = Fn.fc1_cls(x.float(), self._fc1[0].weight, self._fc1[0].bias, self.cls_token, add, mode)   # mil.py:227-240
         h = self.layer1(h)
         h = self.pos_layer(h, side, side)
         h = self.layer2(h)

@@ -240,15 +240,17 @@ class NystromAttentionFn(torch.autograd.Function):
         ops.softmax_bwd_(a2_f.view(-1, m), da2.view(-1, m))
         ops.softmax_bwd_(a3.f.view(-1, npad), ds3.f.view(-1, npad), ds3.hi, ds3.lo)
         ds2 = TB.of(da2, mode)
-        # ---- similarities
-        mm(ds1, kl_b, TB(dq))                                                                   # dq = dS1 kl
+        # ---- similarities; the landmark-mean backward (dq[t] += dql[t // l] / l, same for k) rides in the epilogue of
+        #      the dq / dk contractions, which also emit the bf16 copy of dqkv for the projection backward
+        l = npad // m
         dkl = mm(ds1.T(), q_b)                                                                  # dkl = dS1^T q
-        dql = mm(ds2, kl_b)
         mm(ds2.T(), ql_b, dkl, beta=1.0)
+        dql = mm(ds2, kl_b)
         mm(ds3, k_b, dql, beta=1.0)
-        mm(ds3.T(), ql_b, TB(dk))                                                               # dk = dS3^T ql
-        check(lib.sml_nystrom_landmarks_bwd(ptr(dqkv.f), ptr(dql.f), ptr(dkl.f), c_i32(b), c_i32(npad), c_i32(h), c_i32(d),
-                                            c_i32(m), ptr(dqkv.hi), ptr(dqkv.lo), stream()), "landmarks_bwd")
+        dq_b = TB(dq, *(hv(t, 0) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
+        dk_b = TB(dk, *(hv(t, 1) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
+        mm(ds1, kl_b, dq_b, rowtab=dql.f, rowdiv=l, rowtab_scale=1.0 / l)                       # dq = dS1 kl + bcast(dql)/l
+        mm(ds3.T(), ql_b, dk_b, rowtab=dkl.f, rowdiv=l, rowtab_scale=1.0 / l)                   # dk = dS3^T ql + bcast(dkl)/l
         if tc and not fused_cvt:
             s = ops.to_bf16(dqkv.f, split=(mode == "bf16x3"))
             dqkv.hi, dqkv.lo = s.hi, s.lo

@@ -112,7 +112,7 @@ def _batch_strides(t, nb):
 
 
 def gemm(A, B, out=None, *, alpha=1.0, beta=0.0, diag=0.0, bias=None, relu=False, softmax=False,
-         out_bf16=None, out_bf16_lo=None, want_f32=True):
+         out_bf16=None, out_bf16_lo=None, want_f32=True, rowtab=None, rowdiv=1, rowtab_scale=1.0):
     """out[..., M, N] = epi(alpha * A[..., M, K] @ B[..., K, N]).
 
     fp32 tensors -> SIMT fp32 engine (sml_gemm_f32); ``Split`` operands -> tcgen05 engine (sml_gemm_tc).
@@ -147,6 +147,11 @@ def gemm(A, B, out=None, *, alpha=1.0, beta=0.0, diag=0.0, bias=None, relu=False
     d.alpha, d.beta, d.diag = alpha, beta, diag
     d.bias = bias.data_ptr() if bias is not None else None
     d.relu = (1 if relu else 0) | (2 if softmax else 0)
+    if rowtab is not None:        # + rowtab_scale * rowtab[..., m // rowdiv, n]
+        assert rowtab.dtype == F32 and rowtab.stride(-1) == 1 and rowtab.shape[-1] == N
+        d.rowtab = rowtab.data_ptr(); d.rt_m = rowtab.stride(-2)
+        d.rt_b1, d.rt_b2 = _batch_strides(rowtab, nb)
+        d.rowdiv, d.rowtab_scale = int(rowdiv), float(rowtab_scale)
     if tc:
         assert a.dtype == BF16 and b.dtype == BF16
         if (A.lo is None) != (B.lo is None):     # mixed: give the single-precision side a zero residual? no: drop to single pass
