@@ -107,9 +107,10 @@ struct EpiParams {
   float alpha, beta, diag;
   const float* bias;
   int relu, softmax;
-  int ksplit, kb_per_split;     // split-K: blockIdx.z = batch*ksplit + ks; partial sums are red.add'ed into a zeroed C
+  int ksplit, kb_per_split;     // split-K: extra tile-list dimension; partial sums are red.add'ed into a zeroed C
   const float* rowtab; int64_t rt_m, rt_b1, rt_b2; int rowdiv; float rowtab_scale;
   int vec_ok;                   // rows 16-byte aligned, unit column stride: 128-bit epilogue loads / stores
+  int tiles_n, tiles_m, total_tiles;   // persistent tile list: n fastest, then m, then split-K index, then batch
 };
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -119,7 +120,7 @@ template <int BN, bool SPLIT, int STAGES>
 struct TcSmem {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = (TC_A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 2 * 2 * TC_BM * 8 + 1024;  // ring + barriers + softmax stats + slack
 };
 
 __device__ __forceinline__ void store_row_chunk(const EpiParams& ep, float* crow, __nv_bfloat16* hrow,
@@ -151,6 +152,25 @@ __device__ __forceinline__ void store_row_chunk(const EpiParams& ep, float* crow
 }
 
 
+struct TileCoord { int n0, m0, b1, b2, ks, kb_lo, nkb; };
+__device__ __forceinline__ TileCoord decode_tile(const EpiParams& ep, int tile, int BN) {
+  TileCoord t;
+  const int nt = tile % ep.tiles_n;
+  int rest = tile / ep.tiles_n;
+  const int mt = rest % ep.tiles_m;
+  rest /= ep.tiles_m;
+  t.ks = rest % ep.ksplit;
+  const int bz = rest / ep.ksplit;
+  t.n0 = nt * BN; t.m0 = mt * TC_BM;
+  t.b1 = bz / ep.nb2; t.b2 = bz % ep.nb2;
+  const int nkb_all = (ep.K + TC_BK - 1) / TC_BK;
+  t.kb_lo = t.ks * ep.kb_per_split;
+  t.nkb = min(nkb_all, t.kb_lo + ep.kb_per_split) - t.kb_lo;
+  return t;
+}
+
+// Persistent kernel: gridDim.x CTAs (<= #SMs) walk the tile list with stride gridDim.x.  The fp32 accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the TMA + MMA main loop of tile i+1.
 template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
@@ -160,24 +180,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float2* stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(tmem_slot) + 16);   // [2 bufs][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
-  const int bz = blockIdx.z / ep.ksplit, ks = blockIdx.z % ep.ksplit;
-  const int b1 = bz / ep.nb2, b2 = bz % ep.nb2;
-  const int nkb_all = (ep.K + TC_BK - 1) / TC_BK;
-  const int kb_lo = ks * ep.kb_per_split;
-  const int nkb = min(nkb_all, kb_lo + ep.kb_per_split) - kb_lo;      // k-blocks of this CTA (>= 1 by construction)
+  constexpr uint32_t TMEM_COLS = 2 * BN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }   // 8 epilogue warps arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation: BN fp32 columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+  if (warp == 1) {   // TMEM allocation: two accumulator buffers of BN fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -188,30 +205,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        if (!mbar_wait(&empty_bar[s], ph ^ 1u)) break;
-        mbar_expect_tx(&full_bar[s], (uint32_t)S::STAGE_BYTES);
-        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + TC_A_BYTES * (SPLIT ? 2 : 1);
-        const int k0 = (kb_lo + kb) * TC_BK;
+      uint32_t it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < ep.total_tiles && ok; tile += gridDim.x) {
+        const TileCoord t = decode_tile(ep, tile, BN);
+        const int ab1 = t.b1 * ep.a_c1, ab2 = t.b2 * ep.a_c2, bb1 = t.b1 * ep.b_c1, bb2 = t.b2 * ep.b_c2;
+        for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          if (!mbar_wait(&empty_bar[s], ph ^ 1u)) { ok = false; break; }
+          mbar_expect_tx(&full_bar[s], (uint32_t)S::STAGE_BYTES);
+          uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + TC_A_BYTES * (SPLIT ? 2 : 1);
+          const int k0 = (t.kb_lo + kb) * TC_BK;
 #pragma unroll
-        for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
-          const CUtensorMap* ta = part ? &tmAl : &tmA;
-          const CUtensorMap* tb = part ? &tmBl : &tmB;
-          uint8_t* ad = a_dst + part * TC_A_BYTES;
-          uint8_t* bd = b_dst + part * S::B_BYTES;
-          const int ab1 = b1 * ep.a_c1, ab2 = b2 * ep.a_c2, bb1 = b1 * ep.b_c1, bb2 = b2 * ep.b_c2;
-          if (!A_MN) tma_load_4d(ad, ta, &full_bar[s], k0, m0, ab2, ab1);
-          else {
+          for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+            const CUtensorMap* ta = part ? &tmAl : &tmA;
+            const CUtensorMap* tb = part ? &tmBl : &tmB;
+            uint8_t* ad = a_dst + part * TC_A_BYTES;
+            uint8_t* bd = b_dst + part * S::B_BYTES;
+            if (!A_MN) tma_load_4d(ad, ta, &full_bar[s], k0, t.m0, ab2, ab1);
+            else {
 #pragma unroll
-            for (int c = 0; c < TC_BM / 64; ++c) tma_load_4d(ad + c * 8192, ta, &full_bar[s], m0 + c * 64, k0, ab2, ab1);
-          }
-          if (!B_MN) tma_load_4d(bd, tb, &full_bar[s], k0, n0, bb2, bb1);
-          else {
+              for (int c = 0; c < TC_BM / 64; ++c) tma_load_4d(ad + c * 8192, ta, &full_bar[s], t.m0 + c * 64, k0, ab2, ab1);
+            }
+            if (!B_MN) tma_load_4d(bd, tb, &full_bar[s], k0, t.n0, bb2, bb1);
+            else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_4d(bd + c * 8192, tb, &full_bar[s], n0 + c * 64, k0, bb2, bb1);
+              for (int c = 0; c < BN / 64; ++c) tma_load_4d(bd + c * 8192, tb, &full_bar[s], t.n0 + c * 64, k0, bb2, bb1);
+            }
           }
         }
       }
@@ -224,194 +246,213 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // 8-k-row groups 1024 B apart (SBO).
       constexpr uint32_t a_lbo = A_MN ? 8192u : 16u, b_lbo = B_MN ? 8192u : 16u;
       constexpr uint32_t a_kstep = A_MN ? 2048u : 32u, b_kstep = B_MN ? 2048u : 32u;   // bytes per UMMA_K = 16
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        if (!mbar_wait(&full_bar[s], ph)) break;
+      uint32_t it = 0, lt = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < ep.total_tiles && ok; tile += gridDim.x, ++lt) {
+        const TileCoord t = decode_tile(ep, tile, BN);
+        const uint32_t a = lt & 1u;
+        if (!mbar_wait(&tmem_empty[a], ((lt >> 1) & 1u) ^ 1u)) break;    // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + TC_A_BYTES * (SPLIT ? 2 : 1);
+        const uint32_t acc = tmem_base + a * BN;
+        for (int kb = 0; kb < t.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          if (!mbar_wait(&full_bar[s], ph)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + TC_A_BYTES * (SPLIT ? 2 : 1);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024u);
-          const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024u);
-          tc_mma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (SPLIT) {
-            const uint64_t dal = make_smem_desc(a_addr + TC_A_BYTES + k * a_kstep, a_lbo, 1024u);
-            const uint64_t dbl = make_smem_desc(b_addr + S::B_BYTES + k * b_kstep, b_lbo, 1024u);
-            tc_mma_bf16(tmem_base, da, dbl, idesc, 1u);
-            tc_mma_bf16(tmem_base, dal, db, idesc, 1u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * a_kstep, a_lbo, 1024u);
+            const uint64_t db = make_smem_desc(b_addr + k * b_kstep, b_lbo, 1024u);
+            tc_mma_bf16(acc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (SPLIT) {
+              const uint64_t dal = make_smem_desc(a_addr + TC_A_BYTES + k * a_kstep, a_lbo, 1024u);
+              const uint64_t dbl = make_smem_desc(b_addr + S::B_BYTES + k * b_kstep, b_lbo, 1024u);
+              tc_mma_bf16(acc, da, dbl, idesc, 1u);
+              tc_mma_bf16(acc, dal, db, idesc, 1u);
+            }
           }
+          tc_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
         }
-        tc_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+        if (ok) tc_commit(&tmem_full[a]);   // accumulator of this tile complete
       }
-      tc_commit(tmem_full);         // accumulator complete
     }
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp handles
     const int row = q * 32 + lane;
-    const int gm = m0 + row;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool row_ok = gm < ep.M;
-    const int64_t coff = (int64_t)b1 * ep.sc_b1 + (int64_t)b2 * ep.sc_b2 + (int64_t)gm * ep.sc_m;
-    float* crow = ep.C ? ep.C + coff : nullptr;
-    __nv_bfloat16* hrow = ep.Cb_hi ? ep.Cb_hi + coff : nullptr;
-    __nv_bfloat16* lrow = ep.Cb_lo ? ep.Cb_lo + coff : nullptr;
-    uint32_t r[32];
     constexpr int CH = BN / 2;                    // columns per epilogue warp
     const int cbeg = half * CH;
-    if (ep.ksplit > 1) {
-      // split-K partial: alpha * acc (+ bias / diag on split 0) accumulated with red.global.add into the zeroed C
-      for (int c = cbeg; c < cbeg + CH; c += 32) {
-        tc_ld32(trow + c, r);
-        if (!(row_ok && n0 + c < ep.N)) continue;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int gn = n0 + c + j;
-          if (gn < ep.N) {
-            float x = ep.alpha * __uint_as_float(r[j]);
-            if (ks == 0) { if (gn == gm) x += ep.diag; if (ep.bias) x += __ldg(ep.bias + gn); }
-            atomicAdd(crow + (int64_t)gn * ep.sc_n, x);
-          }
-        }
-      }
-    } else {
-      float mx = -INFINITY, inv = 1.f;
-      if (ep.softmax) {
-        // Row softmax fused in the epilogue.  A row lives in one TMEM lane; the two warps sharing a lane quarter each
-        // scan their own half of the columns ONCE with an online (max, sum) update and swap the pair through shared
-        // memory (operand stage 0 is free once tmem_full has fired), so statistics cost one TMEM pass, not two full ones.
-        float m_ = -INFINITY, l_ = 0.f;
+    uint32_t r[32];
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < ep.total_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord t = decode_tile(ep, tile, BN);
+      const int n0 = t.n0, m0 = t.m0, b1 = t.b1, b2 = t.b2, ks = t.ks;
+      const uint32_t a = lt & 1u;
+      const int gm = m0 + row;
+      mbar_wait(&tmem_full[a], (lt >> 1) & 1u);   // on a (bounded) timeout keep going: all 8 warps must reach the named barrier
+      tc_fence_after();
+      const uint32_t trow = tmem_base + a * BN + ((uint32_t)(q * 32) << 16);
+      const bool row_ok = gm < ep.M;
+      const int64_t coff = (int64_t)b1 * ep.sc_b1 + (int64_t)b2 * ep.sc_b2 + (int64_t)gm * ep.sc_m;
+      float* crow = ep.C ? ep.C + coff : nullptr;
+      __nv_bfloat16* hrow = ep.Cb_hi ? ep.Cb_hi + coff : nullptr;
+      __nv_bfloat16* lrow = ep.Cb_lo ? ep.Cb_lo + coff : nullptr;
+      if (ep.ksplit > 1) {
+        // split-K partial: alpha * acc (+ bias / diag on split 0) accumulated with red.global.add into the zeroed C
         for (int c = cbeg; c < cbeg + CH; c += 32) {
-          if (n0 + c >= ep.N) break;
           tc_ld32(trow + c, r);
-          float cm = -INFINITY;
+          if (!(row_ok && n0 + c < ep.N)) continue;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c + j < ep.N) cm = fmaxf(cm, ep.alpha * __uint_as_float(r[j]));
-          const float mn = fmaxf(m_, cm);
-          float acc = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c + j < ep.N) acc += __expf(ep.alpha * __uint_as_float(r[j]) - mn);
-          l_ = l_ * __expf(m_ - mn) + acc;            // exp(-inf) = 0 on the first chunk
-          m_ = mn;
-        }
-        float2* stats = reinterpret_cast<float2*>(smem);          // [2 halves][128 rows]
-        stats[half * TC_BM + row] = make_float2(m_, l_);
-        asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
-        const float2 o = stats[(half ^ 1) * TC_BM + row];
-        mx = fmaxf(m_, o.x);
-        const float lsum = (m_ == -INFINITY ? 0.f : l_ * __expf(m_ - mx)) + (o.x == -INFINITY ? 0.f : o.y * __expf(o.x - mx));
-        inv = 1.f / lsum;
-      }
-      for (int c = cbeg; c < cbeg + CH; c += 32) {
-        tc_ld32(trow + c, r);
-        const int gn0 = n0 + c;
-        if (gn0 >= ep.N) break;
-        float v[32];
-        if (ep.vec_ok && gn0 + 32 <= ep.N) {
-          // ---- lean path: full 32-column chunk, 16-byte aligned rows, unit column stride
-          if (ep.softmax) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __expf(ep.alpha * __uint_as_float(r[j]) - mx) * inv;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ep.alpha * __uint_as_float(r[j]);
-            if (ep.beta != 0.f && row_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 cv = *reinterpret_cast<const float4*>(crow + gn0 + j);
-                v[j] = fmaf(ep.beta, cv.x, v[j]); v[j + 1] = fmaf(ep.beta, cv.y, v[j + 1]);
-                v[j + 2] = fmaf(ep.beta, cv.z, v[j + 2]); v[j + 3] = fmaf(ep.beta, cv.w, v[j + 3]);
-              }
-            }
-            if (ep.diag != 0.f) {
-              const int dj = gm - gn0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += (j == dj) ? ep.diag : 0.f;
-            }
-            if (ep.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gn0 + j));
-                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-              }
-            }
-            if (ep.rowtab) {
-              const float* tr = ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 tv = __ldg(reinterpret_cast<const float4*>(tr + j));
-                v[j] = fmaf(ep.rowtab_scale, tv.x, v[j]); v[j + 1] = fmaf(ep.rowtab_scale, tv.y, v[j + 1]);
-                v[j + 2] = fmaf(ep.rowtab_scale, tv.z, v[j + 2]); v[j + 3] = fmaf(ep.rowtab_scale, tv.w, v[j + 3]);
-              }
-            }
-            if (ep.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int j = 0; j < 32; ++j) {
+            const int gn = n0 + c + j;
+            if (gn < ep.N) {
+              float x = ep.alpha * __uint_as_float(r[j]);
+              if (ks == 0) { if (gn == gm) x += ep.diag; if (ep.bias) x += __ldg(ep.bias + gn); }
+              atomicAdd(crow + (int64_t)gn * ep.sc_n, x);
             }
           }
-          if (row_ok) {
-            if (crow) {
+        }
+      } else {
+        float mx = -INFINITY, inv = 1.f;
+        if (ep.softmax) {
+          // Row softmax fused in the epilogue.  A row lives in one TMEM lane; the two warps sharing a lane quarter each
+          // scan their own half of the columns ONCE with an online (max, sum) update and swap the pair through shared
+          // memory, so the statistics cost one TMEM pass.
+          float m_ = -INFINITY, l_ = 0.f;
+          for (int c = cbeg; c < cbeg + CH; c += 32) {
+            if (n0 + c >= ep.N) break;
+            tc_ld32(trow + c, r);
+            float cm = -INFINITY;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + gn0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c + j < ep.N) cm = fmaxf(cm, ep.alpha * __uint_as_float(r[j]));
+            const float mn = fmaxf(m_, cm);
+            float accs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c + j < ep.N) accs += __expf(ep.alpha * __uint_as_float(r[j]) - mn);
+            l_ = l_ * __expf(m_ - mn) + accs;            // exp(-inf) = 0 on the first chunk
+            m_ = mn;
+          }
+          float2* st = stats + (lt & 1u) * 2 * TC_BM;
+          st[half * TC_BM + row] = make_float2(m_, l_);
+          asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
+          const float2 o = st[(half ^ 1) * TC_BM + row];
+          mx = fmaxf(m_, o.x);
+          const float lsum = (m_ == -INFINITY ? 0.f : l_ * __expf(m_ - mx)) + (o.x == -INFINITY ? 0.f : o.y * __expf(o.x - mx));
+          inv = 1.f / lsum;
+        }
+        for (int c = cbeg; c < cbeg + CH; c += 32) {
+          tc_ld32(trow + c, r);
+          const int gn0 = n0 + c;
+          if (gn0 >= ep.N) break;
+          float v[32];
+          if (ep.vec_ok && gn0 + 32 <= ep.N) {
+            // ---- lean path: full 32-column chunk, 16-byte aligned rows, unit column stride
+            if (ep.softmax) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __expf(ep.alpha * __uint_as_float(r[j]) - mx) * inv;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = ep.alpha * __uint_as_float(r[j]);
+              if (ep.beta != 0.f && row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 cv = *reinterpret_cast<const float4*>(crow + gn0 + j);
+                  v[j] = fmaf(ep.beta, cv.x, v[j]); v[j + 1] = fmaf(ep.beta, cv.y, v[j + 1]);
+                  v[j + 2] = fmaf(ep.beta, cv.z, v[j + 2]); v[j + 3] = fmaf(ep.beta, cv.w, v[j + 3]);
+                }
+              }
+              if (ep.diag != 0.f) {
+                const int dj = gm - gn0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += (j == dj) ? ep.diag : 0.f;
+              }
+              if (ep.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gn0 + j));
+                  v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                }
+              }
+              if (ep.rowtab) {
+                const float* tr = ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 tv = __ldg(reinterpret_cast<const float4*>(tr + j));
+                  v[j] = fmaf(ep.rowtab_scale, tv.x, v[j]); v[j + 1] = fmaf(ep.rowtab_scale, tv.y, v[j + 1]);
+                  v[j + 2] = fmaf(ep.rowtab_scale, tv.z, v[j + 2]); v[j + 3] = fmaf(ep.rowtab_scale, tv.w, v[j + 3]);
+                }
+              }
+              if (ep.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
             }
-            if (hrow) {
+            if (row_ok) {
+              if (crow) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __nv_bfloat162 h[4];
-                uint4 pk;
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + gn0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+              if (hrow) {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h[0]); pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
-                pk.z = *reinterpret_cast<uint32_t*>(&h[2]); pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
-                *reinterpret_cast<uint4*>(hrow + gn0 + j) = pk;
-                if (lrow) {
-                  __nv_bfloat162 l[4];
+                for (int j = 0; j < 32; j += 8) {
+                  __nv_bfloat162 h[4];
+                  uint4 pk;
 #pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float2 f = __bfloat1622float2(h[t]);
-                    l[t] = __floats2bfloat162_rn(v[j + 2 * t] - f.x, v[j + 2 * t + 1] - f.y);
+                  for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(v[j + 2 * u], v[j + 2 * u + 1]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&h[0]); pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                  pk.z = *reinterpret_cast<uint32_t*>(&h[2]); pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                  *reinterpret_cast<uint4*>(hrow + gn0 + j) = pk;
+                  if (lrow) {
+                    __nv_bfloat162 l[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const float2 f = __bfloat1622float2(h[u]);
+                      l[u] = __floats2bfloat162_rn(v[j + 2 * u] - f.x, v[j + 2 * u + 1] - f.y);
+                    }
+                    pk.x = *reinterpret_cast<uint32_t*>(&l[0]); pk.y = *reinterpret_cast<uint32_t*>(&l[1]);
+                    pk.z = *reinterpret_cast<uint32_t*>(&l[2]); pk.w = *reinterpret_cast<uint32_t*>(&l[3]);
+                    *reinterpret_cast<uint4*>(lrow + gn0 + j) = pk;
                   }
-                  pk.x = *reinterpret_cast<uint32_t*>(&l[0]); pk.y = *reinterpret_cast<uint32_t*>(&l[1]);
-                  pk.z = *reinterpret_cast<uint32_t*>(&l[2]); pk.w = *reinterpret_cast<uint32_t*>(&l[3]);
-                  *reinterpret_cast<uint4*>(lrow + gn0 + j) = pk;
                 }
               }
             }
-          }
-        } else {
-          // ---- general path (N tail, odd strides)
-          if (!row_ok) continue;
+          } else {
+            // ---- general path (N tail, odd strides)
+            if (!row_ok) continue;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int gn = gn0 + j;
-            float x = ep.alpha * __uint_as_float(r[j]);
-            if (ep.softmax) x = __expf(x - mx) * inv;
-            else if (gn < ep.N) {
-              if (ep.beta != 0.f) x = fmaf(ep.beta, crow[(int64_t)gn * ep.sc_n], x);
-              if (gn == gm) x += ep.diag;
-              if (ep.bias) x += __ldg(ep.bias + gn);
-              if (ep.rowtab) x = fmaf(ep.rowtab_scale, __ldg(ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn), x);
-              if (ep.relu) x = fmaxf(x, 0.f);
+            for (int j = 0; j < 32; ++j) {
+              const int gn = gn0 + j;
+              float x = ep.alpha * __uint_as_float(r[j]);
+              if (ep.softmax) x = __expf(x - mx) * inv;
+              else if (gn < ep.N) {
+                if (ep.beta != 0.f) x = fmaf(ep.beta, crow[(int64_t)gn * ep.sc_n], x);
+                if (gn == gm) x += ep.diag;
+                if (ep.bias) x += __ldg(ep.bias + gn);
+                if (ep.rowtab) x = fmaf(ep.rowtab_scale, __ldg(ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn), x);
+                if (ep.relu) x = fmaxf(x, 0.f);
+              }
+              v[j] = x;
             }
-            v[j] = x;
+            store_row_chunk(ep, crow, hrow, lrow, gm, gn0, v);
           }
-          store_row_chunk(ep, crow, hrow, lrow, gm, gn0, v);
         }
       }
+      // this accumulator buffer may be overwritten by the MMA of tile lt + 2
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[a])) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -566,21 +607,22 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
                (!ep.Cb_lo || (reinterpret_cast<uintptr_t>(ep.Cb_lo) & 15) == 0) &&
                (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
                (!ep.rowtab || ((reinterpret_cast<uintptr_t>(ep.rowtab) & 15) == 0 && ep.rt_m % 4 == 0 && ep.rt_b1 % 4 == 0 && ep.rt_b2 % 4 == 0))) ? 1 : 0;
-  nbz *= ep.ksplit;
-  SML_CHECK(nbz <= 65535, "sml_gemm_tc: batch %lld > 65535", nbz);
-  dim3 grid((d->N + BN - 1) / BN, (d->M + TC_BM - 1) / TC_BM, (unsigned)nbz);
-  SML_CHECK(grid.y <= 65535, "sml_gemm_tc: M too large for grid.y");
+  ep.tiles_n = (d->N + BN - 1) / BN;
+  ep.tiles_m = (d->M + TC_BM - 1) / TC_BM;
+  const long long total = (long long)ep.tiles_n * ep.tiles_m * nbz * ep.ksplit;
+  SML_CHECK(total < (1ll << 31), "sml_gemm_tc: too many tiles");
+  ep.total_tiles = (int)total;
+  dim3 grid((unsigned)(total < kNumSMs ? total : kNumSMs));      // persistent: one CTA per SM walks the tile list
   cudaStream_t st = as_stream(stream);
-  // ring depths sized so that two CTAs share an SM (<= ~100 KB each): one CTA's epilogue overlaps the other's
-  // TMA + MMA main loop.  The bf16x3 variants carry twice the operand bytes per stage.
+  // one persistent CTA per SM: ~192 KB operand ring
   if (!split) {
-    if (BN == 256) return dispatch_major<256, false, 2>(a_mn, b_mn, tms, ep, grid, st);
-    if (BN == 128) return dispatch_major<128, false, 3>(a_mn, b_mn, tms, ep, grid, st);
-    return dispatch_major<64, false, 4>(a_mn, b_mn, tms, ep, grid, st);
+    if (BN == 256) return dispatch_major<256, false, 4>(a_mn, b_mn, tms, ep, grid, st);
+    if (BN == 128) return dispatch_major<128, false, 6>(a_mn, b_mn, tms, ep, grid, st);
+    return dispatch_major<64, false, 8>(a_mn, b_mn, tms, ep, grid, st);
   } else {
     if (BN == 256) return dispatch_major<256, true, 2>(a_mn, b_mn, tms, ep, grid, st);
     if (BN == 128) return dispatch_major<128, true, 3>(a_mn, b_mn, tms, ep, grid, st);
-    return dispatch_major<64, true, 2>(a_mn, b_mn, tms, ep, grid, st);
+    return dispatch_major<64, true, 4>(a_mn, b_mn, tms, ep, grid, st);
   }
 }
 
