@@ -161,7 +161,7 @@ def run_ours(args):
     Fn.manual_seed(42 + rank)
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
                                                         broadcast_buffers=False, gradient_as_bucket_view=True)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
     B, N = args.batch, args.patches

@@ -74,9 +74,12 @@ int sml_layernorm_bwd(const float* dy, const float* x, const float* w, const flo
                       float* dx, float* dw_part, float* db_part, int64_t R, int32_t D, int64_t n, int64_t npad,
                       int64_t pad, void* stream);   /* dy is read in the padded layout, dx written dense */
 /* y[r,:] = softmax(x[r,:]) in place over C columns (models/NystromAttention.py:137) */
-int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi, void* lo, void* stream);   /* hi/lo: optional bf16 copies */
+/* hi/lo: optional bf16 copies; write_f32 = 0 leaves x untouched (probabilities kept in bf16 only) */
+int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi, void* lo, int32_t write_f32, void* stream);
 /* in place on dA: dS = A * (dA - sum(dA*A)) */
-int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* hi, void* lo, void* stream);
+/* probabilities from A (fp32) or A_bf16; dS to dA in place (write_f32) and/or to the bf16 copies */
+int sml_softmax_bwd(const float* A, const void* A_bf16, float* dA, int64_t R, int64_t C, void* hi, void* lo, int32_t write_f32,
+                    void* stream);
 /* y = x + dropout(u, p) with a counter-based generator (seed, offset); p == 0 -> plain add.
  * Same call with grad tensors regenerates the mask in backward (models/mil.py:183 dropout=0.1) */
 int sml_dropout_add(const float* x, const float* u, float* y, int64_t n, float p, uint64_t seed, uint64_t offset,

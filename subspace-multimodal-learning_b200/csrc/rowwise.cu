@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
 // short rows (C <= 1024): one warp per row, row kept in registers
 template <int VPT>
 __global__ void __launch_bounds__(256) softmax_fwd_warp_kernel(float* __restrict__ x, int64_t R, int C,
-                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                               int write_f32) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -151,42 +152,43 @@ __global__ void __launch_bounds__(256) softmax_fwd_warp_kernel(float* __restrict
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = lane + i * 32;
-    if (c < C) { xr[c] = v[i] * inv; store_split(hi, lo, row * C + c, v[i] * inv); }
+    if (c < C) { if (write_f32) xr[c] = v[i] * inv; store_split(hi, lo, row * C + c, v[i] * inv); }
   }
 }
 // long rows: one block per row, three passes through L2-resident data
 __global__ void __launch_bounds__(1024) softmax_fwd_block_kernel(float* __restrict__ x, int64_t C,
-                                                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                                 int write_f32) {
   __shared__ float red[32];
   float* xr = x + (int64_t)blockIdx.x * C;
   float mx = -INFINITY;
   for (int64_t c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, xr[c]);
   mx = block_max(mx, red);
   float s = 0.f;
-  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) { const float e = __expf(xr[c] - mx); xr[c] = e; s += e; }
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) s += __expf(xr[c] - mx);
   s = block_sum(s, red);
   const float inv = 1.f / s;
-  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
-    const float pv = xr[c] * inv;
-    xr[c] = pv;
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {     // the row (<= a few hundred KB) is L2-resident by now
+    const float pv = __expf(xr[c] - mx) * inv;
+    if (write_f32) xr[c] = pv;
     store_split(hi, lo, (int64_t)blockIdx.x * C + c, pv);
   }
 }
 template <int VPT>
-__global__ void __launch_bounds__(256) softmax_bwd_warp_kernel(const float* __restrict__ A, float* __restrict__ dA,
-                                                               int64_t R, int C, __nv_bfloat16* __restrict__ hi,
-                                                               __nv_bfloat16* __restrict__ lo) {
+__global__ void __launch_bounds__(256) softmax_bwd_warp_kernel(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Ab,
+                                                               float* __restrict__ dA, int64_t R, int C,
+                                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                               int write_f32) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
-  const float* ar = A + row * C;
   float* gr = dA + row * C;
   float a[VPT], g[VPT];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = lane + i * 32;
-    a[i] = (c < C) ? ar[c] : 0.f;
+    a[i] = (c < C) ? (A ? A[row * C + c] : __bfloat162float(Ab[row * C + c])) : 0.f;
     g[i] = (c < C) ? gr[c] : 0.f;
     s += a[i] * g[i];
   }
@@ -194,22 +196,22 @@ __global__ void __launch_bounds__(256) softmax_bwd_warp_kernel(const float* __re
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = lane + i * 32;
-    if (c < C) { const float dsv = a[i] * (g[i] - s); gr[c] = dsv; store_split(hi, lo, row * C + c, dsv); }
+    if (c < C) { const float dsv = a[i] * (g[i] - s); if (write_f32) gr[c] = dsv; store_split(hi, lo, row * C + c, dsv); }
   }
 }
-__global__ void __launch_bounds__(1024) softmax_bwd_block_kernel(const float* __restrict__ A, float* __restrict__ dA,
-                                                                 int64_t C, __nv_bfloat16* __restrict__ hi,
-                                                                 __nv_bfloat16* __restrict__ lo) {
+__global__ void __launch_bounds__(1024) softmax_bwd_block_kernel(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Ab,
+                                                                 float* __restrict__ dA, int64_t C, __nv_bfloat16* __restrict__ hi,
+                                                                 __nv_bfloat16* __restrict__ lo, int write_f32) {
   __shared__ float red[32];
-  const float* ar = A + (int64_t)blockIdx.x * C;
-  float* gr = dA + (int64_t)blockIdx.x * C;
+  const int64_t base = (int64_t)blockIdx.x * C;
+  float* gr = dA + base;
   float s = 0.f;
-  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) s += ar[c] * gr[c];
+  for (int64_t c = threadIdx.x; c < C; c += blockDim.x) s += (A ? A[base + c] : __bfloat162float(Ab[base + c])) * gr[c];
   s = block_sum(s, red);
   for (int64_t c = threadIdx.x; c < C; c += blockDim.x) {
-    const float dsv = ar[c] * (gr[c] - s);
-    gr[c] = dsv;
-    store_split(hi, lo, (int64_t)blockIdx.x * C + c, dsv);
+    const float dsv = (A ? A[base + c] : __bfloat162float(Ab[base + c])) * (gr[c] - s);
+    if (write_f32) gr[c] = dsv;
+    store_split(hi, lo, base + c, dsv);
   }
 }
 
@@ -359,30 +361,33 @@ extern "C" int sml_layernorm_bwd(const float* dy, const float* x, const float* w
   SML_LAUNCH_OK("sml_layernorm_bwd");
   return 0;
 }
-extern "C" int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi_, void* lo_, void* stream) {
+extern "C" int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi_, void* lo_, int32_t write_f32, void* stream) {
   __nv_bfloat16* hi = (__nv_bfloat16*)hi_; __nv_bfloat16* lo = (__nv_bfloat16*)lo_;
   if (R == 0 || C == 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned gw = (unsigned)((R + 7) / 8);
-  if (C <= 128) softmax_fwd_warp_kernel<4><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo);
-  else if (C <= 256) softmax_fwd_warp_kernel<8><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo);
-  else if (C <= 512) softmax_fwd_warp_kernel<16><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo);
+  if (C <= 128) softmax_fwd_warp_kernel<4><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo, write_f32);
+  else if (C <= 256) softmax_fwd_warp_kernel<8><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo, write_f32);
+  else if (C <= 512) softmax_fwd_warp_kernel<16><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo, write_f32);
   else {
     SML_CHECK(R <= 2147483647LL, "sml_softmax_fwd: too many rows");
-    softmax_fwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(x, C, hi, lo);
+    softmax_fwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(x, C, hi, lo, write_f32);
   }
   SML_LAUNCH_OK("sml_softmax_fwd");
   return 0;
 }
-extern "C" int sml_softmax_bwd(const float* A, float* dA, int64_t R, int64_t C, void* hi_, void* lo_, void* stream) {
+extern "C" int sml_softmax_bwd(const float* A, const void* A_bf16, float* dA, int64_t R, int64_t C, void* hi_, void* lo_,
+                               int32_t write_f32, void* stream) {
   __nv_bfloat16* hi = (__nv_bfloat16*)hi_; __nv_bfloat16* lo = (__nv_bfloat16*)lo_;
+  const __nv_bfloat16* Ab = (const __nv_bfloat16*)A_bf16;
+  SML_CHECK(A || Ab, "sml_softmax_bwd: need the probabilities in fp32 or bf16");
   if (R == 0 || C == 0) return 0;
   cudaStream_t s = as_stream(stream);
   const unsigned gw = (unsigned)((R + 7) / 8);
-  if (C <= 128) softmax_bwd_warp_kernel<4><<<gw, 256, 0, s>>>(A, dA, R, (int)C, hi, lo);
-  else if (C <= 256) softmax_bwd_warp_kernel<8><<<gw, 256, 0, s>>>(A, dA, R, (int)C, hi, lo);
-  else if (C <= 512) softmax_bwd_warp_kernel<16><<<gw, 256, 0, s>>>(A, dA, R, (int)C, hi, lo);
-  else softmax_bwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(A, dA, C, hi, lo);
+  if (C <= 128) softmax_bwd_warp_kernel<4><<<gw, 256, 0, s>>>(A, Ab, dA, R, (int)C, hi, lo, write_f32);
+  else if (C <= 256) softmax_bwd_warp_kernel<8><<<gw, 256, 0, s>>>(A, Ab, dA, R, (int)C, hi, lo, write_f32);
+  else if (C <= 512) softmax_bwd_warp_kernel<16><<<gw, 256, 0, s>>>(A, Ab, dA, R, (int)C, hi, lo, write_f32);
+  else softmax_bwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(A, Ab, dA, C, hi, lo, write_f32);
   SML_LAUNCH_OK("sml_softmax_bwd");
   return 0;
 }

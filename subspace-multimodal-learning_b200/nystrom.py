@@ -149,17 +149,20 @@ class NystromAttentionFn(torch.autograd.Function):
         ql_b, kl_b = TB.of(ql, mode), TB.of(kl, mode)
         q_b, k_b, v_b = (qkv.map(lambda t, i=i: hv(t, i)) for i in range(3))
         # ---- similarities + softmaxes (:122-137)
-        a1 = TB.new((b, h, npad, m), dev, mode)
-        a2 = TB.new((b, h, m, m), dev, mode, hp=True)
-        a3 = TB.new((b, h, m, npad), dev, mode)
         fuse = tc and m <= 256
+        lowp = mode == "bf16" and fuse          # keep the big probability tensors (A1, A3) in bf16 only
+        a1 = TB.new((b, h, npad, m), dev, mode, f32=not lowp)
+        a2 = TB.new((b, h, m, m), dev, mode, hp=True)
+        a3 = TB.new((b, h, m, npad), dev, mode, f32=not lowp)
+        s3 = a3.f if a3.f is not None else torch.empty(b, h, m, npad, device=dev, dtype=F32)   # logits scratch
         mm(q_b, kl_b.T(), a1, softmax=fuse)
         mm(ql_b, kl_b.T(), a2, softmax=fuse)
-        mm(ql_b, k_b.T(), TB(a3.f))
+        mm(ql_b, k_b.T(), TB(s3))
         if not fuse:
             ops.softmax_(a1.f.view(-1, m), a1.hi, a1.lo)
             ops.softmax_(a2.f.view(-1, m), a2.hi, a2.lo)
-        ops.softmax_(a3.f.view(-1, npad), a3.hi, a3.lo)                              # softmax over tokens
+        ops.softmax_(s3.view(-1, npad), a3.hi, a3.lo, write_f32=not lowp)            # softmax over tokens
+        del s3
         z, pinv_saved = pinv_fwd(a2.f, iters, mode, a2)                              # :138
         a3v = mm(a3, v_b, TB.new((b, h, m, d), dev, mode))                           # [b,h,m,d]
         z_op = z if mode != "bf16" else TB(z.f, z.hi, None)
@@ -236,9 +239,14 @@ class NystromAttentionFn(torch.autograd.Function):
         da2 = pinv_bwd(a2_f, (zs, scal, arg), dz, mode)
         ds1 = TB.new((b, h, npad, m), dev, mode, f32=False); ds1.f = da1.f
         ds3 = TB.new((b, h, m, npad), dev, mode, f32=False); ds3.f = da3.f
-        ops.softmax_bwd_(a1.f.view(-1, m), ds1.f.view(-1, m), ds1.hi, ds1.lo)
+        lowp = a1.f is None                     # bf16-only probabilities: dS also only needs its bf16 copy
+        p1 = a1.f if a1.f is not None else a1.hi
+        p3 = a3.f if a3.f is not None else a3.hi
+        ops.softmax_bwd_(p1.view(-1, m), ds1.f.view(-1, m), ds1.hi, ds1.lo, write_f32=not lowp)
         ops.softmax_bwd_(a2_f.view(-1, m), da2.view(-1, m))
-        ops.softmax_bwd_(a3.f.view(-1, npad), ds3.f.view(-1, npad), ds3.hi, ds3.lo)
+        ops.softmax_bwd_(p3.view(-1, npad), ds3.f.view(-1, npad), ds3.hi, ds3.lo, write_f32=not lowp)
+        if lowp:
+            ds1.f = ds3.f = None
         ds2 = TB.of(da2, mode)
         # ---- similarities; the landmark-mean backward (dq[t] += dql[t // l] / l, same for k) rides in the epilogue of
         #      the dq / dk contractions, which also emit the bf16 copy of dqkv for the projection backward

@@ -210,17 +210,20 @@ def colsum(x2d, out=None, beta=0.0):
     return out
 
 
-def softmax_(x2d, hi=None, lo=None):
+def softmax_(x2d, hi=None, lo=None, write_f32=True):
     R, C = x2d.shape
     assert x2d.is_contiguous()
-    check(lib.sml_softmax_fwd(ptr(x2d), c_i64(R), c_i64(C), ptr(hi), ptr(lo), stream()), "softmax_fwd")
+    check(lib.sml_softmax_fwd(ptr(x2d), c_i64(R), c_i64(C), ptr(hi), ptr(lo), c_i32(1 if write_f32 else 0), stream()), "softmax_fwd")
     return x2d
 
 
-def softmax_bwd_(A2d, dA2d, hi=None, lo=None):
+def softmax_bwd_(A2d, dA2d, hi=None, lo=None, write_f32=True):
+    """A2d: fp32 or bf16 probabilities; dS overwrites dA2d (write_f32) and/or goes to the bf16 copies."""
     R, C = A2d.shape
     assert A2d.is_contiguous() and dA2d.is_contiguous()
-    check(lib.sml_softmax_bwd(ptr(A2d), ptr(dA2d), c_i64(R), c_i64(C), ptr(hi), ptr(lo), stream()), "softmax_bwd")
+    a32, a16 = (A2d, None) if A2d.dtype == F32 else (None, A2d)
+    check(lib.sml_softmax_bwd(ptr(a32), ptr(a16), ptr(dA2d), c_i64(R), c_i64(C), ptr(hi), ptr(lo), c_i32(1 if write_f32 else 0),
+                              stream()), "softmax_bwd")
     return dA2d
 
 
