@@ -87,6 +87,34 @@ __global__ void __launch_bounds__(NT, 2) gemm_f32_kernel(const sml_gemm_desc d, 
   }
 }
 
+
+// Skinny outputs (per-slide heads: [B,512] x [512,4] ...): one warp per output element, lanes stride over K.
+// The tiled kernel above would run a single CTA through K/16 dependent global round trips (measured 89 us).
+__global__ void __launch_bounds__(256) gemm_f32_small_kernel(const sml_gemm_desc d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t per = (int64_t)d.M * d.N;
+  if (w >= per * d.nb1 * d.nb2) return;
+  const int bz = (int)(w / per);
+  const int gm = (int)((w % per) / d.N), gn = (int)(w % d.N);
+  const int b1 = bz / d.nb2, b2 = bz % d.nb2;
+  const float* A = (const float*)d.A + b1 * d.sa_b1 + b2 * d.sa_b2 + (int64_t)gm * d.sa_m;
+  const float* B = (const float*)d.B + b1 * d.sb_b1 + b2 * d.sb_b2 + (int64_t)gn * d.sb_n;
+  float acc = 0.f;
+  for (int k = lane; k < d.K; k += 32) acc = fmaf(__ldg(A + (int64_t)k * d.sa_k), __ldg(B + (int64_t)k * d.sb_k), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float* p = (float*)d.C + b1 * d.sc_b1 + b2 * d.sc_b2 + (int64_t)gm * d.sc_m + (int64_t)gn * d.sc_n;
+    float v = d.alpha * acc;
+    if (d.beta != 0.f) v = fmaf(d.beta, *p, v);
+    if (gm == gn) v += d.diag;
+    if (d.bias) v += __ldg(d.bias + gn);
+    if (d.rowtab) v = fmaf(d.rowtab_scale, __ldg(d.rowtab + b1 * d.rt_b1 + b2 * d.rt_b2 + (int64_t)(gm / d.rowdiv) * d.rt_m + gn), v);
+    if (d.relu) v = fmaxf(v, 0.f);
+    *p = v;
+  }
+}
+
 }  // namespace sml
 
 extern "C" int sml_gemm_f32(const sml_gemm_desc* d, void* stream) {
@@ -94,6 +122,12 @@ extern "C" int sml_gemm_f32(const sml_gemm_desc* d, void* stream) {
   SML_CHECK(d->M > 0 && d->N > 0 && d->K > 0 && d->nb1 > 0 && d->nb2 > 0, "sml_gemm_f32: bad sizes M=%d N=%d K=%d nb=%d,%d",
             d->M, d->N, d->K, d->nb1, d->nb2);
   const long long nbz = (long long)d->nb1 * d->nb2;
+  const long long outs = (long long)d->M * d->N * nbz;
+  if (outs <= 32768 && d->K >= 32) {          // skinny: warp per output element
+    sml::gemm_f32_small_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, sml::as_stream(stream)>>>(*d);
+    SML_LAUNCH_OK("sml_gemm_f32(small)");
+    return 0;
+  }
   SML_CHECK(nbz <= 65535, "sml_gemm_f32: batch %lld > 65535", nbz);
   dim3 grid((d->N + sml::BN - 1) / sml::BN, (d->M + sml::BM - 1) / sml::BM, (unsigned)nbz);
   SML_CHECK(grid.y <= 65535, "sml_gemm_f32: M too large for grid.y");

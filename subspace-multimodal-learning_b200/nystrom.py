@@ -47,8 +47,9 @@ def _pinv_step(pa2, z, mode, need_t=False):
     xz = mm(pa2, z, _new_like(z.f, mode))                                        # x z
     t1 = _new_like(z.f, mode)
     ops.diag_axpby(xz.f, -1.0, 7.0, out=t1.f, hi=t1.hi, lo=t1.lo)                # 7I - xz
-    t2 = mm(xz, t1, _new_like(z.f, mode), alpha=-1.0, diag=15.0)                 # 15I - xz t1
-    t3 = mm(xz, t2, _new_like(z.f, mode), alpha=-1.0, diag=13.0)                 # 13I - xz t2
+    op_only = mode != "fp32"     # t2, t3 are only ever GEMM operands: in tensor-core modes emit just their bf16 hi/lo
+    t2 = mm(xz, t1, TB.new(z.f.shape, z.f.device, mode, hp=True, f32=not op_only), alpha=-1.0, diag=15.0)   # 15I - xz t1
+    t3 = mm(xz, t2, TB.new(z.f.shape, z.f.device, mode, hp=True, f32=not op_only), alpha=-1.0, diag=13.0)   # 13I - xz t2
     return xz, t1, t2, t3
 
 
