@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // Each block owns a contiguous slab of rows; a warp handles rows, accumulating dw/db partials in registers,
 // then the block reduces them through shared memory into dw_part[blk], db_part[blk].
 constexpr int LNB_WARPS = 8;
+template <int VPL>
 __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
@@ -70,9 +71,9 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
   extern __shared__ float sm[];   // [LNB_WARPS][2][D]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nv = D >> 2;
-  float4 aw[8], ab[8];
+  float4 aw[VPL], ab[VPL];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < VPL; ++i) { aw[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(R, r0 + rows_per_block);
   const float4* w4 = reinterpret_cast<const float4*>(w);
@@ -80,10 +81,10 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const float4* gr = reinterpret_cast<const float4*>(dy + ((row / n) * npad + pad + (row % n)) * D);
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[8], g[8];
+    float4 xh[VPL], g[VPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
         const float4 xv = xr[c], gv = gr[c], ww = __ldg(w4 + c);
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
     float4* dr = reinterpret_cast<float4*>(dx + row * D);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
         float4 o;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
   }
   float4* sw = reinterpret_cast<float4*>(sm) + (size_t)wid * 2 * nv;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < VPL; ++i) {
     const int c = lane + i * 32;
     if (c < nv) { sw[c] = aw[i]; sw[nv + c] = ab[i]; }
   }
@@ -212,6 +213,95 @@ __global__ void __launch_bounds__(1024) softmax_bwd_block_kernel(const float* __
     const float dsv = (A ? A[base + c] : __bfloat162float(Ab[base + c])) * (gr[c] - s);
     if (write_f32) gr[c] = dsv;
     store_split(hi, lo, base + c, dsv);
+  }
+}
+
+
+// ---- long rows, register-resident: one 1024-thread block per row, NV float4 per thread (C <= 4096*NV, C % 4 == 0).
+// One global read, exp evaluated once, 128-bit loads / 64-bit bf16 stores; replaces the 3-pass kernel whose time went
+// into per-element 64-bit index arithmetic (ncu: 45 % integer instructions, 29 % of DRAM peak).
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t e, float4 v) {
+  if (hi) {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(hi + e) = pk;
+    if (lo) {
+      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+      const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+      pk.x = *reinterpret_cast<const uint32_t*>(&l0); pk.y = *reinterpret_cast<const uint32_t*>(&l1);
+      *reinterpret_cast<uint2*>(lo + e) = pk;
+    }
+  }
+}
+template <int NV>
+__global__ void __launch_bounds__(1024) softmax_fwd_reg_kernel(float* __restrict__ x, int C4, __nv_bfloat16* __restrict__ hi,
+                                                               __nv_bfloat16* __restrict__ lo, int write_f32) {
+  __shared__ float red[32];
+  const int64_t base = (int64_t)blockIdx.x * C4 * 4;
+  float4* xr = reinterpret_cast<float4*>(x + base);
+  float4 v[NV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 1024;
+    if (c < C4) { v[i] = xr[c]; mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w))); }
+  }
+  mx = block_max(mx, red);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 1024;
+    if (c < C4) {
+      v[i].x = __expf(v[i].x - mx); v[i].y = __expf(v[i].y - mx); v[i].z = __expf(v[i].z - mx); v[i].w = __expf(v[i].w - mx);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  s = block_sum(s, red);
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 1024;
+    if (c < C4) {
+      const float4 p = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+      if (write_f32) xr[c] = p;
+      store_bf16x4(hi, lo, base + 4 * (int64_t)c, p);
+    }
+  }
+}
+template <int NV>
+__global__ void __launch_bounds__(1024) softmax_bwd_reg_kernel(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Ab,
+                                                               float* __restrict__ dA, int C4, __nv_bfloat16* __restrict__ hi,
+                                                               __nv_bfloat16* __restrict__ lo, int write_f32) {
+  __shared__ float red[32];
+  const int64_t base = (int64_t)blockIdx.x * C4 * 4;
+  float4* gr = reinterpret_cast<float4*>(dA + base);
+  float4 a[NV], g[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 1024;
+    if (c < C4) {
+      g[i] = gr[c];
+      if (A) a[i] = reinterpret_cast<const float4*>(A + base)[c];
+      else {
+        const uint2 pk = reinterpret_cast<const uint2*>(Ab + base)[c];
+        const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+        const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+        a[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+      }
+      s += (a[i].x * g[i].x + a[i].y * g[i].y) + (a[i].z * g[i].z + a[i].w * g[i].w);
+    }
+  }
+  s = block_sum(s, red);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * 1024;
+    if (c < C4) {
+      const float4 d4 = make_float4(a[i].x * (g[i].x - s), a[i].y * (g[i].y - s), a[i].z * (g[i].z - s), a[i].w * (g[i].w - s));
+      if (write_f32) gr[c] = d4;
+      store_bf16x4(hi, lo, base + 4 * (int64_t)c, d4);
+    }
   }
 }
 
@@ -341,7 +431,7 @@ extern "C" int sml_layernorm_fwd(const float* x, const float* w, const float* b,
 }
 extern "C" int sml_layernorm_bwd_blocks(int64_t R) {
   int64_t nb = (R + 63) / 64;
-  if (nb > 2 * kNumSMs) nb = 2 * kNumSMs;
+  if (nb > 4 * kNumSMs) nb = 4 * kNumSMs;
   if (nb < 1) nb = 1;
   return (int)nb;
 }
@@ -353,11 +443,16 @@ extern "C" int sml_layernorm_bwd(const float* dy, const float* x, const float* w
   const int64_t rpb = (R + nb - 1) / nb;
   const size_t smem = (size_t)LNB_WARPS * 2 * D * sizeof(float);
   static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (!attr_set) {
+    cudaFuncSetAttribute(layernorm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
-  layernorm_bwd_kernel<<<nb, LNB_WARPS * 32, smem, as_stream(stream)>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
+  const int nv = D / 4;
+  cudaStream_t st = as_stream(stream);
+  if (nv <= 32) layernorm_bwd_kernel<1><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
+  else if (nv <= 64) layernorm_bwd_kernel<2><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
+  else if (nv <= 128) layernorm_bwd_kernel<4><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
+  else layernorm_bwd_kernel<8><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
   SML_LAUNCH_OK("sml_layernorm_bwd");
   return 0;
 }
@@ -371,7 +466,15 @@ extern "C" int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi_, void* 
   else if (C <= 512) softmax_fwd_warp_kernel<16><<<gw, 256, 0, s>>>(x, R, (int)C, hi, lo, write_f32);
   else {
     SML_CHECK(R <= 2147483647LL, "sml_softmax_fwd: too many rows");
-    softmax_fwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(x, C, hi, lo, write_f32);
+    const bool al = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (!hi || (reinterpret_cast<uintptr_t>(hi) & 7) == 0) &&
+                    (!lo || (reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+    const int C4 = (int)(C / 4);
+    if (al && C4 <= 1024) softmax_fwd_reg_kernel<1><<<(unsigned)R, 1024, 0, s>>>(x, C4, hi, lo, write_f32);
+    else if (al && C4 <= 2048) softmax_fwd_reg_kernel<2><<<(unsigned)R, 1024, 0, s>>>(x, C4, hi, lo, write_f32);
+    else if (al && C4 <= 4096) softmax_fwd_reg_kernel<4><<<(unsigned)R, 1024, 0, s>>>(x, C4, hi, lo, write_f32);
+    else if (al && C4 <= 5120) softmax_fwd_reg_kernel<5><<<(unsigned)R, 1024, 0, s>>>(x, C4, hi, lo, write_f32);
+    else if (al && C4 <= 8192) softmax_fwd_reg_kernel<8><<<(unsigned)R, 1024, 0, s>>>(x, C4, hi, lo, write_f32);
+    else softmax_fwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(x, C, hi, lo, write_f32);
   }
   SML_LAUNCH_OK("sml_softmax_fwd");
   return 0;
@@ -387,7 +490,18 @@ extern "C" int sml_softmax_bwd(const float* A, const void* A_bf16, float* dA, in
   if (C <= 128) softmax_bwd_warp_kernel<4><<<gw, 256, 0, s>>>(A, Ab, dA, R, (int)C, hi, lo, write_f32);
   else if (C <= 256) softmax_bwd_warp_kernel<8><<<gw, 256, 0, s>>>(A, Ab, dA, R, (int)C, hi, lo, write_f32);
   else if (C <= 512) softmax_bwd_warp_kernel<16><<<gw, 256, 0, s>>>(A, Ab, dA, R, (int)C, hi, lo, write_f32);
-  else softmax_bwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(A, Ab, dA, C, hi, lo, write_f32);
+  else {
+    const bool al = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(dA) & 15) == 0) && (!A || (reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+                    (!Ab || (reinterpret_cast<uintptr_t>(Ab) & 7) == 0) && (!hi || (reinterpret_cast<uintptr_t>(hi) & 7) == 0) &&
+                    (!lo || (reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+    const int C4 = (int)(C / 4);
+    if (al && C4 <= 1024) softmax_bwd_reg_kernel<1><<<(unsigned)R, 1024, 0, s>>>(A, Ab, dA, C4, hi, lo, write_f32);
+    else if (al && C4 <= 2048) softmax_bwd_reg_kernel<2><<<(unsigned)R, 1024, 0, s>>>(A, Ab, dA, C4, hi, lo, write_f32);
+    else if (al && C4 <= 4096) softmax_bwd_reg_kernel<4><<<(unsigned)R, 1024, 0, s>>>(A, Ab, dA, C4, hi, lo, write_f32);
+    else if (al && C4 <= 5120) softmax_bwd_reg_kernel<5><<<(unsigned)R, 1024, 0, s>>>(A, Ab, dA, C4, hi, lo, write_f32);
+    else if (al && C4 <= 8192) softmax_bwd_reg_kernel<8><<<(unsigned)R, 1024, 0, s>>>(A, Ab, dA, C4, hi, lo, write_f32);
+    else softmax_bwd_block_kernel<<<(unsigned)R, C >= 8192 ? 1024 : 256, 0, s>>>(A, Ab, dA, C, hi, lo, write_f32);
+  }
   SML_LAUNCH_OK("sml_softmax_bwd");
   return 0;
 }
