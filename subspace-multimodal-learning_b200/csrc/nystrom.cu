@@ -154,42 +154,59 @@ __global__ void pinv_init_bwd_scalar_kernel(const float* __restrict__ x, const f
 // src rows have stride src_ld, channel c; dst rows stride dst_ld.  dst[t,c] += sum_k w[c/d][k'] src[t + k - half, c]
 // with k' = k (fwd) or K-1-k (FLIP: the transposed conv of the backward).  Each thread owns TT consecutive tokens of
 // one channel: the K taps live in registers and every (tap, output) pair is resolved at compile time.
-constexpr int RC_TT = 16;
+constexpr int RC_TT = 8;
 template <bool FLIP, int K>
-__global__ void __launch_bounds__(256) resconv_kernel(const float* __restrict__ src, int64_t src_ld,
+__global__ void __launch_bounds__(128) resconv_kernel(const float* __restrict__ src, int64_t src_ld,
                                                       const float* __restrict__ w, float* __restrict__ dst,
                                                       int64_t dst_ld, int npad, int hd, int d,
                                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  // thread = 4 adjacent channels (one 128-bit load per token) x RC_TT tokens; requires d % 4 == 0 and 16-byte rows
   constexpr int HALF = K / 2;
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * RC_TT;
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (c >= hd) return;
   float wr[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) wr[k] = __ldg(w + (c / d) * K + (FLIP ? (K - 1 - k) : k));
   const float* s = src + (int64_t)b * npad * src_ld + c;
-  float acc[RC_TT];
+  float4 acc[RC_TT];
 #pragma unroll
-  for (int i = 0; i < RC_TT; ++i) acc[i] = 0.f;
+  for (int i = 0; i < RC_TT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int u = -HALF; u < RC_TT + HALF; ++u) {       // source token t0+u feeds output i through tap k = u - i + HALF
     const int ts = t0 + u;
-    const float v = (ts >= 0 && ts < npad) ? s[(int64_t)ts * src_ld] : 0.f;
+    const float4 v = (ts >= 0 && ts < npad) ? *reinterpret_cast<const float4*>(s + (int64_t)ts * src_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < RC_TT; ++i) {
       const int k = u - i + HALF;
-      if (k >= 0 && k < K) acc[i] = fmaf(wr[k], v, acc[i]);
+      if (k >= 0 && k < K) {
+        acc[i].x = fmaf(wr[k], v.x, acc[i].x); acc[i].y = fmaf(wr[k], v.y, acc[i].y);
+        acc[i].z = fmaf(wr[k], v.z, acc[i].z); acc[i].w = fmaf(wr[k], v.w, acc[i].w);
+      }
     }
   }
-  float* o = dst + (int64_t)b * npad * dst_ld + c;
-  const int64_t ooff = (int64_t)b * npad * dst_ld + c;   // same offset inside the (already chunk-shifted) bf16 buffers
+  const int64_t ooff = (int64_t)b * npad * dst_ld + c;
 #pragma unroll
   for (int i = 0; i < RC_TT; ++i)
     if (t0 + i < npad) {
-      const float v = o[(int64_t)(t0 + i) * dst_ld] + acc[i];
-      o[(int64_t)(t0 + i) * dst_ld] = v;
-      store_split(hi, lo, ooff + (int64_t)(t0 + i) * dst_ld, v);
+      float4* o = reinterpret_cast<float4*>(dst + ooff + (int64_t)(t0 + i) * dst_ld);
+      float4 v = *o;
+      v.x += acc[i].x; v.y += acc[i].y; v.z += acc[i].z; v.w += acc[i].w;
+      *o = v;
+      if (hi) {
+        const int64_t e = ooff + (int64_t)(t0 + i) * dst_ld;
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(hi + e) = pk;
+        if (lo) {
+          const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+          const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+          pk.x = *reinterpret_cast<const uint32_t*>(&l0); pk.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(lo + e) = pk;
+        }
+      }
     }
 }
 // dw_part[blk, head, k] = sum over the block's token strip and the head's d channels of dout[t,c] * v[t+k-half, c].
@@ -300,10 +317,15 @@ __global__ void __launch_bounds__(256) ppeg_kernel(const float* __restrict__ x, 
   const int lc = threadIdx.x & 31, lr = threadIdx.x >> 5;     // channel lane, 8 row groups
   const int c = c0 + lc;
   if (blockIdx.x == 0 && lr == 0 && c < C) y[base + c] = x[base + c];      // cls row passes through (mil.py:201-205)
-  for (int e = lr; e < (PT_H + 6) * (PT_W + 6); e += 8) {
-    const int ry = e / (PT_W + 6), rx = e % (PT_W + 6);
-    const int gy = ty0 + ry - 3, gx = tx0 + rx - 3;
-    tile[ry][rx][lc] = (gy >= 0 && gy < H && gx >= 0 && gx < W && c < C) ? x[base + (int64_t)(1 + gy * W + gx) * C + c] : 0.f;
+  for (int ry = lr; ry < PT_H + 6; ry += 8) {                 // one warp per halo row: row checks and base address hoisted
+    const int gy = ty0 + ry - 3;
+    const bool rok = gy >= 0 && gy < H && c < C;
+    const float* rp = x + base + (int64_t)(1 + gy * W + tx0 - 3) * C + c;
+#pragma unroll
+    for (int rx = 0; rx < PT_W + 6; ++rx) {
+      const int gx = tx0 + rx - 3;
+      tile[ry][rx][lc] = (rok && gx >= 0 && gx < W) ? rp[(int64_t)rx * C] : 0.f;
+    }
   }
   __syncthreads();
   if (c >= C) return;
@@ -348,10 +370,15 @@ __global__ void __launch_bounds__(256) ppeg_dw_kernel(const float* __restrict__ 
   for (int tl = blockIdx.y; tl < ntiles; tl += gridDim.y) {
     const int ty0 = (tl / tiles_x) * PT_H, tx0 = (tl % tiles_x) * PT_W;
     __syncthreads();
-    for (int e = lr; e < (PT_H + 6) * (PT_W + 6); e += 8) {
-      const int ry = e / (PT_W + 6), rx = e % (PT_W + 6);
-      const int gy = ty0 + ry - 3, gx = tx0 + rx - 3;
-      tile[ry][rx][lc] = (gy >= 0 && gy < H && gx >= 0 && gx < W && c < C) ? x[base + (int64_t)(1 + gy * W + gx) * C + c] : 0.f;
+    for (int ry = lr; ry < PT_H + 6; ry += 8) {
+      const int gy = ty0 + ry - 3;
+      const bool rok = gy >= 0 && gy < H && c < C;
+      const float* rp = x + base + (int64_t)(1 + gy * W + tx0 - 3) * C + c;
+#pragma unroll
+      for (int rx = 0; rx < PT_W + 6; ++rx) {
+        const int gx = tx0 + rx - 3;
+        tile[ry][rx][lc] = (rok && gx >= 0 && gx < W) ? rp[(int64_t)rx * C] : 0.f;
+      }
     }
     __syncthreads();
     const int oy = ty0 + lr;
@@ -441,12 +468,13 @@ extern "C" int sml_pinv_init_bwd(const float* x, const float* scal, const int32_
   return 0;
 }
 static inline dim3 rc_grid(int npad, int hd, int B, int tok) { return dim3((npad + tok - 1) / tok, (hd + 255) / 256, B); }
+static inline dim3 rc_grid4(int npad, int hd, int B, int tok) { return dim3((npad + tok - 1) / tok, (hd / 4 + 127) / 128, B); }
 extern "C" int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
                                        int32_t d, int32_t ksize, void* out_hi, void* out_lo, void* stream) {
   const int hd = h * d;
   SML_CHECK(ksize % 2 == 1, "sml_nystrom_resconv_fwd: kernel size must be odd");
-  if (ksize == 33)
-    resconv_kernel<false, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+  if (ksize == 33 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    resconv_kernel<false, 33><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
   else
     resconv_generic_kernel<false><<<rc_grid(npad, hd, B, 1), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, ksize);
   SML_LAUNCH_OK("sml_nystrom_resconv_fwd");
@@ -460,8 +488,9 @@ extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const f
                                        void* stream) {
   const int hd = h * d;
   cudaStream_t s = as_stream(stream);
-  if (ksize == 33) {
-    resconv_kernel<true, 33><<<rc_grid(npad, hd, B, RC_TT), 256, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d,
+  if (ksize == 33 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
+    resconv_kernel<true, 33><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d,
         dqkv_hi ? (__nv_bfloat16*)dqkv_hi + 2 * hd : nullptr, dqkv_lo ? (__nv_bfloat16*)dqkv_lo + 2 * hd : nullptr);
     SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
     resconv_dw_kernel<33><<<rc_grid(npad, hd, B, RCB_TOK), 256, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
