@@ -213,17 +213,18 @@ __global__ void __launch_bounds__(128) resconv_kernel(const float* __restrict__ 
 // Thread = one channel; it walks its strip in chunks of 16 tokens with a (16 + K - 1)-wide register window of v.
 constexpr int RCB_TOK = 256;
 template <int K>
-__global__ void __launch_bounds__(256) resconv_dw_kernel(const float* __restrict__ v, int64_t v_ld,
+__global__ void __launch_bounds__(128) resconv_dw_kernel(const float* __restrict__ v, int64_t v_ld,
                                                          const float* __restrict__ dout, int64_t o_ld,
                                                          float* __restrict__ dw_part, int npad, int hd, int d) {
-  constexpr int HALF = K / 2, CH = 16;
+  // thread = 4 adjacent channels of one head (128-bit loads); the 4 channel products fold into one scalar per tap
+  constexpr int HALF = K / 2, CH = 8;
   extern __shared__ float sdw[];   // [h*K]
   const int h = hd / d;
   for (int i = threadIdx.x; i < h * K; i += blockDim.x) sdw[i] = 0.f;
   __syncthreads();
   const int b = blockIdx.z, t0 = blockIdx.x * RCB_TOK;
   const int t1 = min(npad, t0 + RCB_TOK);
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (c < hd) {
     const float* vp = v + (int64_t)b * npad * v_ld + c;
     const float* gp = dout + (int64_t)b * npad * o_ld + c;
@@ -231,25 +232,28 @@ __global__ void __launch_bounds__(256) resconv_dw_kernel(const float* __restrict
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
     for (int tc = t0; tc < t1; tc += CH) {
-      float win[CH + K - 1], g[CH];
+      float4 g[CH];
 #pragma unroll
-      for (int u = 0; u < CH + K - 1; ++u) {
-        const int ts = tc + u - HALF;
-        win[u] = (ts >= 0 && ts < npad) ? vp[(int64_t)ts * v_ld] : 0.f;
+      for (int i = 0; i < CH; ++i)
+        g[i] = (tc + i < t1) ? *reinterpret_cast<const float4*>(gp + (int64_t)(tc + i) * o_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = -HALF; u < CH + HALF; ++u) {          // v token tc+u pairs with output i through tap k = u - i + HALF
+        const int ts = tc + u;
+        const float4 x = (ts >= 0 && ts < npad) ? *reinterpret_cast<const float4*>(vp + (int64_t)ts * v_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int k = u - i + HALF;
+          if (k >= 0 && k < K) acc[k] = fmaf(g[i].x, x.x, fmaf(g[i].y, x.y, fmaf(g[i].z, x.z, fmaf(g[i].w, x.w, acc[k]))));
+        }
       }
-#pragma unroll
-      for (int i = 0; i < CH; ++i) g[i] = (tc + i < t1) ? gp[(int64_t)(tc + i) * o_ld] : 0.f;
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int i = 0; i < CH; ++i) acc[k] = fmaf(g[i], win[i + k], acc[k]);
     }
-    const bool whole_warp_one_head = (d & 31) == 0;
+    // reduce over the d/4 threads of a head: whole warps when d/4 >= 32, else per-thread shared atomics
+    const bool whole_warp_one_head = ((d / 4) & 31) == 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (whole_warp_one_head) {
-        const float s = warp_sum(acc[k]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[(c / d) * K + k], s);
+        const float sum = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[(c / d) * K + k], sum);
       } else {
         atomicAdd(&sdw[(c / d) * K + k], acc[k]);
       }
@@ -481,7 +485,7 @@ extern "C" int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* 
   return 0;
 }
 extern "C" int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad, int32_t hd) {
-  return B * ((hd + 255) / 256) * ((npad + RCB_TOK - 1) / RCB_TOK);
+  return B * ((hd + 255) / 256) * ((npad + RCB_TOK - 1) / RCB_TOK);   // upper bound for both the vector and the generic grid
 }
 extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
                                        int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* dqkv_hi, void* dqkv_lo,
@@ -493,7 +497,7 @@ extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const f
     resconv_kernel<true, 33><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d,
         dqkv_hi ? (__nv_bfloat16*)dqkv_hi + 2 * hd : nullptr, dqkv_lo ? (__nv_bfloat16*)dqkv_lo + 2 * hd : nullptr);
     SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
-    resconv_dw_kernel<33><<<rc_grid(npad, hd, B, RCB_TOK), 256, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
+    resconv_dw_kernel<33><<<rc_grid4(npad, hd, B, RCB_TOK), 128, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
   } else {
     resconv_generic_kernel<true><<<rc_grid(npad, hd, B, 1), 256, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d, ksize);
     SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");

@@ -229,8 +229,8 @@ class NystromAttentionFn(torch.autograd.Function):
         da3v = mm(TB.of(z_f, mode).T(), dwm, TB.new((b, h, m, d), dev, mode))                   # [b,h,m,d]
         da3 = mm(da3v, v_b.T(), TB(torch.empty(b, h, m, npad, device=dev, dtype=F32)))
         mm(a3.T(), da3v, TB(dv))                                                                # dv = A3^T dA3V
-        dwc_part = torch.empty(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad), c_i32(h * d)), h * ksize, device=dev,
-                               dtype=F32)
+        dwc_part = torch.zeros(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad), c_i32(h * d)), h * ksize, device=dev,
+                               dtype=F32)      # upper bound on the partial rows; unused rows stay zero
         fused_cvt = ksize == 33
         check(lib.sml_nystrom_resconv_bwd(ptr(qkv.f), ptr(wc), ptr(dmerged.f), ptr(dqkv.f), ptr(dwc_part), c_i32(b), c_i32(npad),
                                           c_i32(h), c_i32(d), c_i32(ksize), ptr(dqkv.hi) if fused_cvt else None,
