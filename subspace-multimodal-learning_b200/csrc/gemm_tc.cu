@@ -238,10 +238,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Programmatic dependent launch: let the next kernel in the stream start its own prologue now, and do not touch
+  // global memory ourselves until every prerequisite kernel has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -553,7 +557,14 @@ static int launch_tc(const CUtensorMap* tms, const EpiParams& ep, dim3 grid, cud
     SML_CHECK(e == cudaSuccess, "sml_gemm_tc: cudaFuncSetAttribute(%d B) failed: %s", S::TOTAL, cudaGetErrorString(e));
     attr = true;
   }
-  kern<<<grid, TC_THREADS, S::TOTAL, st>>>(tms[0], tms[1], tms[2], tms[3], ep);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr1[1];
+  attr1[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr1[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr1; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tms[0], tms[1], tms[2], tms[3], ep);
+  SML_CHECK(le == cudaSuccess, "sml_gemm_tc: launch failed: %s", cudaGetErrorString(le));
   SML_LAUNCH_OK("sml_gemm_tc");
   return 0;
 }

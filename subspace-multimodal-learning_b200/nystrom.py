@@ -42,15 +42,15 @@ def _new_like(t, mode):
     return TB.new(t.shape, t.device, mode, hp=True)
 
 
-def _pinv_step(pa2, z, mode, need_t=False):
-    """one Moore-Penrose iteration on bundles: returns (xz, t1, t2, t3) bundles"""
-    xz = mm(pa2, z, _new_like(z.f, mode))                                        # x z
-    t1 = _new_like(z.f, mode)
-    ops.diag_axpby(xz.f, -1.0, 7.0, out=t1.f, hi=t1.hi, lo=t1.lo)                # 7I - xz
+def _pinv_step(pa2, z, mode):
+    """one Moore-Penrose iteration on bundles: returns (xz, t2, t3).  With t1 = 7I - xz folded in,
+    t2 = 15I - xz (7I - xz) = xz xz - 7 xz + 15 I is ONE contraction whose epilogue adds the -7 xz and 15 I terms."""
     op_only = mode != "fp32"     # t2, t3 are only ever GEMM operands: in tensor-core modes emit just their bf16 hi/lo
-    t2 = mm(xz, t1, TB.new(z.f.shape, z.f.device, mode, hp=True, f32=not op_only), alpha=-1.0, diag=15.0)   # 15I - xz t1
+    xz = mm(pa2, z, _new_like(z.f, mode))                                        # x z
+    t2 = mm(xz, xz, TB.new(z.f.shape, z.f.device, mode, hp=True, f32=not op_only), diag=15.0,
+            rowtab=xz.f, rowdiv=1, rowtab_scale=-7.0)                            # 15I - xz (7I - xz)
     t3 = mm(xz, t2, TB.new(z.f.shape, z.f.device, mode, hp=True, f32=not op_only), alpha=-1.0, diag=13.0)   # 13I - xz t2
-    return xz, t1, t2, t3
+    return xz, t2, t3
 
 
 def pinv_fwd(a2, iters, mode, a2_bundle=None):
@@ -67,7 +67,7 @@ def pinv_fwd(a2, iters, mode, a2_bundle=None):
     z = TB.of(z0, mode, hp=True)
     zs = [z.f]
     for _ in range(iters):
-        _, _, _, t3 = _pinv_step(pa2, z, mode)
+        _, _, t3 = _pinv_step(pa2, z, mode)
         z = mm(z, t3, _new_like(z.f, mode), alpha=0.25)                          # z <- 1/4 z t3
         zs.append(z.f)
     return z, (zs[:-1], scal, arg)
@@ -82,17 +82,16 @@ def pinv_bwd(a2, saved, dz, mode):
     g = TB.of(dz.contiguous(), mode, hp=True)
     for zk in reversed(zs):
         z = TB.of(zk, mode, hp=True)
-        xz, t1, t2, t3 = _pinv_step(pa2, z, mode)
+        xz, t2, t3 = _pinv_step(pa2, z, mode)
         dzk = mm(g, t3.T(), _new_like(zk, mode), alpha=0.25)                     # 1/4 G t3^T
         dt3 = mm(z.T(), g, _new_like(zk, mode), alpha=0.25)                      # 1/4 z^T G
         dxz = TB(torch.empty_like(zk))
-        mm(dt3, t2.T(), dxz, alpha=-1.0)                                         # -dt3 t2^T
-        dt2 = mm(xz.T(), dt3, _new_like(zk, mode), alpha=-1.0)                   # -xz^T dt3
-        mm(dt2, t1.T(), dxz, alpha=-1.0, beta=1.0)                               # -dt2 t1^T
-        dt1 = mm(xz.T(), dt2, TB(torch.empty_like(zk)), alpha=-1.0)              # -xz^T dt2
+        mm(dt3, t2.T(), dxz, alpha=-1.0)                                         # t3 = 13I - xz t2:  dxz  = -dt3 t2^T
+        dt2 = mm(xz.T(), dt3, _new_like(zk, mode), alpha=-1.0)                   #                    dt2  = -xz^T dt3
+        mm(dt2, xz.T(), dxz, beta=1.0, rowtab=dt2.f, rowdiv=1, rowtab_scale=-7.0)   # t2 = xz xz - 7 xz + 15 I:  dxz += dt2 xz^T - 7 dt2
         dxz_b = _new_like(zk, mode)
         dxz_b.f = dxz.f
-        ops.axpby_(dxz.f, dt1.f, -1.0, 1.0, hi=dxz_b.hi, lo=dxz_b.lo)            # t1 = 7I - xz  ->  dxz -= dt1
+        mm(xz.T(), dt2, dxz_b, beta=1.0)                                         #                    dxz += xz^T dt2  (emits hi/lo)
         mm(dxz_b, z.T(), TB(da2), beta=1.0)                                      # dx += dxz z^T
         dzk2 = _new_like(zk, mode)
         dzk2.f = dzk.f

@@ -34,10 +34,12 @@ def test_deform1d_upstream_order_vs_oracle():
     mod = sml_b200.DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6,
                                           pad_order="upstream").cuda().eval()
     mod.load_state_dict(g["state"])
-    p = {k: v.clone().requires_grad_() for k, v in g["state"].items()}
-    x1c = g["x1"].clone().requires_grad_(); x2c = g["x2"].clone().requires_grad_()
+    # the oracle is evaluated in fp64: some GPU-box host CPUs run fp32 matmul/conv through reduced-precision fast paths
+    # (observed: the fp32 CPU oracle itself 3.5e-4 off its fp64 evaluation on one box, the kernel 2.4e-6)
+    p = {k: v.double().requires_grad_() for k, v in g["state"].items()}
+    x1c = g["x1"].double().requires_grad_(); x2c = g["x2"].double().requires_grad_()
     yo = oracle.deform.deform_attn_1d(x1c, x2c, p, pad_order="upstream")
-    yo.backward(g["gy"])
+    yo.backward(g["gy"].double())
     x1 = g["x1"].cuda().requires_grad_(); x2 = g["x2"].cuda().requires_grad_()
     y = mod(x1, x2)
     assert rel_err(y, yo) < 1e-4
@@ -94,12 +96,12 @@ def test_deform2d_vs_oracle_64x64_batch2():
     sd = mod.state_dict()
     sd["to_offsets.2.weight"] = sd["to_offsets.2.weight"] * 8.0
     mod.load_state_dict(sd)
-    p = {k: v.detach().cpu().clone().requires_grad_() for k, v in mod.state_dict().items()}
-    x1c = randn((2, 128, 4096), 11).requires_grad_(); x2c = randn((2, 128, 4096), 12).requires_grad_()
+    p = {k: v.detach().cpu().double().requires_grad_() for k, v in mod.state_dict().items()}      # fp64 oracle (see above)
+    x1c = randn((2, 128, 4096), 11).double().requires_grad_(); x2c = randn((2, 128, 4096), 12).double().requires_grad_()
     gy = randn((2, 128, 4096), 13); gv = randn((16, 2, 16, 16), 14)
-    yo, vo = oracle.deform.deform_attn_2d(x1c, x2c, p, side=64, q_chunk=1024)
-    (yo * gy).sum().add((vo * gv).sum()).backward()
-    x1 = x1c.detach().cuda().requires_grad_(); x2 = x2c.detach().cuda().requires_grad_()
+    yo, vo = oracle.deform.deform_attn_2d(x1c, x2c, p, side=64, q_chunk=512)
+    (yo * gy.double()).sum().add((vo * gv.double()).sum()).backward()
+    x1 = x1c.detach().float().cuda().requires_grad_(); x2 = x2c.detach().float().cuda().requires_grad_()
     y, v = mod(x1, x2, return_vgrid=True)
     assert rel_err(y, yo) < 1e-4 and rel_err(v, vo) < 1e-5
     (y * gy.cuda()).sum().add((v * gv.cuda()).sum()).backward()

@@ -14,21 +14,21 @@ def test_two_rank_batchloss_and_syncbn():
     res = run_ranks("gpu")
     check_gather(res)
     B = res[0]["om"].shape[0]
-    om = torch.cat([r["om"] for r in res]).requires_grad_(); vg = torch.cat([r["vg"] for r in res]).requires_grad_()
+    om = torch.cat([r["om"] for r in res]).double().requires_grad_(); vg = torch.cat([r["vg"] for r in res]).double().requires_grad_()
     want = oracle.loss.batch_loss(om.unsqueeze(1).repeat(1, 7, 1), vg, 2 * B)
     for rk, r in enumerate(res):
         assert rel_err(r["bl"], want) < 1e-4
-    want.backward(res[0]["gl"])
+    want.backward(res[0]["gl"].double())
     for rk, r in enumerate(res):
         assert rel_err(r["bl_gom"], om.grad[rk * B:(rk + 1) * B]) < 1e-3
         assert rel_err(r["bl_gvg"], vg.grad[rk * 8 * B:(rk + 1) * 8 * B]) < 1e-3
     # sync BN vs BatchNorm1d on the concatenated (ragged) batch
-    x = torch.cat([r["bn_x"] for r in res]).requires_grad_()
-    bn = torch.nn.BatchNorm1d(16).train()
+    x = torch.cat([r["bn_x"] for r in res]).double().requires_grad_()
+    bn = torch.nn.BatchNorm1d(16).double().train()
     with torch.no_grad():
         bn.weight.copy_(res[0]["bn_w"]); bn.bias.copy_(res[0]["bn_b"])
     y = bn(x)
-    y.backward(torch.cat([r["bn_gy"] for r in res]))
+    y.backward(torch.cat([r["bn_gy"] for r in res]).double())
     o = 0
     for r in res:
         n = r["bn_x"].shape[0]

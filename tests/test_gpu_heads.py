@@ -74,10 +74,10 @@ def test_batchloss_collapsed_gram_equals_repeated():
     B, N = 6, 400
     base = randn((B, 128), 1).abs()
     vg = randn((8 * B, 2, 5, 5), 2)
-    bc = base.clone().requires_grad_(); vc = vg.clone().requires_grad_()
+    bc = base.double().requires_grad_(); vc = vg.double().requires_grad_()          # fp64 oracle
     want = oracle.loss.batch_loss(bc.unsqueeze(1).repeat(1, N, 1), vc, B)
     gl = randn(want.shape, 3)
-    want.backward(gl)
+    want.backward(gl.double())
     b1 = base.cuda().requires_grad_(); v1 = vg.cuda().requires_grad_()
     rep = b1.unsqueeze(1).repeat(1, N, 1)
     rep._sml_base = b1

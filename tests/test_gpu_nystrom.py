@@ -68,12 +68,13 @@ def test_nystrom_vs_oracle_mid_size(mode):
     torch.manual_seed(0)
     mod = sml_b200.NystromAttention(dim=512, dim_head=64, heads=8, num_landmarks=256, pinv_iterations=6).cuda().eval()
     mod.precision = mode
-    p = {k: v.detach().cpu().clone().requires_grad_() for k, v in mod.state_dict().items()}
-    xc = randn((2, 1001, 512), 5).requires_grad_()
+    # fp64 evaluation of the oracle (host-CPU independent; the fp32 reference path agrees with it to ~1e-6)
+    p = {k: v.detach().cpu().double().requires_grad_() for k, v in mod.state_dict().items()}
+    xc = randn((2, 1001, 512), 5).double().requires_grad_()
     gy = randn((2, 1001, 512), 6)
     yo = oracle.nystrom.nystrom_attention(xc, p, heads=8, num_landmarks=256, pinv_iterations=6)
-    yo.backward(gy)
-    x = xc.detach().cuda().requires_grad_()
+    yo.backward(gy.double())
+    x = xc.detach().float().cuda().requires_grad_()
     y = mod(x)
     assert rel_err(y, yo) < TOL[mode]
     y.backward(gy.cuda())
