@@ -55,6 +55,10 @@ typedef struct sml_gemm_desc {
 
 int sml_gemm_f32(const sml_gemm_desc* d, void* stream);
 int sml_gemm_tc(const sml_gemm_desc* d, void* stream);
+/* n DEPENDENT bf16x3 GEMMs (each step may read what earlier steps wrote: the Moore-Penrose chain of
+ * models/NystromAttention.py:31-33 and its backward) in one persistent cooperative launch with in-kernel grid barriers;
+ * counter = 4 bytes of device scratch */
+int sml_gemm_tc_program(const sml_gemm_desc* descs, int32_t n, void* counter, void* stream);
 /* fp32 -> bf16 hi (and lo = bf16(x - hi) when lo != NULL), n elements */
 int sml_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 

@@ -21,6 +21,10 @@ from ._lib import c_i32, check, lib, ptr, stream
 from .ops import F32, TB, mm
 
 PRECISIONS = ("fp32", "bf16x3", "bf16")
+# Run the Moore-Penrose GEMM chains as single persistent cooperative launches (sml_gemm_tc_program).  Measured on B200 at
+# batch 64 x 256^3: no gain over back-to-back launches (each step is bound by L2->SMEM operand traffic, 64 MB/step, not by
+# launch latency), so it is off by default; tests/test_gpu_nystrom.py keeps the path parity-checked.
+FUSE_PINV_CHAIN = False
 
 
 def landmarks_fwd(qkv, b, npad, h, d, m):
@@ -66,10 +70,11 @@ def pinv_fwd(a2, iters, mode, a2_bundle=None):
     pa2 = a2_bundle if (a2_bundle is not None and (mode == "fp32" or a2_bundle.lo is not None)) else TB.of(a2, mode, hp=True)
     z = TB.of(z0, mode, hp=True)
     zs = [z.f]
-    for _ in range(iters):
-        _, _, t3 = _pinv_step(pa2, z, mode)
-        z = mm(z, t3, _new_like(z.f, mode), alpha=0.25)                          # z <- 1/4 z t3
-        zs.append(z.f)
+    with ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN)):         # 4 * iters dependent GEMMs, one launch
+        for _ in range(iters):
+            _, _, t3 = _pinv_step(pa2, z, mode)
+            z = mm(z, t3, _new_like(z.f, mode), alpha=0.25)                      # z <- 1/4 z t3
+            zs.append(z.f)
     return z, (zs[:-1], scal, arg)
 
 
@@ -80,8 +85,10 @@ def pinv_bwd(a2, saved, dz, mode):
     pa2 = TB.of(a2, mode, hp=True)
     da2 = torch.zeros_like(a2)
     g = TB.of(dz.contiguous(), mode, hp=True)
-    for zk in reversed(zs):
-        z = TB.of(zk, mode, hp=True)
+    zbs = [TB.of(zk, mode, hp=True) for zk in zs]                                # conversions first: only GEMMs inside the program
+    prog = ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN))
+    prog.__enter__()
+    for zk, z in zip(reversed(zs), reversed(zbs)):
         xz, t2, t3 = _pinv_step(pa2, z, mode)
         dzk = mm(g, t3.T(), _new_like(zk, mode), alpha=0.25)                     # 1/4 G t3^T
         dt3 = mm(z.T(), g, _new_like(zk, mode), alpha=0.25)                      # 1/4 z^T G
@@ -97,6 +104,7 @@ def pinv_bwd(a2, saved, dz, mode):
         dzk2.f = dzk.f
         mm(pa2.T(), dxz_b, dzk2, beta=1.0)                                       # dz += x^T dxz  (re-emits hi/lo of the sum)
         g = dzk2
+    prog.__exit__(None, None, None)                                              # 11 * iters dependent GEMMs, <= 2 launches
     tmp = torch.empty(1, device=a2.device, dtype=F32)
     check(lib.sml_pinv_init_bwd(ptr(a2), ptr(scal), ptr(arg), ptr(g.f), ptr(da2), ptr(tmp), c_i32(bh), c_i32(m), stream()),
           "pinv_init_bwd")

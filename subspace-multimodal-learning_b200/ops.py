@@ -7,6 +7,54 @@ from ._lib import GemmDesc, c_f32, c_i32, c_i64, c_u64, c_vp, check, lib, ptr, r
 
 F32, BF16 = torch.float32, torch.bfloat16
 
+class GemmProgram:
+    """Record the tensor-core GEMMs issued inside the ``with`` block and run them as ONE persistent cooperative launch
+    (sml_gemm_tc_program): for chains of small dependent products (the Moore-Penrose iteration) whose individual
+    launches are dominated by fixed per-launch latency.  Only GEMMs may depend on each other inside the block; every
+    tensor a recorded step touches is kept alive until the launch, so the caching allocator cannot recycle it early."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.descs, self.keep, self.flops = [], [], 0.0
+
+    def __enter__(self):
+        global _PROGRAM
+        if self.enabled:
+            assert _PROGRAM is None, "GemmProgram blocks do not nest"
+            _PROGRAM = self
+        return self
+
+    def __exit__(self, et, ev, tb):
+        global _PROGRAM
+        if not self.enabled:
+            return False
+        _PROGRAM = None
+        if et is None and self.descs:
+            self.launch()
+        return False
+
+    def launch(self):
+        n = len(self.descs)
+        arr = (GemmDesc * n)(*self.descs)
+        dev = self.keep[0].device
+        counter = torch.empty(1, device=dev, dtype=torch.int32)
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(lib.sml_gemm_tc_program(arr, c_i32(n), ptr(counter), stream()), "gemm_tc_program")
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append(("tc", self.flops, e0, e1, ("program", n)))
+        self.descs, self.keep = [], []
+
+
+_PROGRAM = None
+
+
+def gemm_program(enabled=True):
+    return GemmProgram(enabled)
+
+
 # bench instrumentation: when a list, every gemm() appends (engine, algorithmic flops, start event, end event)
 PROFILE = None
 
@@ -166,6 +214,11 @@ def gemm(A, B, out=None, *, alpha=1.0, beta=0.0, diag=0.0, bias=None, relu=False
         d.Cb_hi = out_bf16.data_ptr() if out_bf16 is not None else None
         d.Cb_lo = out_bf16_lo.data_ptr() if out_bf16_lo is not None else None
         fn, eng = lib.sml_gemm_tc, "tc"
+        if _PROGRAM is not None and A.lo is not None and not softmax:
+            _PROGRAM.descs.append(d)
+            _PROGRAM.keep.extend(t for t in (a, b, A.lo, B.lo, out, out_bf16, out_bf16_lo, bias, rowtab) if t is not None)
+            _PROGRAM.flops += 2.0 * M * N * K * nb[0] * nb[1]
+            return out
     else:
         assert a.dtype == F32 and b.dtype == F32 and not softmax and out_bf16 is None
         fn, eng = lib.sml_gemm_f32, "simt"

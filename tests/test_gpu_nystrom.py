@@ -82,6 +82,26 @@ def test_nystrom_vs_oracle_mid_size(mode):
     grads_close({k: q.grad for k, q in mod.named_parameters()}, {k: v.grad for k, v in p.items()}, 10 * TOL[mode])
 
 
+def test_pinv_chain_as_gemm_program():
+    """the fused persistent-launch variant of the pinv chain (sml_gemm_tc_program) gives the same result"""
+    import sml_b200
+    from sml_b200 import nystrom as ny
+    g = load_golden("pinv")
+    x = g["x"].cuda()
+    ny.FUSE_PINV_CHAIN = True
+    try:
+        z, saved = ny.pinv_fwd(x, g["iters"], "bf16x3")
+        gx = ny.pinv_bwd(x, saved, g["gz"].cuda(), "bf16x3")
+    finally:
+        ny.FUSE_PINV_CHAIN = False
+    z2, saved2 = ny.pinv_fwd(x, g["iters"], "bf16x3")
+    gx2 = ny.pinv_bwd(x, saved2, g["gz"].cuda(), "bf16x3")
+    assert rel_err(z.f, g["z"]) < 1e-4 and rel_err(z.f, z2.f) < 1e-4
+    assert rel_err(gx, gx2) < 1e-3
+    torch.cuda.synchronize()
+    assert sml_b200._lib.lib.sml_tc_timeout_flag() == 0
+
+
 def test_translayer_ppeg_golden():
     import sml_b200
     g = load_golden("translayer_ppeg")
