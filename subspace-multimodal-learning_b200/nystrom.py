@@ -25,6 +25,12 @@ PRECISIONS = ("fp32", "bf16x3", "bf16")
 # batch 64 x 256^3: no gain over back-to-back launches (each step is bound by L2->SMEM operand traffic, 64 MB/step, not by
 # launch latency), so it is off by default; tests/test_gpu_nystrom.py keeps the path parity-checked.
 FUSE_PINV_CHAIN = False
+# bf16 mode, d = 64, m = 256: run the backward of the token-by-landmark path (dA1, softmax backward, dq, dk~) as the fused
+# tcgen05 kernel sml_nystrom_a1_bwd instead of two GEMMs + a softmax-backward pass + two more GEMMs over [n', m] tensors
+FUSE_A1_BWD = True
+import os as _os
+FUSE_A1_BWD = _os.environ.get("SML_FUSE_A1_BWD", "1") != "0"
+FUSE_PINV_CHAIN = _os.environ.get("SML_FUSE_PINV_CHAIN", "0") == "1"
 
 
 def landmarks_fwd(qkv, b, npad, h, d, m):
@@ -230,7 +236,9 @@ class NystromAttentionFn(torch.autograd.Function):
         dqkv = TB.new((b, npad, 3, h, d), dev, mode)
         dq, dk, dv = (hv(dqkv.f, i) for i in range(3))
         # ---- out = A1 Wm ; Wm = Z A3V ; A3V = A3 V
-        da1 = mm(dout_b, TB.of(wm_f, mode).T(), TB(torch.empty(b, h, npad, m, device=dev, dtype=F32)))
+        wm_b = TB.of(wm_f, mode)
+        fuse_a1 = FUSE_A1_BWD and mode == "bf16" and a1.f is None and m == 256 and d == 64 and fused_cvt_ok(ksize)
+        da1 = None if fuse_a1 else mm(dout_b, wm_b.T(), TB(torch.empty(b, h, npad, m, device=dev, dtype=F32)))
         dwm = mm(a1.T(), dout_b, TB.new((b, h, m, d), dev, mode))                               # [b,h,m,d]
         dz = mm(dwm, TB.of(a3v_f, mode).T()).f                                                  # [b,h,m,m]
         da3v = mm(TB.of(z_f, mode).T(), dwm, TB.new((b, h, m, d), dev, mode))                   # [b,h,m,d]
@@ -245,27 +253,36 @@ class NystromAttentionFn(torch.autograd.Function):
         dw_conv = ops.colsum(dwc_part).view(h, 1, ksize, 1)
         # ---- pinv + softmaxes (dS emitted with its bf16 copy by the softmax-backward kernel)
         da2 = pinv_bwd(a2_f, (zs, scal, arg), dz, mode)
-        ds1 = TB.new((b, h, npad, m), dev, mode, f32=False); ds1.f = da1.f
         ds3 = TB.new((b, h, m, npad), dev, mode, f32=False); ds3.f = da3.f
         lowp = a1.f is None                     # bf16-only probabilities: dS also only needs its bf16 copy
         p1 = a1.f if a1.f is not None else a1.hi
         p3 = a3.f if a3.f is not None else a3.hi
-        ops.softmax_bwd_(p1.view(-1, m), ds1.f.view(-1, m), ds1.hi, ds1.lo, write_f32=not lowp)
+        if not fuse_a1:
+            ds1 = TB.new((b, h, npad, m), dev, mode, f32=False); ds1.f = da1.f
+            ops.softmax_bwd_(p1.view(-1, m), ds1.f.view(-1, m), ds1.hi, ds1.lo, write_f32=not lowp)
         ops.softmax_bwd_(a2_f.view(-1, m), da2.view(-1, m))
         ops.softmax_bwd_(p3.view(-1, npad), ds3.f.view(-1, npad), ds3.hi, ds3.lo, write_f32=not lowp)
         if lowp:
-            ds1.f = ds3.f = None
+            ds3.f = None
+            if not fuse_a1:
+                ds1.f = None
         ds2 = TB.of(da2, mode)
         # ---- similarities; the landmark-mean backward (dq[t] += dql[t // l] / l, same for k) rides in the epilogue of
         #      the dq / dk contractions, which also emit the bf16 copy of dqkv for the projection backward
         l = npad // m
-        dkl = mm(ds1.T(), q_b)                                                                  # dkl = dS1^T q
-        mm(ds2.T(), ql_b, dkl, beta=1.0)
+        dkl = mm(ds2.T(), ql_b)                                                                 # dkl = dS2^T ql (+ dS1^T q below)
         dql = mm(ds2, kl_b)
         mm(ds3, k_b, dql, beta=1.0)
         dq_b = TB(dq, *(hv(t, 0) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
         dk_b = TB(dk, *(hv(t, 1) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
-        mm(ds1, kl_b, dq_b, rowtab=dql.f, rowdiv=l, rowtab_scale=1.0 / l)                       # dq = dS1 kl + bcast(dql)/l
+        if fuse_a1:
+            # dA1 = dout W^T, softmax backward, dq = dS1 kl + bcast(dql)/l and dkl += dS1^T q in one tcgen05 kernel
+            check(lib.sml_nystrom_a1_bwd(ptr(dmerged.hi), ptr(wm_b.hi), ptr(a1.hi), ptr(kl_b.hi), ptr(qkv.hi), ptr(dql.f), ptr(dqkv.f),
+                                         ptr(dqkv.hi), ptr(dkl.f), c_i32(b), c_i32(npad), c_i32(h), c_i32(d), c_i32(m), stream()),
+                  "nystrom_a1_bwd")
+        else:
+            mm(ds1.T(), q_b, dkl, beta=1.0)                                                     # dkl += dS1^T q
+            mm(ds1, kl_b, dq_b, rowtab=dql.f, rowdiv=l, rowtab_scale=1.0 / l)                   # dq = dS1 kl + bcast(dql)/l
         mm(ds3.T(), ql_b, dk_b, rowtab=dkl.f, rowdiv=l, rowtab_scale=1.0 / l)                   # dk = dS3^T ql + bcast(dkl)/l
         if tc and not fused_cvt:
             s = ops.to_bf16(dqkv.f, split=(mode == "bf16x3"))
@@ -282,6 +299,10 @@ class NystromAttentionFn(torch.autograd.Function):
         else:
             dx = dxp[:, pad:]
         return dx, dw_qkv, dw_out, db_out, dw_conv, dln_w, dln_b, None, None, None, None, None
+
+
+def fused_cvt_ok(ksize):
+    return ksize == 33
 
 
 def nystrom_attention(x, w_qkv, w_out, b_out, w_conv, heads, num_landmarks, pinv_iterations, precision="fp32",
