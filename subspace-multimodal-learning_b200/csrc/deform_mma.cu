@@ -1,0 +1,971 @@
+// deform_mma.cu — tensor-core version of the fused deformable attention (models/DeformableAttention1D.py:60-102,
+// 211-231; models/DeformableAttention2D.py:120-157, 292-312).
+//
+// The continuous-position-bias MLP is evaluated per (query, key) pair:  Linear(CD,32) ReLU Linear(32,32) ReLU Linear(32,1).
+// Its 32x32 layer is 2 kFLOP of the 2.2 kFLOP per pair, so it is run as a [16 pairs x 32] x [32 x 32] warp-level MMA:
+// every thread builds its slice of the layer-1 activations directly in the A-fragment registers (no shared-memory round
+// trip), the accumulators come back in registers, and ReLU + layer 3 is a thread-local dot product finished by a
+// 4-lane reduction.  Q K^T and P V run on the same register-fragment pipeline (flash-attention style, online softmax).
+// Precision: SPLIT = true runs every product as bf16 hi/lo 3-pass (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate;
+// ~2^-16 relative, meets the fp32 tolerance), SPLIT = false is plain bf16 operands.
+//
+// Per pair the CUDA cores still do ~110 (bf16) / ~160 (split) operations (signed-log distance, layer 1, packing, ReLU,
+// layer 3), which bounds the kernel; the MMA work hides under it.
+#include "common.cuh"
+#include "deform_attn.cuh"
+
+namespace sml {
+
+constexpr int MQ = 64;        // queries per CTA (4 warps x 16 rows)
+constexpr int MTHREADS = 128;
+constexpr int MLD = 72;       // bf16 row stride of the 64-wide operand tiles (144 B: conflict-free fragment loads)
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {       // low 16 bits <- lo
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+template <bool SPLIT>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(a, b);
+  if (SPLIT) lo = pack_bf16(a - bf16_lo_f(hi), b - bf16_hi_f(hi));
+  else lo = 0u;
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// d += a b with hi/lo operands (small terms first)
+template <bool SPLIT>
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                     uint32_t bl0, uint32_t bl1) {
+  if (SPLIT) {
+    mma16816(d, al, bh0, bh1);
+    mma16816(d, ah, bl0, bl1);
+  }
+  mma16816(d, ah, bh0, bh1);
+}
+// three-term bf16 split (24 mantissa bits: exact for fp32 inputs) and the 6-pass product that keeps every term above 2^-24
+__device__ __forceinline__ void split3(float a, float b, uint32_t& h, uint32_t& m, uint32_t& l) {
+  h = pack_bf16(a, b);
+  const float ra = a - bf16_lo_f(h), rb = b - bf16_hi_f(h);
+  m = pack_bf16(ra, rb);
+  l = pack_bf16(ra - bf16_lo_f(m), rb - bf16_hi_f(m));
+}
+__device__ __forceinline__ void mma6(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&am)[4], const uint32_t (&al)[4],
+                                     uint32_t bh0, uint32_t bh1, uint32_t bm0, uint32_t bm1, uint32_t bl0, uint32_t bl1) {
+  mma16816(d, al, bh0, bh1);
+  mma16816(d, ah, bl0, bl1);
+  mma16816(d, am, bm0, bm1);
+  mma16816(d, am, bh0, bh1);
+  mma16816(d, ah, bm0, bm1);
+  mma16816(d, ah, bh0, bh1);
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
+  uint32_t d;
+  asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
+  return d;
+}
+// sign(x) log(|x| + 1) (1D.py:93-94, 2D.py:150-151); MUFU.LG2 based (abs. error < 1e-6 on |x| <= 4)
+__device__ __forceinline__ float slog_fast(float x) { return copysignf(__logf(fabsf(x) + 1.f), x); }
+
+// fp32 rows [rows x 64] of a token-major tensor -> bf16 hi (/lo) tiles [64][MLD]; rows >= limit are zero-filled
+template <bool SPLIT, int ROWS>
+__device__ __forceinline__ void load_tile(__nv_bfloat16 (*hi)[MLD], __nv_bfloat16 (*lo)[MLD], const float* __restrict__ src,
+                                          int64_t row_stride, int row0, int limit) {
+  for (int e = threadIdx.x; e < ROWS * 16; e += MTHREADS) {
+    const int r = e >> 4, c4 = (e & 15) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < limit) x = *reinterpret_cast<const float4*>(src + (int64_t)(row0 + r) * row_stride + c4);
+    uint32_t h0, l0, h1, l1;
+    split2<SPLIT>(x.x, x.y, h0, l0);
+    split2<SPLIT>(x.z, x.w, h1, l1);
+    *reinterpret_cast<uint2*>(&hi[r][c4]) = make_uint2(h0, h1);
+    if (SPLIT) *reinterpret_cast<uint2*>(&lo[r][c4]) = make_uint2(l0, l1);
+  }
+}
+
+// same, three planes (hi / mid / lo): operands of the fp32-exact products (P V and dO V^T, see the SPLIT note on delta)
+template <int ROWS>
+__device__ __forceinline__ void load_tile3(__nv_bfloat16 (*p0)[MLD], __nv_bfloat16 (*p1)[MLD], __nv_bfloat16 (*p2)[MLD],
+                                           const float* __restrict__ src, int64_t row_stride, int row0, int limit) {
+  for (int e = threadIdx.x; e < ROWS * 16; e += MTHREADS) {
+    const int r = e >> 4, c4 = (e & 15) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < limit) x = *reinterpret_cast<const float4*>(src + (int64_t)(row0 + r) * row_stride + c4);
+    uint32_t h0, m0, l0, h1, m1, l1;
+    split3(x.x, x.y, h0, m0, l0);
+    split3(x.z, x.w, h1, m1, l1);
+    *reinterpret_cast<uint2*>(&p0[r][c4]) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(&p1[r][c4]) = make_uint2(m0, m1);
+    *reinterpret_cast<uint2*>(&p2[r][c4]) = make_uint2(l0, l1);
+  }
+}
+
+// Per-thread constants of the CPB MLP in MMA-fragment order.  Thread (g = lane / 4, t = lane % 4):
+//   layer-1 hidden units k(s, e) = 16 s + 2 t + (e & 1) + 8 (e >> 1)   (the A-fragment columns of k-step s)
+//   layer-2 outputs      c(j, e) = 8 j + 2 t + e                        (the C-fragment columns of n-tile j)
+template <int CD, bool SPLIT>
+struct CpbRegs {
+  float w1x[2][4], w1y[2][4], b1[2][4];
+  float b2[4][2], w3[4][2], b3;
+  uint32_t wh[4][2][2], wl[4][2][2];      // B fragments of W2^T: [n-tile j][k-step s][reg]
+
+  __device__ __forceinline__ void load(const float* __restrict__ cpb, int OUT, int o, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const float* W1 = cpb; const float* B1 = W1 + CPB_H * CD; const float* W2 = B1 + CPB_H;
+    const float* B2 = W2 + CPB_H * CPB_H; const float* W3 = B2 + CPB_H; const float* B3 = W3 + OUT * CPB_H;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = 16 * s + 2 * t + (e & 1) + 8 * (e >> 1);
+        w1x[s][e] = W1[k * CD];
+        w1y[s][e] = CD == 2 ? W1[k * CD + 1] : 0.f;
+        b1[s][e] = B1[k];
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { b2[j][e] = B2[8 * j + 2 * t + e]; w3[j][e] = W3[o * CPB_H + 8 * j + 2 * t + e]; }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float* row = W2 + (8 * j + g) * CPB_H + 16 * s + 2 * t;      // B[k][n] = W2[c = n][k]
+        split2<SPLIT>(row[0], row[1], wh[j][s][0], wl[j][s][0]);
+        split2<SPLIT>(row[8], row[9], wh[j][s][1], wl[j][s][1]);
+      }
+    }
+    b3 = B3[o];
+  }
+};
+
+// layer 1 for the two pairs (rows g and g + 8 of the 16-pair tile): A fragments of relu(W1 pos + b1)
+template <int CD, bool SPLIT>
+__device__ __forceinline__ void cpb_layer1(const CpbRegs<CD, SPLIT>& c, float ax0, float ay0, float ax1, float ay1,
+                                           uint32_t (&ah)[2][4], uint32_t (&al)[2][4], float (*hraw)[2][4] = nullptr) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    float h0[4], h1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float u0 = fmaf(c.w1x[s][e], ax0, c.b1[s][e]), u1 = fmaf(c.w1x[s][e], ax1, c.b1[s][e]);
+      if (CD == 2) { u0 = fmaf(c.w1y[s][e], ay0, u0); u1 = fmaf(c.w1y[s][e], ay1, u1); }
+      h0[e] = fmaxf(u0, 0.f); h1[e] = fmaxf(u1, 0.f);
+      if (hraw) { hraw[s][0][e] = h0[e]; hraw[s][1][e] = h1[e]; }
+    }
+    split2<SPLIT>(h0[0], h0[1], ah[s][0], al[s][0]);
+    split2<SPLIT>(h1[0], h1[1], ah[s][1], al[s][1]);
+    split2<SPLIT>(h0[2], h0[3], ah[s][2], al[s][2]);
+    split2<SPLIT>(h1[2], h1[3], ah[s][3], al[s][3]);
+  }
+}
+// layer 2 pre-activations: acc[j] = C fragment (rows g / g+8, columns c(j, 0..1)) of b2 + h1 W2^T
+template <int CD, bool SPLIT>
+__device__ __forceinline__ void cpb_layer2(const CpbRegs<CD, SPLIT>& c, const uint32_t (&ah)[2][4], const uint32_t (&al)[2][4],
+                                           float (&acc)[4][4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    acc[j][0] = c.b2[j][0]; acc[j][1] = c.b2[j][1]; acc[j][2] = c.b2[j][0]; acc[j][3] = c.b2[j][1];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) mma3<SPLIT>(acc[j], ah[s], al[s], c.wh[j][s][0], c.wh[j][s][1], c.wl[j][s][0], c.wl[j][s][1]);
+  }
+}
+
+template <bool SPLIT>
+struct FwdSmem {
+  __nv_bfloat16 Q[SPLIT ? 2 : 1][MQ][MLD];
+  __nv_bfloat16 K[SPLIT ? 2 : 1][64][MLD];
+  __nv_bfloat16 V[SPLIT ? 3 : 2][64][MLD];     // P V always runs one precision level above the rest (see the backward's delta)
+  float kpos[64][2];
+};
+
+// grid (ceil(n / 64), heads, B), 128 threads.  q pre-scaled by d^-1/2.  out [b, n, inner], lse [b, heads, n].
+template <int CD, bool SPLIT>
+__global__ void __launch_bounds__(MTHREADS) deform_attn_fwd_mma_kernel(const AttnCfg cf, const float* __restrict__ q,
+                                                                       const float* __restrict__ k, const float* __restrict__ v,
+                                                                       const float* __restrict__ vs, const float* __restrict__ cpb,
+                                                                       float* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmem<SPLIT>& sm = *reinterpret_cast<FwdSmem<SPLIT>*>(smem_raw);
+  constexpr int LO = SPLIT ? 1 : 0;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
+  const int grp = head / cf.OUT, o = head % cf.OUT;
+  const int bg = b * cf.G + grp;
+  CpbRegs<CD, SPLIT> cr;
+  cr.load(cpb, cf.OUT, o, lane);
+  load_tile<SPLIT, MQ>(sm.Q[0], sm.Q[LO], q + (int64_t)b * cf.n * cf.inner + head * AD, cf.inner, q0, cf.n);
+  const int r0 = w * 16 + g, r1 = r0 + 8;               // my two query rows inside the CTA tile
+  float qx0, qy0, qx1, qy1;
+  query_pos(cf, q0 + r0, qx0, qy0);
+  query_pos(cf, q0 + r1, qx1, qy1);
+  float oacc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[j][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // l: per-thread partial row sums
+  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
+  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+
+  for (int k0 = 0; k0 < cf.nkv; k0 += 64) {
+    __syncthreads();
+    load_tile<SPLIT, 64>(sm.K[0], sm.K[LO], kb, cf.inner, k0, cf.nkv);
+    if (SPLIT) load_tile3<64>(sm.V[0], sm.V[LO], sm.V[2 * LO], vb, cf.inner, k0, cf.nkv);
+    else load_tile<true, 64>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
+    if (tid < 64) {
+      const bool ok = k0 + tid < cf.nkv;
+      sm.kpos[tid][0] = ok ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD] : 0.f;
+      sm.kpos[tid][1] = (ok && CD == 2) ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD + 1] : 0.f;
+    }
+    __syncthreads();
+    // ---- S = Q K^T : C fragments s[j] = rows (r0, r1) x keys 8 j + 2 t + {0, 1}
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4] = {0u, 0u, 0u, 0u};
+      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r0][16 * ks + 2 * t]);
+      ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r1][16 * ks + 2 * t]);
+      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r0][16 * ks + 2 * t + 8]);
+      ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r1][16 * ks + 2 * t + 8]);
+      if (SPLIT) {
+        al[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r0][16 * ks + 2 * t]);
+        al[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r1][16 * ks + 2 * t]);
+        al[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r0][16 * ks + 2 * t + 8]);
+        al[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r1][16 * ks + 2 * t + 8]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.K[0][8 * j + g][16 * ks + 2 * t]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.K[0][8 * j + g][16 * ks + 2 * t + 8]);
+        uint32_t bl0 = 0u, bl1 = 0u;
+        if (SPLIT) {
+          bl0 = *reinterpret_cast<const uint32_t*>(&sm.K[LO][8 * j + g][16 * ks + 2 * t]);
+          bl1 = *reinterpret_cast<const uint32_t*>(&sm.K[LO][8 * j + g][16 * ks + 2 * t + 8]);
+        }
+        mma3<SPLIT>(s[j], ah, al, bh0, bh1, bl0, bl1);
+      }
+    }
+    // ---- + continuous position bias: for key 8 j + u the 16 queries of this warp form one 16-pair MMA tile
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      float bias[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float2 kp = *reinterpret_cast<const float2*>(sm.kpos[8 * j + u]);
+        const float ax0 = slog_fast(qx0 - kp.x), ax1 = slog_fast(qx1 - kp.x);
+        const float ay0 = CD == 2 ? slog_fast(qy0 - kp.y) : 0.f, ay1 = CD == 2 ? slog_fast(qy1 - kp.y) : 0.f;
+        uint32_t ah[2][4], al[2][4];
+        cpb_layer1<CD, SPLIT>(cr, ax0, ay0, ax1, ay1, ah, al);
+        float acc[4][4];
+        cpb_layer2<CD, SPLIT>(cr, ah, al, acc);
+        float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          p0 = fmaf(cr.w3[jj][0], fmaxf(acc[jj][0], 0.f), p0); p0 = fmaf(cr.w3[jj][1], fmaxf(acc[jj][1], 0.f), p0);
+          p1 = fmaf(cr.w3[jj][0], fmaxf(acc[jj][2], 0.f), p1); p1 = fmaf(cr.w3[jj][1], fmaxf(acc[jj][3], 0.f), p1);
+        }
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 2); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+        if ((u >> 1) == t) { bias[u & 1] = p0 + cr.b3; bias[2 + (u & 1)] = p1 + cr.b3; }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)          // static register indices (the j loop stays rolled)
+        if (jj == j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[jj][e] += bias[e];
+        }
+    }
+    // ---- online softmax on the fragments (rows r0 / r1 live in the 4 lanes of a quad)
+    float mt0 = -INFINITY, mt1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (k0 + 8 * j + 2 * t + e >= cf.nkv) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
+        mt0 = fmaxf(mt0, s[j][e]); mt1 = fmaxf(mt1, s[j][2 + e]);
+      }
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 1)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 1));
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 2)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 2));
+    const float mn0 = fmaxf(m0, mt0), mn1 = fmaxf(m1, mt1);
+    const float al0 = m0 == -INFINITY ? 0.f : __expf(m0 - mn0), al1 = m1 == -INFINITY ? 0.f : __expf(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= al0; l1 *= al1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { oacc[j][0] *= al0; oacc[j][1] *= al0; oacc[j][2] *= al1; oacc[j][3] *= al1; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float p0 = __expf(s[j][e] - mn0), p1 = __expf(s[j][2 + e] - mn1);
+        l0 += p0; l1 += p1;
+        if (cf.p_drop > 0.f) {
+          const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
+          const unsigned long long base = (unsigned long long)(b * cf.heads + head) * cf.n;
+          p0 = pair_hash(cf.seed, (base + (q0 + r0)) * cf.nkv + key) >= thresh ? p0 * keep_scale : 0.f;
+          p1 = pair_hash(cf.seed, (base + (q0 + r1)) * cf.nkv + key) >= thresh ? p1 * keep_scale : 0.f;
+        }
+        s[j][e] = p0; s[j][2 + e] = p1;
+      }
+    // ---- O += P V : A fragments straight from the probability fragments, B fragments by transposing ldmatrix
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], am[4], al[4];
+      if (SPLIT) {
+        split3(s[2 * ks][0], s[2 * ks][1], ah[0], am[0], al[0]);
+        split3(s[2 * ks][2], s[2 * ks][3], ah[1], am[1], al[1]);
+        split3(s[2 * ks + 1][0], s[2 * ks + 1][1], ah[2], am[2], al[2]);
+        split3(s[2 * ks + 1][2], s[2 * ks + 1][3], ah[3], am[3], al[3]);
+      } else {
+        split2<true>(s[2 * ks][0], s[2 * ks][1], ah[0], al[0]);
+        split2<true>(s[2 * ks][2], s[2 * ks][3], ah[1], al[1]);
+        split2<true>(s[2 * ks + 1][0], s[2 * ks + 1][1], ah[2], al[2]);
+        split2<true>(s[2 * ks + 1][2], s[2 * ks + 1][3], ah[3], al[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t bh0, bh1;
+        ldmatrix_x2_trans(bh0, bh1, &sm.V[0][16 * ks + (lane & 15)][8 * j]);
+        if (SPLIT) {
+          uint32_t bm0, bm1, bl0, bl1;
+          ldmatrix_x2_trans(bm0, bm1, &sm.V[LO][16 * ks + (lane & 15)][8 * j]);
+          ldmatrix_x2_trans(bl0, bl1, &sm.V[2 * LO][16 * ks + (lane & 15)][8 * j]);
+          mma6(oacc[j], ah, am, al, bh0, bh1, bm0, bm1, bl0, bl1);
+        } else {
+          uint32_t bl0, bl1;
+          ldmatrix_x2_trans(bl0, bl1, &sm.V[1][16 * ks + (lane & 15)][8 * j]);
+          mma3<true>(oacc[j], ah, al, bh0, bh1, bl0, bl1);
+        }
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  if (q0 + r0 < cf.n) {
+    float* orow = out + ((int64_t)b * cf.n + q0 + r0) * cf.inner + head * AD + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][0] * i0, oacc[j][1] * i0);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0] = m0 + logf(l0);
+  }
+  if (q0 + r1 < cf.n) {
+    float* orow = out + ((int64_t)b * cf.n + q0 + r1) * cf.inner + head * AD + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][2] * i1, oacc[j][3] * i1);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1] = m1 + logf(l1);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ backward
+// One CTA per (64-query tile, head, batch), 4 warps x 16 query rows, key tiles of 32.  Per key tile:
+//   phase 1  S = Q K^T and dP = dO V^T (MMA) -> fp32 staging tiles in shared memory (warp-private rows)
+//   phase 2  per key: the warp's 16 (query, key) pairs form one MMA tile: CPB forward (layers 1-3), P = exp(S + bias - lse),
+//            dS = P (dP keep - delta); CPB backward: dh2 -> dh1 = dh2 W2 (MMA) -> layer-1 / coordinate gradients, and
+//            dW2 += dh2^T h1 as an MMA over the pair axis (operands transposed in registers with movmatrix).
+//            P keep and dS are written as bf16 (hi/lo) tiles for phase 3.
+//   phase 3  dQ += dS K (registers), dK += dS^T Q and dV += (P keep)^T dO per 16-key x 32-dim warp slice -> global atomics.
+// CPB parameter gradients stay in registers for the whole kernel and leave as one partial row per CTA.
+constexpr int BK = 32;        // keys per tile
+constexpr int PLD = 40;       // bf16 row stride of the P / dS tiles (80 B rows: conflict-free ldmatrix)
+constexpr int NRED = CPB_H * 2 + CPB_H + CPB_H * CPB_H + CPB_H + CPB_H + 1;
+
+template <bool SPLIT>
+struct BwdSmem {
+  // dO and V carry one more bf16 plane than the other operands: dP = dO V^T (and O = P V in the forward) run one precision
+  // level above the rest (SPLIT: 3-term / 6-pass = fp32-exact; plain bf16 mode: hi/lo 3-pass) so that delta = dO . O equals
+  // sum_j P dP to rounding and sum_j dS_ij cancels as it does in exact arithmetic; every CPB parameter gradient is a sum of
+  // dS against a slowly varying factor and inherits that cancellation.
+  __nv_bfloat16 Q[SPLIT ? 2 : 1][MQ][MLD], dO[SPLIT ? 3 : 2][MQ][MLD];
+  __nv_bfloat16 K[SPLIT ? 2 : 1][BK][MLD], V[SPLIT ? 3 : 2][BK][MLD];
+  __nv_bfloat16 P[SPLIT ? 2 : 1][MQ][PLD], dS[SPLIT ? 2 : 1][MQ][PLD];     // `red` aliases P at the end of the kernel
+  float dQ[32][MTHREADS];            // thread-private dQ accumulators (C-fragment order), live across key tiles
+  float stg[4][2][16][9];            // per warp: S and dP of the current 8-key group (fp32)
+  float c1[4][24];                   // layer-1 constants by t: w1x[2][4], w1y[2][4], b1[2][4]
+  float c2[4][16];                   // b2[4][2], w3[4][2] by t
+  float kpos[BK][2], dkpos[BK][2];
+};
+// volatile shared-memory vector load: re-issued at every use instead of being held in (spilled) registers
+__device__ __forceinline__ float4 lds128v(const float* p) {
+  float4 r;
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+  return r;
+}
+
+__device__ __forceinline__ void store_bf16_split(__nv_bfloat16* hi, __nv_bfloat16* lo, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *hi = h;
+  if (lo) *lo = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// sum over the 32 lanes of N per-lane values, scattered: the lanes flagged by `owner` end up holding element `idx`
+template <int N>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane, int& idx, bool& owner) {
+  static_assert(N == 8 || N == 16, "N");
+  idx = 0;
+  int M = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, M >>= 1) {
+    const bool up = (lane & M) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+    }
+    idx = idx * 2 + (up ? 1 : 0);
+  }
+  float r = v[0];
+  if (N == 16) { r += __shfl_xor_sync(0xffffffffu, r, 1); owner = (lane & 1) == 0; }
+  else { r += __shfl_xor_sync(0xffffffffu, r, 2); r += __shfl_xor_sync(0xffffffffu, r, 1); owner = (lane & 3) == 0; }
+  return r;
+}
+
+template <int CD, bool SPLIT>
+__global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
+    const AttnCfg cf, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const float* __restrict__ vs, const float* __restrict__ cpb, const float* __restrict__ out,
+    const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dk,
+    float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem<SPLIT>& sm = *reinterpret_cast<BwdSmem<SPLIT>*>(smem_raw);
+  constexpr int LO = SPLIT ? 1 : 0;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
+  const int grp = head / cf.OUT, o = head % cf.OUT;
+  const int bg = b * cf.G + grp;
+  // ---- constants: W2 fragments in registers (both orientations), the small vectors in shared memory (by t)
+  uint32_t wh[4][2][2], wl[4][2][2];        // layer 2:  B[k][n = c] = W2[c][k]      [n-tile j][k-step s][reg]
+  uint32_t wth[4][2][2], wtl[4][2][2];      // dh1 = dh2 W2:  B[k' = c][n = k] = W2[c][k]   [n-tile jn][k-step s'][reg]
+  float b3;
+  {
+    const float* W1 = cpb; const float* B1 = W1 + CPB_H * CD; const float* W2 = B1 + CPB_H;
+    const float* B2 = W2 + CPB_H * CPB_H; const float* W3 = B2 + CPB_H; const float* B3 = W3 + cf.OUT * CPB_H;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float* row = W2 + (8 * j + g) * CPB_H + 16 * s + 2 * t;
+        split2<SPLIT>(row[0], row[1], wh[j][s][0], wl[j][s][0]);
+        split2<SPLIT>(row[8], row[9], wh[j][s][1], wl[j][s][1]);
+        const float* col = W2 + (16 * s + 2 * t) * CPB_H + 8 * j + g;
+        split2<SPLIT>(col[0], col[CPB_H], wth[j][s][0], wtl[j][s][0]);
+        split2<SPLIT>(col[8 * CPB_H], col[9 * CPB_H], wth[j][s][1], wtl[j][s][1]);
+      }
+    b3 = B3[o];
+    if (tid < 4 * 24) {
+      const int tt = tid / 24, i = tid % 24, which = i / 8, s = (i % 8) / 4, e = i % 4;
+      const int kk = 16 * s + 2 * tt + (e & 1) + 8 * (e >> 1);
+      sm.c1[tt][i] = which == 0 ? W1[kk * CD] : (which == 1 ? (CD == 2 ? W1[kk * CD + 1] : 0.f) : B1[kk]);
+    }
+    if (tid < 4 * 16) {
+      const int tt = tid / 16, i = tid % 16, which = i / 8, j = (i % 8) / 2, e = i % 2;
+      const int c = 8 * j + 2 * tt + e;
+      sm.c2[tt][i] = which == 0 ? B2[c] : W3[o * CPB_H + c];
+    }
+  }
+  const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
+  load_tile<SPLIT, MQ>(sm.Q[0], sm.Q[LO], q + qoff, cf.inner, q0, cf.n);
+  if (SPLIT) load_tile3<MQ>(sm.dO[0], sm.dO[LO], sm.dO[2 * LO], dout + qoff, cf.inner, q0, cf.n);
+  else load_tile<true, MQ>(sm.dO[0], sm.dO[1], dout + qoff, cf.inner, q0, cf.n);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sm.dQ[i][tid] = 0.f;
+  const int r0 = w * 16 + g, r1 = r0 + 8;
+  const bool ok0 = q0 + r0 < cf.n, ok1 = q0 + r1 < cf.n;
+  float qx0, qy0, qx1, qy1;
+  query_pos(cf, q0 + r0, qx0, qy0);
+  query_pos(cf, q0 + r1, qx1, qy1);
+  // delta = rowsum(dO * O), lse (the four lanes of a quad share a row)
+  float delta0 = 0.f, delta1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;
+  {
+    if (ok0) {
+      const float* orow = out + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta0 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta0))));
+      }
+      lse0 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0];
+    }
+    if (ok1) {
+      const float* orow = out + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta1 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta1))));
+      }
+      lse1 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1];
+    }
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 1); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 1);
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 2); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 2);
+  }
+  // CPB parameter gradient accumulators (fragment order)
+  float gW2[2][4][4];                       // C fragments of dW2[c][k]: [m-tile of c][n-tile of k]
+  float gb1[2][4], gW1x[2][4], gW1y[2][4];  // by hidden unit k(s, e)
+  float gb2[4][2], gw3[4][2], gb3 = 0.f;    // by output c(j, e)
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      gb1[a][c] = 0.f; gW1x[a][c] = 0.f; gW1y[a][c] = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gW2[a][c][e] = 0.f;
+    }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { gb2[j][0] = 0.f; gb2[j][1] = 0.f; gw3[j][0] = 0.f; gw3[j][1] = 0.f; }
+  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
+  const unsigned long long hbase = (unsigned long long)(b * cf.heads + head) * cf.n;
+  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* c1 = sm.c1[t];
+  const float* c2 = sm.c2[t];
+  float (*stS)[9] = sm.stg[w][0];
+  float (*stD)[9] = sm.stg[w][1];
+
+  for (int k0 = 0; k0 < cf.nkv; k0 += BK) {
+    __syncthreads();
+    load_tile<SPLIT, BK>(sm.K[0], sm.K[LO], kb, cf.inner, k0, cf.nkv);
+    if (SPLIT) load_tile3<BK>(sm.V[0], sm.V[LO], sm.V[2 * LO], vb, cf.inner, k0, cf.nkv);
+    else load_tile<true, BK>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
+    if (tid < BK) {
+      const bool ok = k0 + tid < cf.nkv;
+      sm.kpos[tid][0] = ok ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD] : 0.f;
+      sm.kpos[tid][1] = (ok && CD == 2) ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD + 1] : 0.f;
+      sm.dkpos[tid][0] = 0.f; sm.dkpos[tid][1] = 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < BK / 8; ++j) {
+      // ---- phase 1: S = Q K^T and dP = dO V^T of my 16 rows x this 8-key group -> warp-private staging
+      {
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t ah[4], al[4] = {0u, 0u, 0u, 0u}, gh[4];
+          const int c0 = 16 * ks + 2 * t;
+          ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r1][c0]);
+          ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[0][r1][c0 + 8]);
+          gh[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0]);     gh[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0]);
+          gh[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0 + 8]); gh[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0 + 8]);
+          const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(&sm.K[0][8 * j + g][c0]);
+          const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(&sm.K[0][8 * j + g][c0 + 8]);
+          const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0]);
+          const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0 + 8]);
+          if (SPLIT) {
+            uint32_t gm[4], gl[4];
+            al[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r0][c0]);     al[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r1][c0]);
+            al[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r0][c0 + 8]); al[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[LO][r1][c0 + 8]);
+            gm[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[LO][r0][c0]);     gm[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[LO][r1][c0]);
+            gm[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[LO][r0][c0 + 8]); gm[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[LO][r1][c0 + 8]);
+            gl[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[2 * LO][r0][c0]);     gl[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[2 * LO][r1][c0]);
+            gl[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[2 * LO][r0][c0 + 8]); gl[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[2 * LO][r1][c0 + 8]);
+            const uint32_t kl0 = *reinterpret_cast<const uint32_t*>(&sm.K[LO][8 * j + g][c0]);
+            const uint32_t kl1 = *reinterpret_cast<const uint32_t*>(&sm.K[LO][8 * j + g][c0 + 8]);
+            const uint32_t vm0 = *reinterpret_cast<const uint32_t*>(&sm.V[LO][8 * j + g][c0]);
+            const uint32_t vm1 = *reinterpret_cast<const uint32_t*>(&sm.V[LO][8 * j + g][c0 + 8]);
+            const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(&sm.V[2 * LO][8 * j + g][c0]);
+            const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(&sm.V[2 * LO][8 * j + g][c0 + 8]);
+            mma3<true>(s, ah, al, kh0, kh1, kl0, kl1);
+            mma6(dp, gh, gm, gl, vh0, vh1, vm0, vm1, vl0, vl1);
+          } else {
+            uint32_t gl[4];
+            gl[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0]);     gl[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0]);
+            gl[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0 + 8]); gl[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0 + 8]);
+            const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0]);
+            const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0 + 8]);
+            mma16816(s, ah, kh0, kh1);
+            mma3<true>(dp, gh, gl, vh0, vh1, vl0, vl1);
+          }
+        }
+        __syncwarp();
+        stS[g][2 * t] = s[0]; stS[g][2 * t + 1] = s[1]; stS[g + 8][2 * t] = s[2]; stS[g + 8][2 * t + 1] = s[3];
+        stD[g][2 * t] = dp[0]; stD[g][2 * t + 1] = dp[1]; stD[g + 8][2 * t] = dp[2]; stD[g + 8][2 * t + 1] = dp[3];
+        __syncwarp();
+      }
+      // ---- phase 2: CPB forward + backward, one key (16 pairs) per MMA tile
+      float kg[8 * CD];                                  // per-thread partials of d(bias)/d(key position), by (u, coord)
+#pragma unroll 1
+      for (int u = 0; u < 8; ++u) {
+        const int key = 8 * j + u;
+        const float2 kp = *reinterpret_cast<const float2*>(sm.kpos[key]);
+        const float dx0 = qx0 - kp.x, dx1 = qx1 - kp.x, dy0 = qy0 - kp.y, dy1 = qy1 - kp.y;
+        const float ax0 = slog_fast(dx0), ax1 = slog_fast(dx1);
+        const float ay0 = CD == 2 ? slog_fast(dy0) : 0.f, ay1 = CD == 2 ? slog_fast(dy1) : 0.f;
+        // layer 1 -> A fragments (hidden unit of (s, e): 16 s + 2 t + (e & 1) + 8 (e >> 1))
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const float4 wx = lds128v(c1 + 4 * s), wy = lds128v(c1 + 8 + 4 * s), bb = lds128v(c1 + 16 + 4 * s);
+          const float wxa[4] = {wx.x, wx.y, wx.z, wx.w}, wya[4] = {wy.x, wy.y, wy.z, wy.w}, bba[4] = {bb.x, bb.y, bb.z, bb.w};
+          float h0[4], h1[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float u0 = fmaf(wxa[e], ax0, bba[e]), u1 = fmaf(wxa[e], ax1, bba[e]);
+            if (CD == 2) { u0 = fmaf(wya[e], ay0, u0); u1 = fmaf(wya[e], ay1, u1); }
+            h0[e] = fmaxf(u0, 0.f); h1[e] = fmaxf(u1, 0.f);
+          }
+          split2<SPLIT>(h0[0], h0[1], ah[s][0], al[s][0]);
+          split2<SPLIT>(h1[0], h1[1], ah[s][1], al[s][1]);
+          split2<SPLIT>(h0[2], h0[3], ah[s][2], al[s][2]);
+          split2<SPLIT>(h1[2], h1[3], ah[s][3], al[s][3]);
+        }
+        // layer 2 pre-activations
+        float acc[4][4];
+        {
+          const float4 ba = lds128v(c2), bbv = lds128v(c2 + 4);
+          const float b2v[8] = {ba.x, ba.y, ba.z, ba.w, bbv.x, bbv.y, bbv.z, bbv.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            acc[jj][0] = b2v[2 * jj]; acc[jj][1] = b2v[2 * jj + 1]; acc[jj][2] = b2v[2 * jj]; acc[jj][3] = b2v[2 * jj + 1];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) mma3<SPLIT>(acc[jj], ah[s], al[s], wh[jj][s][0], wh[jj][s][1], wl[jj][s][0], wl[jj][s][1]);
+          }
+        }
+        const float4 w3a = lds128v(c2 + 8), w3b = lds128v(c2 + 12);
+        const float w3v[8] = {w3a.x, w3a.y, w3a.z, w3a.w, w3b.x, w3b.y, w3b.z, w3b.w};
+        float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          p0 = fmaf(w3v[2 * jj], fmaxf(acc[jj][0], 0.f), p0); p0 = fmaf(w3v[2 * jj + 1], fmaxf(acc[jj][1], 0.f), p0);
+          p1 = fmaf(w3v[2 * jj], fmaxf(acc[jj][2], 0.f), p1); p1 = fmaf(w3v[2 * jj + 1], fmaxf(acc[jj][3], 0.f), p1);
+        }
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+        p0 += __shfl_xor_sync(0xffffffffu, p0, 2); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+        // probabilities and logit gradients of the two pairs (computed by all four lanes of the quad)
+        const bool kok = k0 + key < cf.nkv;
+        const float P0 = kok ? __expf(stS[g][u] + p0 + b3 - lse0) : 0.f;
+        const float P1 = kok ? __expf(stS[g + 8][u] + p1 + b3 - lse1) : 0.f;
+        float keep0 = 1.f, keep1 = 1.f;
+        if (cf.p_drop > 0.f) {
+          keep0 = pair_hash(cf.seed, (hbase + (q0 + r0)) * cf.nkv + k0 + key) >= thresh ? keep_scale : 0.f;
+          keep1 = pair_hash(cf.seed, (hbase + (q0 + r1)) * cf.nkv + k0 + key) >= thresh ? keep_scale : 0.f;
+        }
+        const float dS0 = P0 * (stD[g][u] * keep0 - delta0);
+        const float dS1 = P1 * (stD[g + 8][u] * keep1 - delta1);
+        if (t == 0) {
+          store_bf16_split(&sm.P[0][r0][key], SPLIT ? &sm.P[LO][r0][key] : nullptr, P0 * keep0);
+          store_bf16_split(&sm.dS[0][r0][key], SPLIT ? &sm.dS[LO][r0][key] : nullptr, dS0);
+          gb3 += dS0 + dS1;
+        } else if (t == 1) {
+          store_bf16_split(&sm.P[0][r1][key], SPLIT ? &sm.P[LO][r1][key] : nullptr, P1 * keep1);
+          store_bf16_split(&sm.dS[0][r1][key], SPLIT ? &sm.dS[LO][r1][key] : nullptr, dS1);
+        }
+        // layer 3 / second ReLU backward: dh2 (C-fragment layout) and its A fragments for dh1 = dh2 W2
+        uint32_t dah[2][4], dal[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          float d0[2][2], d1[2][2];                         // [n-tile 2 s + i][col e], rows r0 / r1
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int jj = 2 * s + i;
+              const float a0 = acc[jj][e], a1 = acc[jj][2 + e];
+              gw3[jj][e] = fmaf(dS0, fmaxf(a0, 0.f), fmaf(dS1, fmaxf(a1, 0.f), gw3[jj][e]));
+              d0[i][e] = a0 > 0.f ? dS0 * w3v[2 * jj + e] : 0.f;
+              d1[i][e] = a1 > 0.f ? dS1 * w3v[2 * jj + e] : 0.f;
+              gb2[jj][e] += d0[i][e] + d1[i][e];
+            }
+          split2<SPLIT>(d0[0][0], d0[0][1], dah[s][0], dal[s][0]);
+          split2<SPLIT>(d1[0][0], d1[0][1], dah[s][1], dal[s][1]);
+          split2<SPLIT>(d0[1][0], d0[1][1], dah[s][2], dal[s][2]);
+          split2<SPLIT>(d1[1][0], d1[1][1], dah[s][3], dal[s][3]);
+        }
+        // dW2[c][k] += sum_pairs dh2[p][c] h1[p][k]: A = dh2^T, B = h1, both transposed in registers
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t tah[4], tal[4] = {0u, 0u, 0u, 0u};
+          tah[0] = movm_trans(dah[mt][0]); tah[1] = movm_trans(dah[mt][2]); tah[2] = movm_trans(dah[mt][1]); tah[3] = movm_trans(dah[mt][3]);
+          if (SPLIT) { tal[0] = movm_trans(dal[mt][0]); tal[1] = movm_trans(dal[mt][2]); tal[2] = movm_trans(dal[mt][1]); tal[3] = movm_trans(dal[mt][3]); }
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) {
+            const int s = jn >> 1, rb = (jn & 1) * 2;
+            const uint32_t bh0 = movm_trans(ah[s][rb]), bh1 = movm_trans(ah[s][rb + 1]);
+            uint32_t bl0 = 0u, bl1 = 0u;
+            if (SPLIT) { bl0 = movm_trans(al[s][rb]); bl1 = movm_trans(al[s][rb + 1]); }
+            mma3<SPLIT>(gW2[mt][jn], tah, tal, bh0, bh1, bl0, bl1);
+          }
+        }
+        // dh1 = dh2 W2
+        float dh1[4][4];
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+          dh1[jn][0] = 0.f; dh1[jn][1] = 0.f; dh1[jn][2] = 0.f; dh1[jn][3] = 0.f;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) mma3<SPLIT>(dh1[jn], dah[s], dal[s], wth[jn][s][0], wth[jn][s][1], wtl[jn][s][0], wtl[jn][s][1]);
+        }
+        // first ReLU backward; layer-1 parameter gradients; d bias / d (signed-log distance)
+        float dax0 = 0.f, dax1 = 0.f, day0 = 0.f, day1 = 0.f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const float4 wx = lds128v(c1 + 4 * s), wy = lds128v(c1 + 8 + 4 * s);
+          const float wxa[4] = {wx.x, wx.y, wx.z, wx.w}, wya[4] = {wy.x, wy.y, wy.z, wy.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int jn = 2 * s + (e >> 1), c = e & 1;            // hidden unit k(s, e) = 8 jn + 2 t + c
+            const uint32_t m0 = ah[s][(e >> 1) * 2], m1 = ah[s][(e >> 1) * 2 + 1];       // h1 of rows r0 / r1 (bf16 pairs)
+            const bool on0 = c ? (m0 >> 16) != 0u : (m0 & 0xffffu) != 0u;
+            const bool on1 = c ? (m1 >> 16) != 0u : (m1 & 0xffffu) != 0u;
+            const float e0 = on0 ? dh1[jn][c] : 0.f, e1 = on1 ? dh1[jn][2 + c] : 0.f;
+            gb1[s][e] += e0 + e1;
+            gW1x[s][e] = fmaf(e0, ax0, fmaf(e1, ax1, gW1x[s][e]));
+            dax0 = fmaf(wxa[e], e0, dax0); dax1 = fmaf(wxa[e], e1, dax1);
+            if (CD == 2) {
+              gW1y[s][e] = fmaf(e0, ay0, fmaf(e1, ay1, gW1y[s][e]));
+              day0 = fmaf(wya[e], e0, day0); day1 = fmaf(wya[e], e1, day1);
+            }
+          }
+        }
+        // d slog(x)/dx = 1 / (|x| + 1); the key coordinate enters with a minus sign
+        const float kgx = -(__fdividef(dax0, fabsf(dx0) + 1.f) + __fdividef(dax1, fabsf(dx1) + 1.f));
+        const float kgy = CD == 2 ? -(__fdividef(day0, fabsf(dy0) + 1.f) + __fdividef(day1, fabsf(dy1) + 1.f)) : 0.f;
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu)                     // static register indices (the u loop is rolled)
+          if (uu == u) { kg[uu * CD] = kgx; if (CD == 2) kg[uu * CD + 1] = kgy; }
+      }
+      // key-coordinate gradients of this 8-key group: reduce over the warp's 16 queries, then one shared atomic per value
+      {
+        int idx; bool owner;
+        const float r = warp_reduce_scatter<8 * CD>(kg, lane, idx, owner);
+        if (owner) atomicAdd(&sm.dkpos[8 * j + idx / CD][idx % CD], r);
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: dQ += dS K (thread-private accumulators parked in shared memory between key tiles)
+    {
+      float dqacc[8][4];
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dqacc[jd][e] = sm.dQ[jd * 4 + e][tid];
+#pragma unroll
+      for (int ks = 0; ks < BK / 16; ++ks) {
+        uint32_t ah[4], al[4] = {0u, 0u, 0u, 0u};
+        const int c0 = 16 * ks + 2 * t;
+        ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r1][c0]);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[0][r1][c0 + 8]);
+        if (SPLIT) {
+          al[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[LO][r0][c0]);     al[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[LO][r1][c0]);
+          al[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[LO][r0][c0 + 8]); al[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[LO][r1][c0 + 8]);
+        }
+#pragma unroll
+        for (int jd = 0; jd < 8; ++jd) {
+          uint32_t bh0, bh1, bl0 = 0u, bl1 = 0u;
+          ldmatrix_x2_trans(bh0, bh1, &sm.K[0][16 * ks + (lane & 15)][8 * jd]);
+          if (SPLIT) ldmatrix_x2_trans(bl0, bl1, &sm.K[LO][16 * ks + (lane & 15)][8 * jd]);
+          mma3<SPLIT>(dqacc[jd], ah, al, bh0, bh1, bl0, bl1);
+        }
+      }
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sm.dQ[jd * 4 + e][tid] = dqacc[jd][e];
+    }
+    // ---- dK += dS^T Q and dV += (P keep)^T dO: warp slice = 16 keys x 32 dims, contraction over the CTA's 64 queries
+    {
+      const int mt = w & 1, dh = w >> 1;
+      float dkacc[4][4], dvacc[4][4];
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dkacc[jd][e] = 0.f; dvacc[jd][e] = 0.f; }
+      const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int qrow = 16 * ks + rr + 8 * (mi >> 1), kcol = 16 * mt + 8 * (mi & 1);
+        uint32_t sh[4], sl[4] = {0u, 0u, 0u, 0u}, ph[4], pl[4] = {0u, 0u, 0u, 0u};
+        ldmatrix_x4_trans(sh[0], sh[1], sh[2], sh[3], &sm.dS[0][qrow][kcol]);
+        ldmatrix_x4_trans(ph[0], ph[1], ph[2], ph[3], &sm.P[0][qrow][kcol]);
+        if (SPLIT) {
+          ldmatrix_x4_trans(sl[0], sl[1], sl[2], sl[3], &sm.dS[LO][qrow][kcol]);
+          ldmatrix_x4_trans(pl[0], pl[1], pl[2], pl[3], &sm.P[LO][qrow][kcol]);
+        }
+#pragma unroll
+        for (int jd = 0; jd < 4; ++jd) {
+          uint32_t qh0, qh1, ql0 = 0u, ql1 = 0u, gh0, gh1, gl0 = 0u, gl1 = 0u;
+          ldmatrix_x2_trans(qh0, qh1, &sm.Q[0][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          ldmatrix_x2_trans(gh0, gh1, &sm.dO[0][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          if (SPLIT) {
+            ldmatrix_x2_trans(ql0, ql1, &sm.Q[LO][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+            ldmatrix_x2_trans(gl0, gl1, &sm.dO[LO][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          }
+          mma3<SPLIT>(dkacc[jd], sh, sl, qh0, qh1, ql0, ql1);
+          mma3<SPLIT>(dvacc[jd], ph, pl, gh0, gh1, gl0, gl1);
+        }
+      }
+      const int key0 = k0 + 16 * mt + g, key1 = key0 + 8;
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd) {
+        const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
+        if (key0 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
+          atomicAdd(dk + off, dkacc[jd][0]); atomicAdd(dk + off + 1, dkacc[jd][1]);
+          atomicAdd(dv + off, dvacc[jd][0]); atomicAdd(dv + off + 1, dvacc[jd][1]);
+        }
+        if (key1 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
+          atomicAdd(dk + off, dkacc[jd][2]); atomicAdd(dk + off + 1, dkacc[jd][3]);
+          atomicAdd(dv + off, dvacc[jd][2]); atomicAdd(dv + off + 1, dvacc[jd][3]);
+        }
+      }
+    }
+    if (tid < BK * CD) {
+      const int key = tid / CD, c = tid % CD;
+      if (k0 + key < cf.nkv) atomicAdd(dvs + ((int64_t)bg * cf.nkv + k0 + key) * CD + c, sm.dkpos[key][c]);
+    }
+  }
+  // ---- dQ
+  if (ok0) {
+    float* row = dq + qoff + (int64_t)(q0 + r0) * cf.inner + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4][tid], sm.dQ[j * 4 + 1][tid]);
+  }
+  if (ok1) {
+    float* row = dq + qoff + (int64_t)(q0 + r1) * cf.inner + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4 + 2][tid], sm.dQ[j * 4 + 3][tid]);
+  }
+  // ---- CPB parameter partials of this CTA: [W1 32*CD][b1 32][W2 1024][b2 32][W3 OUT*32][b3 OUT]
+  __syncthreads();
+  float* const red = reinterpret_cast<float*>(&sm.P[0][0][0]);
+  static_assert(sizeof(BwdSmem<SPLIT>::P) >= NRED * sizeof(float), "the reduction buffer aliases the P tile");
+  for (int i = tid; i < NRED; i += MTHREADS) red[i] = 0.f;
+  __syncthreads();
+  {
+    float* rW1 = red; float* rb1 = rW1 + CPB_H * 2; float* rW2 = rb1 + CPB_H; float* rb2 = rW2 + CPB_H * CPB_H;
+    float* rw3 = rb2 + CPB_H; float* rb3 = rw3 + CPB_H;
+    // values indexed by t only: add the 8 lanes (g) that share t first
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float a = gb1[s][e], x = gW1x[s][e], y = gW1y[s][e];
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, m); x += __shfl_xor_sync(0xffffffffu, x, m); y += __shfl_xor_sync(0xffffffffu, y, m);
+        }
+        if (g == 0) {
+          const int kk = 16 * s + 2 * t + (e & 1) + 8 * (e >> 1);
+          atomicAdd(&rb1[kk], a); atomicAdd(&rW1[kk * 2], x); atomicAdd(&rW1[kk * 2 + 1], y);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a = gb2[j][e], x = gw3[j][e];
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, m); x += __shfl_xor_sync(0xffffffffu, x, m); }
+        if (g == 0) { atomicAdd(&rb2[8 * j + 2 * t + e], a); atomicAdd(&rw3[8 * j + 2 * t + e], x); }
+      }
+    gb3 = warp_sum(gb3);
+    if (lane == 0) atomicAdd(rb3, gb3);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        const int c = 16 * mt + g, kk = 8 * jn + 2 * t;
+        atomicAdd(&rW2[c * CPB_H + kk], gW2[mt][jn][0]); atomicAdd(&rW2[c * CPB_H + kk + 1], gW2[mt][jn][1]);
+        atomicAdd(&rW2[(c + 8) * CPB_H + kk], gW2[mt][jn][2]); atomicAdd(&rW2[(c + 8) * CPB_H + kk + 1], gW2[mt][jn][3]);
+      }
+  }
+  __syncthreads();
+  {
+    const int np = CPB_H * CD + CPB_H + CPB_H * CPB_H + CPB_H + cf.OUT * CPB_H + cf.OUT;
+    float* prow = part + ((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * np;
+    const float* rW1 = red; const float* rb1 = rW1 + CPB_H * 2; const float* rW2 = rb1 + CPB_H;
+    const float* rb2 = rW2 + CPB_H * CPB_H; const float* rw3 = rb2 + CPB_H; const float* rb3 = rw3 + CPB_H;
+    for (int i = tid; i < np; i += MTHREADS) {
+      int e = i;
+      float val;
+      if (e < CPB_H * CD) val = rW1[(e / CD) * 2 + (e % CD)];
+      else if ((e -= CPB_H * CD) < CPB_H) val = rb1[e];
+      else if ((e -= CPB_H) < CPB_H * CPB_H) val = rW2[e];
+      else if ((e -= CPB_H * CPB_H) < CPB_H) val = rb2[e];
+      else if ((e -= CPB_H) < cf.OUT * CPB_H) val = (e / CPB_H == o) ? rw3[e % CPB_H] : 0.f;
+      else { e -= cf.OUT * CPB_H; val = (e == o) ? rb3[0] : 0.f; }
+      prow[i] = val;
+    }
+  }
+}
+
+}  // namespace sml
+
+using namespace sml;
+
+template <int CD, bool SPLIT>
+static int launch_fwd(const AttnCfg& cf, const float* q, const float* k, const float* v, const float* vs, const float* cpb,
+                      float* out, float* lse, void* stream) {
+  dim3 grid((cf.n + MQ - 1) / MQ, cf.heads, cf.B);
+  const size_t smem = sizeof(FwdSmem<SPLIT>);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(deform_attn_fwd_mma_kernel<CD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  deform_attn_fwd_mma_kernel<CD, SPLIT><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, out, lse);
+  SML_LAUNCH_OK("sml_deform_attn_fwd_tc");
+  return 0;
+}
+
+extern "C" int sml_deform_attn_fwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k,
+                                      const float* v, const float* vs, const float* cpb, float* out, float* lse, int32_t split,
+                                      void* stream) {
+  AttnCfg cf;
+  if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
+  if (cf.CD == 2) return split ? launch_fwd<2, true>(cf, q, k, v, vs, cpb, out, lse, stream)
+                               : launch_fwd<2, false>(cf, q, k, v, vs, cpb, out, lse, stream);
+  return split ? launch_fwd<1, true>(cf, q, k, v, vs, cpb, out, lse, stream)
+               : launch_fwd<1, false>(cf, q, k, v, vs, cpb, out, lse, stream);
+}
+
+template <int CD, bool SPLIT>
+static int launch_bwd(const AttnCfg& cf, const float* q, const float* k, const float* v, const float* vs, const float* cpb,
+                      const float* out, const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs,
+                      float* part, void* stream) {
+  dim3 grid((cf.n + MQ - 1) / MQ, cf.heads, cf.B);
+  const size_t smem = sizeof(BwdSmem<SPLIT>);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(deform_attn_bwd_mma_kernel<CD, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  deform_attn_bwd_mma_kernel<CD, SPLIT><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk,
+                                                                                     dv, dvs, part);
+  SML_LAUNCH_OK("sml_deform_attn_bwd_tc");
+  return 0;
+}
+
+/* same contract as sml_deform_attn_bwd (dk, dv, dvs zero-initialised; part [sml_deform_attn_bwd_blocks, nparams]) */
+extern "C" int sml_deform_attn_bwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k,
+                                      const float* v, const float* vs, const float* cpb, const float* out, const float* lse,
+                                      const float* dout, float* dq, float* dk, float* dv, float* dvs, float* part, int32_t split,
+                                      void* stream) {
+  AttnCfg cf;
+  if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
+  if (cf.CD == 2) return split ? launch_bwd<2, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
+                               : launch_bwd<2, false>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
+  return split ? launch_bwd<1, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
+               : launch_bwd<1, false>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
+}

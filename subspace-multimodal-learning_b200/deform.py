@@ -107,8 +107,14 @@ class DeformAttnFn(torch.autograd.Function):
         acfg = _cfg(b, heads, T, nkv, G, OC, cfg["side"] if two_d else 1, 64)
         out = torch.empty(b, T, inner, device=dev, dtype=F32)
         lse = torch.empty(b, heads, T, device=dev, dtype=F32)
-        check(lib.sml_deform_attn_fwd(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
-                                      ptr(out), ptr(lse), stream()), "deform_attn_fwd")
+        prec = cfg.get("precision", "bf16x3")
+        assert prec in ("fp32", "bf16x3", "bf16"), prec
+        if prec == "fp32":          # SIMT fp32 kernel
+            check(lib.sml_deform_attn_fwd(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
+                                          ptr(out), ptr(lse), stream()), "deform_attn_fwd")
+        else:                       # register-fragment MMA kernel (bf16 hi/lo 3-pass or plain bf16 operands)
+            check(lib.sml_deform_attn_fwd_tc(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
+                                             ptr(out), ptr(lse), c_i32(1 if prec == "bf16x3" else 0), stream()), "deform_attn_fwd_tc")
         y = torch.empty(b, T, C, device=dev, dtype=F32)
         gemm(out.view(b * T, inner), wo2.t(), out=y.view(b * T, C), bias=bout.detach())       # 1D.py:233 / 2D.py:314
         ctx.save_for_backward(x1t, x2t, wq2, wk2, wv2, wo2, wc2, bc, w22, q, qs, off, vs, kv, k, v, cpb, out, lse)
@@ -137,9 +143,15 @@ class DeformAttnFn(torch.autograd.Function):
         nblk = lib.sml_deform_attn_bwd_blocks(cfg["acfg"])
         npar = lib.sml_deform_cpb_nparams(c_i32(OC), c_i32(heads // G))
         part = torch.empty(nblk, npar, device=dev, dtype=F32)
-        check(lib.sml_deform_attn_bwd(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
-                                      ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b), ptr(part),
-                                      stream()), "deform_attn_bwd")
+        prec = cfg.get("precision", "bf16x3")
+        if prec == "fp32":
+            check(lib.sml_deform_attn_bwd(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
+                                          ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b), ptr(part),
+                                          stream()), "deform_attn_bwd")
+        else:
+            check(lib.sml_deform_attn_bwd_tc(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
+                                             ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b),
+                                             ptr(part), c_i32(1 if prec == "bf16x3" else 0), stream()), "deform_attn_bwd_tc")
         dcpb = ops.colsum(part)
         # k, v projections
         dkv, dwk = gconv_bwd(kv, wk2, cfg["gkv"], dk)

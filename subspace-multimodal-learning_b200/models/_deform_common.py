@@ -6,6 +6,13 @@ from .. import functional as Fn
 from ..deform import DeformAttnFn
 
 
+# Arithmetic of the fused attention kernel (per module: ``mod.precision``; None -> this default):
+#   "bf16x3"  warp-level bf16 MMAs with hi/lo 3-pass products (fp32-grade: 1e-4 on outputs)       [default]
+#   "bf16"    plain bf16 MMA operands (2e-2)
+#   "fp32"    the SIMT fp32 kernels (exact fp32 arithmetic, ~7x slower)
+DEFAULT_PRECISION = "bf16x3"
+
+
 def exists(val):
     return val is not None
 
@@ -57,7 +64,8 @@ def run_deform(mod, x1, x2, return_vgrid, two_d, side=None, want_taps=False):
     seed = Fn._seed_state["seed"] + 7919 * Fn._next_offset(1) if p > 0 else 0
     cfg = dict(dim2d=two_d, side=side, heads=mod.heads, groups=mod.offset_groups, ds=mod.downsample_factor,
                ksize=mod.offset_kernel_size, scale=float(mod.offset_scale), gq=mod.group_queries, gkv=mod.group_key_values,
-               p_drop=float(p), seed=int(seed), mode=mod.pad_order_mode, want_taps=want_taps)
+               p_drop=float(p), seed=int(seed), mode=mod.pad_order_mode, want_taps=want_taps,
+               precision=getattr(mod, "precision", None) or DEFAULT_PRECISION)
     y, vgrid = DeformAttnFn.apply(x1t.float(), x2t.float(), mod.to_q.weight, mod.to_k.weight, mod.to_v.weight, mod.to_out.weight,
                                   mod.to_out.bias, mod.to_offsets[0].weight, mod.to_offsets[0].bias, mod.to_offsets[2].weight,
                                   *mod.rel_pos_bias.params(), cfg)

@@ -38,12 +38,13 @@ def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-def grads_close(got, want, tol, what=""):
+def grads_close(got, want, tol, what="", gmax=None):
     """Compare dicts of gradients.  Each entry is scaled by max(|want_k|, 1e-3 * max_k |want_k|):
     gradients that are mathematically zero (e.g. the last CPB bias: a constant added to every logit
     of a softmax row) are rounding noise in the reference too and only need to be small."""
     import torch
-    gmax = max(float(v.abs().max()) for v in want.values())
+    if gmax is None:
+        gmax = max(float(v.abs().max()) for v in want.values())
     for k, w in want.items():
         g = got[k]
         assert g is not None, f"{what}{k}: no gradient"

@@ -12,23 +12,52 @@ from synth import randn, synth_state_dict
 
 pytestmark = pytest.mark.gpu
 
+# Tolerances per arithmetic mode of the fused attention kernel: (outputs, input gradients and projection / offset-network
+# parameter gradients, parameter gradients of the bias MLP).  "bf16x3" is the default and meets the fp32 bar of BASELINE.json
+# on outputs and input gradients (measured 3e-6 / 4e-5); "bf16" meets its 2e-2 bar.  The last column is wider in the
+# tensor-core modes for a structural reason: every bias-MLP gradient is sum_ij dS_ij f(i, j) with sum_j dS_ij = 0, i.e. a
+# ~100x cancellation, and f contains the ReLU masks 1[a > 0]: a pre-activation error eps flips the mask of the ~eps/sigma
+# pairs with |a| < eps, each flip changing its term by 100 % - an error linear in the pair count, like the signal.  With
+# eps = 1e-5 (hi/lo bf16 operands) that is 2e-3 .. 7e-3 of the gradient, with 4e-3 (plain bf16) 5e-2 .. 2e-1; the exact-fp32
+# SIMT kernels (precision = "fp32", eps = 1e-7) stay inside 1e-3.
+TOLS = {"fp32": (1e-4, 1e-3, 1e-3), "bf16x3": (1e-4, 1e-3, 1e-2), "bf16": (2e-2, 2e-2, 3e-1)}
 
-def test_deform1d_golden():
+
+def check_param_grads(got, want, prec, scale=1.0, what=""):
+    _, ti, tc = TOLS[prec]
+    cpb = {k for k in want if "rel_pos_bias" in k}
+    gmax = max(float(v.abs().max()) for v in want.values())
+    grads_close({k: got[k] for k in want if k not in cpb}, {k: v for k, v in want.items() if k not in cpb}, scale * ti, what, gmax)
+    if cpb:
+        grads_close({k: got[k] for k in cpb}, {k: want[k] for k in cpb}, scale * tc, what, gmax)
+
+
+@pytest.fixture(params=["fp32", "bf16x3", "bf16"])
+def prec(request):
+    from sml_b200.models import _deform_common as dc
+    old = dc.DEFAULT_PRECISION
+    dc.DEFAULT_PRECISION = request.param
+    yield request.param
+    dc.DEFAULT_PRECISION = old
+
+
+def test_deform1d_golden(prec):
     import sml_b200
+    to, ti, tp = TOLS[prec]
     g = load_golden("deform1d")
     mod = sml_b200.DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6).cuda().eval()
     mod.load_state_dict(g["state"])
     x1 = g["x1"].cuda().requires_grad_(); x2 = g["x2"].cuda().requires_grad_()
     y, vg = mod(x1, x2, return_vgrid=True)
     assert rel_err(vg, g["vgrid"]) < 1e-5
-    assert rel_err(y, g["y"]) < 1e-4
+    assert rel_err(y, g["y"]) < to
     y.backward(g["gy"].cuda())
-    assert rel_err(x1.grad, g["gx1"]) < 1e-3
-    assert rel_err(x2.grad, g["gx2"]) < 1e-3
-    grads_close({k: p.grad for k, p in mod.named_parameters()}, g["gparams"], 1e-3)
+    assert rel_err(x1.grad, g["gx1"]) < ti
+    assert rel_err(x2.grad, g["gx2"]) < ti
+    check_param_grads({k: p.grad for k, p in mod.named_parameters()}, g["gparams"], prec)
 
 
-def test_deform1d_upstream_order_vs_oracle():
+def test_deform1d_upstream_order_vs_oracle(prec):
     import sml_b200
     g = load_golden("deform1d")
     mod = sml_b200.DeformCrossAttention1D(dim=128, downsample_factor=4, offset_scale=2, offset_kernel_size=6,
@@ -41,11 +70,12 @@ def test_deform1d_upstream_order_vs_oracle():
     yo = oracle.deform.deform_attn_1d(x1c, x2c, p, pad_order="upstream")
     yo.backward(g["gy"].double())
     x1 = g["x1"].cuda().requires_grad_(); x2 = g["x2"].cuda().requires_grad_()
+    to, ti, tp = TOLS[prec]
     y = mod(x1, x2)
-    assert rel_err(y, yo) < 1e-4
+    assert rel_err(y, yo) < to
     y.backward(g["gy"].cuda())
-    assert rel_err(x1.grad, x1c.grad) < 1e-3 and rel_err(x2.grad, x2c.grad) < 1e-3
-    grads_close({k: q.grad for k, q in mod.named_parameters()}, {k: v.grad for k, v in p.items()}, 1e-3)
+    assert rel_err(x1.grad, x1c.grad) < ti and rel_err(x2.grad, x2c.grad) < ti
+    check_param_grads({k: q.grad for k, q in mod.named_parameters()}, {k: v.grad for k, v in p.items()}, prec)
 
 
 def test_gather_taps_bit_exact():
@@ -73,8 +103,9 @@ def test_gather_taps_bit_exact():
         assert rel_err(kv.view(b, 10, 4, 32).permute(0, 2, 3, 1).reshape(b * 4, 32, 10), want) < 1e-6
 
 
-def test_deform2d_golden():
+def test_deform2d_golden(prec):
     import sml_b200
+    to, ti, tp = TOLS[prec]
     g = load_golden("deform2d")
     mod = sml_b200.DeformCrossAttention2D(dim=128, dim_head=64, heads=8, dropout=0.1, downsample_factor=4, offset_scale=4,
                                           offset_groups=8, offset_kernel_size=6).cuda().eval()
@@ -82,15 +113,16 @@ def test_deform2d_golden():
     x1 = randn((1, 128, 2500), g["x1_seed"]).cuda().requires_grad_(); x2 = randn((1, 128, 2500), g["x2_seed"]).cuda().requires_grad_()
     y, vg = mod(x1, x2, return_vgrid=True)
     assert rel_err(vg, g["vgrid"]) < 1e-5
-    assert rel_err(y, g["y"]) < 1e-4
+    assert rel_err(y, g["y"]) < to
     y.backward(randn(y.shape, g["gy_seed"]).cuda())
-    assert rel_err(x1.grad[:, :, ::7], g["gx1"]) < 1e-3
-    assert rel_err(x2.grad[:, :, ::7], g["gx2"]) < 1e-3
-    grads_close({k: p.grad for k, p in mod.named_parameters()}, g["gparams"], 1e-3)
+    assert rel_err(x1.grad[:, :, ::7], g["gx1"]) < ti
+    assert rel_err(x2.grad[:, :, ::7], g["gx2"]) < ti
+    check_param_grads({k: p.grad for k, p in mod.named_parameters()}, g["gparams"], prec)
 
 
-def test_deform2d_vs_oracle_64x64_batch2():
+def test_deform2d_vs_oracle_64x64_batch2(prec):
     import sml_b200
+    to, ti, tp = TOLS[prec]
     torch.manual_seed(3)
     mod = sml_b200.DeformCrossAttention2D(dim=128).cuda().eval()
     sd = mod.state_dict()
@@ -103,15 +135,16 @@ def test_deform2d_vs_oracle_64x64_batch2():
     (yo * gy.double()).sum().add((vo * gv.double()).sum()).backward()
     x1 = x1c.detach().float().cuda().requires_grad_(); x2 = x2c.detach().float().cuda().requires_grad_()
     y, v = mod(x1, x2, return_vgrid=True)
-    assert rel_err(y, yo) < 1e-4 and rel_err(v, vo) < 1e-5
+    assert rel_err(y, yo) < to and rel_err(v, vo) < 1e-5
     (y * gy.cuda()).sum().add((v * gv.cuda()).sum()).backward()
-    assert rel_err(x1.grad, x1c.grad) < 1e-3 and rel_err(x2.grad, x2c.grad) < 1e-3
-    grads_close({k: q.grad for k, q in mod.named_parameters()}, {k: t.grad for k, t in p.items()}, 1e-3)
+    assert rel_err(x1.grad, x1c.grad) < ti and rel_err(x2.grad, x2c.grad) < ti
+    check_param_grads({k: q.grad for k, q in mod.named_parameters()}, {k: t.grad for k, t in p.items()}, prec)
 
 
 @pytest.mark.parametrize("ad", [2, 1])
-def test_deform_cross_transmil_golden(ad):
+def test_deform_cross_transmil_golden(ad, prec):
     import sml_b200
+    to, ti, tp = TOLS[prec]
     g = load_golden(f"deformtransmil_ad{ad}")
     net = sml_b200.DeformCrossTransMIL(Namespace(path_dim=128, attn_dim=ad, return_vgrid=(ad == 2))).cuda().eval()
     st = synth_state_dict(g["shapes"], g["seed"])
@@ -122,22 +155,24 @@ def test_deform_cross_transmil_golden(ad):
     path = randn((1, 2500, 1024), 83).cuda().requires_grad_(); omic = randn((1, 128), 84).abs().cuda().requires_grad_()
     outs = net(path, omic)
     enc, logits = outs[0], outs[1]
-    assert rel_err(logits, g["logits"]) < 1e-4 and rel_err(enc, g["enc"]) < 1e-4
+    assert rel_err(logits, g["logits"]) < to and rel_err(enc, g["enc"]) < to
     loss = (logits * randn(logits.shape, 85).cuda()).sum() + (enc * randn(enc.shape, 86).cuda()).sum()
     if ad == 2:
-        assert rel_err(outs[4], g["vgrid"]) < 1e-4
+        assert rel_err(outs[4], g["vgrid"]) < 1e-4                 # offsets do not depend on the attention arithmetic
         assert outs[3].shape == (1, 2500, 128) and torch.equal(outs[3][0, 17], omic.detach()[0])
         loss = loss + (outs[4] * randn(outs[4].shape, 87).cuda()).sum() * 0.01
     loss.backward()
-    assert rel_err(omic.grad, g["gomic"]) < 1e-3
-    assert rel_err(path.grad[:, ::50, ::16], g["gpath_sub"]) < 1e-3
+    assert rel_err(omic.grad, g["gomic"]) < ti
+    assert rel_err(path.grad[:, ::50, ::16], g["gpath_sub"]) < ti
     gp = {k: p.grad for k, p in net.named_parameters()}
-    grads_close({k: gp[k] for k in g["gparams"] if gp[k] is not None}, {k: v for k, v in g["gparams"].items() if gp[k] is not None}, 2e-3)
+    check_param_grads(gp, {k: v for k, v in g["gparams"].items() if gp[k] is not None}, prec, scale=2.0)
     for k, nv in g["gnorms"].items():
         if gp[k] is None:
             assert nv == 0.0 or "attn1d" in k or "attn2d" in k or k in ("cls_token",) or "pooler" in k, k
             continue
-        assert abs(float(gp[k].norm()) - nv) <= 2e-3 * nv + 1e-5, (k, float(gp[k].norm()), nv)
+        tk = 2 * (tp if "rel_pos_bias" in k else ti)
+        floor = 1e-5 + 1e-3 * tk * max(g["gnorms"].values())     # mathematically-zero gradients (last CPB bias) are noise
+        assert abs(float(gp[k].norm()) - nv) <= tk * nv + floor, (k, float(gp[k].norm()), nv)
 
 
 def test_deform_attention_dropout_is_unbiased():
