@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SML_PRECISION", "bf16"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=8, help="slides per step per GPU (config_mine.yaml batch_size: 8)")
     ap.add_argument("--patches", type=int, default=16384)
+    ap.add_argument("--workload", default="transmil", choices=["transmil", "deform2d", "deform1d"],
+                    help="transmil = BASELINE.json configs[1] (the headline); deform2d / deform1d = configs[2], the full "
+                         "DeformCrossTransMIL (attn_dim 2 / 1) train step")
     ap.add_argument("--cpu-sample", type=int, default=1, help="slides in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-out", default=None, help="write the per-shape GEMM timing table of the instrumented pass here")
@@ -156,22 +159,29 @@ def run_ours(args):
     from sml_b200 import ops
 
     torch.manual_seed(42)
-    model = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev).train()
-    model.set_precision(args.precision)
+    deform = args.workload != "transmil"
+    if deform:
+        model = sml_b200.DeformCrossTransMIL(Namespace(path_dim=128, attn_dim=2 if args.workload == "deform2d" else 1,
+                                                       return_vgrid=False)).to(dev).train()
+        model.set_precision(args.precision)
+    else:
+        model = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev).train()
+        model.set_precision(args.precision)
     Fn.manual_seed(42 + rank)
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=False,
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=deform,
                                                         broadcast_buffers=False, gradient_as_bucket_view=True)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
     B, N = args.batch, args.patches
     x_dev, y_dev = synth_bag(B, N, 42 + rank, dev)
     x_host = x_dev.cpu().pin_memory()
     y_host = y_dev.cpu().pin_memory()
+    omic = torch.randn(B, 128, generator=torch.Generator(device=dev).manual_seed(7 + rank), device=dev).abs() if deform else None
 
     def step(x, y):
         opt.zero_grad(set_to_none=True)
-        _, logits, _ = net(x)
+        logits = net(x, omic)[1] if deform else net(x)[1]
         loss = torch.nn.functional.cross_entropy(logits, y)
         loss.backward()
         opt.step()
@@ -255,7 +265,19 @@ def run_ours(args):
                 f.write("%s : %d %.1f %.1f %.1f\n" % (" ".join(str(x) for x in k), v[2], v[1] * 1e6, v[1] * 1e6 / v[2], v[0] / v[1] / 1e12))
     pk, pk_src = peaks()
     roof = None
-    if "tc" in agg and agg["tc"][1] > 0:
+    if deform and "deform_bwd" in agg:
+        f, t, n = agg["deform_bwd"]
+        ach = f / t / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"kernel": "deform_attn_bwd_mma_kernel (fused bias-MLP + attention backward, %d launch)" % n, "bound": "tensor",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": pk_src + " (sustained, tcgen05 dense bf16)", "share_of_step": t / (ms * 1e-3 / args.steps),
+                "forward_kernel": {"achieved": agg["deform_fwd"][0] / agg["deform_fwd"][1] / 1e12,
+                                   "share_of_step": agg["deform_fwd"][1] / (ms * 1e-3 / args.steps)},
+                "note": "algorithmic FLOPs: 2*(2240 (2-D) | 2176 (1-D) + 256) per (query, key) pair for the backward; the in-kernel "
+                        "forward recomputation and the 3-pass split are not counted.  Warp-level mma.sync (legacy tensor pipe, "
+                        "~576 TFLOP/s), bounded by the per-pair CUDA-core work, not by the tensor pipe"}
+    elif "tc" in agg and agg["tc"][1] > 0:
         f, t, n = agg["tc"]
         ach = f / t / 1e12
         peak = pk["bf16_tflops_sustained"]
@@ -275,7 +297,9 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "f32 (bf16x3 split)", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags"
+                "config": {"workload": ("DeformCrossTransMIL(attn_dim=%d: fc1 + genomic fusion + deformable cross-attention + heads) "
+                                        "fwd+CE+bwd+Adam on %d-patch x 1024-d bags" % (2 if args.workload == "deform2d" else 1, N)) if deform
+                           else "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags"
                                        % N, "slides_per_step_per_gpu": B, "global_batch": B * world, "precision": args.precision,
                            "parallelism": "dp%d" % world, "l2": "inputs (%d MB/step) and activations exceed the 126 MB L2"
                                                               % (B * N * 1024 * 4 // 2 ** 20)},
@@ -283,7 +307,7 @@ def run_ours(args):
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
                         "d2h_bytes_per_step": 4},
                 "clocks": sampler.summary(), "roofline": roof}
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not deform:
             threads = os.cpu_count() or 1
             cstep = cpu_port_step_fn(N, threads)
             xs, ys = synth_bag(1, N, 42, "cpu")

@@ -663,14 +663,12 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
         }
         const float dS0 = P0 * (stD[g][u] * keep0 - delta0);
         const float dS1 = P1 * (stD[g + 8][u] * keep1 - delta1);
-        if (t == 0) {
-          store_bf16_split(&sm.P[0][r0][key], SPLIT ? &sm.P[LO][r0][key] : nullptr, P0 * keep0);
-          store_bf16_split(&sm.dS[0][r0][key], SPLIT ? &sm.dS[LO][r0][key] : nullptr, dS0);
-          gb3 += dS0 + dS1;
-        } else if (t == 1) {
-          store_bf16_split(&sm.P[0][r1][key], SPLIT ? &sm.P[LO][r1][key] : nullptr, P1 * keep1);
-          store_bf16_split(&sm.dS[0][r1][key], SPLIT ? &sm.dS[LO][r1][key] : nullptr, dS1);
+        if (t < 2) {                                     // lane t = 0 stores row r0, lane t = 1 row r1
+          const int rs = t ? r1 : r0;
+          store_bf16_split(&sm.P[0][rs][key], SPLIT ? &sm.P[LO][rs][key] : nullptr, t ? P1 * keep1 : P0 * keep0);
+          store_bf16_split(&sm.dS[0][rs][key], SPLIT ? &sm.dS[LO][rs][key] : nullptr, t ? dS1 : dS0);
         }
+        if (t == 0) gb3 += dS0 + dS1;
         // layer 3 / second ReLU backward: dh2 (C-fragment layout) and its A fragments for dh1 = dh2 W2
         uint32_t dah[2][4], dal[2][4];
 #pragma unroll

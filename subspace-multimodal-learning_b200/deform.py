@@ -9,50 +9,80 @@ import torch
 
 from . import ops
 from ._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
-from .ops import F32, gemm
+from .ops import F32, Split, gemm, to_bf16
+
+
+def _prof_begin():
+    if ops.PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, eng, flops, tag):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        ops.PROFILE.append((eng, flops, e0, e1, tag))
 
 
 def _cfg(*vals):
     return (c_i32 * len(vals))(*[int(v) for v in vals])
 
 
-def gconv(x, w2d, G, out=None):
+def _op(t, mode):
+    """GEMM operand for the engine of ``mode``: fp32 tensor (SIMT engine, "fp32") or bf16 hi + lo copies (tcgen05 engine,
+    3-pass split).  Both tensor-core modes run the projections fp32-grade: q feeds the offset network, whose outputs decide
+    the integer sampling taps (bit-exact contract), and the GEMMs are < 10 % of the step either way; "bf16" only changes the
+    arithmetic inside the fused attention kernel."""
+    return t if mode == "fp32" else to_bf16(t.contiguous(), split=True)
+
+
+def _v(op, fn):
+    return op.map(fn) if isinstance(op, Split) else fn(op)
+
+
+def gconv(x, w2d, G, out=None, mode="fp32"):
     """grouped 1x1 conv on token-major x [b,T,Cin]: w2d [Cout, Cin/G] -> [b,T,Cout]."""
     b, T, Cin = x.shape
     Cout = w2d.shape[0]
     if out is None:
         out = torch.empty(b, T, Cout, device=x.device, dtype=F32)
+    xo, wo = _op(x, mode), _op(w2d, mode)
     if G == 1:
-        gemm(x, w2d.t(), out=out)
+        gemm(xo, _v(wo, lambda t: t.t()), out=out)
     else:
         ci, co = Cin // G, Cout // G
-        gemm(x.view(b, T, G, ci).permute(0, 2, 1, 3), w2d.view(1, G, co, ci).transpose(-1, -2),
+        gemm(_v(xo, lambda t: t.view(b, T, G, ci).permute(0, 2, 1, 3)), _v(wo, lambda t: t.view(1, G, co, ci).transpose(-1, -2)),
              out=out.view(b, T, G, co).permute(0, 2, 1, 3))
     return out
 
 
-def gconv_bwd(x, w2d, G, dy, need_dx=True, dx_out=None, dx_beta=0.0):
+def gconv_bwd(x, w2d, G, dy, need_dx=True, dx_out=None, dx_beta=0.0, mode="fp32"):
     """returns (dx [b,T,Cin] or None, dw [Cout, Cin/G])."""
     b, T, Cin = x.shape
     Cout = w2d.shape[0]
     dx = None
+    xo, dyo = _op(x, mode), _op(dy, mode)
+    wo = _op(w2d, mode) if need_dx else None
     if G == 1:
-        dw = gemm(dy.reshape(b * T, Cout).t(), x.reshape(b * T, Cin))
+        dw = gemm(_v(dyo, lambda t: t.reshape(b * T, Cout).t()), _v(xo, lambda t: t.reshape(b * T, Cin)))
         if need_dx:
             dx = dx_out if dx_out is not None else torch.empty_like(x)
-            gemm(dy, w2d, out=dx, beta=dx_beta)
+            gemm(dyo, wo, out=dx, beta=dx_beta)
     else:
         ci, co = Cin // G, Cout // G
         # dw_g = sum_b dy_g^T x_g : fold the batch into the contraction by looping b with beta accumulation
         dw = torch.empty(G, co, ci, device=x.device, dtype=F32)
-        xg = x.view(b, T, G, ci).permute(0, 2, 1, 3)            # [b,G,T,ci]
-        dyg = dy.view(b, T, G, co).permute(0, 2, 1, 3)          # [b,G,T,co]
+        xg = _v(xo, lambda t: t.view(b, T, G, ci).permute(0, 2, 1, 3))            # [b,G,T,ci]
+        dyg = _v(dyo, lambda t: t.view(b, T, G, co).permute(0, 2, 1, 3))          # [b,G,T,co]
         for bi in range(b):
-            gemm(dyg[bi].transpose(-1, -2), xg[bi], out=dw, beta=0.0 if bi == 0 else 1.0)
+            gemm(_v(dyg, lambda t: t[bi].transpose(-1, -2)), _v(xg, lambda t: t[bi]), out=dw, beta=0.0 if bi == 0 else 1.0)
         dw = dw.view(Cout, ci)
         if need_dx:
             dx = dx_out if dx_out is not None else torch.empty_like(x)
-            gemm(dyg, w2d.view(1, G, co, ci), out=dx.view(b, T, G, ci).permute(0, 2, 1, 3), beta=dx_beta)
+            gemm(dyg, _v(wo, lambda t: t.view(1, G, co, ci)), out=dx.view(b, T, G, ci).permute(0, 2, 1, 3), beta=dx_beta)
     return dx, dw
 
 
@@ -74,7 +104,9 @@ class DeformAttnFn(torch.autograd.Function):
         gkv = G if cfg["gkv"] else 1
         wq2, wk2, wv2 = (w.detach().reshape(w.shape[0], -1).contiguous() for w in (wq, wk, wv))
         wo2 = wout.detach().reshape(wout.shape[0], -1).contiguous()
-        q = gconv(x1t, wq2, gq)                                                  # 1D.py:175 / 2D.py:246
+        prec = cfg.get("precision", "bf16x3")
+        assert prec in ("fp32", "bf16x3", "bf16"), prec
+        q = gconv(x1t, wq2, gq, mode=prec)                                       # 1D.py:175 / 2D.py:246
         pad = (ks - ds) // 2
         if two_d:
             side = cfg["side"]
@@ -99,24 +131,27 @@ class DeformAttnFn(torch.autograd.Function):
         kv = torch.empty(b, nkv, C, device=dev, dtype=F32)
         taps = torch.empty(b * G, nkv, 2, device=dev, dtype=torch.int32) if cfg.get("want_taps") else None
         check(lib.sml_deform_gather_fwd(gcfg, ptr(x2t), ptr(vs), ptr(kv), ptr(taps), stream()), "deform_gather_fwd")
-        k = gconv(kv, wk2, gkv)                                                  # 1D.py:199 / 2D.py:279
-        v = gconv(kv, wv2, gkv)
+        k = gconv(kv, wk2, gkv, mode=prec)                                       # 1D.py:199 / 2D.py:279
+        v = gconv(kv, wv2, gkv, mode=prec)
         qs = torch.empty_like(q)
         ops.axpby_(qs, q, 64 ** -0.5, 0.0)                                       # q * scale after the offsets (1D.py:203)
         cpb = torch.cat([t.detach().reshape(-1) for t in (cw1, cb1, cw2, cb2, cw3, cb3)]).contiguous()
         acfg = _cfg(b, heads, T, nkv, G, OC, cfg["side"] if two_d else 1, 64)
         out = torch.empty(b, T, inner, device=dev, dtype=F32)
         lse = torch.empty(b, heads, T, device=dev, dtype=F32)
-        prec = cfg.get("precision", "bf16x3")
-        assert prec in ("fp32", "bf16x3", "bf16"), prec
+        pairs = float(b) * heads * T * nkv
+        prof = _prof_begin()
         if prec == "fp32":          # SIMT fp32 kernel
             check(lib.sml_deform_attn_fwd(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                           ptr(out), ptr(lse), stream()), "deform_attn_fwd")
         else:                       # register-fragment MMA kernel (bf16 hi/lo 3-pass or plain bf16 operands)
             check(lib.sml_deform_attn_fwd_tc(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                              ptr(out), ptr(lse), c_i32(1 if prec == "bf16x3" else 0), stream()), "deform_attn_fwd_tc")
+        # algorithmic work per (query, key) pair: bias MLP 2 (CD 32 + 32 32 + 32) + q.k and p.v 4 d  
+        _prof_end(prof, "deform_fwd", pairs * (2 * (OC * 32 + 32 * 32 + 32) + 4 * 64), (b, heads, T, nkv, OC, prec))
         y = torch.empty(b, T, C, device=dev, dtype=F32)
-        gemm(out.view(b * T, inner), wo2.t(), out=y.view(b * T, C), bias=bout.detach())       # 1D.py:233 / 2D.py:314
+        gemm(_op(out.view(b * T, inner), prec), _v(_op(wo2, prec), lambda t: t.t()), out=y.view(b * T, C),
+             bias=bout.detach())                                                               # 1D.py:233 / 2D.py:314
         ctx.save_for_backward(x1t, x2t, wq2, wk2, wv2, wo2, wc2, bc, w22, q, qs, off, vs, kv, k, v, cpb, out, lse)
         ctx.cfg = dict(cfg, ocfg=ocfg, gcfg=gcfg, acfg=acfg, nkv=nkv, OC=OC, gd=gd, gq=gq, gkv=gkv, inner=inner,
                        shapes=[t.shape for t in (wq, wk, wv, wout, wc, w2, cw1, cb1, cw2, cb2, cw3, cb3)])
@@ -133,9 +168,11 @@ class DeformAttnFn(torch.autograd.Function):
         dev = x1t.device
         dy = dy.contiguous()
         dy2 = dy.view(b * T, C)
+        prec = cfg.get("precision", "bf16x3")
         db_out = ops.colsum(dy2)
-        dw_out = gemm(dy2.t(), out.view(b * T, inner))
-        dout = gemm(dy2, wo2).view(b, T, inner)
+        dy2o = _op(dy2, prec)
+        dw_out = gemm(_v(dy2o, lambda t: t.t()), _op(out.view(b * T, inner), prec))
+        dout = gemm(dy2o, _op(wo2, prec)).view(b, T, inner)
         dqs = torch.empty_like(q)
         dk = torch.zeros_like(k)
         dv = torch.zeros_like(v)
@@ -143,7 +180,7 @@ class DeformAttnFn(torch.autograd.Function):
         nblk = lib.sml_deform_attn_bwd_blocks(cfg["acfg"])
         npar = lib.sml_deform_cpb_nparams(c_i32(OC), c_i32(heads // G))
         part = torch.empty(nblk, npar, device=dev, dtype=F32)
-        prec = cfg.get("precision", "bf16x3")
+        prof = _prof_begin()
         if prec == "fp32":
             check(lib.sml_deform_attn_bwd(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
                                           ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b), ptr(part),
@@ -152,10 +189,13 @@ class DeformAttnFn(torch.autograd.Function):
             check(lib.sml_deform_attn_bwd_tc(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
                                              ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b),
                                              ptr(part), c_i32(1 if prec == "bf16x3" else 0), stream()), "deform_attn_bwd_tc")
+        # backward = 2x the forward contractions (the forward recomputation inside the kernel is not counted)
+        _prof_end(prof, "deform_bwd", float(b) * heads * T * nkv * 2 * (2 * (OC * 32 + 32 * 32 + 32) + 4 * 64),
+                  (b, heads, T, nkv, OC, prec))
         dcpb = ops.colsum(part)
         # k, v projections
-        dkv, dwk = gconv_bwd(kv, wk2, cfg["gkv"], dk)
-        _, dwv = gconv_bwd(kv, wv2, cfg["gkv"], dv, dx_out=dkv, dx_beta=1.0)
+        dkv, dwk = gconv_bwd(kv, wk2, cfg["gkv"], dk, mode=prec)
+        _, dwv = gconv_bwd(kv, wv2, cfg["gkv"], dv, dx_out=dkv, dx_beta=1.0, mode=prec)
         # sampling
         dx2t = torch.zeros_like(x2t)
         dvs = torch.empty_like(vs)
@@ -174,7 +214,7 @@ class DeformAttnFn(torch.autograd.Function):
                                          ptr(dvs), ptr(dvg), ptr(dpre), ptr(opart), ptr(dq), stream()), "deform_offsets_bwd")
         osum = ops.colsum(opart)
         dwc, dbc, dw2 = osum[:gd * KK], osum[gd * KK:gd * KK + gd], osum[gd * KK + gd:]
-        dx1t, dwq = gconv_bwd(x1t, wq2, cfg["gq"], dq)
+        dx1t, dwq = gconv_bwd(x1t, wq2, cfg["gq"], dq, mode=prec)
         sh = cfg["shapes"]
         sizes = [int(torch.Size(s).numel()) for s in sh[6:]]
         dc = torch.split(dcpb, sizes)

@@ -7,6 +7,7 @@ import torch
 from torch import nn
 
 from .. import functional as Fn
+from . import _deform_common as dc
 from .DeformableAttention1D import DeformCrossAttention1D
 from .DeformableAttention2D import DeformCrossAttention2D
 
@@ -22,7 +23,7 @@ class FusionNet(nn.Module):
         token-repeated tensor (how DeformCrossTransMIL calls it) — then only a rank-1 row bias is added."""
         f = self.feature_dim
         w, b = self.fusion_layer.weight, self.fusion_layer.bias
-        h = Fn.linear(gene_features, w[:, :f].contiguous(), None)
+        h = Fn.linear(gene_features, w[:, :f].contiguous(), None, mode=dc.gemm_mode(getattr(self, "precision", None)))
         if image_features.dim() == 2:
             return Fn.add_rowvec(h, Fn.linear(image_features, w[:, f:].contiguous(), b))
         return h + Fn.linear(image_features, w[:, f:].contiguous(), b)
@@ -73,9 +74,18 @@ class DeformCrossTransMIL(nn.Module):
         self._fc2 = nn.Linear(args.path_dim, self.n_classes)
         self.pooler = Pooler(args.path_dim)
         self.multimodal_projection = nn.Linear(args.path_dim, self.args.path_dim)
+        self.precision = None
+
+    def set_precision(self, p):
+        """arithmetic of the fused deformable attention kernels: "bf16x3" (default, fp32-grade), "bf16" or "fp32" (SIMT)"""
+        self.precision = p
+        self.fusion_layer.precision = p
+        self.layer3.attn1d.precision = p
+        self.layer3.attn2d.precision = p
 
     def forward(self, path, omic):
-        path = Fn.linear(path.float(), self._fc1[0].weight, self._fc1[0].bias, relu=True)      # :99-100
+        mode = dc.gemm_mode(self.precision)                    # engine of the big token-level GEMMs (fc1, fusion)
+        path = Fn.linear(path.float(), self._fc1[0].weight, self._fc1[0].bias, relu=True, mode=mode)      # :99-100
         omic = omic.float()
         B, N = path.shape[0], path.shape[1]
         h = self.fusion_layer(path, omic)                                                        # :104-110 (repeat folded)

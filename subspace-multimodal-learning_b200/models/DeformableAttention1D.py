@@ -29,6 +29,7 @@ class DeformCrossAttention1D(nn.Module):
         self.offset_kernel_size = offset_kernel_size
         self.offset_scale = offset_scale
         self.group_queries, self.group_key_values = group_queries, group_key_values
+        self.precision = None          # None -> _deform_common.DEFAULT_PRECISION ("bf16x3"); "bf16" / "fp32"
         self.log_distance_ok = bool(cpb_log_distance)
         assert pad_order in ("reference", "upstream")
         self.pad_order_mode = 0 if pad_order == "reference" else 1

@@ -13,6 +13,12 @@ from ..deform import DeformAttnFn
 DEFAULT_PRECISION = "bf16x3"
 
 
+def gemm_mode(precision):
+    """engine of the projection GEMMs around the attention kernel: SIMT fp32 for "fp32", else the tcgen05 engine with the
+    fp32-grade hi/lo split (see deform._op)."""
+    return "fp32" if (precision or DEFAULT_PRECISION) == "fp32" else "bf16x3"
+
+
 def exists(val):
     return val is not None
 
