@@ -170,7 +170,8 @@ def run_ours(args):
     Fn.manual_seed(42 + rank)
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=deform,
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,    # the multimodal_projection head (and the unused attn1d/attn2d twin) gets no gradient from the CE loss
+                                                       
                                                         broadcast_buffers=False, gradient_as_bucket_view=True)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
     B, N = args.batch, args.patches

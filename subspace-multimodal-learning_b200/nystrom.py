@@ -31,6 +31,8 @@ FUSE_A1_BWD = True
 import os as _os
 FUSE_A1_BWD = _os.environ.get("SML_FUSE_A1_BWD", "1") != "0"
 FUSE_PINV_CHAIN = _os.environ.get("SML_FUSE_PINV_CHAIN", "0") == "1"
+# "bf16" mode: run the Moore-Penrose chain with hi/lo split operands (True, fp32-grade) or in plain bf16 (False)
+PINV_HP = _os.environ.get("SML_PINV_HP", "1") != "0"
 
 
 def landmarks_fwd(qkv, b, npad, h, d, m):
@@ -49,7 +51,7 @@ def landmark_ids(npad, m, device):
 
 def _new_like(t, mode):
     """bundle for a pinv-chain matrix batch: fp32 + (hi, lo) in tensor-core modes (the chain is always bf16x3)."""
-    return TB.new(t.shape, t.device, mode, hp=True)
+    return TB.new(t.shape, t.device, mode, hp=PINV_HP)
 
 
 def _pinv_step(pa2, z, mode):
@@ -57,9 +59,9 @@ def _pinv_step(pa2, z, mode):
     t2 = 15I - xz (7I - xz) = xz xz - 7 xz + 15 I is ONE contraction whose epilogue adds the -7 xz and 15 I terms."""
     op_only = mode != "fp32"     # t2, t3 are only ever GEMM operands: in tensor-core modes emit just their bf16 hi/lo
     xz = mm(pa2, z, _new_like(z.f, mode))                                        # x z
-    t2 = mm(xz, xz, TB.new(z.f.shape, z.f.device, mode, hp=True, f32=not op_only), diag=15.0,
+    t2 = mm(xz, xz, TB.new(z.f.shape, z.f.device, mode, hp=PINV_HP, f32=not op_only), diag=15.0,
             rowtab=xz.f, rowdiv=1, rowtab_scale=-7.0)                            # 15I - xz (7I - xz)
-    t3 = mm(xz, t2, TB.new(z.f.shape, z.f.device, mode, hp=True, f32=not op_only), alpha=-1.0, diag=13.0)   # 13I - xz t2
+    t3 = mm(xz, t2, TB.new(z.f.shape, z.f.device, mode, hp=PINV_HP, f32=not op_only), alpha=-1.0, diag=13.0)   # 13I - xz t2
     return xz, t2, t3
 
 
@@ -73,8 +75,8 @@ def pinv_fwd(a2, iters, mode, a2_bundle=None):
     check(lib.sml_pinv_scale(ptr(a2), ptr(scal), ptr(arg), ptr(ws), c_i32(bh), c_i32(m), stream()), "pinv_scale")
     z0 = torch.empty_like(a2)
     check(lib.sml_pinv_init(ptr(a2), ptr(scal), ptr(z0), c_i32(bh), c_i32(m), stream()), "pinv_init")
-    pa2 = a2_bundle if (a2_bundle is not None and (mode == "fp32" or a2_bundle.lo is not None)) else TB.of(a2, mode, hp=True)
-    z = TB.of(z0, mode, hp=True)
+    pa2 = a2_bundle if (a2_bundle is not None and (mode == "fp32" or a2_bundle.lo is not None)) else TB.of(a2, mode, hp=PINV_HP)
+    z = TB.of(z0, mode, hp=PINV_HP)
     zs = [z.f]
     with ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN)):         # 4 * iters dependent GEMMs, one launch
         for _ in range(iters):
@@ -88,10 +90,10 @@ def pinv_bwd(a2, saved, dz, mode):
     """d a2 given d z_final; recomputes xz, t1..t3 per iteration from the saved z_k."""
     zs, scal, arg = saved
     bh, m = a2.numel() // (a2.shape[-1] ** 2), a2.shape[-1]
-    pa2 = TB.of(a2, mode, hp=True)
+    pa2 = TB.of(a2, mode, hp=PINV_HP)
     da2 = torch.zeros_like(a2)
-    g = TB.of(dz.contiguous(), mode, hp=True)
-    zbs = [TB.of(zk, mode, hp=True) for zk in zs]                                # conversions first: only GEMMs inside the program
+    g = TB.of(dz.contiguous(), mode, hp=PINV_HP)
+    zbs = [TB.of(zk, mode, hp=PINV_HP) for zk in zs]                                # conversions first: only GEMMs inside the program
     prog = ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN))
     prog.__enter__()
     for zk, z in zip(reversed(zs), reversed(zbs)):
@@ -166,7 +168,7 @@ class NystromAttentionFn(torch.autograd.Function):
         fuse = tc and m <= 256
         lowp = mode == "bf16" and fuse          # keep the big probability tensors (A1, A3) in bf16 only
         a1 = TB.new((b, h, npad, m), dev, mode, f32=not lowp)
-        a2 = TB.new((b, h, m, m), dev, mode, hp=True)
+        a2 = TB.new((b, h, m, m), dev, mode, hp=PINV_HP)
         a3 = TB.new((b, h, m, npad), dev, mode, f32=not lowp)
         s3 = a3.f if a3.f is not None else torch.empty(b, h, m, npad, device=dev, dtype=F32)   # logits scratch
         mm(q_b, kl_b.T(), a1, softmax=fuse)
