@@ -113,7 +113,7 @@ def cpu_port_step_fn(patches, threads):
         loss = torch.nn.functional.cross_entropy(logits, y)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
@@ -134,8 +134,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TransMIL(Nystrom m=256, 6 pinv iters) fwd+loss+bwd+Adam, %d-patch bags, 1 slide/step"
-                                   % args.patches, "arm": "oracle port of the reference algorithm on host cores"},
+            "config": {"workload": "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags"
+                                   % args.patches, "slides_per_step_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                       "precision": "fp32", "parallelism": "host threads",
+                       "arm": "oracle port of the reference algorithm (models/mil.py + NystromAttention) on the host cores; each "
+                              "timed step is a bounded sample of 1 slide of the workload"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "%d steps x 1 slide of %d patches, fp32, %d of %d host threads"
                                        % (args.steps, args.patches, torch.get_num_threads(), threads)},
