@@ -398,6 +398,7 @@ struct BwdSmem {
   __nv_bfloat16 P[SPLIT ? 2 : 1][MQ][PLD], dS[SPLIT ? 2 : 1][MQ][PLD];     // `red` aliases P at the end of the kernel
   float dQ[32][MTHREADS];            // thread-private dQ accumulators (C-fragment order), live across key tiles
   float stg[4][2][16][9];            // per warp: S and dP of the current 8-key group (fp32)
+  float kgs[4][8][16];               // per warp: key-coordinate gradient partials of the current 8-key group [g][2 u + coord]
   float c1[4][24];                   // layer-1 constants by t: w1x[2][4], w1y[2][4], b1[2][4]
   float c2[4][16];                   // b2[4][2], w3[4][2] by t
   float kpos[BK][2], dkpos[BK][2];
@@ -416,29 +417,6 @@ __device__ __forceinline__ void store_bf16_split(__nv_bfloat16* hi, __nv_bfloat1
   if (lo) *lo = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// sum over the 32 lanes of N per-lane values, scattered: the lanes flagged by `owner` end up holding element `idx`
-template <int N>
-__device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane, int& idx, bool& owner) {
-  static_assert(N == 8 || N == 16, "N");
-  idx = 0;
-  int M = 16;
-#pragma unroll
-  for (int n = N; n > 1; n >>= 1, M >>= 1) {
-    const bool up = (lane & M) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float send = up ? v[i] : v[i + n / 2];
-      const float keep = up ? v[i + n / 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
-    }
-    idx = idx * 2 + (up ? 1 : 0);
-  }
-  float r = v[0];
-  if (N == 16) { r += __shfl_xor_sync(0xffffffffu, r, 1); owner = (lane & 1) == 0; }
-  else { r += __shfl_xor_sync(0xffffffffu, r, 2); r += __shfl_xor_sync(0xffffffffu, r, 1); owner = (lane & 3) == 0; }
-  return r;
-}
-
 template <int CD, bool SPLIT>
 __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
     const AttnCfg cf, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
@@ -455,6 +433,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
   // ---- constants: W2 fragments in registers (both orientations), the small vectors in shared memory (by t)
   uint32_t wh[4][2][2], wl[4][2][2];        // layer 2:  B[k][n = c] = W2[c][k]      [n-tile j][k-step s][reg]
   uint32_t wth[4][2][2], wtl[4][2][2];      // dh1 = dh2 W2:  B[k' = c][n = k] = W2[c][k]   [n-tile jn][k-step s'][reg]
+  uint32_t w1bh[2][2], w1bl[2][2];          // d pos = dpre W1:  B[k][n < CD] = W1[k][n]     [k-step s][reg]
   float b3;
   {
     const float* W1 = cpb; const float* B1 = W1 + CPB_H * CD; const float* W2 = B1 + CPB_H;
@@ -471,6 +450,15 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
         split2<SPLIT>(col[8 * CPB_H], col[9 * CPB_H], wth[j][s][1], wtl[j][s][1]);
       }
     b3 = B3[o];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {            // B[k][n] = W1[k][n] for n < CD (else 0): operand of d pos = dpre W1
+      const int k0_ = 16 * s + 2 * t;
+      const bool on = g < CD;
+      const float v0 = on ? W1[k0_ * CD + g] : 0.f, v1 = on ? W1[(k0_ + 1) * CD + g] : 0.f;
+      const float v2 = on ? W1[(k0_ + 8) * CD + g] : 0.f, v3 = on ? W1[(k0_ + 9) * CD + g] : 0.f;
+      split2<SPLIT>(v0, v1, w1bh[s][0], w1bl[s][0]);
+      split2<SPLIT>(v2, v3, w1bh[s][1], w1bl[s][1]);
+    }
     if (tid < 4 * 24) {
       const int tt = tid / 24, i = tid % 24, which = i / 8, s = (i % 8) / 4, e = i % 4;
       const int kk = 16 * s + 2 * tt + (e & 1) + 8 * (e >> 1);
@@ -521,13 +509,13 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
   }
   // CPB parameter gradient accumulators (fragment order)
   float gW2[2][4][4];                       // C fragments of dW2[c][k]: [m-tile of c][n-tile of k]
-  float gb1[2][4], gW1x[2][4], gW1y[2][4];  // by hidden unit k(s, e)
+  float gL1[2][4];                          // C fragments of [dW1x | dW1y | db1 | 0...][k][n]: [m-tile of k]
   float gb2[4][2], gw3[4][2], gb3 = 0.f;    // by output c(j, e)
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      gb1[a][c] = 0.f; gW1x[a][c] = 0.f; gW1y[a][c] = 0.f;
+      gL1[a][c] = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) gW2[a][c][e] = 0.f;
     }
@@ -604,7 +592,6 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
         __syncwarp();
       }
       // ---- phase 2: CPB forward + backward, one key (16 pairs) per MMA tile
-      float kg[8 * CD];                                  // per-thread partials of d(bias)/d(key position), by (u, coord)
 #pragma unroll 1
       for (int u = 0; u < 8; ++u) {
         const int key = 8 * j + u;
@@ -713,41 +700,65 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
 #pragma unroll
           for (int s = 0; s < 2; ++s) mma3<SPLIT>(dh1[jn], dah[s], dal[s], wth[jn][s][0], wth[jn][s][1], wtl[jn][s][0], wtl[jn][s][1]);
         }
-        // first ReLU backward; layer-1 parameter gradients; d bias / d (signed-log distance)
-        float dax0 = 0.f, dax1 = 0.f, day0 = 0.f, day1 = 0.f;
+        // first ReLU backward: dpre = 1[h1 > 0] dh1 (C-fragment layout) packed as bf16 A fragments
+        uint32_t peh[4][2], pel[4][2];                     // [n-tile jn of k][row r0 / r1]
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t mk = ah[jn >> 1][(jn & 1) * 2 + r];            // h1 (bf16 pair) of hidden units 8 jn + 2 t + {0, 1}
+            const float v0 = (mk & 0xffffu) != 0u ? dh1[jn][2 * r] : 0.f;
+            const float v1 = (mk >> 16) != 0u ? dh1[jn][2 * r + 1] : 0.f;
+            split2<SPLIT>(v0, v1, peh[jn][r], pel[jn][r]);
+          }
+        // d bias / d (signed-log distance) = dpre W1: MMA over the hidden axis; lanes t == 0 hold (x, y) of rows r0 / r1
+        float dpo[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          const float4 wx = lds128v(c1 + 4 * s), wy = lds128v(c1 + 8 + 4 * s);
-          const float wxa[4] = {wx.x, wx.y, wx.z, wx.w}, wya[4] = {wy.x, wy.y, wy.z, wy.w};
+          const uint32_t pah[4] = {peh[2 * s][0], peh[2 * s][1], peh[2 * s + 1][0], peh[2 * s + 1][1]};
+          const uint32_t pal[4] = {pel[2 * s][0], pel[2 * s][1], pel[2 * s + 1][0], pel[2 * s + 1][1]};
+          mma3<SPLIT>(dpo, pah, pal, w1bh[s][0], w1bh[s][1], w1bl[s][0], w1bl[s][1]);
+        }
+        const float dax0 = dpo[0], day0 = dpo[1], dax1 = dpo[2], day1 = dpo[3];
+        // layer-1 parameter gradients [dW1x | dW1y | db1] = dpre^T [ax ay 1]: MMA over the pair axis (operands transposed in
+        // registers); the [16 pairs x 8] right operand lives in C-fragment layout: lanes t == 0 hold (ax, ay), t == 1 (1, 0)
+        {
+          uint32_t xh0, xl0, xh1, xl1;
+          split2<SPLIT>(ax0, ay0, xh0, xl0);
+          split2<SPLIT>(ax1, ay1, xh1, xl1);
+          if (t != 0) { xh0 = t == 1 ? 0x00003f80u : 0u; xh1 = xh0; xl0 = 0u; xl1 = 0u; }
+          const uint32_t bxh0 = movm_trans(xh0), bxh1 = movm_trans(xh1);
+          uint32_t bxl0 = 0u, bxl1 = 0u;
+          if (SPLIT) { bxl0 = movm_trans(xl0); bxl1 = movm_trans(xl1); }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int jn = 2 * s + (e >> 1), c = e & 1;            // hidden unit k(s, e) = 8 jn + 2 t + c
-            const uint32_t m0 = ah[s][(e >> 1) * 2], m1 = ah[s][(e >> 1) * 2 + 1];       // h1 of rows r0 / r1 (bf16 pairs)
-            const bool on0 = c ? (m0 >> 16) != 0u : (m0 & 0xffffu) != 0u;
-            const bool on1 = c ? (m1 >> 16) != 0u : (m1 & 0xffffu) != 0u;
-            const float e0 = on0 ? dh1[jn][c] : 0.f, e1 = on1 ? dh1[jn][2 + c] : 0.f;
-            gb1[s][e] += e0 + e1;
-            gW1x[s][e] = fmaf(e0, ax0, fmaf(e1, ax1, gW1x[s][e]));
-            dax0 = fmaf(wxa[e], e0, dax0); dax1 = fmaf(wxa[e], e1, dax1);
-            if (CD == 2) {
-              gW1y[s][e] = fmaf(e0, ay0, fmaf(e1, ay1, gW1y[s][e]));
-              day0 = fmaf(wya[e], e0, day0); day1 = fmaf(wya[e], e1, day1);
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t tah[4], tal[4] = {0u, 0u, 0u, 0u};
+            tah[0] = movm_trans(peh[2 * mt][0]); tah[1] = movm_trans(peh[2 * mt + 1][0]);
+            tah[2] = movm_trans(peh[2 * mt][1]); tah[3] = movm_trans(peh[2 * mt + 1][1]);
+            if (SPLIT) {
+              tal[0] = movm_trans(pel[2 * mt][0]); tal[1] = movm_trans(pel[2 * mt + 1][0]);
+              tal[2] = movm_trans(pel[2 * mt][1]); tal[3] = movm_trans(pel[2 * mt + 1][1]);
             }
+            mma3<SPLIT>(gL1[mt], tah, tal, bxh0, bxh1, bxl0, bxl1);
           }
         }
         // d slog(x)/dx = 1 / (|x| + 1); the key coordinate enters with a minus sign
-        const float kgx = -(__fdividef(dax0, fabsf(dx0) + 1.f) + __fdividef(dax1, fabsf(dx1) + 1.f));
-        const float kgy = CD == 2 ? -(__fdividef(day0, fabsf(dy0) + 1.f) + __fdividef(day1, fabsf(dy1) + 1.f)) : 0.f;
+        // only the lanes t == 0 hold (dax, day): park this key's per-lane partials (2 query rows each) in the warp's staging
+        // rows; they are summed over the 8 lanes once per 8-key group
+        if (t == 0) {
+          const float kgx = -(__fdividef(dax0, fabsf(dx0) + 1.f) + __fdividef(dax1, fabsf(dx1) + 1.f));
+          const float kgy = CD == 2 ? -(__fdividef(day0, fabsf(dy0) + 1.f) + __fdividef(day1, fabsf(dy1) + 1.f)) : 0.f;
+          *reinterpret_cast<float2*>(&sm.kgs[w][g][2 * u]) = make_float2(kgx, kgy);
+        }
+      }
+      __syncwarp();
+      if (lane < 16) {                                     // lane = 2 u + coord
+        float r = 0.f;
 #pragma unroll
-        for (int uu = 0; uu < 8; ++uu)                     // static register indices (the u loop is rolled)
-          if (uu == u) { kg[uu * CD] = kgx; if (CD == 2) kg[uu * CD + 1] = kgy; }
+        for (int gg = 0; gg < 8; ++gg) r += sm.kgs[w][gg][lane];
+        if (CD == 2 || (lane & 1) == 0) atomicAdd(&sm.dkpos[8 * j + (lane >> 1)][lane & 1], r);
       }
-      // key-coordinate gradients of this 8-key group: reduce over the warp's 16 queries, then one shared atomic per value
-      {
-        int idx; bool owner;
-        const float r = warp_reduce_scatter<8 * CD>(kg, lane, idx, owner);
-        if (owner) atomicAdd(&sm.dkpos[8 * j + idx / CD][idx % CD], r);
-      }
+      __syncwarp();
     }
     __syncthreads();
     // ---- phase 3: dQ += dS K (thread-private accumulators parked in shared memory between key tiles)
@@ -853,21 +864,18 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
   {
     float* rW1 = red; float* rb1 = rW1 + CPB_H * 2; float* rW2 = rb1 + CPB_H; float* rb2 = rW2 + CPB_H * CPB_H;
     float* rw3 = rb2 + CPB_H; float* rb3 = rw3 + CPB_H;
-    // values indexed by t only: add the 8 lanes (g) that share t first
+    // layer 1: rows of the gL1 fragments are hidden units (distinct per g), columns (dW1x, dW1y | db1, -)
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float a = gb1[s][e], x = gW1x[s][e], y = gW1y[s][e];
-#pragma unroll
-        for (int m = 4; m < 32; m <<= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, m); x += __shfl_xor_sync(0xffffffffu, x, m); y += __shfl_xor_sync(0xffffffffu, y, m);
-        }
-        if (g == 0) {
-          const int kk = 16 * s + 2 * t + (e & 1) + 8 * (e >> 1);
-          atomicAdd(&rb1[kk], a); atomicAdd(&rW1[kk * 2], x); atomicAdd(&rW1[kk * 2 + 1], y);
-        }
+    for (int mt = 0; mt < 2; ++mt) {
+      const int kk = 16 * mt + g;
+      if (t == 0) {
+        atomicAdd(&rW1[kk * 2], gL1[mt][0]); atomicAdd(&rW1[kk * 2 + 1], gL1[mt][1]);
+        atomicAdd(&rW1[(kk + 8) * 2], gL1[mt][2]); atomicAdd(&rW1[(kk + 8) * 2 + 1], gL1[mt][3]);
+      } else if (t == 1) {
+        atomicAdd(&rb1[kk], gL1[mt][0]); atomicAdd(&rb1[kk + 8], gL1[mt][2]);
       }
+    }
+    // values indexed by t only: add the 8 lanes (g) that share t first
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
