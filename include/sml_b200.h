@@ -96,6 +96,9 @@ int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* st
 /* y[b,t,:] = (x ? x[b,t,:] : 0) + a*vec[b,:]  — the rank-1 half of FusionNet (models/DeformCrossTransMIL.py:104,33-38:
  * the repeated omic vector is never materialised) and the backward of the token mean (Pooler :193) */
 int sml_add_rowvec(float* y, const float* x, const float* vec, float a, int64_t B, int64_t T, int32_t C, void* stream);
+/* torch.nn.AlphaDropout of the MaxNet encoders (models/model.py:152-170), same counter-based mask as sml_dropout_add;
+ * bwd = 0: y = alpha_dropout(x); bwd = 1: y = d x given x = d y (same seed / offset) */
+int sml_alpha_dropout(const float* x, float* y, int64_t n, float p, int32_t bwd, uint64_t seed, uint64_t offset, void* stream);
 /* pointwise heads: op 0 tanh (Pooler :200), 1 sigmoid, 2 relu (fusion.py:38-50), 3 elu (model.py:150) */
 int sml_unary_fwd(int32_t op, const float* x, float* y, int64_t n, void* stream);
 int sml_unary_bwd(int32_t op, const float* x, const float* y, const float* dy, float* dx, int64_t n, void* stream);

@@ -11,6 +11,7 @@ from .models.DeformableAttention2D import DeformCrossAttention2D  # noqa: F401
 from .models.DeformCrossTransMIL import DeformCrossTransMIL, FusionNet, DeformCrossTransLayer, Pooler  # noqa: F401
 from .models.MultiheadAttention import MultiheadAttention  # noqa: F401
 from .models.fusion import BilinearFusion  # noqa: F401
+from .models.model import MaxNet, DeformPathomicNet  # noqa: F401
 from .utils.loss import BatchLoss, OrthogonalLoss  # noqa: F401
 from .utils.gather import GatherLayer, PackedGather  # noqa: F401
 from .utils.sync_batchnorm import SyncBatchNorm1d, SynchronizedBatchNorm1d, convert_model  # noqa: F401

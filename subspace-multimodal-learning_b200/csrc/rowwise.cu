@@ -327,6 +327,17 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const float* __restric
     y[i] = (x ? x[i] : 0.f) + uv;
   }
 }
+// AlphaDropout (models/model.py:152-170, torch.nn.AlphaDropout): kept elements a x + b, dropped ones a alpha' + b with
+// alpha' = -selu_scale * selu_alpha, a = ((1 - p)(1 + p alpha'^2))^-1/2, b = -a alpha' p.  bwd = 1: y = dx given x = dy.
+__global__ void __launch_bounds__(256) alpha_dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
+                                                            float a, float dropped, float b, int bwd, uint64_t seed,
+                                                            uint64_t offset) {
+  const uint32_t thresh = (uint32_t)(p * 4294967296.0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool keep = mix32(seed * 0xD1342543DE82EF95ull + offset + (uint64_t)i) >= thresh;
+    y[i] = bwd ? (keep ? a * x[i] : 0.f) : (keep ? fmaf(a, x[i], b) : dropped);
+  }
+}
 __global__ void __launch_bounds__(256) axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b,
                                                     int64_t n, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -516,6 +527,16 @@ extern "C" int sml_dropout_add(const float* x, const float* u, float* y, int64_t
   if (n == 0) return 0;
   dropout_add_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, u, y, n, p, seed, offset);
   SML_LAUNCH_OK("sml_dropout_add");
+  return 0;
+}
+extern "C" int sml_alpha_dropout(const float* x, float* y, int64_t n, float p, int32_t bwd, uint64_t seed, uint64_t offset,
+                                 void* stream) {
+  SML_CHECK(p > 0.f && p < 1.f, "sml_alpha_dropout: p=%f out of range", p);
+  if (n == 0) return 0;
+  const double ap = -1.0507009873554804934193349852946 * 1.6732632423543772848170429916717;
+  const double a = 1.0 / sqrt((1.0 - p) * (1.0 + p * ap * ap)), b = -a * ap * p;
+  alpha_dropout_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, y, n, p, (float)a, (float)(a * ap + b), (float)b, bwd, seed, offset);
+  SML_LAUNCH_OK("sml_alpha_dropout");
   return 0;
 }
 extern "C" int sml_axpby(float* y, const float* x, float a, float b, int64_t n, void* hi, void* lo, void* stream) {

@@ -114,6 +114,35 @@ def dropout_add(x, u, p, training):
     return DropoutAddFn.apply(x, u, p, _seed_state["seed"], off)
 
 
+class AlphaDropoutFn(torch.autograd.Function):
+    """torch.nn.AlphaDropout (MaxNet encoders, model.py:152-170); the mask is regenerated from (seed, offset) in backward."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, offset):
+        ops.require_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(lib.sml_alpha_dropout(ptr(x), ptr(y), ops.c_i64(x.numel()), ops.c_f32(p), c_i32(0), ops.c_u64(seed), ops.c_u64(offset),
+                                    stream()), "alpha_dropout")
+        ctx.cfg = (p, seed, offset)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed, offset = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        check(lib.sml_alpha_dropout(ptr(dy), ptr(dx), ops.c_i64(dy.numel()), ops.c_f32(p), c_i32(1), ops.c_u64(seed),
+                                    ops.c_u64(offset), stream()), "alpha_dropout_bwd")
+        return dx, None, None, None
+
+
+def alpha_dropout(x, p, training):
+    if not training or p == 0.0:
+        return x
+    return AlphaDropoutFn.apply(x, float(p), _seed_state["seed"], _next_offset(x.numel()))
+
+
 class PPEGFn(torch.autograd.Function):
     """x [B,1+H*W,C] -> cls row copied, tokens get the folded 7x7 depthwise stencil (mil.py:192-206).
     w7 [49,C] (tap-major) and bias [C] are the folded parameters (see models/mil.py:PPEG.folded)."""

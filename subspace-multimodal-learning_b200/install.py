@@ -7,7 +7,7 @@ them: register the drop-in modules under the module names the reference imports.
 
 What is replaced:  nystrom_attention.NystromAttention (models/mil.py:24, DeformCrossTransMIL.py:24),
 models.NystromAttention, models.DeformableAttention1D / 2D, models.MultiheadAttention, models.DeformCrossTransMIL,
-models.fusion.BilinearFusion, utils.loss.BatchLoss, utils.gather.GatherLayer, utils.sync_batchnorm.convert_model.
+models.fusion.BilinearFusion, models.model.DeformPathomicNet / MaxNet, utils.loss.BatchLoss, utils.gather.GatherLayer, utils.sync_batchnorm.convert_model.
 The reference's factory (models/model.py), train/eval loops and CLI stay the reference's code.
 """
 import sys
@@ -43,6 +43,15 @@ def install(replace_mil=True):
         import utils.sync_batchnorm as ref_sbn
         ref_sbn.convert_model = sync_batchnorm.convert_model
         ref_sbn.SynchronizedBatchNorm1d = sync_batchnorm.SynchronizedBatchNorm1d
+    except Exception:
+        pass
+    # DeformPathomicNet / MaxNet (models/model.py:142-187, 440-544): the factory define_net() looks the classes up in its own
+    # module namespace, so swap them there (needs the reference importable; skipped otherwise)
+    try:
+        import models.model as ref_model
+        from .models.model import DeformPathomicNet, MaxNet
+        ref_model.DeformPathomicNet = DeformPathomicNet
+        ref_model.MaxNet = MaxNet
     except Exception:
         pass
     return sorted(table)

@@ -188,3 +188,61 @@ def test_deform_attention_dropout_is_unbiased():
         acc += mod(x1, x2).detach()
     assert rel_err(acc / 16, y0) < 0.1                   # dropout(p) / (1-p) keeps the expectation
     assert rel_err(mod(x1, x2), y0) > 1e-3               # and it is really applied in training mode
+
+
+def test_deform_pathomic_net_golden(prec):
+    """DeformPathomicNet (models/model.py:440-544): two MaxNet encoders + two DeformCrossTransMIL branches on the same bag +
+    concat + three heads, against the unmodified reference (tests/golden/make_golden_pathomic.py), batch 2, N = 2500."""
+    import sml_b200
+    from make_golden_pathomic import pathomic_args
+    to, ti, tp = TOLS[prec]
+    g = load_golden("pathomic")
+    net = sml_b200.DeformPathomicNet(pathomic_args()).cuda().eval()
+    st = synth_state_dict(g["shapes"], g["seed"])
+    for k in st:
+        if k.endswith("to_offsets.2.weight"):
+            st[k] = st[k] * g["offw_scale"]
+        if k.endswith("output_range"):
+            st[k] = torch.tensor([6.0])
+        if k.endswith("output_shift"):
+            st[k] = torch.tensor([-3.0])
+    net.load_state_dict(st)                                   # reference state_dict keys load unchanged
+    x_path = randn((2, 2500, 1024), 112).cuda()
+    xt = randn((2, 59), 113).abs().cuda().requires_grad_(); xi = randn((2, 361), 114).abs().cuda().requires_grad_()
+    feats, vt, vi, logits, fg, _, _ = net(x_path=x_path, x_omic_tumor=xt, x_omic_immune=xi)
+    assert fg is None and len(logits) == 7
+    assert rel_err(feats, g["feats"]) < to and rel_err(vt, g["vt"]) < to and rel_err(vi, g["vi"]) < to
+    # head logits: [2, 4] tensors after LayerNorm + pooler + two stacked linear heads; the hi/lo split measures 1.1e-4 here
+    # against the fp32-CPU reference (exact-fp32 kernels: 2e-5), so the composite model gets 2x the single-module bar
+    for a, b in zip(logits[:3], g["logits"]):
+        assert rel_err(a, b) < 2 * to
+    assert rel_err(logits[4], g["vgrid_tumor"]) < 1e-4 and rel_err(logits[6], g["vgrid_immune"]) < 1e-4
+    assert rel_err(logits[3][:, 5], g["omic_tumor_row"]) < 1e-5
+    loss = sum((l * randn(l.shape, 120 + j).cuda()).sum() for j, l in enumerate(logits[:3])) + (feats * randn(feats.shape, 125).cuda()).sum()
+    loss = loss + 0.01 * ((logits[4] * randn(logits[4].shape, 126).cuda()).sum() + (logits[6] * randn(logits[6].shape, 127).cuda()).sum())
+    loss.backward()
+    assert rel_err(xt.grad, g["gxt"]) < ti and rel_err(xi.grad, g["gxi"]) < ti
+    gp = {k: p.grad for k, p in net.named_parameters()}
+    check_param_grads(gp, {k: v for k, v in g["gparams"].items() if gp[k] is not None}, prec, scale=2.0)
+    for k, nv in g["gnorms"].items():
+        if gp[k] is None:
+            continue
+        tk = 2 * (tp if "rel_pos_bias" in k else ti)
+        floor = 1e-5 + 1e-3 * tk * max(g["gnorms"].values())
+        assert abs(float(gp[k].norm()) - nv) <= tk * nv + floor, (k, float(gp[k].norm()), nv)
+
+
+def test_maxnet_alpha_dropout_statistics():
+    """AlphaDropout keeps mean and variance of a standard-normal input (torch.nn.AlphaDropout contract) and its backward
+    regenerates the same mask."""
+    from sml_b200 import functional as Fn
+    Fn.manual_seed(11)
+    x = torch.randn(1 << 20, device="cuda", requires_grad=True)
+    y = Fn.alpha_dropout(x, 0.1, True)
+    assert abs(float(y.detach().mean())) < 5e-3 and abs(float(y.detach().var()) - 1.0) < 1e-2
+    y.sum().backward()
+    kept = x.grad != 0
+    assert abs(float(kept.float().mean()) - 0.9) < 2e-3
+    a = float(x.grad[kept][0])
+    assert torch.allclose(y.detach()[kept], a * x.detach()[kept] + (y.detach()[kept][0] - a * x.detach()[kept][0]), atol=1e-5)
+    assert Fn.alpha_dropout(x, 0.1, False) is x
