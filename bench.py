@@ -39,9 +39,11 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SML_PRECISION", "bf16"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=8, help="slides per step per GPU (config_mine.yaml batch_size: 8)")
     ap.add_argument("--patches", type=int, default=16384)
-    ap.add_argument("--workload", default="transmil", choices=["transmil", "deform2d", "deform1d"],
+    ap.add_argument("--workload", default="transmil", choices=["transmil", "deform2d", "deform1d", "pathomic"],
                     help="transmil = BASELINE.json configs[1] (the headline); deform2d / deform1d = configs[2], the full "
-                         "DeformCrossTransMIL (attn_dim 2 / 1) train step")
+                         "DeformCrossTransMIL (attn_dim 2 / 1) train step; pathomic = DeformPathomicNet (two genomic encoders + two "
+                         "DeformCrossTransMIL branches + heads) with the reference's loss: weighted CE + BatchLoss over all ranks "
+                         "(train_test.py:63-83)")
     ap.add_argument("--cpu-sample", type=int, default=1, help="slides in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-out", default=None, help="write the per-shape GEMM timing table of the instrumented pass here")
@@ -163,7 +165,16 @@ def run_ours(args):
 
     torch.manual_seed(42)
     deform = args.workload != "transmil"
-    if deform:
+    pathomic = args.workload == "pathomic"
+    if pathomic:
+        margs = Namespace(init_type="max", input_size_omic_tumor=59, input_size_omic_immune=361, omic_dim=128, path_dim=128,
+                          mmhid=128, return_grad="False", dropout_rate=0.1, label_dim=4, fusion_type="concat", cut_fuse_grad=False,
+                          return_vgrid=True, attn_dim=2, task_type="diag2021")          # config/config_mine.yaml
+        model = sml_b200.DeformPathomicNet(margs).to(dev).train()
+        model.set_precision(args.precision)
+        bloss = sml_b200.BatchLoss(args.batch, world)
+        ce_w = torch.tensor([1.0, 4.15, 2.93, 2.43], device=dev)                        # train_test.py:25
+    elif deform:
         model = sml_b200.DeformCrossTransMIL(Namespace(path_dim=128, attn_dim=2 if args.workload == "deform2d" else 1,
                                                        return_vgrid=False)).to(dev).train()
         model.set_precision(args.precision)
@@ -183,8 +194,19 @@ def run_ours(args):
     y_host = y_dev.cpu().pin_memory()
     omic = torch.randn(B, 128, generator=torch.Generator(device=dev).manual_seed(7 + rank), device=dev).abs() if deform else None
 
+    if pathomic:
+        gen = torch.Generator(device=dev).manual_seed(9 + rank)
+        x_t = torch.randn(B, 59, generator=gen, device=dev).abs()
+        x_i = torch.randn(B, 361, generator=gen, device=dev).abs()
+
     def step(x, y):
         opt.zero_grad(set_to_none=True)
+        if pathomic:
+            lg = net(x_path=x, x_omic_tumor=x_t, x_omic_immune=x_i)[3]
+            loss = torch.nn.functional.cross_entropy(lg[2], y, weight=ce_w) + 0.5 * bloss(lg[3], lg[4]).sum() + 0.5 * bloss(lg[5], lg[6]).sum()
+            loss.backward()
+            opt.step()
+            return loss
         logits = net(x, omic)[1] if deform else net(x)[1]
         loss = torch.nn.functional.cross_entropy(logits, y)
         loss.backward()
@@ -301,7 +323,9 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "f32 (bf16x3 split)", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": ("DeformCrossTransMIL(attn_dim=%d: fc1 + genomic fusion + deformable cross-attention + heads) "
+                "config": {"workload": ("DeformPathomicNet (2 x MaxNet + 2 x DeformCrossTransMIL attn_dim=2 + concat heads) fwd + weighted CE + "
+                                        "BatchLoss(all ranks) + bwd + Adam on %d-patch x 1024-d bags" % N) if pathomic else
+                                       ("DeformCrossTransMIL(attn_dim=%d: fc1 + genomic fusion + deformable cross-attention + heads) "
                                         "fwd+CE+bwd+Adam on %d-patch x 1024-d bags" % (2 if args.workload == "deform2d" else 1, N)) if deform
                            else "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags"
                                        % N, "slides_per_step_per_gpu": B, "global_batch": B * world, "precision": args.precision,

@@ -20,12 +20,18 @@ class _BatchLossFn(torch.autograd.Function):
         ops.require_cuda(O, V)
         O, V = O.contiguous(), V.contiguous()
         Ng, NS = O.shape[0], V.shape[0]
-        S = gemm(O, O.t())
+        # Long rows (the reference's token-repeated omic tensor: N*128 = 2.1 M columns at 16 k patches, which is what reaches
+        # the loss once DistributedDataParallel has cloned the model outputs) go through the tcgen05 engine with the hi/lo
+        # split and split-K; short rows (the [Ng,128] base, vgrid) stay on the exact-fp32 SIMT engine.
+        big = O.shape[1] > 4096
+        Oop = ops.to_bf16(O, split=True) if big else O
+        S = gemm(Oop, Oop.map(lambda t: t.t()) if big else O.t())
         T = gemm(V, V.transpose(-1, -2))
         loss = torch.empty(Ng, Ng, device=O.device, dtype=F32)
         rn = torch.empty(1 + NS, Ng, device=O.device, dtype=F32)
         check(lib.sml_batchloss_fwd(ptr(S), ptr(T), ptr(loss), ptr(rn), c_i32(Ng), c_i32(NS), stream()), "batchloss_fwd")
         ctx.save_for_backward(O, V, S, T, rn)
+        ctx.big = big
         return loss
 
     @staticmethod
@@ -35,8 +41,17 @@ class _BatchLossFn(torch.autograd.Function):
         dS, dT = torch.empty_like(S), torch.empty_like(T)
         check(lib.sml_batchloss_bwd(ptr(S), ptr(T), ptr(rn), ptr(dloss.contiguous()), ptr(dS), ptr(dT), c_i32(Ng), c_i32(NS), stream()),
               "batchloss_bwd")
-        dO = gemm(dS, O)
-        gemm(dS.t(), O, out=dO, beta=1.0)
+        if ctx.big:
+            Ngp = (Ng + 7) // 8 * 8                      # TMA wants 16-byte row pitches: pad the tiny [Ng,Ng] operand
+            dSp = torch.zeros(Ng, Ngp, device=dS.device, dtype=F32)
+            dSp[:, :Ng].copy_(dS)
+            Oop = ops.to_bf16(O, split=True)
+            dSop = ops.to_bf16(dSp, split=True).map(lambda t: t[:, :Ng])
+            dO = gemm(dSop, Oop)
+            gemm(dSop.map(lambda t: t.t()), Oop, out=dO, beta=1.0)
+        else:
+            dO = gemm(dS, O)
+            gemm(dS.t(), O, out=dO, beta=1.0)
         dV = gemm(dT, V)
         gemm(dT.transpose(-1, -2), V, out=dV, beta=1.0)
         return dO, dV
@@ -51,6 +66,8 @@ class BatchLoss(nn.Module):
     def forward(self, omic, vgrid):
         N = self.batch_size * self.world_size
         base = getattr(omic, "_sml_base", None)          # [B,128] base of the token-repeated omic (DeformCrossTransMIL)
+        if base is None and omic.dim() == 3 and omic.stride(1) == 0:
+            base = omic[:, 0]                            # stride-0 token axis: the same rows repeated (survives DDP re-wrapping)
         o = base if base is not None else omic.reshape(omic.shape[0], -1)
         if self.world_size > 1:
             o, vgrid = PackedGather.apply(o.float(), vgrid.float())

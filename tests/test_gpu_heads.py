@@ -88,3 +88,23 @@ def test_batchloss_collapsed_gram_equals_repeated():
     b2 = base.cuda().requires_grad_()
     got2 = sml_b200.BatchLoss(B, 1)(b2.unsqueeze(1).repeat(1, N, 1), vg.cuda())     # untagged: generic [Ng, N*128] Gram
     assert rel_err(got2, want) < 5e-4       # 51 200-long fp32 dot products on both sides, then a cancelling difference
+
+
+def test_batchloss_long_rows_match_collapsed_base():
+    """The token-repeated omic tensor (what DDP hands to the loss after cloning the outputs) and its [B,128] base give the
+    same loss and the same gradient w.r.t. the base (row normalisation cancels the repetition, utils/loss.py:26-38)."""
+    import sml_b200
+    torch.manual_seed(4)
+    B, N = 4, 4096
+    base = torch.randn(B, 128, device="cuda").abs()
+    vg = torch.randn(8 * B, 2, 12, 12, device="cuda", requires_grad=True)
+    bl = sml_b200.BatchLoss(B, 1)
+    b1 = base.clone().requires_grad_()
+    l1 = bl(b1.unsqueeze(1).expand(B, N, 128), vg)               # stride-0 view -> collapsed path
+    l1.sum().backward()
+    g_v1 = vg.grad.clone(); vg.grad = None
+    b2 = base.clone().requires_grad_()
+    l2 = bl(b2.unsqueeze(1).repeat(1, N, 1), vg)                   # materialised rows -> tensor-core Gram with split-K
+    l2.sum().backward()
+    assert rel_err(l2, l1) < 1e-4
+    assert rel_err(b2.grad, b1.grad) < 1e-3 and rel_err(vg.grad, g_v1) < 1e-3
