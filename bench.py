@@ -290,6 +290,24 @@ def run_ours(args):
             for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
                 f.write("%s : %d %.1f %.1f %.1f\n" % (" ".join(str(x) for x in k), v[2], v[1] * 1e6, v[1] * 1e6 / v[2], v[0] / v[1] / 1e12))
     pk, pk_src = peaks()
+    # per-shape roofline of the heaviest tcgen05 GEMM shapes: bound by their outputs (HBM) when K = 64, by the tensor pipe
+    # otherwise.  `traffic` = dram read + write per launch from the round's `ncu --set full` capture (profiles/r01_ncu_summary.txt)
+    ncu_traffic = {(256, 16640, 64, 64, 0): 138.8e6 + 1032.6e6, (16640, 256, 64, 64, 2): 138.6e6 + 492.2e6,
+                   (133120, 1536, 512, 1, 0): 138.0e6 + 1170.8e6, (256, 256, 256, 64, 0): 33.6e6 + 0.9e6}
+    by_shape = []
+    for key, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+        if key[0] != "tc" or len(by_shape) >= 5:
+            continue
+        M_, N_, K_, nb_, _, _, split_, relu_, c_, hi_, lo_, _ = key[1:]
+        t_avg = v[1] / v[2]
+        bytes_ = nb_ * (2.0 * (1 + split_) * (M_ * K_ + K_ * N_) + M_ * N_ * (4.0 * c_ + 2.0 * hi_ + 2.0 * lo_))
+        hbm_frac = bytes_ / t_avg / 1e9 / pk["hbm_gbs"]
+        tc_frac = v[0] / v[1] / 1e12 / pk["bf16_tflops_sustained"]
+        by_shape.append({"shape": "%dx%dx%d x%d%s%s" % (M_, N_, K_, nb_, " bf16x3" if split_ else "", " +softmax" if relu_ & 2 else ""),
+                         "launches": v[2], "avg_us": t_avg * 1e6, "bound": "hbm" if hbm_frac > tc_frac else "tensor",
+                         "achieved": (bytes_ / t_avg / 1e9) if hbm_frac > tc_frac else v[0] / v[1] / 1e12,
+                         "unit": "GB/s" if hbm_frac > tc_frac else "TFLOP/s", "frac": max(hbm_frac, tc_frac),
+                         "traffic": ncu_traffic.get((M_, N_, K_, nb_, relu_ & 2))})
     roof = None
     if deform and "deform_bwd" in agg:
         f, t, n = agg["deform_bwd"]
@@ -310,7 +328,7 @@ def run_ours(args):
         roof = {"kernel": "gemm_tc_kernel (tcgen05, all %d launches of one step)" % n, "bound": "tensor", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " (sustained)",
                 "share_of_step": t / (ms * 1e-3 / args.steps),
-                "note": "bf16x3 launches count 1x algorithmic FLOPs (3 MMA passes executed)"}
+                "note": "bf16x3 launches count 1x algorithmic FLOPs (3 MMA passes executed)", "by_shape": by_shape}
     elif "simt" in agg:
         f, t, n = agg["simt"]
         roof = {"kernel": "gemm_f32_kernel (SIMT fp32, %d launches)" % n, "bound": "tensor", "achieved": f / t / 1e12,

@@ -166,6 +166,62 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
         }
       } else {
         float mx = -INFINITY, inv = 1.f;
+        if (ep.softmax && !ep.C && !ep.Cb_lo && ep.Cb_hi && ep.vec_ok && n0 + BN <= ep.N) {
+          // bf16-only probabilities (bf16 mode): ONE exp per element.  Pass 1 finds the row maximum (no exp), pass 2 forms
+          // e = exp(x - max) once, keeps it as packed bf16 pairs in registers and sums it in fp32; the pairs are then
+          // scaled by 1 / sum and stored (the two-exp path below costs twice the MUFU work, which bounds this epilogue).
+          float m_ = -INFINITY;
+          for (int c = cbeg; c < cbeg + CH; c += 32) {
+            tc_ld32(trow + c, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m_ = fmaxf(m_, ep.alpha * __uint_as_float(r[j]));
+          }
+          float2* st = stats_buf;
+          st[half * TC_BM + row].x = m_;
+          asm volatile("bar.sync 1, 256;" ::: "memory");            // the 8 epilogue warps only
+          mx = fmaxf(m_, st[(half ^ 1) * TC_BM + row].x);
+          uint32_t eb[CH / 2];
+          float l_ = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < CH / 32; ++cc) {
+            tc_ld32(trow + cbeg + cc * 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float e0 = __expf(ep.alpha * __uint_as_float(r[j]) - mx), e1 = __expf(ep.alpha * __uint_as_float(r[j + 1]) - mx);
+              l_ += e0 + e1;
+              const __nv_bfloat162 pe = __floats2bfloat162_rn(e0, e1);
+              eb[cc * 16 + j / 2] = *reinterpret_cast<const uint32_t*>(&pe);
+            }
+          }
+          st[half * TC_BM + row].y = l_;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          inv = 1.f / (l_ + st[(half ^ 1) * TC_BM + row].y);
+#pragma unroll
+          for (int cc = 0; cc < CH / 32; ++cc) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const uint32_t pe = eb[cc * 16 + j / 2];
+              v[j] = __uint_as_float(pe << 16) * inv; v[j + 1] = __uint_as_float(pe & 0xffff0000u) * inv;
+            }
+            const int gn0 = n0 + cbeg + cc * 32;
+            if (STAGED) {
+              store_chunk_staged(ep, staging + (warp - 2) * 32 * TC_STG_LD, lane, m0 + q * 32, (int64_t)b1 * ep.sc_b1 + (int64_t)b2 * ep.sc_b2, gn0, v);
+            } else if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __nv_bfloat162 h[4];
+                uint4 pk;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(v[j + 2 * u], v[j + 2 * u + 1]);
+                pk.x = *reinterpret_cast<uint32_t*>(&h[0]); pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+                pk.z = *reinterpret_cast<uint32_t*>(&h[2]); pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+                *reinterpret_cast<uint4*>(hrow + gn0 + j) = pk;
+              }
+            }
+          }
+          return;
+        }
         if (ep.softmax) {
           // Row softmax fused in the epilogue.  A row lives in one TMEM lane; the two warps sharing a lane quarter each
           // scan their own half of the columns ONCE with an online (max, sum) update and swap the pair through shared
@@ -645,6 +701,8 @@ static int prepare_tc(const sml_gemm_desc* d, int force_bn, bool allow_splitk, c
 
   const int softmax = (d->relu & 2) ? 1 : 0;
   int BN = d->N > 128 ? 256 : (d->N > 64 ? 128 : 64);
+  // bf16x3: 128-wide tiles (measured on the 64 x 256^3 pinv steps: 256-wide tiles 34 us vs 30 us, and a 3-stage ring that
+  // forfeits the staged epilogue 33 us)
   if (split && BN == 256 && !softmax) BN = 128;
   if (force_bn > 0) BN = force_bn;
   SML_CHECK(!softmax || d->N <= BN, "sml_gemm_tc: fused row softmax needs N <= %d (N=%d)", BN, d->N);
