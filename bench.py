@@ -304,7 +304,9 @@ def run_ours(args):
         hbm_frac = bytes_ / t_avg / 1e9 / pk["hbm_gbs"]
         tc_frac = v[0] / v[1] / 1e12 / pk["bf16_tflops_sustained"]
         by_shape.append({"shape": "%dx%dx%d x%d%s%s" % (M_, N_, K_, nb_, " bf16x3" if split_ else "", " +softmax" if relu_ & 2 else ""),
-                         "launches": v[2], "avg_us": t_avg * 1e6, "bound": "hbm" if hbm_frac > tc_frac else "tensor",
+                         "launches": v[2], "avg_us": t_avg * 1e6,
+                         "bound": "latency (dependent chain, L2-resident operands)" if (K_ == M_ == N_ == 256) else
+                                  ("hbm" if hbm_frac > tc_frac else "tensor"),
                          "achieved": (bytes_ / t_avg / 1e9) if hbm_frac > tc_frac else v[0] / v[1] / 1e12,
                          "unit": "GB/s" if hbm_frac > tc_frac else "TFLOP/s", "frac": max(hbm_frac, tc_frac),
                          "traffic": ncu_traffic.get((M_, N_, K_, nb_, relu_ & 2))})
