@@ -192,7 +192,7 @@ struct FwdSmem {
 
 // grid (ceil(n / 64), heads, B), 128 threads.  q pre-scaled by d^-1/2.  out [b, n, inner], lse [b, heads, n].
 template <int CD, bool SPLIT>
-__global__ void __launch_bounds__(MTHREADS) deform_attn_fwd_mma_kernel(const AttnCfg cf, const float* __restrict__ q,
+__global__ void __launch_bounds__(MTHREADS, SPLIT ? 2 : 3) deform_attn_fwd_mma_kernel(const AttnCfg cf, const float* __restrict__ q,
                                                                        const float* __restrict__ k, const float* __restrict__ v,
                                                                        const float* __restrict__ vs, const float* __restrict__ cpb,
                                                                        float* __restrict__ out, float* __restrict__ lse) {
