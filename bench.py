@@ -59,25 +59,53 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md clocks line), sampled every 50 ms through NVML
+    (no process spawn; nvidia-smi is the fallback).  Rank 0 samples its own GPU only: eight samplers on one host would
+    perturb what they measure."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(v) for v in vis.split(",") if v.strip() != ""]
+            index = ids[index] if ids else index
+        except ValueError:
+            pass
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.handle))
+        act = lambda bit: "Active" if r & bit else "Not Active"
+        return [str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)]     # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [s.strip() for s in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [s.strip() for s in out.strip().split(",")]
+                    if len(f) >= 6:
+                        self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.05 if self.nvml is not None else 0.2)
 
     def summary(self):
         if not self.samples:
@@ -86,7 +114,8 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def synth_bag(batch, patches, seed, device):
@@ -157,7 +186,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    real_stdout = None
     if world > 1:
+        # NCCL (NCCL_DEBUG=VERSION in this image) writes its version banner to fd 1; rank 0 has to print ONE JSON line, so
+        # everything else goes to stderr and the line is written to the saved descriptor at the end
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     import sml_b200
     from sml_b200 import functional as Fn
@@ -184,8 +219,8 @@ def run_ours(args):
     Fn.manual_seed(42 + rank)
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,    # the multimodal_projection head (and the unused attn1d/attn2d twin) gets no gradient from the CE loss
-                                                       
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=deform,  # DeformCrossTransMIL: the attn1d / attn2d twin module is unused
+                                                        
                                                         broadcast_buffers=False, gradient_as_bucket_view=True)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
     B, N = args.batch, args.patches
@@ -207,8 +242,14 @@ def run_ours(args):
             loss.backward()
             opt.step()
             return loss
-        logits = net(x, omic)[1] if deform else net(x)[1]
-        loss = torch.nn.functional.cross_entropy(logits, y)
+        if deform:
+            logits = net(x, omic)[1]
+            loss = torch.nn.functional.cross_entropy(logits, y)
+        else:
+            enc, logits, _ = net(x)
+            # the multimodal_projection head takes part with zero weight so that every parameter gets a gradient and DDP needs
+            # no unused-parameter search (the reference's loop feeds both heads, train_test.py:347-373)
+            loss = torch.nn.functional.cross_entropy(logits, y) + 0.0 * enc.sum()
         loss.backward()
         opt.step()
         return loss
@@ -232,7 +273,8 @@ def run_ours(args):
         return float(ms)
 
     sampler = ClockSampler(local)
-    sampler.start()                      # samples from the last warm-up steps through the timed and e2e regions (all under load)
+    if rank == 0:
+        sampler.start()                      # samples from the last warm-up steps through the timed and e2e regions (all under load)
     for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
     l0 = sml_b200._lib.launch_count()
@@ -366,7 +408,11 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": args.cpu_sample / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d slide(s) of %d patches, fwd+CE+bwd+Adam, fp32 oracle port, %d host threads"
                                               % (args.cpu_sample, N, torch.get_num_threads())}
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
