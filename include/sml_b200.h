@@ -175,7 +175,9 @@ int sml_deform_offsets_bwd(const int32_t* cfg13, float scale, const float* q, co
  * (1D.py:36-43 with mode 0 = the reference's (x=vgrid, y=0) pad order on an [n,1] image, mode 1 = upstream order;
  * 2D.py:268-271).  taps (optional) [(b g), nkv, 2] int32 = floor of the pixel coordinate (x0, y0): bit-exact contract */
 int sml_deform_gather_fwd(const int32_t* cfg8, const float* x2, const float* vs, float* kv, int32_t* taps, void* stream);
-/* dx2 must be zeroed by the caller; dvs_out = dvs_in (may be NULL) + sampling-path gradient */
+/* dx2 must be zeroed by the caller; dvs_out = dvs_in (may be NULL) + sampling-path gradient.  d x2 is scattered without
+ * atomics (per-(b,g) shared-memory sort by destination + one warp per run of equal destinations: deterministic) when
+ * 4 nkv <= 4096 entries (2-D lattices up to 128 x 128), with fp32 atomics otherwise */
 int sml_deform_gather_bwd(const int32_t* cfg8, const float* x2, const float* vs, const float* dkv, float* dx2,
                           const float* dvs_in, float* dvs_out, void* stream);
 /* cfg8 = {B, heads, n, nkv, G, CD, W, 64}: out = softmax(q k^T + CPB(q_pos - k_pos)) v with the bias MLP evaluated per

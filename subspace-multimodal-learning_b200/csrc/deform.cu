@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) gather_fwd_kernel(const GatherCfg cf, con
 __global__ void __launch_bounds__(256) gather_bwd_kernel(const GatherCfg cf, const float* __restrict__ x2,
                                                          const float* __restrict__ vs, const float* __restrict__ dkv,
                                                          float* __restrict__ dx2, const float* __restrict__ dvs_in,
-                                                         float* __restrict__ dvs_out) {
+                                                         float* __restrict__ dvs_out, const bool scatter) {
   const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * cf.cg;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < total;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const GatherCfg cf, con
       if (xx < 0 || xx >= cf.W || yy < 0 || yy >= cf.H) continue;
       const float wx = (k & 1) ? t.wx1 : 1.f - t.wx1, wy = (k >> 1) ? t.wy1 : 1.f - t.wy1;
       const int64_t o = base + (int64_t)(yy * cf.W + xx) * cf.C;
-      atomicAdd(dx2 + o, wx * wy * gout);
+      if (scatter) atomicAdd(dx2 + o, wx * wy * gout);
       const float v = x2[o];
       gix += ((k & 1) ? 1.f : -1.f) * wy * v * gout;
       giy += ((k >> 1) ? 1.f : -1.f) * wx * v * gout;
@@ -254,6 +254,64 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const GatherCfg cf, con
     } else {
       dvs_out[loc] = (dvs_in ? dvs_in[loc] : 0.f) + (cf.mode == 0 ? dgx : dgy);
     }
+  }
+}
+
+// Atomic-free, deterministic scatter of d kv into d x2: one block per (b, g) owns every destination pixel of its channel
+// group.  The 4 nkv (sample, tap) entries are sorted by destination in shared memory (bitonic network on the composite key
+// dest * NP + entry, so the order inside a destination is canonical), then every run of equal destinations is reduced by one
+// warp (lanes = the group's channels: coalesced d kv reads, one coalesced store per destination).  dx2 must be zeroed by the
+// caller (pixels no sample touches).
+constexpr int GS_THREADS = 512;
+template <int NP>
+__global__ void __launch_bounds__(GS_THREADS) gather_bwd_sorted_kernel(const GatherCfg cf, const float* __restrict__ vs,
+                                                                       const float* __restrict__ dkv, float* __restrict__ dx2) {
+  __shared__ uint32_t skey[NP];
+  __shared__ float wgt[NP];
+  const int bg = blockIdx.x, b = bg / cf.G, g = bg % cf.G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t INVALID = 0xffffffffu;
+  for (int e = tid; e < NP; e += GS_THREADS) {
+    uint32_t key = INVALID;
+    float w = 0.f;
+    if (e < 4 * cf.nkv) {
+      const int p = e >> 2, k = e & 3;
+      const Taps t = make_taps(cf, vs, (int64_t)bg * cf.nkv + p);
+      const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+      if (xx >= 0 && xx < cf.W && yy >= 0 && yy < cf.H) {
+        key = (uint32_t)(yy * cf.W + xx) * (uint32_t)NP + (uint32_t)e;
+        w = ((k & 1) ? t.wx1 : 1.f - t.wx1) * ((k >> 1) ? t.wy1 : 1.f - t.wy1);
+      }
+    }
+    skey[e] = key; wgt[e] = w;
+  }
+  __syncthreads();
+  for (int k = 2; k <= NP; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < NP; i += GS_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = skey[i], c = skey[ixj];
+          if ((a > c) == ((i & k) == 0)) { skey[i] = c; skey[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  // runs of equal destination -> one warp each (the warp that owns the run's first position)
+  constexpr int PER_WARP = NP / (GS_THREADS / 32);
+  for (int pos = warp * PER_WARP; pos < (warp + 1) * PER_WARP; ++pos) {
+    const uint32_t ck = skey[pos];
+    if (ck == INVALID) break;
+    const uint32_t dest = ck / NP;
+    if (pos > 0 && skey[pos - 1] / NP == dest) continue;
+    float acc = 0.f;
+    for (int qn = pos; qn < NP; ++qn) {
+      const uint32_t kq = skey[qn];
+      if (kq == INVALID || kq / NP != dest) break;
+      const int e = (int)(kq % NP);
+      if (lane < cf.cg) acc = fmaf(wgt[e], dkv[((int64_t)b * cf.nkv + (e >> 2)) * cf.C + g * cf.cg + lane], acc);
+    }
+    if (lane < cf.cg) dx2[((int64_t)b * cf.H * cf.W + dest) * cf.C + g * cf.cg + lane] = acc;
   }
 }
 
@@ -846,8 +904,18 @@ extern "C" int sml_deform_gather_bwd(const int32_t* cfg8, const float* x2, const
   const GatherCfg cf = make_gcfg(cfg8);
   SML_CHECK(cf.cg <= 32 && (cf.cg & (cf.cg - 1)) == 0, "sml_deform_gather_bwd: channels per group must be a power of two <= 32");
   const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * cf.cg;
-  gather_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(cf, x2, vs, dkv, dx2, dvs_in, dvs_out);
+  // d x2: sorted, atomic-free scatter when the (b, g) entry list fits shared memory and the composite key 32 bits;
+  // else (n_kv > 1024: 1-D bags beyond 4 k tokens, 2-D beyond 128 x 128) fp32 atomics
+  const int entries = 4 * cf.nkv;
+  const bool sorted = entries <= 4096 && (int64_t)cf.H * cf.W < (1 << 20);
+  gather_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(cf, x2, vs, dkv, dx2, dvs_in, dvs_out, !sorted);
   SML_LAUNCH_OK("sml_deform_gather_bwd");
+  if (sorted) {
+    const unsigned blocks = (unsigned)(cf.B * cf.G);
+    if (entries <= 1024) gather_bwd_sorted_kernel<1024><<<blocks, GS_THREADS, 0, as_stream(stream)>>>(cf, vs, dkv, dx2);
+    else gather_bwd_sorted_kernel<4096><<<blocks, GS_THREADS, 0, as_stream(stream)>>>(cf, vs, dkv, dx2);
+    SML_LAUNCH_OK("sml_deform_gather_bwd(sorted scatter)");
+  }
   return 0;
 }
 

@@ -250,3 +250,29 @@ def test_maxnet_alpha_dropout_statistics():
     a = float(x.grad[kept][0])
     assert torch.allclose(y.detach()[kept], a * x.detach()[kept] + (y.detach()[kept][0] - a * x.detach()[kept][0]), atol=1e-5)
     assert Fn.alpha_dropout(x, 0.1, False) is x
+
+
+def test_gather_backward_sorted_scatter_is_deterministic_and_matches_autograd():
+    """d x2 of the bilinear gather: sorted, atomic-free scatter (2-D, 64x64 lattice, n_kv = 256) against torch autograd of
+    F.grid_sample on the same coordinates, bitwise identical across repeated launches (no atomics)."""
+    from sml_b200._lib import c_i32, check, lib, ptr, stream
+    b, G, H, W, cg, nkv = 2, 8, 64, 64, 16, 256
+    torch.manual_seed(9)
+    x2 = torch.randn(b, H * W, G * cg, device="cuda")
+    vs = (torch.randn(b * G, nkv, 2, device="cuda") * 0.6).clamp(-1.3, 1.3)
+    dkv = torch.randn(b, nkv, G * cg, device="cuda")
+    cfg = (c_i32 * 8)(b, G, cg, H, W, nkv, 2, 0)
+    outs = []
+    for _ in range(3):
+        dx2 = torch.zeros_like(x2); dvs = torch.empty_like(vs)
+        check(lib.sml_deform_gather_bwd(cfg, ptr(x2), ptr(vs), ptr(dkv), ptr(dx2), None, ptr(dvs), stream()), "gather_bwd")
+        outs.append((dx2.clone(), dvs.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
+    feat = x2.view(b, H, W, G, cg).permute(0, 3, 4, 1, 2).reshape(b * G, cg, H, W).clone().requires_grad_()
+    grid = vs.view(b * G, nkv, 1, 2).clone().requires_grad_()
+    samp = torch.nn.functional.grid_sample(feat, grid, mode="bilinear", padding_mode="zeros", align_corners=False)   # [bG, cg, nkv, 1]
+    gout = dkv.view(b, nkv, G, cg).permute(0, 2, 3, 1).reshape(b * G, cg, nkv, 1)
+    samp.backward(gout)
+    want_dx2 = feat.grad.view(b, G, cg, H, W).permute(0, 3, 4, 1, 2).reshape(b, H * W, G * cg)
+    assert rel_err(outs[0][0], want_dx2) < 1e-5
+    assert rel_err(outs[0][1], grid.grad.view(b * G, nkv, 2)) < 1e-4
