@@ -237,9 +237,10 @@ def run_ours(args):
     def step(x, y):
         opt.zero_grad(set_to_none=True)
         if pathomic:
-            lg = net(x_path=x, x_omic_tumor=x_t, x_omic_immune=x_i)[3]
+            _, f_t, f_i, lg, _, _, _ = net(x_path=x, x_omic_tumor=x_t, x_omic_immune=x_i)
             loss = torch.nn.functional.cross_entropy(lg[2], y, weight=ce_w) + 0.5 * bloss(lg[3], lg[4]).sum() + 0.5 * bloss(lg[5], lg[6]).sum()
             loss.backward()
+            sml_b200.modulate_classifier_grads(model.classifier, f_t, f_i, y)       # train_test.py:87-184 (gradient_modulate: True)
             opt.step()
             return loss
         if deform:

@@ -96,6 +96,12 @@ int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* st
 /* y[b,t,:] = (x ? x[b,t,:] : 0) + a*vec[b,:]  — the rank-1 half of FusionNet (models/DeformCrossTransMIL.py:104,33-38:
  * the repeated omic vector is never materialised) and the backward of the token mean (Pooler :193) */
 int sml_add_rowvec(float* y, const float* x, const float* vec, float a, int64_t B, int64_t T, int32_t C, void* stream);
+/* Gradient modulation of the fusion classifier after backward (train_test.py:87-184; diag2021 / grade / subtype tasks):
+ * W, Wgrad [L, 2 hs], bias [L], feat_t / feat_i [B, hs] (the two branch embeddings), labels [B] int64.  Rewrites the
+ * conflicting half of every row of Wgrad in place; info (optional) [4] = (score_t, score_i, #rows re-projected on the tumor
+ * half, on the immune half).  One kernel, no host synchronisation (the reference syncs once per classifier row). */
+int sml_grad_modulate(const float* W, const float* bias, float* Wgrad, const float* feat_t, const float* feat_i,
+                      const int64_t* labels, int32_t B, int32_t L, int32_t hs, float* info, void* stream);
 /* torch.nn.AlphaDropout of the MaxNet encoders (models/model.py:152-170), same counter-based mask as sml_dropout_add;
  * bwd = 0: y = alpha_dropout(x); bwd = 1: y = d x given x = d y (same seed / offset) */
 int sml_alpha_dropout(const float* x, float* y, int64_t n, float p, int32_t bwd, uint64_t seed, uint64_t offset, void* stream);

@@ -108,3 +108,28 @@ def test_batchloss_long_rows_match_collapsed_base():
     l2.sum().backward()
     assert rel_err(l2, l1) < 1e-4
     assert rel_err(b2.grad, b1.grad) < 1e-3 and rel_err(vg.grad, g_v1) < 1e-3
+
+
+def test_gradient_modulation_kernel_matches_reference_lines():
+    """sml_grad_modulate (one kernel, no host sync) vs the reference's gradient-modulation block executed verbatim
+    (train_test.py:87-184, fixture tests/golden/modulation.pt) and vs the fp64 oracle on a fresh case."""
+    import sml_b200
+    for c in load_golden("modulation"):
+        cls = torch.nn.Linear(c["W"].shape[1], c["W"].shape[0]).cuda()
+        with torch.no_grad():
+            cls.weight.copy_(c["W"]); cls.bias.copy_(c["b"])
+        cls.weight.grad = c["G"].clone().cuda()
+        info = sml_b200.modulate_classifier_grads(cls, c["ft"].cuda(), c["fi"].cuda(), c["labels"].cuda(), return_info=True)
+        assert rel_err(cls.weight.grad, c["G_out"]) < 1e-5
+        assert abs(float(info[0] / info[1]) - c["ratio_t"]) < 1e-4 * abs(c["ratio_t"])
+        assert int(info[2] + info[3]) == int((c["G_out"] != c["G"]).any(dim=1).sum())
+    torch.manual_seed(12)
+    W = torch.randn(3, 64) * 0.2; b = torch.randn(3) * 0.1; G = torch.randn(3, 64); G[:, 32:] = -G[:, :32] + 0.2 * torch.randn(3, 32)
+    ft = torch.randn(5, 32); fi = torch.randn(5, 32); lab = torch.randint(0, 3, (5,))
+    want = oracle.modulation.modulate(W.double(), b.double(), G.double(), ft.double(), fi.double(), lab)
+    cls = torch.nn.Linear(64, 3).cuda()
+    with torch.no_grad():
+        cls.weight.copy_(W); cls.bias.copy_(b)
+    cls.weight.grad = G.clone().cuda()
+    sml_b200.modulate_classifier_grads(cls, ft.cuda(), fi.cuda(), lab.cuda())
+    assert rel_err(cls.weight.grad, want) < 1e-5

@@ -175,3 +175,14 @@ def test_losses():
     mean, inv_std, unb = oracle.loss.sync_bn_stats([g["bn_x"][:4], g["bn_x"][4:]])
     assert rel_err(mean, g["bn_mean"]) < TOL and rel_err(inv_std, g["bn_inv_std"]) < TOL
     assert rel_err(0.9 * torch.ones(8) + 0.1 * unb, g["bn_running_var"]) < TOL
+
+
+def test_modulation_oracle_matches_reference_source_lines():
+    """oracle.modulation.modulate vs the reference's own lines executed verbatim (tests/golden/make_golden_modulation.py)."""
+    import torch
+    import oracle
+    from conftest import load_golden
+    for c in load_golden("modulation"):
+        got = oracle.modulation.modulate(c["W"], c["b"], c["G"], c["ft"], c["fi"], c["labels"])
+        assert torch.allclose(got, c["G_out"], rtol=1e-5, atol=1e-6)
+        assert (got != c["G"]).any()                      # the fixture exercises the projection
