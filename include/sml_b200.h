@@ -146,7 +146,7 @@ int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout,
 /* Fused backward of out = softmax(q k~^T) W for the token-by-landmark path (models/NystromAttention.py:122,137,140):
  * per 128-token tile dA1 = dout W^T (TMEM), dS = A1 (dA1 - rowsum(dA1 A1)) in registers, dq = dS k~ (+ dql[t / l] / l),
  * dk~ += dS^T q, without materialising dA1 / dS.  bf16 operands (dout [B,n',h*d], W [B,h,m,d], A1 [B,h,n',m],
- * k~ [B,h,m,d], qkv [B,n',3,h,d]); writes the q chunk of dqkv (fp32 + optional bf16) and atomically adds into dkl.
+ * k~ [B,h,m,d], qkv [B,n',3,h,d]); writes the q chunk of dqkv (fp32 and / or bf16, either may be NULL) and atomically adds into dkl.
  * Specialised to d = 64, m = 256. */
 int sml_nystrom_a1_bwd(const void* dout_bf16, const void* wm_bf16, const void* a1_bf16, const void* kl_bf16,
                        const void* qkv_bf16, const float* dql, float* dqkv, void* dqkv_hi, float* dkl, int32_t B,

@@ -214,8 +214,10 @@ nystrom_a1_bwd_kernel(const __grid_constant__ CUtensorMap tmDout, const __grid_c
               v[j] = fmaf(sc, tv.x, v[j]); v[j + 1] = fmaf(sc, tv.y, v[j + 1]); v[j + 2] = fmaf(sc, tv.z, v[j + 2]); v[j + 3] = fmaf(sc, tv.w, v[j + 3]);
             }
           }
+          if (p.dq) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p.dq + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(p.dq + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
           if (p.dq_hi) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {

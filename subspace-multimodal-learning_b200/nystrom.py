@@ -275,12 +275,14 @@ class NystromAttentionFn(torch.autograd.Function):
         dkl = mm(ds2.T(), ql_b)                                                                 # dkl = dS2^T ql (+ dS1^T q below)
         dql = mm(ds2, kl_b)
         mm(ds3, k_b, dql, beta=1.0)
-        dq_b = TB(dq, *(hv(t, 0) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
-        dk_b = TB(dk, *(hv(t, 1) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
+        # bf16 mode: only the bf16 copies of dq / dk are ever read (projection backward), so their fp32 halves are not written
+        skip_f32 = mode == "bf16" and fused_cvt
+        dq_b = TB(None if skip_f32 else dq, *(hv(t, 0) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
+        dk_b = TB(None if skip_f32 else dk, *(hv(t, 1) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
         if fuse_a1:
             # dA1 = dout W^T, softmax backward, dq = dS1 kl + bcast(dql)/l and dkl += dS1^T q in one tcgen05 kernel
-            check(lib.sml_nystrom_a1_bwd(ptr(dmerged.hi), ptr(wm_b.hi), ptr(a1.hi), ptr(kl_b.hi), ptr(qkv.hi), ptr(dql.f), ptr(dqkv.f),
-                                         ptr(dqkv.hi), ptr(dkl.f), c_i32(b), c_i32(npad), c_i32(h), c_i32(d), c_i32(m), stream()),
+            check(lib.sml_nystrom_a1_bwd(ptr(dmerged.hi), ptr(wm_b.hi), ptr(a1.hi), ptr(kl_b.hi), ptr(qkv.hi), ptr(dql.f),
+                                         None if skip_f32 else ptr(dqkv.f), ptr(dqkv.hi), ptr(dkl.f), c_i32(b), c_i32(npad), c_i32(h), c_i32(d), c_i32(m), stream()),
                   "nystrom_a1_bwd")
         else:
             mm(ds1.T(), q_b, dkl, beta=1.0)                                                     # dkl += dS1^T q
