@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
   const float rs = rsqrtf(warp_sum(q) / D + eps);
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
-  float4* yr = reinterpret_cast<float4*>(y + yrow * D);
+  float4* yr = y ? reinterpret_cast<float4*>(y + yrow * D) : nullptr;      // fp32 output optional (tensor-core modes)
   const float4* w4 = reinterpret_cast<const float4*>(w);
   const float4* b4 = reinterpret_cast<const float4*>(b);
 #pragma unroll
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
       o.y = (v[i].y - mu) * rs * ww.y + bb.y;
       o.z = (v[i].z - mu) * rs * ww.z + bb.z;
       o.w = (v[i].w - mu) * rs * ww.w + bb.w;
-      yr[c] = o;
+      if (yr) yr[c] = o;
       if (yhi) {
         const int64_t e = yrow * D + 4 * c;
         store_split(yhi, ylo, e, o.x); store_split(yhi, ylo, e + 1, o.y);

@@ -139,7 +139,8 @@ class NystromAttentionFn(torch.autograd.Function):
         tc = mode != "fp32"
         hv = lambda t, i: t[:, :, i].permute(0, 2, 1, 3)                             # [b,h,npad,d] view of a qkv chunk
         # ---- (LayerNorm +) front pad (:79-82)
-        xp = TB.new((b, npad, D), dev, mode)
+        # tensor-core modes with the fused LayerNorm only ever read the bf16 copies of xp: no fp32 plane then
+        xp = TB.new((b, npad, D), dev, mode, f32=not (tc and ln_w is not None))
         if pad:
             for t in (xp.f, xp.hi, xp.lo):
                 if t is not None:
