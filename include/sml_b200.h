@@ -118,9 +118,10 @@ int sml_colsum(const float* x, float* out, float* part, int64_t R, int64_t C, fl
  * Nystrom attention pieces (models/NystromAttention.py:74-157, :20-35).
  * qkv layout: [B, n', 3, h, d] fp32 (row = token, q|k|v chunks, head-major inside a chunk).
  * ------------------------------------------------------------------------------------- */
-/* landmark segment means of q and k: ql, kl [B,h,m,d]; landmark id of token t is t / l (:102-118) */
+/* landmark segment means of q and k: ql, kl [B,h,m,d]; landmark id of token t is t / l (:102-118).
+ * Here and in the two resconv entries: qkv == NULL -> read the bf16 copy `qkv_bf16` instead (bf16 mode writes no fp32 qkv). */
 int sml_nystrom_landmarks_fwd(const float* qkv, float* ql, float* kl, int32_t B, int32_t npad, int32_t h, int32_t d,
-                              int32_t m, void* stream);
+                              int32_t m, const void* qkv_bf16, void* stream);
 /* dqkv[q,k chunks][t] += d{ql,kl}[t / l] / l */
 int sml_nystrom_landmarks_bwd(float* dqkv, const float* dql, const float* dkl, int32_t B, int32_t npad, int32_t h,
                               int32_t d, int32_t m, void* dqkv_hi, void* dqkv_lo, void* stream);
@@ -137,12 +138,12 @@ int sml_pinv_init_bwd(const float* x, const float* scal, const int32_t* arg, con
                       float* tmp /*4 B*/, int32_t BH, int32_t m, void* stream);
 /* depthwise conv along tokens on the v chunk, per head, shared over d: out[B,n',h*d] += conv(v) (:144-145) */
 int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
-                            int32_t d, int32_t ksize, void* out_hi, void* out_lo, void* stream);
+                            int32_t d, int32_t ksize, void* out_hi, void* out_lo, const void* qkv_bf16, void* stream);
 /* dqkv[v chunk] += conv^T(dout); dw[h,k] = sum dout*v (dw_part [nblk,h,k]; nblk returned by ..._blocks) */
 int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad, int32_t hd);
 int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
                             int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* dqkv_hi, void* dqkv_lo,
-                            void* stream);
+                            const void* qkv_bf16, void* stream);
 /* Fused backward of out = softmax(q k~^T) W for the token-by-landmark path (models/NystromAttention.py:122,137,140):
  * per 128-token tile dA1 = dout W^T (TMEM), dS = A1 (dA1 - rowsum(dA1 A1)) in registers, dq = dS k~ (+ dql[t / l] / l),
  * dk~ += dS^T q, without materialising dA1 / dS.  bf16 operands (dout [B,n',h*d], W [B,h,m,d], A1 [B,h,n',m],

@@ -58,7 +58,14 @@ def ptr(t):
     return None if t is None else c_vp(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream():
+    """raw cudaStream_t of torch's current stream (the fast C accessor when this torch build has it: the Python
+    ``current_stream()`` path costs ~10 us, paid ~330 times per TransMIL train step)"""
+    if _raw_stream is not None:
+        return c_vp(_raw_stream(torch.cuda.current_device()))
     return c_vp(torch.cuda.current_stream().cuda_stream)
 
 

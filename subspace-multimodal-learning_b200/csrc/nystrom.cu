@@ -7,24 +7,35 @@ namespace sml {
 
 // ------------------------------------------------------------------ landmarks
 // grid (m, B); block = h*d threads (<= 1024).  qkv [B, npad, 3, h, d]
-__global__ void landmarks_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ql, float* __restrict__ kl,
+// source-type helpers: the qkv tensor is read as fp32, or as its bf16 copy in bf16 mode (no fp32 plane is written then)
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+
+template <typename TS>
+__global__ void landmarks_fwd_kernel(const TS* __restrict__ qkv, float* __restrict__ ql, float* __restrict__ kl,
                                      int npad, int h, int d, int m) {
   const int j = blockIdx.x, b = blockIdx.y, c = threadIdx.x;   // c = head*d + dd
   const int hd = h * d, l = npad / m;
-  const float* base = qkv + ((int64_t)b * npad + (int64_t)j * l) * 3 * hd;
+  const TS* base = qkv + ((int64_t)b * npad + (int64_t)j * l) * 3 * hd;
   // 5 independent load streams per tensor (l = 65 at 16 k patches): the segment sum is latency-bound otherwise
   float aq[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, ak[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   int t = 0;
   for (; t + 5 <= l; t += 5) {
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
-      aq[u] += base[(int64_t)(t + u) * 3 * hd + c];
-      ak[u] += base[(int64_t)(t + u) * 3 * hd + hd + c];
+      aq[u] += ld1(base + (int64_t)(t + u) * 3 * hd + c);
+      ak[u] += ld1(base + (int64_t)(t + u) * 3 * hd + hd + c);
     }
   }
   for (; t < l; ++t) {
-    aq[0] += base[(int64_t)t * 3 * hd + c];
-    ak[0] += base[(int64_t)t * 3 * hd + hd + c];
+    aq[0] += ld1(base + (int64_t)t * 3 * hd + c);
+    ak[0] += ld1(base + (int64_t)t * 3 * hd + hd + c);
   }
   const float sq = ((aq[0] + aq[1]) + (aq[2] + aq[3])) + aq[4], sk = ((ak[0] + ak[1]) + (ak[2] + ak[3])) + ak[4];
   const int head = c / d, dd = c % d;
@@ -165,8 +176,8 @@ __global__ void pinv_init_bwd_scalar_kernel(const float* __restrict__ x, const f
 // with k' = k (fwd) or K-1-k (FLIP: the transposed conv of the backward).  Each thread owns TT consecutive tokens of
 // one channel: the K taps live in registers and every (tap, output) pair is resolved at compile time.
 constexpr int RC_TT = 8;
-template <bool FLIP, int K>
-__global__ void __launch_bounds__(128) resconv_kernel(const float* __restrict__ src, int64_t src_ld,
+template <bool FLIP, int K, typename TS>
+__global__ void __launch_bounds__(128) resconv_kernel(const TS* __restrict__ src, int64_t src_ld,
                                                       const float* __restrict__ w, float* __restrict__ dst,
                                                       int64_t dst_ld, int npad, int hd, int d,
                                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
@@ -179,14 +190,14 @@ __global__ void __launch_bounds__(128) resconv_kernel(const float* __restrict__ 
   float wr[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) wr[k] = __ldg(w + (c / d) * K + (FLIP ? (K - 1 - k) : k));
-  const float* s = src + (int64_t)b * npad * src_ld + c;
+  const TS* s = src + (int64_t)b * npad * src_ld + c;
   float4 acc[RC_TT];
 #pragma unroll
   for (int i = 0; i < RC_TT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int u = -HALF; u < RC_TT + HALF; ++u) {       // source token t0+u feeds output i through tap k = u - i + HALF
     const int ts = t0 + u;
-    const float4 v = (ts >= 0 && ts < npad) ? *reinterpret_cast<const float4*>(s + (int64_t)ts * src_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = (ts >= 0 && ts < npad) ? ld4(s + (int64_t)ts * src_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < RC_TT; ++i) {
       const int k = u - i + HALF;
@@ -222,8 +233,8 @@ __global__ void __launch_bounds__(128) resconv_kernel(const float* __restrict__ 
 // dw_part[blk, head, k] = sum over the block's token strip and the head's d channels of dout[t,c] * v[t+k-half, c].
 // Thread = one channel; it walks its strip in chunks of 16 tokens with a (16 + K - 1)-wide register window of v.
 constexpr int RCB_TOK = 256;
-template <int K>
-__global__ void __launch_bounds__(128) resconv_dw_kernel(const float* __restrict__ v, int64_t v_ld,
+template <int K, typename TS>
+__global__ void __launch_bounds__(128) resconv_dw_kernel(const TS* __restrict__ v, int64_t v_ld,
                                                          const float* __restrict__ dout, int64_t o_ld,
                                                          float* __restrict__ dw_part, int npad, int hd, int d) {
   // thread = 4 adjacent channels of one head (128-bit loads); the 4 channel products fold into one scalar per tap
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(128) resconv_dw_kernel(const float* __restrict
   const int t1 = min(npad, t0 + RCB_TOK);
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (c < hd) {
-    const float* vp = v + (int64_t)b * npad * v_ld + c;
+    const TS* vp = v + (int64_t)b * npad * v_ld + c;
     const float* gp = dout + (int64_t)b * npad * o_ld + c;
     float acc[K];
 #pragma unroll
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(128) resconv_dw_kernel(const float* __restrict
 #pragma unroll
       for (int u = -HALF; u < CH + HALF; ++u) {          // v token tc+u pairs with output i through tap k = u - i + HALF
         const int ts = tc + u;
-        const float4 x = (ts >= 0 && ts < npad) ? *reinterpret_cast<const float4*>(vp + (int64_t)ts * v_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x = (ts >= 0 && ts < npad) ? ld4(vp + (int64_t)ts * v_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
           const int k = u - i + HALF;
@@ -437,9 +448,11 @@ __global__ void __launch_bounds__(256) ppeg_dw_kernel(const float* __restrict__ 
 using namespace sml;
 
 extern "C" int sml_nystrom_landmarks_fwd(const float* qkv, float* ql, float* kl, int32_t B, int32_t npad, int32_t h,
-                                         int32_t d, int32_t m, void* stream) {
+                                         int32_t d, int32_t m, const void* qkv_bf16, void* stream) {
   SML_CHECK(h * d <= 1024 && npad % m == 0, "sml_nystrom_landmarks_fwd: need h*d<=1024 and npad %% m == 0 (npad=%d m=%d)", npad, m);
-  landmarks_fwd_kernel<<<dim3(m, B), h * d, 0, as_stream(stream)>>>(qkv, ql, kl, npad, h, d, m);
+  SML_CHECK(qkv || qkv_bf16, "sml_nystrom_landmarks_fwd: no source");
+  if (qkv) landmarks_fwd_kernel<float><<<dim3(m, B), h * d, 0, as_stream(stream)>>>(qkv, ql, kl, npad, h, d, m);
+  else landmarks_fwd_kernel<__nv_bfloat16><<<dim3(m, B), h * d, 0, as_stream(stream)>>>((const __nv_bfloat16*)qkv_bf16, ql, kl, npad, h, d, m);
   SML_LAUNCH_OK("sml_nystrom_landmarks_fwd");
   return 0;
 }
@@ -484,11 +497,15 @@ extern "C" int sml_pinv_init_bwd(const float* x, const float* scal, const int32_
 static inline dim3 rc_grid(int npad, int hd, int B, int tok) { return dim3((npad + tok - 1) / tok, (hd + 255) / 256, B); }
 static inline dim3 rc_grid4(int npad, int hd, int B, int tok) { return dim3((npad + tok - 1) / tok, (hd / 4 + 127) / 128, B); }
 extern "C" int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* out, int32_t B, int32_t npad, int32_t h,
-                                       int32_t d, int32_t ksize, void* out_hi, void* out_lo, void* stream) {
+                                       int32_t d, int32_t ksize, void* out_hi, void* out_lo, const void* qkv_bf16, void* stream) {
   const int hd = h * d;
   SML_CHECK(ksize % 2 == 1, "sml_nystrom_resconv_fwd: kernel size must be odd");
-  if (ksize == 33 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
-    resconv_kernel<false, 33><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+  SML_CHECK(qkv || (qkv_bf16 && ksize == 33 && d % 4 == 0), "sml_nystrom_resconv_fwd: the bf16 source needs the 33-tap vector kernel");
+  if (!qkv) {
+    const __nv_bfloat16* qb = (const __nv_bfloat16*)qkv_bf16;
+    resconv_kernel<false, 33, __nv_bfloat16><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qb + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+  } else if (ksize == 33 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+    resconv_kernel<false, 33, float><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
   else
     resconv_generic_kernel<false><<<rc_grid(npad, hd, B, 1), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, ksize);
   SML_LAUNCH_OK("sml_nystrom_resconv_fwd");
@@ -499,15 +516,17 @@ extern "C" int sml_nystrom_resconv_bwd_blocks(int32_t B, int32_t npad, int32_t h
 }
 extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout, float* dqkv, float* dw_part,
                                        int32_t B, int32_t npad, int32_t h, int32_t d, int32_t ksize, void* dqkv_hi, void* dqkv_lo,
-                                       void* stream) {
+                                       const void* qkv_bf16, void* stream) {
   const int hd = h * d;
   cudaStream_t s = as_stream(stream);
+  SML_CHECK(qkv || (qkv_bf16 && ksize == 33 && d % 4 == 0), "sml_nystrom_resconv_bwd: the bf16 source needs the 33-tap vector kernel");
   if (ksize == 33 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dout) & 15) == 0) {
-    resconv_kernel<true, 33><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d,
+    resconv_kernel<true, 33, float><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d,
         dqkv_hi ? (__nv_bfloat16*)dqkv_hi + 2 * hd : nullptr, dqkv_lo ? (__nv_bfloat16*)dqkv_lo + 2 * hd : nullptr);
     SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");
-    resconv_dw_kernel<33><<<rc_grid4(npad, hd, B, RCB_TOK), 128, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
+    if (qkv) resconv_dw_kernel<33, float><<<rc_grid4(npad, hd, B, RCB_TOK), 128, h * ksize * sizeof(float), s>>>(qkv + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
+    else resconv_dw_kernel<33, __nv_bfloat16><<<rc_grid4(npad, hd, B, RCB_TOK), 128, h * ksize * sizeof(float), s>>>((const __nv_bfloat16*)qkv_bf16 + 2 * hd, 3 * hd, dout, hd, dw_part, npad, hd, d);
   } else {
     resconv_generic_kernel<true><<<rc_grid(npad, hd, B, 1), 256, 0, s>>>(dout, hd, w, dqkv + 2 * hd, 3 * hd, npad, hd, d, ksize);
     SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dv)");

@@ -33,13 +33,19 @@ FUSE_A1_BWD = _os.environ.get("SML_FUSE_A1_BWD", "1") != "0"
 FUSE_PINV_CHAIN = _os.environ.get("SML_FUSE_PINV_CHAIN", "0") == "1"
 # "bf16" mode: run the Moore-Penrose chain with hi/lo split operands (True, fp32-grade) or in plain bf16 (False)
 PINV_HP = _os.environ.get("SML_PINV_HP", "1") != "0"
+# bf16 mode: keep q, k, v as bf16 only (landmark / residual-conv kernels read the bf16 copy).  Measured neutral on the 16 k
+# step (the projection is not bound by its fp32 output and the conv kernels lose what it gains), so off by default; it saves
+# 0.8 GB of activations per layer at B = 8 and stays parity-tested.
+QKV_BF16_ONLY = _os.environ.get("SML_QKV_BF16_ONLY", "0") != "0"
 
 
-def landmarks_fwd(qkv, b, npad, h, d, m):
-    ql = torch.empty(b, h, m, d, device=qkv.device, dtype=F32)
+def landmarks_fwd(qkv, b, npad, h, d, m, qkv_bf16=None):
+    """qkv: the fp32 tensor, or None to read its bf16 copy ``qkv_bf16`` (bf16 mode keeps no fp32 qkv)."""
+    ref = qkv if qkv is not None else qkv_bf16
+    ql = torch.empty(b, h, m, d, device=ref.device, dtype=F32)
     kl = torch.empty_like(ql)
     check(lib.sml_nystrom_landmarks_fwd(ptr(qkv), ptr(ql), ptr(kl), c_i32(b), c_i32(npad), c_i32(h), c_i32(d), c_i32(m),
-                                        stream()), "landmarks_fwd")
+                                        None if qkv is not None else ptr(qkv_bf16), stream()), "landmarks_fwd")
     return ql, kl
 
 
@@ -160,9 +166,12 @@ class NystromAttentionFn(torch.autograd.Function):
         ops.axpby_(weff[:inner], w_qkv.detach()[:inner].contiguous(), d ** -0.5, 0.0)    # fold q * scale (:98)
         weff_b = TB.of(weff, mode)
         # ---- qkv projection (:89), fp32 + bf16 copy from the same epilogue
-        qkv = TB.new((b, npad, 3, h, d), dev, mode)
+        # bf16 mode (33-tap conv: the vector kernels read either type): q, k, v live as bf16 only - the projection writes a
+        # third of the bytes and the landmark / residual-conv kernels read half
+        ksize = w_conv.shape[2]
+        qkv = TB.new((b, npad, 3, h, d), dev, mode, f32=not (QKV_BF16_ONLY and mode == "bf16" and ksize == 33 and d % 4 == 0))
         mm(xp2, weff_b.T(), qkv.map(lambda t: t.view(b * npad, 3 * inner)))
-        ql, kl = landmarks_fwd(qkv.f, b, npad, h, d, m)                              # :102-118
+        ql, kl = landmarks_fwd(qkv.f, b, npad, h, d, m, qkv.hi)                      # :102-118
         ql_b, kl_b = TB.of(ql, mode), TB.of(kl, mode)
         q_b, k_b, v_b = (qkv.map(lambda t, i=i: hv(t, i)) for i in range(3))
         # ---- similarities + softmaxes (:122-137)
@@ -191,7 +200,8 @@ class NystromAttentionFn(torch.autograd.Function):
         fused_cvt = ksize == 33
         check(lib.sml_nystrom_resconv_fwd(ptr(qkv.f), ptr(wc), ptr(merged.f), c_i32(b), c_i32(npad), c_i32(h), c_i32(d),
                                           c_i32(ksize), ptr(merged.hi) if fused_cvt else None,
-                                          ptr(merged.lo) if fused_cvt else None, stream()), "resconv_fwd")   # :144-145
+                                          ptr(merged.lo) if fused_cvt else None, None if qkv.f is not None else ptr(qkv.hi),
+                                          stream()), "resconv_fwd")   # :144-145
         if tc and not fused_cvt:
             s = ops.to_bf16(merged.f, split=(mode == "bf16x3"))
             merged.hi, merged.lo = s.hi, s.lo
@@ -252,7 +262,8 @@ class NystromAttentionFn(torch.autograd.Function):
         fused_cvt = ksize == 33
         check(lib.sml_nystrom_resconv_bwd(ptr(qkv.f), ptr(wc), ptr(dmerged.f), ptr(dqkv.f), ptr(dwc_part), c_i32(b), c_i32(npad),
                                           c_i32(h), c_i32(d), c_i32(ksize), ptr(dqkv.hi) if fused_cvt else None,
-                                          ptr(dqkv.lo) if fused_cvt else None, stream()), "resconv_bwd")   # dv += conv^T
+                                          ptr(dqkv.lo) if fused_cvt else None, None if qkv.f is not None else ptr(qkv.hi),
+                                          stream()), "resconv_bwd")   # dv += conv^T
         dw_conv = ops.colsum(dwc_part).view(h, 1, ksize, 1)
         # ---- pinv + softmaxes (dS emitted with its bf16 copy by the softmax-backward kernel)
         da2 = pinv_bwd(a2_f, (zs, scal, arg), dz, mode)

@@ -174,8 +174,14 @@ def gemm(A, B, out=None, *, alpha=1.0, beta=0.0, diag=0.0, bias=None, relu=False
     M, K = a.shape[-2:]
     K2, N = b.shape[-2:]
     assert K == K2, "inner dims differ: %s @ %s" % (tuple(a.shape), tuple(b.shape))
-    ba, bb = a.shape[:-2], b.shape[:-2]
-    nbs = torch.broadcast_shapes(ba, bb)
+    ba, bb = tuple(a.shape[:-2]), tuple(b.shape[:-2])
+    if ba == bb:
+        nbs = ba
+    else:                                       # broadcast of the (at most two) batch dims, without torch's generic machinery
+        n_ = max(len(ba), len(bb))
+        pa, pb = (1,) * (n_ - len(ba)) + ba, (1,) * (n_ - len(bb)) + bb
+        assert all(x == y or x == 1 or y == 1 for x, y in zip(pa, pb)), "batch dims %s / %s do not broadcast" % (ba, bb)
+        nbs = tuple(max(x, y) for x, y in zip(pa, pb))
     assert len(nbs) <= 2
     nb = (1,) * (2 - len(nbs)) + tuple(nbs)
     if out is None and (want_f32 or not tc):

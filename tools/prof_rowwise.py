@@ -24,7 +24,7 @@ mean, rstd = ops.layernorm_fwd(xln, lw, lb, yln, 16385, npad, 255)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 for r in range(2):
     ev[0].record()
-    check(lib.sml_nystrom_resconv_fwd(ptr(qkv), ptr(wc), ptr(merged), c_i32(B), c_i32(npad), c_i32(h), c_i32(d), c_i32(33), ptr(mh), None, stream()))
+    check(lib.sml_nystrom_resconv_fwd(ptr(qkv), ptr(wc), ptr(merged), c_i32(B), c_i32(npad), c_i32(h), c_i32(d), c_i32(33), ptr(mh), None, None, stream()))
     ev[1].record()
     check(lib.sml_ppeg_fwd(ptr(x), ptr(w7), ptr(b7), ptr(y), c_i32(B), c_i32(128), c_i32(128), c_i32(512), stream()))
     ev[2].record()
