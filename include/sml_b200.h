@@ -152,6 +152,11 @@ int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout,
 int sml_nystrom_a1_bwd(const void* dout_bf16, const void* wm_bf16, const void* a1_bf16, const void* kl_bf16,
                        const void* qkv_bf16, const float* dql, float* dqkv, void* dqkv_hi, float* dkl, int32_t B,
                        int32_t npad, int32_t h, int32_t d, int32_t m, void* stream);
+/* PPEG parameter folding and its backward: w7 [C,49], w5 [C,25], w3 [C,9] depthwise kernels + biases [C] (models/mil.py:195-198)
+ * -> wf [49,C] tap-major stencil incl. the identity, bf [C]; unfold scatters d wf back to the three kernels (d bias is shared) */
+int sml_ppeg_fold(const float* w7, const float* w5, const float* w3, const float* b7, const float* b5, const float* b3,
+                  float* wf, float* bf, int32_t C, void* stream);
+int sml_ppeg_unfold(const float* dwf, float* dw7, float* dw5, float* dw3, int32_t C, void* stream);
 /* PPEG: identity + depthwise 7x7 + 5x5 + 3x3 folded into one 7x7 stencil, token-major [B,1+H*W,C];
  * the cls row is copied through (models/mil.py:192-206).  w7 [49,C] folded tap-major weights, bias [C] folded.
  * Backward: dw_part [nblk,49,C], db_part [nblk,C]. */

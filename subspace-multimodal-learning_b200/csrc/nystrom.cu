@@ -535,6 +535,42 @@ extern "C" int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const f
   SML_LAUNCH_OK("sml_nystrom_resconv_bwd(dw)");
   return 0;
 }
+// PPEG parameter folding (models/mil.py:192-206): identity + 7x7 + 5x5 + 3x3 depthwise kernels -> one tap-major [49,C] stencil
+// and one bias; `unfold` is its backward (slices of d w7 and three copies of d bias).  One thread per (tap, channel).
+__global__ void ppeg_fold_kernel(const float* __restrict__ w7, const float* __restrict__ w5, const float* __restrict__ w3,
+                                 const float* __restrict__ b7, const float* __restrict__ b5, const float* __restrict__ b3,
+                                 float* __restrict__ wf, float* __restrict__ bf, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 49 * C) return;
+  const int tap = i / C, c = i % C, ky = tap / 7, kx = tap % 7;
+  float v = w7[c * 49 + tap];
+  if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) v += w5[c * 25 + (ky - 1) * 5 + (kx - 1)];
+  if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) v += w3[c * 9 + (ky - 2) * 3 + (kx - 2)];
+  if (tap == 24) v += 1.f;                                  // the residual identity
+  wf[i] = v;
+  if (tap == 0) bf[c] = b7[c] + b5[c] + b3[c];
+}
+__global__ void ppeg_unfold_kernel(const float* __restrict__ dwf, float* __restrict__ dw7, float* __restrict__ dw5,
+                                   float* __restrict__ dw3, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 49 * C) return;
+  const int tap = i / C, c = i % C, ky = tap / 7, kx = tap % 7;
+  const float g = dwf[i];
+  dw7[c * 49 + tap] = g;
+  if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) dw5[c * 25 + (ky - 1) * 5 + (kx - 1)] = g;
+  if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) dw3[c * 9 + (ky - 2) * 3 + (kx - 2)] = g;
+}
+extern "C" int sml_ppeg_fold(const float* w7, const float* w5, const float* w3, const float* b7, const float* b5, const float* b3,
+                             float* wf, float* bf, int32_t C, void* stream) {
+  ppeg_fold_kernel<<<(49 * C + 255) / 256, 256, 0, as_stream(stream)>>>(w7, w5, w3, b7, b5, b3, wf, bf, C);
+  SML_LAUNCH_OK("sml_ppeg_fold");
+  return 0;
+}
+extern "C" int sml_ppeg_unfold(const float* dwf, float* dw7, float* dw5, float* dw3, int32_t C, void* stream) {
+  ppeg_unfold_kernel<<<(49 * C + 255) / 256, 256, 0, as_stream(stream)>>>(dwf, dw7, dw5, dw3, C);
+  SML_LAUNCH_OK("sml_ppeg_unfold");
+  return 0;
+}
 extern "C" int sml_ppeg_fwd(const float* x, const float* w7, const float* bias, float* y, int32_t B, int32_t H, int32_t W,
                             int32_t C, void* stream) {
   const int tx = (W + PT_W - 1) / PT_W, tyc = (H + PT_H - 1) / PT_H;

@@ -36,15 +36,9 @@ class PPEG(nn.Module):
         self.proj2 = nn.Conv2d(dim, dim, 3, 1, 3 // 2, groups=dim)
 
     def folded(self):
-        """identity + 7x7 + 5x5 + 3x3 depthwise kernels summed into one tap-major [49,C] stencil (exact)."""
-        C = self.proj.weight.shape[0]
-        w = self.proj.weight.reshape(C, 7, 7)
-        w = w + torch.nn.functional.pad(self.proj1.weight.reshape(C, 5, 5), (1, 1, 1, 1))
-        w = w + torch.nn.functional.pad(self.proj2.weight.reshape(C, 3, 3), (2, 2, 2, 2))
-        eye = torch.zeros(7, 7, device=w.device, dtype=w.dtype)
-        eye[3, 3] = 1.0
-        w = w + eye
-        return w.reshape(C, 49).t().contiguous(), self.proj.bias + self.proj1.bias + self.proj2.bias
+        """identity + 7x7 + 5x5 + 3x3 depthwise kernels summed into one tap-major [49,C] stencil (exact), one kernel."""
+        return Fn.ppeg_fold(self.proj.weight, self.proj.bias, self.proj1.weight, self.proj1.bias, self.proj2.weight,
+                            self.proj2.bias)
 
     def forward(self, x, H, W):
         w7, bias = self.folded()
