@@ -71,8 +71,10 @@ def _pinv_step(pa2, z, mode):
     return xz, t2, t3
 
 
-def pinv_fwd(a2, iters, mode, a2_bundle=None):
-    """Moore-Penrose iteration (NystromAttention.py:20-35).  Returns z (fp32) and what backward needs."""
+def pinv_fwd(a2, iters, mode, a2_bundle=None, keep_steps=False):
+    """Moore-Penrose iteration (NystromAttention.py:20-35).  Returns z (fp32) and what backward needs.  ``keep_steps`` (tensor-
+    core modes) also keeps the bf16 operands xz, t2, t3 of every iteration (50 MB per iteration at 64 x 256^2) so that the
+    backward does not recompute them: 18 of its 66 dependent, latency-bound GEMM launches."""
     bh, m = a2.numel() // (a2.shape[-1] ** 2), a2.shape[-1]
     dev = a2.device
     scal = torch.empty(2, device=dev, dtype=F32)
@@ -84,17 +86,24 @@ def pinv_fwd(a2, iters, mode, a2_bundle=None):
     pa2 = a2_bundle if (a2_bundle is not None and (mode == "fp32" or a2_bundle.lo is not None)) else TB.of(a2, mode, hp=PINV_HP)
     z = TB.of(z0, mode, hp=PINV_HP)
     zs = [z.f]
+    keep_steps = keep_steps and mode != "fp32"
+    steps = []
     with ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN)):         # 4 * iters dependent GEMMs, one launch
         for _ in range(iters):
-            _, _, t3 = _pinv_step(pa2, z, mode)
+            xz, t2, t3 = _pinv_step(pa2, z, mode)
+            if keep_steps:
+                steps.append((TB(None, xz.hi, xz.lo), TB(None, t2.hi, t2.lo), TB(None, t3.hi, t3.lo)))
             z = mm(z, t3, _new_like(z.f, mode), alpha=0.25)                      # z <- 1/4 z t3
             zs.append(z.f)
+    if keep_steps:
+        return z, (zs[:-1], scal, arg, steps)
     return z, (zs[:-1], scal, arg)
 
 
 def pinv_bwd(a2, saved, dz, mode):
     """d a2 given d z_final; recomputes xz, t1..t3 per iteration from the saved z_k."""
-    zs, scal, arg = saved
+    zs, scal, arg = saved[:3]
+    steps = saved[3] if len(saved) > 3 else None                                 # (xz, t2, t3) operands kept by the forward
     bh, m = a2.numel() // (a2.shape[-1] ** 2), a2.shape[-1]
     pa2 = TB.of(a2, mode, hp=PINV_HP)
     da2 = torch.zeros_like(a2)
@@ -102,8 +111,8 @@ def pinv_bwd(a2, saved, dz, mode):
     zbs = [TB.of(zk, mode, hp=PINV_HP) for zk in zs]                                # conversions first: only GEMMs inside the program
     prog = ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN))
     prog.__enter__()
-    for zk, z in zip(reversed(zs), reversed(zbs)):
-        xz, t2, t3 = _pinv_step(pa2, z, mode)
+    for it, (zk, z) in enumerate(zip(reversed(zs), reversed(zbs))):
+        xz, t2, t3 = steps[len(zs) - 1 - it] if steps else _pinv_step(pa2, z, mode)
         dzk = mm(g, t3.T(), _new_like(zk, mode), alpha=0.25)                     # 1/4 G t3^T
         dt3 = mm(z.T(), g, _new_like(zk, mode), alpha=0.25)                      # 1/4 z^T G
         dxz = TB(torch.empty_like(zk))
@@ -189,7 +198,7 @@ class NystromAttentionFn(torch.autograd.Function):
             ops.softmax_(a2.f.view(-1, m), a2.hi, a2.lo)
         ops.softmax_(s3.view(-1, npad), a3.hi, a3.lo, write_f32=not lowp)            # softmax over tokens
         del s3
-        z, pinv_saved = pinv_fwd(a2.f, iters, mode, a2)                              # :138
+        z, pinv_saved = pinv_fwd(a2.f, iters, mode, a2, keep_steps=any(ctx.needs_input_grad))     # :138
         a3v = mm(a3, v_b, TB.new((b, h, m, d), dev, mode))                           # [b,h,m,d]
         z_op = z if mode != "bf16" else TB(z.f, z.hi, None)
         wm = mm(z_op, a3v, TB.new((b, h, m, d), dev, mode))                          # Z (A3 V)
@@ -210,7 +219,8 @@ class NystromAttentionFn(torch.autograd.Function):
         mm(merged.map(lambda t: t[:, pad:]), wout_b.T(), TB(y), bias=b_out.detach())  # :150-151
         ctx.save_for_backward(x, ln_w, ln_b, xp.f, xp.hi, xp.lo, weff, w_out, qkv.f, qkv.hi, qkv.lo, ql, kl, a1.f, a1.hi, a1.lo,
                               a2.f, a3.f, a3.hi, a3.lo, z.f, a3v.f, wm.f, merged.f, merged.hi, merged.lo, wc,
-                              *(ln_saved or ()), *pinv_saved[0], pinv_saved[1], pinv_saved[2])
+                              *(ln_saved or ()), *pinv_saved[0], pinv_saved[1], pinv_saved[2],
+                              *([t for st in pinv_saved[3] for bnd in st for t in (bnd.hi, bnd.lo)] if len(pinv_saved) > 3 else []))
         ctx.cfg = (b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode, ln_w is not None)
         return y
 
@@ -225,6 +235,10 @@ class NystromAttentionFn(torch.autograd.Function):
             mean, rstd = rest[0], rest[1]
             rest = rest[2:]
         zs, scal, arg = list(rest[:iters]), rest[iters], rest[iters + 1]
+        kept = rest[iters + 2:]
+        steps = None
+        if len(kept) == 6 * iters:                                                   # (xz, t2, t3) x (hi, lo) per iteration
+            steps = [tuple(TB(None, kept[6 * i + 2 * j], kept[6 * i + 2 * j + 1]) for j in range(3)) for i in range(iters)]
         dev = dy.device
         tc = mode != "fp32"
         hv = lambda t, i: t[:, :, i].permute(0, 2, 1, 3)
@@ -266,7 +280,7 @@ class NystromAttentionFn(torch.autograd.Function):
                                           stream()), "resconv_bwd")   # dv += conv^T
         dw_conv = ops.colsum(dwc_part).view(h, 1, ksize, 1)
         # ---- pinv + softmaxes (dS emitted with its bf16 copy by the softmax-backward kernel)
-        da2 = pinv_bwd(a2_f, (zs, scal, arg), dz, mode)
+        da2 = pinv_bwd(a2_f, (zs, scal, arg, steps) if steps else (zs, scal, arg), dz, mode)
         ds3 = TB.new((b, h, m, npad), dev, mode, f32=False); ds3.f = da3.f
         lowp = a1.f is None                     # bf16-only probabilities: dS also only needs its bf16 copy
         p1 = a1.f if a1.f is not None else a1.hi
