@@ -22,8 +22,10 @@ cat gpurun_out/${TAG}_stress_100k.json
 python tools/diag_deform_tc.py time > gpurun_out/${TAG}_deform_tc_vs_simt.txt 2>&1
 python tools/prof_all.py 3 bf16 > gpurun_out/${TAG}_kernel_times_plain.txt 2>&1
 if [ "${LAUNCHES:-0}" = "1" ]; then
+  # launch list of ONE steady-state train step of the bench command: skip the 3 warm-up steps (~411 launches each)
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_plain.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches_b8.csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 1240 -c 420 --csv --log-file gpurun_out/${TAG}_launches_b8.csv \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_run.log 2>&1
-  python tools/agg_launches.py gpurun_out/${TAG}_launches_b8.csv 25
+  python tools/agg_launches.py gpurun_out/${TAG}_launches_b8.csv 30 > gpurun_out/${TAG}_launches_b8_by_kernel.txt
+  head -12 gpurun_out/${TAG}_launches_b8_by_kernel.txt
 fi
