@@ -88,6 +88,7 @@ def pinv_fwd(a2, iters, mode, a2_bundle=None, keep_steps=False):
     zs = [z.f]
     keep_steps = keep_steps and mode != "fp32"
     steps = []
+    zbs = [TB(None, z.hi, z.lo)]
     with ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN)):         # 4 * iters dependent GEMMs, one launch
         for _ in range(iters):
             xz, t2, t3 = _pinv_step(pa2, z, mode)
@@ -95,8 +96,9 @@ def pinv_fwd(a2, iters, mode, a2_bundle=None, keep_steps=False):
                 steps.append((TB(None, xz.hi, xz.lo), TB(None, t2.hi, t2.lo), TB(None, t3.hi, t3.lo)))
             z = mm(z, t3, _new_like(z.f, mode), alpha=0.25)                      # z <- 1/4 z t3
             zs.append(z.f)
+            zbs.append(TB(None, z.hi, z.lo))
     if keep_steps:
-        return z, (zs[:-1], scal, arg, steps)
+        return z, (zs[:-1], scal, arg, steps, zbs[:-1])
     return z, (zs[:-1], scal, arg)
 
 
@@ -104,11 +106,16 @@ def pinv_bwd(a2, saved, dz, mode):
     """d a2 given d z_final; recomputes xz, t1..t3 per iteration from the saved z_k."""
     zs, scal, arg = saved[:3]
     steps = saved[3] if len(saved) > 3 else None                                 # (xz, t2, t3) operands kept by the forward
+    zbs_kept = saved[4] if len(saved) > 4 else None                              # bf16 copies of the z_k, idem
+    pa2_kept = saved[5] if len(saved) > 5 else None
     bh, m = a2.numel() // (a2.shape[-1] ** 2), a2.shape[-1]
-    pa2 = TB.of(a2, mode, hp=PINV_HP)
+    pa2 = pa2_kept if pa2_kept is not None else TB.of(a2, mode, hp=PINV_HP)
     da2 = torch.zeros_like(a2)
     g = TB.of(dz.contiguous(), mode, hp=PINV_HP)
-    zbs = [TB.of(zk, mode, hp=PINV_HP) for zk in zs]                                # conversions first: only GEMMs inside the program
+    if zbs_kept is not None:
+        zbs = [TB(zk, zb.hi, zb.lo) for zk, zb in zip(zs, zbs_kept)]
+    else:
+        zbs = [TB.of(zk, mode, hp=PINV_HP) for zk in zs]                            # conversions first: only GEMMs inside the program
     prog = ops.gemm_program(enabled=(mode != "fp32" and FUSE_PINV_CHAIN))
     prog.__enter__()
     for it, (zk, z) in enumerate(zip(reversed(zs), reversed(zbs))):
@@ -217,10 +224,17 @@ class NystromAttentionFn(torch.autograd.Function):
         y = torch.empty(b, n, D, device=dev, dtype=F32)
         wout_b = TB.of(w_out.detach().contiguous(), mode)
         mm(merged.map(lambda t: t[:, pad:]), wout_b.T(), TB(y), bias=b_out.detach())  # :150-151
+        # bf16 operand copies the backward needs again (each re-conversion is a ~13 us latency-bound launch: 14 per layer)
+        extras = []
+        if len(pinv_saved) > 3:
+            for bnd in (ql_b, kl_b, wm, a3v, z, a2, weff_b, wout_b, *pinv_saved[4]):
+                extras += [bnd.hi, bnd.lo]
         ctx.save_for_backward(x, ln_w, ln_b, xp.f, xp.hi, xp.lo, weff, w_out, qkv.f, qkv.hi, qkv.lo, ql, kl, a1.f, a1.hi, a1.lo,
                               a2.f, a3.f, a3.hi, a3.lo, z.f, a3v.f, wm.f, merged.f, merged.hi, merged.lo, wc,
                               *(ln_saved or ()), *pinv_saved[0], pinv_saved[1], pinv_saved[2],
-                              *([t for st in pinv_saved[3] for bnd in st for t in (bnd.hi, bnd.lo)] if len(pinv_saved) > 3 else []))
+                              *([t for st in pinv_saved[3] for bnd in st for t in (bnd.hi, bnd.lo)] if len(pinv_saved) > 3 else []),
+                              *extras)
+        ctx.n_extras = len(extras)
         ctx.cfg = (b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode, ln_w is not None)
         return y
 
@@ -235,10 +249,19 @@ class NystromAttentionFn(torch.autograd.Function):
             mean, rstd = rest[0], rest[1]
             rest = rest[2:]
         zs, scal, arg = list(rest[:iters]), rest[iters], rest[iters + 1]
-        kept = rest[iters + 2:]
+        ex = rest[len(rest) - ctx.n_extras:] if ctx.n_extras else []
+        kept = rest[iters + 2:len(rest) - ctx.n_extras]
         steps = None
         if len(kept) == 6 * iters:                                                   # (xz, t2, t3) x (hi, lo) per iteration
             steps = [tuple(TB(None, kept[6 * i + 2 * j], kept[6 * i + 2 * j + 1]) for j in range(3)) for i in range(iters)]
+        exb = [(ex[2 * i], ex[2 * i + 1]) for i in range(len(ex) // 2)]                # (hi, lo) pairs in the order saved
+
+        def kept_or_of(i, f32, single=False):
+            """bundle of fp32 tensor ``f32`` with the bf16 copies the forward kept (else converted now)"""
+            if not exb:
+                return TB.of(f32, mode)
+            hi, lo = exb[i]
+            return TB(f32, hi, None if (single or mode == "bf16") else lo)
         dev = dy.device
         tc = mode != "fp32"
         hv = lambda t, i: t[:, :, i].permute(0, 2, 1, 3)
@@ -256,19 +279,19 @@ class NystromAttentionFn(torch.autograd.Function):
         db_out = ops.colsum(dyp2)
         dw_out = mm(dy_b.T(), merged.map(lambda t: t.view(b * npad, inner))).f                  # [D, inner]
         dmerged = TB.new((b, npad, inner), dev, mode)
-        mm(dy_b, TB.of(w_out.detach().contiguous(), mode), dmerged.map(lambda t: t.view(b * npad, inner)))
+        mm(dy_b, kept_or_of(7, w_out.detach().contiguous()), dmerged.map(lambda t: t.view(b * npad, inner)))
         dout_b = dmerged.map(lambda t: t.view(b, npad, h, d).permute(0, 2, 1, 3))
         q_b, k_b, v_b = (qkv.map(lambda t, i=i: hv(t, i)) for i in range(3))
-        ql_b, kl_b = TB.of(ql, mode), TB.of(kl, mode)
+        ql_b, kl_b = kept_or_of(0, ql), kept_or_of(1, kl)
         dqkv = TB.new((b, npad, 3, h, d), dev, mode)
         dq, dk, dv = (hv(dqkv.f, i) for i in range(3))
         # ---- out = A1 Wm ; Wm = Z A3V ; A3V = A3 V
-        wm_b = TB.of(wm_f, mode)
+        wm_b = kept_or_of(2, wm_f)
         fuse_a1 = FUSE_A1_BWD and mode == "bf16" and a1.f is None and m == 256 and d == 64 and fused_cvt_ok(ksize)
         da1 = None if fuse_a1 else mm(dout_b, wm_b.T(), TB(torch.empty(b, h, npad, m, device=dev, dtype=F32)))
         dwm = mm(a1.T(), dout_b, TB.new((b, h, m, d), dev, mode))                               # [b,h,m,d]
-        dz = mm(dwm, TB.of(a3v_f, mode).T()).f                                                  # [b,h,m,m]
-        da3v = mm(TB.of(z_f, mode).T(), dwm, TB.new((b, h, m, d), dev, mode))                   # [b,h,m,d]
+        dz = mm(dwm, kept_or_of(3, a3v_f).T()).f                                                # [b,h,m,m]
+        da3v = mm(kept_or_of(4, z_f).T(), dwm, TB.new((b, h, m, d), dev, mode))                 # [b,h,m,d]
         da3 = mm(da3v, v_b.T(), TB(torch.empty(b, h, m, npad, device=dev, dtype=F32)))
         mm(a3.T(), da3v, TB(dv))                                                                # dv = A3^T dA3V
         dwc_part = torch.zeros(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad), c_i32(h * d)), h * ksize, device=dev,
@@ -280,7 +303,12 @@ class NystromAttentionFn(torch.autograd.Function):
                                           stream()), "resconv_bwd")   # dv += conv^T
         dw_conv = ops.colsum(dwc_part).view(h, 1, ksize, 1)
         # ---- pinv + softmaxes (dS emitted with its bf16 copy by the softmax-backward kernel)
-        da2 = pinv_bwd(a2_f, (zs, scal, arg, steps) if steps else (zs, scal, arg), dz, mode)
+        if steps and exb:
+            pa2 = TB(a2_f, *exb[5])
+            zbs_kept = [TB(None, hi, lo) for hi, lo in exb[8:8 + iters]]
+            da2 = pinv_bwd(a2_f, (zs, scal, arg, steps, zbs_kept, pa2), dz, mode)
+        else:
+            da2 = pinv_bwd(a2_f, (zs, scal, arg, steps) if steps else (zs, scal, arg), dz, mode)
         ds3 = TB.new((b, h, m, npad), dev, mode, f32=False); ds3.f = da3.f
         lowp = a1.f is None                     # bf16-only probabilities: dS also only needs its bf16 copy
         p1 = a1.f if a1.f is not None else a1.hi
@@ -319,7 +347,7 @@ class NystromAttentionFn(torch.autograd.Function):
             dqkv.hi, dqkv.lo = s.hi, s.lo
         # ---- qkv projection
         dqkv2 = dqkv.map(lambda t: t.view(b * npad, 3 * inner))
-        dxp = mm(dqkv2, TB.of(weff, mode)).f.view(b, npad, D)
+        dxp = mm(dqkv2, kept_or_of(6, weff)).f.view(b, npad, D)
         dw_qkv = mm(dqkv2.T(), xp.map(lambda t: t.view(b * npad, D))).f                         # [3 inner, D]
         ops.axpby_(dw_qkv[:inner], dw_qkv[:inner].clone(), d ** -0.5, 0.0)
         dln_w = dln_b = None
