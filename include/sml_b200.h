@@ -61,6 +61,9 @@ int sml_gemm_tc(const sml_gemm_desc* d, void* stream);
 int sml_gemm_tc_program(const sml_gemm_desc* descs, int32_t n, void* counter, void* stream);
 /* fp32 -> bf16 hi (and lo = bf16(x - hi) when lo != NULL), n elements */
 int sml_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+/* same on rows: x [B, n, D] fp32 -> hi / lo [B, npad = n + pad, D] with `pad` zero rows in front of every batch (the front
+ * padding of models/NystromAttention.py:79-82 applied to the incoming gradient without a padded fp32 copy) */
+int sml_split_bf16_pad(const float* x, void* hi, void* lo, int64_t B, int64_t n, int64_t npad, int64_t pad, int32_t D, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Row-wise kernels shared by the path.

@@ -830,6 +830,23 @@ extern "C" int sml_gemm_tc_program(const sml_gemm_desc* descs, int32_t n, void* 
 }
 
 namespace sml {
+__device__ __forceinline__ void split4(const float4 v, uint2& h, uint2& l) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  h.x = *reinterpret_cast<const uint32_t*>(&h0); h.y = *reinterpret_cast<const uint32_t*>(&h1);
+  l.x = *reinterpret_cast<const uint32_t*>(&l0); l.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+// 4 elements per thread (128-bit loads, 64-bit stores); n4 = number of float4 groups, tail handled by the scalar kernel
+__global__ void __launch_bounds__(256) split_bf16_vec_kernel(const float4* __restrict__ x, uint2* __restrict__ hi,
+                                                             uint2* __restrict__ lo, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    uint2 h, l;
+    split4(x[i], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                          __nv_bfloat16* __restrict__ lo, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -839,13 +856,40 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
+// rows [B, n, D] fp32 -> bf16 (hi / lo) rows [B, npad, D] with `pad` zero rows in front of every batch (D % 4 == 0)
+__global__ void __launch_bounds__(256) split_bf16_pad_kernel(const float4* __restrict__ x, uint2* __restrict__ hi,
+                                                             uint2* __restrict__ lo, int64_t total4, int64_t n, int64_t npad,
+                                                             int64_t pad, int D4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / D4, c = i % D4;
+    const int64_t b = row / npad, r = row % npad;
+    uint2 h = make_uint2(0u, 0u), l = make_uint2(0u, 0u);
+    if (r >= pad) split4(x[(b * n + (r - pad)) * D4 + c], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
 }  // namespace sml
 
 extern "C" int sml_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
   if (n == 0) return 0;
-  int64_t g = (n + 255) / 256;
+  const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(hi) & 7) == 0) &&
+                   (!lo || (reinterpret_cast<uintptr_t>(lo) & 7) == 0);
+  int64_t g = ((vec ? n / 4 : n) + 255) / 256;
   if (g > kNumSMs * 16) g = kNumSMs * 16;
-  split_bf16_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  if (vec) split_bf16_vec_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n / 4);
+  else split_bf16_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
   SML_LAUNCH_OK("sml_split_bf16");
+  return 0;
+}
+extern "C" int sml_split_bf16_pad(const float* x, void* hi, void* lo, int64_t B, int64_t n, int64_t npad, int64_t pad, int32_t D,
+                                  void* stream) {
+  SML_CHECK(D % 4 == 0 && npad == n + pad && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "sml_split_bf16_pad: bad layout");
+  const int64_t total4 = B * npad * (D / 4);
+  if (total4 == 0) return 0;
+  int64_t g = (total4 + 255) / 256;
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  split_bf16_pad_kernel<<<(unsigned)g, 256, 0, as_stream(stream)>>>((const float4*)x, (uint2*)hi, (uint2*)lo, total4, n, npad, pad, D / 4);
+  SML_LAUNCH_OK("sml_split_bf16_pad");
   return 0;
 }

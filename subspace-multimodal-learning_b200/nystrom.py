@@ -268,15 +268,25 @@ class NystromAttentionFn(torch.autograd.Function):
         xp = TB(xp_f, xp_hi, xp_lo); qkv = TB(qkv_f, qkv_hi, qkv_lo); a1 = TB(a1_f, a1_hi, a1_lo); a3 = TB(a3_f, a3_hi, a3_lo)
         merged = TB(mg_f, mg_hi, mg_lo)
         dy = dy.contiguous()
-        if pad:
-            dyp = torch.zeros(b, npad, D, device=dev, dtype=F32)
-            dyp[:, pad:] = dy
+        if pad and tc and D % 4 == 0:
+            # tensor-core modes: the front-padded gradient only exists as the bf16 GEMM operand (zero pad rows written by the
+            # conversion kernel itself): no padded fp32 copy (zero fill + copy + re-read of 0.27 GB per layer at B = 8)
+            hi = torch.empty(b * npad, D, device=dev, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi) if mode == "bf16x3" else None
+            check(lib.sml_split_bf16_pad(ptr(dy), ptr(hi), ptr(lo), ops.c_i64(b), ops.c_i64(n), ops.c_i64(npad), ops.c_i64(pad),
+                                         c_i32(D), stream()), "split_bf16_pad")
+            dy_b = TB(None, hi, lo)
+            db_out = ops.colsum(dy.view(b * n, D))
         else:
-            dyp = dy
-        dyp2 = dyp.view(b * npad, D)
-        dy_b = TB.of(dyp2, mode)
+            if pad:
+                dyp = torch.zeros(b, npad, D, device=dev, dtype=F32)
+                dyp[:, pad:] = dy
+            else:
+                dyp = dy
+            dyp2 = dyp.view(b * npad, D)
+            dy_b = TB.of(dyp2, mode)
+            db_out = ops.colsum(dyp2)
         # ---- to_out
-        db_out = ops.colsum(dyp2)
         dw_out = mm(dy_b.T(), merged.map(lambda t: t.view(b * npad, inner))).f                  # [D, inner]
         dmerged = TB.new((b, npad, inner), dev, mode)
         mm(dy_b, kept_or_of(7, w_out.detach().contiguous()), dmerged.map(lambda t: t.view(b * npad, inner)))
