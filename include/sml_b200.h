@@ -79,7 +79,8 @@ int sml_layernorm_fwd(const float* x, const float* w, const float* b, float* y, 
 int sml_layernorm_bwd_blocks(int64_t R);
 int sml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                       float* dx, float* dw_part, float* db_part, int64_t R, int32_t D, int64_t n, int64_t npad,
-                      int64_t pad, void* stream);   /* dy is read in the padded layout, dx written dense */
+                      int64_t pad, const float* res, void* stream);   /* dy is read in the padded layout, dx written dense;
+                      res (optional, [R,D]) is added to dx: the gradient of the skip connection of x + f(LN(x)) (mil.py:186) */
 /* y[r,:] = softmax(x[r,:]) in place over C columns (models/NystromAttention.py:137) */
 /* hi/lo: optional bf16 copies; write_f32 = 0 leaves x untouched (probabilities kept in bf16 only) */
 int sml_softmax_fwd(float* x, int64_t R, int64_t C, void* hi, void* lo, int32_t write_f32, void* stream);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx,
     float* __restrict__ dw_part, float* __restrict__ db_part, int64_t R, int D, int64_t rows_per_block, int64_t n,
-    int64_t npad, int64_t pad) {
+    int64_t npad, int64_t pad, const float* __restrict__ res) {
   extern __shared__ float sm[];   // [LNB_WARPS][2][D]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nv = D >> 2;
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
     }
     s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
     float4* dr = reinterpret_cast<float4*>(dx + row * D);
+    const float4* rr = res ? reinterpret_cast<const float4*>(res + row * D) : nullptr;   // + gradient of the skip connection
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = lane + i * 32;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) layernorm_bwd_kernel(
         o.y = rs * (g[i].y - s1 - xh[i].y * s2);
         o.z = rs * (g[i].z - s1 - xh[i].z * s2);
         o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+        if (rr) { const float4 rv = rr[c]; o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w; }
         dr[c] = o;
       }
     }
@@ -448,7 +450,7 @@ extern "C" int sml_layernorm_bwd_blocks(int64_t R) {
 }
 extern "C" int sml_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean, const float* rstd,
                                  float* dx, float* dw_part, float* db_part, int64_t R, int32_t D, int64_t n, int64_t npad,
-                                 int64_t pad, void* stream) {
+                                 int64_t pad, const float* res, void* stream) {
   SML_CHECK(D % 4 == 0 && D <= 1024, "sml_layernorm_bwd: D=%d must be a multiple of 4 and <= 1024", D);
   const int nb = sml_layernorm_bwd_blocks(R);
   const int64_t rpb = (R + nb - 1) / nb;
@@ -460,10 +462,10 @@ extern "C" int sml_layernorm_bwd(const float* dy, const float* x, const float* w
   }
   const int nv = D / 4;
   cudaStream_t st = as_stream(stream);
-  if (nv <= 32) layernorm_bwd_kernel<1><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
-  else if (nv <= 64) layernorm_bwd_kernel<2><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
-  else if (nv <= 128) layernorm_bwd_kernel<4><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
-  else layernorm_bwd_kernel<8><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad);
+  if (nv <= 32) layernorm_bwd_kernel<1><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad, res);
+  else if (nv <= 64) layernorm_bwd_kernel<2><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad, res);
+  else if (nv <= 128) layernorm_bwd_kernel<4><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad, res);
+  else layernorm_bwd_kernel<8><<<nb, LNB_WARPS * 32, smem, st>>>(dy, x, w, mean, rstd, dx, dw_part, db_part, R, D, rpb, n, npad, pad, res);
   SML_LAUNCH_OK("sml_layernorm_bwd");
   return 0;
 }

@@ -22,10 +22,13 @@ class TransLayer(nn.Module):
         from . import NystromAttention as NA
         # LayerNorm fused into the attention function: it writes the normalised rows (and their bf16 copy) straight
         # into the front-padded buffer the qkv GEMM reads
-        y = nystrom_attention(x.float(), a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias, a.res_conv.weight, a.heads,
-                              a.num_landmarks, a.pinv_iterations, a.precision or NA.DEFAULT_PRECISION,
-                              pre_norm=(self.norm.weight, self.norm.bias, self.norm.eps))
-        return Fn.dropout_add(x, y, a.to_out[1].p, self.training)      # x + dropout(attn(norm(x)))
+        # x + dropout(attn(norm(x))) as ONE autograd node: the skip gradient is added inside the LayerNorm-backward kernel
+        p = float(a.to_out[1].p) if self.training else 0.0
+        x = x.float()
+        skip = (p, Fn._seed_state["seed"], Fn._next_offset(x.numel()) if p > 0 else 0)
+        return nystrom_attention(x, a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias, a.res_conv.weight, a.heads,
+                                 a.num_landmarks, a.pinv_iterations, a.precision or NA.DEFAULT_PRECISION,
+                                 pre_norm=(self.norm.weight, self.norm.bias, self.norm.eps), skip=skip)
 
 
 class PPEG(nn.Module):

@@ -148,7 +148,9 @@ class NystromAttentionFn(torch.autograd.Function):
     written straight into the front-padded buffer (and its bf16 copy)."""
 
     @staticmethod
-    def forward(ctx, x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, m, iters, mode, ln_eps):
+    def forward(ctx, x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, m, iters, mode, ln_eps, skip=None):
+        """skip = (p, seed, offset): return x + dropout(attention(LN(x)), p) (TransLayer, mil.py:186) - the skip gradient is then
+        added inside the LayerNorm-backward kernel instead of by autograd's accumulation pass."""
         assert mode in PRECISIONS
         ops.require_cuda(x, w_qkv, w_out, b_out, w_conv)
         b, n, D = x.shape
@@ -236,6 +238,10 @@ class NystromAttentionFn(torch.autograd.Function):
                               *extras)
         ctx.n_extras = len(extras)
         ctx.cfg = (b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode, ln_w is not None)
+        ctx.skip = skip
+        if skip is not None:
+            assert ln_w is not None, "the fused skip connection needs the fused LayerNorm"
+            return ops.dropout_add(x, y, skip[0], skip[1], skip[2])
         return y
 
     @staticmethod
@@ -268,6 +274,11 @@ class NystromAttentionFn(torch.autograd.Function):
         xp = TB(xp_f, xp_hi, xp_lo); qkv = TB(qkv_f, qkv_hi, qkv_lo); a1 = TB(a1_f, a1_hi, a1_lo); a3 = TB(a3_f, a3_hi, a3_lo)
         merged = TB(mg_f, mg_hi, mg_lo)
         dy = dy.contiguous()
+        dy_skip = None
+        if ctx.skip is not None:
+            dy_skip = dy                                                             # gradient of the skip connection
+            if ctx.skip[0] > 0:
+                dy = ops.dropout_add(None, dy, ctx.skip[0], ctx.skip[1], ctx.skip[2])    # same mask as the forward
         if pad and tc and D % 4 == 0:
             # tensor-core modes: the front-padded gradient only exists as the bf16 GEMM operand (zero pad rows written by the
             # conversion kernel itself): no padded fp32 copy (zero fill + copy + re-read of 0.27 GB per layer at B = 8)
@@ -362,11 +373,12 @@ class NystromAttentionFn(torch.autograd.Function):
         ops.axpby_(dw_qkv[:inner], dw_qkv[:inner].clone(), d ** -0.5, 0.0)
         dln_w = dln_b = None
         if has_ln:
-            dx2, dln_w, dln_b = ops.layernorm_bwd(dxp.view(b * npad, D), x.view(b * n, D), ln_w.detach(), mean, rstd, n, npad, pad)
+            dx2, dln_w, dln_b = ops.layernorm_bwd(dxp.view(b * npad, D), x.view(b * n, D), ln_w.detach(), mean, rstd, n, npad, pad,
+                                                  res=None if dy_skip is None else dy_skip.view(b * n, D))
             dx = dx2.view(b, n, D)
         else:
             dx = dxp[:, pad:]
-        return dx, dw_qkv, dw_out, db_out, dw_conv, dln_w, dln_b, None, None, None, None, None
+        return dx, dw_qkv, dw_out, db_out, dw_conv, dln_w, dln_b, None, None, None, None, None, None
 
 
 def fused_cvt_ok(ksize):
@@ -374,7 +386,7 @@ def fused_cvt_ok(ksize):
 
 
 def nystrom_attention(x, w_qkv, w_out, b_out, w_conv, heads, num_landmarks, pinv_iterations, precision="fp32",
-                      pre_norm=None):
+                      pre_norm=None, skip=None):
     ln_w, ln_b, eps = pre_norm if pre_norm is not None else (None, None, 1e-5)
     return NystromAttentionFn.apply(x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, num_landmarks, pinv_iterations,
-                                    precision, eps)
+                                    precision, eps, skip)

@@ -249,14 +249,14 @@ def layernorm_fwd(x2d, w, b, y, n, npad, pad, eps=1e-5, y_hi=None, y_lo=None):
     return mean, rstd
 
 
-def layernorm_bwd(dy, x2d, w, mean, rstd, n, npad, pad):
+def layernorm_bwd(dy, x2d, w, mean, rstd, n, npad, pad, res=None):
     R, D = x2d.shape
     nb = lib.sml_layernorm_bwd_blocks(c_i64(R))
     dx = torch.empty_like(x2d)
     dwp = torch.empty(nb, D, device=x2d.device, dtype=F32)
     dbp = torch.empty(nb, D, device=x2d.device, dtype=F32)
     check(lib.sml_layernorm_bwd(ptr(dy), ptr(x2d), ptr(w), ptr(mean), ptr(rstd), ptr(dx), ptr(dwp), ptr(dbp), c_i64(R),
-                                c_i32(D), c_i64(n), c_i64(npad), c_i64(pad), stream()), "layernorm_bwd")
+                                c_i32(D), c_i64(n), c_i64(npad), c_i64(pad), ptr(res), stream()), "layernorm_bwd")
     return dx, colsum(dwp), colsum(dbp)
 
 

@@ -156,3 +156,27 @@ def test_dropout_statistics():
     assert abs(y.mean().item() - 1.0) < 5e-3
     y.sum().backward()
     assert torch.equal(u.grad != 0, y != 0)          # same mask regenerated in backward
+
+
+def test_translayer_training_mode_skip_and_dropout():
+    """TransLayer in training mode = x + dropout(attn(norm(x)), 0.1) as one autograd node: every element of (out - x) is
+    either 0 or the eval-mode value / 0.9, the kept fraction is ~0.9, and the backward regenerates the same mask: with
+    d out = 1 the gradient w.r.t. the attention bias (to_out.0.bias) is the per-column count of kept elements / 0.9."""
+    import sml_b200
+    from sml_b200 import functional as Fn
+    torch.manual_seed(0)
+    tl = sml_b200.TransLayer(dim=64).cuda()
+    x = randn((2, 300, 64), 31).cuda()
+    tl.eval()
+    y_eval = tl(x).detach() - x
+    tl.train(); Fn.manual_seed(77)
+    xg = x.clone().requires_grad_()
+    out = tl(xg)
+    u = (out.detach() - x)
+    kept = u != 0
+    assert abs(float(kept.float().mean()) - 0.9) < 2e-2
+    assert rel_err(u[kept], y_eval[kept] / 0.9) < 1e-4
+    out.sum().backward()
+    want_db = kept.float().sum(dim=(0, 1)) / 0.9
+    assert rel_err(tl.attn.to_out[0].bias.grad, want_db) < 1e-4
+    assert torch.isfinite(xg.grad).all() and float((xg.grad - 1).abs().max()) > 0          # skip gradient (1) + attention path
