@@ -211,3 +211,27 @@ def deform_cross_transmil(path, omic, p, attn_dim=2, pad_order="reference", q_ch
     logits = z @ p["_fc2.weight"].t() + p["_fc2.bias"]
     encoded = z @ p["multimodal_projection.weight"].t() + p["multimodal_projection.bias"]
     return dict(encoded=encoded, logits=logits, omic=om, vgrid=vgrid)
+
+
+def maxnet(x, p, prefix):
+    """MaxNet.forward, eval mode (models/model.py:142-187): 4 x (Linear, ELU, AlphaDropout = identity), ReLU; classifier."""
+    for i in range(4):
+        x = torch.nn.functional.elu(x @ p[f"{prefix}encoder.{i}.0.weight"].t() + p[f"{prefix}encoder.{i}.0.bias"])
+    feats = torch.relu(x)
+    return feats, feats @ p[f"{prefix}classifier.0.weight"].t() + p[f"{prefix}classifier.0.bias"]
+
+
+def deform_pathomic_net(x_path, x_omic_tumor, x_omic_immune, p, attn_dim=2, q_chunk=0):
+    """DeformPathomicNet.forward, eval mode, fusion_type "concat", task_type != "survival" (models/model.py:481-544):
+    two genomic encoders, two DeformCrossTransMIL branches on the same bag, concat, three linear heads."""
+    om_t, _ = maxnet(x_omic_tumor.float(), p, "omic_net_tumor.")                          # :486-487
+    om_i, _ = maxnet(x_omic_immune.float(), p, "omic_net_immune.")                        # :489-490
+    bt = deform_cross_transmil(x_path, om_t, sub(p, "pathomic_net_tumor."), attn_dim=attn_dim, q_chunk=q_chunk)
+    bi = deform_cross_transmil(x_path, om_i, sub(p, "pathomic_net_immune."), attn_dim=attn_dim, q_chunk=q_chunk)
+    vt, vi = bt["encoded"], bi["encoded"]
+    feats = torch.cat((vt, vi), 1)                                                        # :511-515
+    hazard = feats @ p["classifier.weight"].t() + p["classifier.bias"]                    # :520
+    hz_t = vt @ p["classifier_tumor.0.weight"].t() + p["classifier_tumor.0.bias"]         # :522
+    hz_i = vi @ p["classifier_immune.0.weight"].t() + p["classifier_immune.0.bias"]       # :523
+    return dict(features=feats, vec_tumor=vt, vec_immune=vi, logits=[hz_t, hz_i, hazard], omic_tumor=bt["omic"],
+                vgrid_tumor=bt["vgrid"], omic_immune=bi["omic"], vgrid_immune=bi["vgrid"])

@@ -186,3 +186,29 @@ def test_modulation_oracle_matches_reference_source_lines():
         got = oracle.modulation.modulate(c["W"], c["b"], c["G"], c["ft"], c["fi"], c["labels"])
         assert torch.allclose(got, c["G_out"], rtol=1e-5, atol=1e-6)
         assert (got != c["G"]).any()                      # the fixture exercises the projection
+
+
+def test_deform_pathomic_net():
+    """oracle.deform.deform_pathomic_net vs the unmodified reference (tests/golden/make_golden_pathomic.py), batch 2."""
+    import torch
+    g = load_golden("pathomic")
+    st = synth_state_dict(g["shapes"], g["seed"])
+    for k in st:
+        if k.endswith("to_offsets.2.weight"):
+            st[k] = st[k] * g["offw_scale"]
+    p = _leaf({k: v for k, v in st.items() if v.is_floating_point() and not k.endswith(("output_range", "output_shift"))})
+    x_path = randn((2, 2500, 1024), 112)
+    xt = randn((2, 59), 113).abs().requires_grad_(); xi = randn((2, 361), 114).abs().requires_grad_()
+    o = oracle.deform.deform_pathomic_net(x_path, xt, xi, p, q_chunk=500)
+    assert rel_err(o["features"], g["feats"]) < 1e-4 and rel_err(o["vec_tumor"], g["vt"]) < 1e-4
+    for a, b in zip(o["logits"], g["logits"]):
+        assert rel_err(a, b) < 1e-4
+    assert rel_err(o["vgrid_tumor"], g["vgrid_tumor"]) < 1e-4 and rel_err(o["vgrid_immune"], g["vgrid_immune"]) < 1e-4
+    assert rel_err(o["omic_tumor"][:, 5], g["omic_tumor_row"]) < 1e-5
+    loss = sum((l * randn(l.shape, 120 + j)).sum() for j, l in enumerate(o["logits"])) + (o["features"] * randn(o["features"].shape, 125)).sum()
+    loss = loss + 0.01 * ((o["vgrid_tumor"] * randn(o["vgrid_tumor"].shape, 126)).sum() + (o["vgrid_immune"] * randn(o["vgrid_immune"].shape, 127)).sum())
+    loss.backward()
+    assert rel_err(xt.grad, g["gxt"]) < 1e-3 and rel_err(xi.grad, g["gxi"]) < 1e-3
+    for k, nv in g["gnorms"].items():
+        if k in p and p[k].grad is not None:
+            assert abs(float(p[k].grad.norm()) - nv) <= 2e-3 * nv + 1e-6, k
