@@ -212,3 +212,40 @@ def test_deform_pathomic_net():
     for k, nv in g["gnorms"].items():
         if k in p and p[k].grad is not None:
             assert abs(float(p[k].grad.norm()) - nv) <= 2e-3 * nv + 1e-6, k
+
+
+def _cpb1d_params(seed):
+    import torch
+    torch.manual_seed(seed)
+    return {"mlp.0.0.weight": torch.randn(32, 1) * 1.5, "mlp.0.0.bias": torch.randn(32) * 0.7, "mlp.1.0.weight": torch.randn(32, 32) * 0.4,
+            "mlp.1.0.bias": torch.randn(32) * 0.3, "mlp.2.weight": torch.randn(2, 32) * 0.5, "mlp.2.bias": torch.randn(2) * 0.1}
+
+
+def test_pwl_table_equals_bias_mlp():
+    """The 1-D bias MLP is exactly a piecewise-linear table of the signed-log distance (oracle/pwl.py)."""
+    import torch
+    for seed in (0, 1, 2):
+        p = _cpb1d_params(seed)
+        table = oracle.pwl.build_table(p)
+        assert 32 <= table[0].numel() <= 32 + 33 * 32
+        dx = (torch.rand(20000, dtype=torch.float64) * 2 - 1) * 2.4
+        t = oracle.deform.slog(dx)
+        want = oracle.deform.cpb_mlp(t.unsqueeze(1), {k: v.double() for k, v in p.items()}, "")
+        got = oracle.pwl.eval_table(t, table)
+        assert float((got - want).abs().max()) < 1e-10
+
+
+def test_pwl_table_backward_equals_mlp_backward():
+    """Per-segment sums of (d bias, d bias * t) reproduce the MLP's parameter and position gradients."""
+    import torch
+    p = _cpb1d_params(3)
+    table = oracle.pwl.build_table(p)
+    t = oracle.deform.slog((torch.rand(5000, dtype=torch.float64) * 2 - 1) * 2.2).requires_grad_()
+    g = torch.randn(5000, 2, dtype=torch.float64)
+    q = {k: v.double().requires_grad_() for k, v in p.items()}
+    oracle.deform.cpb_mlp(t.unsqueeze(1), q, "").backward(g)
+    G0, G1, dt = oracle.pwl.segment_sums(t.detach(), g, table)
+    assert float((dt - t.grad).abs().max()) < 1e-10
+    got = oracle.pwl.param_grads_from_segments(p, "", table, G0, G1)
+    for k in q:
+        assert float((got[k] - q[k].grad).abs().max()) < 1e-8 * max(1.0, float(q[k].grad.abs().max())), k
