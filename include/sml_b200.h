@@ -100,6 +100,13 @@ int sml_relu_bwd(const float* y, const float* dy, float* dx, int64_t n, void* st
 /* y[b,t,:] = (x ? x[b,t,:] : 0) + a*vec[b,:]  — the rank-1 half of FusionNet (models/DeformCrossTransMIL.py:104,33-38:
  * the repeated omic vector is never materialised) and the backward of the token mean (Pooler :193) */
 int sml_add_rowvec(float* y, const float* x, const float* vec, float a, int64_t B, int64_t T, int32_t C, void* stream);
+/* 1-D bias MLP as an exact piecewise-linear table of t = sign(dx) log(|dx| + 1) (models/DeformableAttention1D.py:60-102; cpb =
+ * the packed parameters of sml_deform_attn_fwd with CD = 1): brk [sml_cpb1d_table_slots()] ascending breakpoints (+inf
+ * padded), coef [(slots + 1), OUT, 2] = (slope, intercept) per segment and output, nseg [1].  eval: out [n, OUT]. */
+int sml_cpb1d_table_slots(void);
+int sml_cpb1d_table_build(const float* cpb, int32_t OUT, float* brk, float* coef, int32_t* nseg, void* stream);
+int sml_cpb1d_table_eval(const float* t, int64_t n, const float* brk, const float* coef, const int32_t* nseg, int32_t OUT,
+                         float* out, void* stream);
 /* Gradient modulation of the fusion classifier after backward (train_test.py:87-184; diag2021 / grade / subtype tasks):
  * W, Wgrad [L, 2 hs], bias [L], feat_t / feat_i [B, hs] (the two branch embeddings), labels [B] int64.  Rewrites the
  * conflicting half of every row of Wgrad in place; info (optional) [4] = (score_t, score_i, #rows re-projected on the tumor

@@ -276,3 +276,28 @@ def test_gather_backward_sorted_scatter_is_deterministic_and_matches_autograd():
     want_dx2 = feat.grad.view(b, G, cg, H, W).permute(0, 3, 4, 1, 2).reshape(b, H * W, G * cg)
     assert rel_err(outs[0][0], want_dx2) < 1e-5
     assert rel_err(outs[0][1], grid.grad.view(b * G, nkv, 2)) < 1e-4
+
+
+@pytest.mark.parametrize("seed,OUT", [(0, 2), (1, 2), (2, 1)])
+def test_cpb1d_table_matches_mlp(seed, OUT):
+    """The 1-D bias MLP as an exact piecewise-linear table (csrc/cpb_table.cu; specification oracle/pwl.py): same number of
+    segments as the fp64 oracle table and the MLP's values to fp32 rounding on a million random signed-log distances."""
+    from sml_b200._lib import c_i32, c_i64, check, lib, ptr, stream
+    torch.manual_seed(seed)
+    p = {"mlp.0.0.weight": torch.randn(32, 1) * 1.5, "mlp.0.0.bias": torch.randn(32) * 0.7, "mlp.1.0.weight": torch.randn(32, 32) * 0.4,
+         "mlp.1.0.bias": torch.randn(32) * 0.3, "mlp.2.weight": torch.randn(OUT, 32) * 0.5, "mlp.2.bias": torch.randn(OUT) * 0.1}
+    cpb = torch.cat([p[k].reshape(-1) for k in ("mlp.0.0.weight", "mlp.0.0.bias", "mlp.1.0.weight", "mlp.1.0.bias", "mlp.2.weight",
+                                                "mlp.2.bias")]).cuda()
+    slots = lib.sml_cpb1d_table_slots()
+    brk = torch.empty(slots, device="cuda"); coef = torch.empty(slots + 1, OUT, 2, device="cuda")
+    nseg = torch.zeros(1, device="cuda", dtype=torch.int32)
+    check(lib.sml_cpb1d_table_build(ptr(cpb), c_i32(OUT), ptr(brk), ptr(coef), ptr(nseg), stream()), "table_build")
+    dx = (torch.rand(1 << 20, device="cuda") * 2 - 1) * 2.4
+    t = torch.sign(dx) * torch.log(dx.abs() + 1)
+    out = torch.empty(t.numel(), OUT, device="cuda")
+    check(lib.sml_cpb1d_table_eval(ptr(t), c_i64(t.numel()), ptr(brk), ptr(coef), ptr(nseg), c_i32(OUT), ptr(out), stream()), "table_eval")
+    want = oracle.deform.cpb_mlp(t.double().cpu().unsqueeze(1), {k: v.double() for k, v in p.items()}, "")
+    assert rel_err(out, want) < 1e-5
+    ns = int(nseg.item())
+    assert ns == oracle.pwl.build_table(p)[0].numel() + 1
+    assert bool((brk[:ns - 1][1:] >= brk[:ns - 1][:-1]).all())
