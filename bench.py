@@ -44,7 +44,7 @@ def parse():
                          "DeformCrossTransMIL (attn_dim 2 / 1) train step; pathomic = DeformPathomicNet (two genomic encoders + two "
                          "DeformCrossTransMIL branches + heads) with the reference's loss: weighted CE + BatchLoss over all ranks "
                          "(train_test.py:63-83)")
-    ap.add_argument("--cpu-sample", type=int, default=1, help="slides in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=5, help="slides in the CPU baseline sample (~2 s each on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-out", default=None, help="write the per-shape GEMM timing table of the instrumented pass here")
     return ap.parse_args()
