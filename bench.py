@@ -47,7 +47,39 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=5, help="slides in the CPU baseline sample (~2 s each on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-out", default=None, help="write the per-shape GEMM timing table of the instrumented pass here")
+    ap.add_argument("--secondary", default=os.environ.get("SML_BENCH_SECONDARY", "transmil_bf16x3,pathomic,batchloss64"),
+                    help="comma list of extra workloads measured after the headline and reported under `secondary` "
+                         "(transmil_bf16x3 = the fp32-grade mode of configs[1]; pathomic = configs[2]; batchloss64 = configs[3]: "
+                         "BatchLoss + cross-rank gather + sync-BN BilinearFusion at global batch 64); empty string = none")
+    ap.add_argument("--secondary-steps", type=int, default=5)
     return ap.parse_args()
+
+
+def workload_name(workload, patches):
+    return {"transmil": "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags" % patches,
+            "pathomic": "DeformPathomicNet (2 x MaxNet + 2 x DeformCrossTransMIL attn_dim=2 + concat heads) fwd + weighted CE + "
+                        "BatchLoss(all ranks) + bwd + Adam on %d-patch x 1024-d bags" % patches,
+            "deform2d": "DeformCrossTransMIL(attn_dim=2: fc1 + genomic fusion + deformable cross-attention + heads) fwd+CE+bwd+Adam "
+                        "on %d-patch x 1024-d bags" % patches,
+            "deform1d": "DeformCrossTransMIL(attn_dim=1: fc1 + genomic fusion + deformable cross-attention + heads) fwd+CE+bwd+Adam "
+                        "on %d-patch x 1024-d bags" % patches}[workload]
+
+
+def workload_config(args, world):
+    """the `config` object of the JSON line - identical for both arms (`--impl ours` / `--impl reference`)"""
+    B, N = args.batch, args.patches
+    return {"workload": workload_name(args.workload, N), "slides_per_step_per_gpu": B, "global_batch": B * world,
+            "precision": args.precision, "parallelism": "dp%d" % world,
+            "l2": "inputs (%d MB/step) and activations exceed the 126 MB L2" % (B * N * 1024 * 4 // 2 ** 20)}
+
+
+def transmil_shapes():
+    """parameter shapes of TransMIL (models/mil.py:209-259) from the committed golden fixture - the CPU arm must not import
+    the product package (no libsml_b200.so in the reference process)"""
+    return torch.load(os.path.join(ROOT, "tests", "golden", "transmil.pt"), weights_only=False)["shapes"]
+
+
+PARAM_SEED = 7          # both arms start from synth_state_dict(transmil_shapes(), PARAM_SEED)
 
 
 def peaks():
@@ -127,15 +159,13 @@ def synth_bag(batch, patches, seed, device):
 
 # ------------------------------------------------------------------------------------------- reference arm / CPU
 def cpu_port_step_fn(patches, threads):
-    """The reference algorithm (oracle restatement of models/mil.py:209-259 + NystromAttention) on host cores."""
+    """The reference algorithm (oracle restatement of models/mil.py:209-259 + NystromAttention) on host cores.  Imports only
+    `oracle/` and the fixture helpers: nothing of the product package is loaded in this process."""
     import oracle
-    from argparse import Namespace
     torch.set_num_threads(threads)
     torch.manual_seed(42)
-    import sml_b200
-    shapes = {k: tuple(v.shape) for k, v in sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).state_dict().items()}
     from synth import synth_state_dict
-    params = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in synth_state_dict(shapes, 7).items()}
+    params = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in synth_state_dict(transmil_shapes(), PARAM_SEED).items()}
     opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-3, weight_decay=0.1)
 
     def step(x, y):
@@ -149,13 +179,18 @@ def cpu_port_step_fn(patches, threads):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU path (oracle port; the reference itself is 30 plain .py files with no
+    setup.py, its TransMIL needs CUDA-only calls and an un-vendored PyPI package) on all host threads, on the
+    SAME config / metric / unit / steps / warm-up as our arm.  Each step is a bounded sample of the configured step: ONE slide
+    of the `--batch` slides (a full 8-slide step is ~13 s of CPU); value = slides / second."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
     step = cpu_port_step_fn(args.patches, threads)
     x, y = synth_bag(1, args.patches, 42, "cpu")
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         step(x, y)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -163,24 +198,115 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags"
-                                   % args.patches, "slides_per_step_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
-                       "precision": "fp32", "parallelism": "host threads",
-                       "arm": "oracle port of the reference algorithm (models/mil.py + NystromAttention) on the host cores; each "
-                              "timed step is a bounded sample of 1 slide of the workload"},
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d steps x 1 slide of %d patches, fp32, %d of %d host threads"
-                                       % (args.steps, args.patches, torch.get_num_threads(), threads)},
+                             "sample": "each of the %d timed steps = 1 slide (of the %d per configured step) of %d patches, "
+                                       "fwd+CE+bwd+Adam, fp32 oracle port of models/mil.py + NystromAttention, %d of %d host threads"
+                                       % (args.steps, args.batch, args.patches, torch.get_num_threads(), threads)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------- our arm
+def load_ncu_traffic():
+    """dram read + write bytes per launch of the dominant GEMM shapes, from the round's `ncu --set full` capture.  The file
+    is written by tools/ncu_traffic.py from the .ncu-rep and names the capture it came from (commit, date); None when absent."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            d = json.load(open(path))
+            return {tuple(e["key"]): e["bytes"] for e in d.get("shapes", [])}, {k: d.get(k) for k in ("source", "commit", "captured")}
+    return {}, None
+
+
+class Workload:
+    """one train-step workload on this rank: model + optimizer + synthetic inputs + step function"""
+
+    def __init__(self, name, precision, batch, patches, dev, rank, world, local):
+        import sml_b200
+        from argparse import Namespace
+        from sml_b200 import functional as Fn
+        self.name, self.precision, self.B, self.N = name, precision, batch, patches
+        self.deform = name in ("deform2d", "deform1d", "pathomic")
+        torch.manual_seed(42)
+        B, N = batch, patches
+        if name == "pathomic":
+            margs = Namespace(init_type="max", input_size_omic_tumor=59, input_size_omic_immune=361, omic_dim=128, path_dim=128,
+                              mmhid=128, return_grad="False", dropout_rate=0.1, label_dim=4, fusion_type="concat", cut_fuse_grad=False,
+                              return_vgrid=True, attn_dim=2, task_type="diag2021")          # config/config_mine.yaml
+            model = sml_b200.DeformPathomicNet(margs).to(dev).train()
+            self.bloss = sml_b200.BatchLoss(B, world)
+            self.ce_w = torch.tensor([1.0, 4.15, 2.93, 2.43], device=dev)                   # train_test.py:25
+            gen = torch.Generator(device=dev).manual_seed(9 + rank)
+            self.x_t = torch.randn(B, 59, generator=gen, device=dev).abs()
+            self.x_i = torch.randn(B, 361, generator=gen, device=dev).abs()
+        elif self.deform:
+            model = sml_b200.DeformCrossTransMIL(Namespace(path_dim=128, attn_dim=2 if name == "deform2d" else 1,
+                                                           return_vgrid=False)).to(dev).train()
+            self.omic = torch.randn(B, 128, generator=torch.Generator(device=dev).manual_seed(7 + rank), device=dev).abs()
+        elif name == "batchloss64":
+            # configs[3]: the subspace loss with its cross-rank gather (utils/loss.py:13-40, utils/gather.py) + the sync-BN
+            # statistics exchange of BilinearFusion's two BatchNorm1d (models/fusion.py:29-32), global batch 64
+            model = sml_b200.BilinearFusion(skip=0, use_bilinear=1, gate1=1, gate2=1, dim1=128, dim2=128, scale_dim1=1, scale_dim2=1,
+                                            mmhid=128, dropout_rate=0.1).to(dev).train()
+            self.bloss = sml_b200.BatchLoss(B, world)
+            gen = torch.Generator(device=dev).manual_seed(11 + rank)
+            self.vec1 = torch.randn(B, 128, generator=gen, device=dev)
+            self.vec2 = torch.randn(B, 128, generator=gen, device=dev)
+            self.vg = (torch.randn(8 * B, 2, 32, 32, generator=gen, device=dev) * 4 + 16).requires_grad_()
+        else:
+            from synth import synth_state_dict
+            model = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev)
+            model.load_state_dict(synth_state_dict(transmil_shapes(), PARAM_SEED))          # same start as the CPU arm
+            model.train()
+        if hasattr(model, "set_precision"):
+            model.set_precision(precision)
+        Fn.manual_seed(42 + rank)
+        self.model = self.net = model
+        if world > 1:
+            # DeformCrossTransMIL: the attn1d / attn2d twin module is unused -> find_unused_parameters
+            self.net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=self.deform,
+                                                                 broadcast_buffers=False, gradient_as_bucket_view=True)
+        self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
+        if name == "batchloss64":
+            self.x_dev = torch.zeros(1, device=dev); self.y_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        else:
+            self.x_dev, self.y_dev = synth_bag(B, N, 42 + rank, dev)
+
+    def step(self, x, y):
+        import sml_b200
+        F = torch.nn.functional
+        self.opt.zero_grad(set_to_none=True)
+        if self.name == "pathomic":
+            _, f_t, f_i, lg, _, _, _ = self.net(x_path=x, x_omic_tumor=self.x_t, x_omic_immune=self.x_i)
+            loss = F.cross_entropy(lg[2], y, weight=self.ce_w) + 0.5 * self.bloss(lg[3], lg[4]).sum() + 0.5 * self.bloss(lg[5], lg[6]).sum()
+            loss.backward()
+            sml_b200.modulate_classifier_grads(self.model.classifier, f_t, f_i, y)       # train_test.py:87-184 (gradient_modulate: True)
+            self.opt.step()
+            return loss
+        if self.name == "batchloss64":
+            self.vg.grad = None
+            emb = self.net(self.vec1, self.vec2)                                         # BilinearFusion: 2 x sync-BN (train mode)
+            loss = self.bloss(emb, self.vg).sum() + emb.square().mean()                  # gather of [B,128] + vgrid, Gram epilogue
+            loss.backward()
+            self.opt.step()
+            return loss
+        if self.deform:
+            logits = self.net(x, self.omic)[1]
+            loss = F.cross_entropy(logits, y)
+        else:
+            enc, logits, _ = self.net(x)
+            # the multimodal_projection head takes part with zero weight so that every parameter gets a gradient and DDP needs
+            # no unused-parameter search (the reference's loop feeds both heads, train_test.py:347-373)
+            loss = F.cross_entropy(logits, y) + 0.0 * enc.sum()
+        loss.backward()
+        self.opt.step()
+        return loss
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from argparse import Namespace
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -195,65 +321,7 @@ def run_ours(args):
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     import sml_b200
-    from sml_b200 import functional as Fn
     from sml_b200 import ops
-
-    torch.manual_seed(42)
-    deform = args.workload != "transmil"
-    pathomic = args.workload == "pathomic"
-    if pathomic:
-        margs = Namespace(init_type="max", input_size_omic_tumor=59, input_size_omic_immune=361, omic_dim=128, path_dim=128,
-                          mmhid=128, return_grad="False", dropout_rate=0.1, label_dim=4, fusion_type="concat", cut_fuse_grad=False,
-                          return_vgrid=True, attn_dim=2, task_type="diag2021")          # config/config_mine.yaml
-        model = sml_b200.DeformPathomicNet(margs).to(dev).train()
-        model.set_precision(args.precision)
-        bloss = sml_b200.BatchLoss(args.batch, world)
-        ce_w = torch.tensor([1.0, 4.15, 2.93, 2.43], device=dev)                        # train_test.py:25
-    elif deform:
-        model = sml_b200.DeformCrossTransMIL(Namespace(path_dim=128, attn_dim=2 if args.workload == "deform2d" else 1,
-                                                       return_vgrid=False)).to(dev).train()
-        model.set_precision(args.precision)
-    else:
-        model = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev).train()
-        model.set_precision(args.precision)
-    Fn.manual_seed(42 + rank)
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=deform,  # DeformCrossTransMIL: the attn1d / attn2d twin module is unused
-                                                        
-                                                        broadcast_buffers=False, gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
-    B, N = args.batch, args.patches
-    x_dev, y_dev = synth_bag(B, N, 42 + rank, dev)
-    x_host = x_dev.cpu().pin_memory()
-    y_host = y_dev.cpu().pin_memory()
-    omic = torch.randn(B, 128, generator=torch.Generator(device=dev).manual_seed(7 + rank), device=dev).abs() if deform else None
-
-    if pathomic:
-        gen = torch.Generator(device=dev).manual_seed(9 + rank)
-        x_t = torch.randn(B, 59, generator=gen, device=dev).abs()
-        x_i = torch.randn(B, 361, generator=gen, device=dev).abs()
-
-    def step(x, y):
-        opt.zero_grad(set_to_none=True)
-        if pathomic:
-            _, f_t, f_i, lg, _, _, _ = net(x_path=x, x_omic_tumor=x_t, x_omic_immune=x_i)
-            loss = torch.nn.functional.cross_entropy(lg[2], y, weight=ce_w) + 0.5 * bloss(lg[3], lg[4]).sum() + 0.5 * bloss(lg[5], lg[6]).sum()
-            loss.backward()
-            sml_b200.modulate_classifier_grads(model.classifier, f_t, f_i, y)       # train_test.py:87-184 (gradient_modulate: True)
-            opt.step()
-            return loss
-        if deform:
-            logits = net(x, omic)[1]
-            loss = torch.nn.functional.cross_entropy(logits, y)
-        else:
-            enc, logits, _ = net(x)
-            # the multimodal_projection head takes part with zero weight so that every parameter gets a gradient and DDP needs
-            # no unused-parameter search (the reference's loop feeds both heads, train_test.py:347-373)
-            loss = torch.nn.functional.cross_entropy(logits, y) + 0.0 * enc.sum()
-        loss.backward()
-        opt.step()
-        return loss
 
     def barrier():
         if world > 1:
@@ -273,20 +341,49 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    pk, pk_src = peaks()
+    B, N = args.batch, args.patches
+    wl = Workload(args.workload, args.precision, B, N, dev, rank, world, local)
+    deform = wl.deform
+
+    # ---- step-0 parity probe (rank 0): eval-mode logits / CE loss of slide 0 from the SAME initial parameters as the CPU
+    #      arm, against the CPU oracle held in this process for the cpu_baseline leg
+    parity = None
+    if args.workload == "transmil" and rank == 0 and not args.no_cpu_baseline:
+        import oracle
+        from synth import synth_state_dict
+        wl.model.eval()
+        with torch.no_grad():
+            _, lg, _ = wl.model(wl.x_dev[:1])
+            loss_gpu = float(torch.nn.functional.cross_entropy(lg, wl.y_dev[:1]))
+            p_cpu = synth_state_dict(transmil_shapes(), PARAM_SEED)
+            _, lg_o = oracle.nystrom.transmil(wl.x_dev[:1].cpu(), p_cpu)
+            loss_o = float(torch.nn.functional.cross_entropy(lg_o, wl.y_dev[:1].cpu()))
+        wl.model.train()
+        tol = {"fp32": 1e-4, "bf16x3": 1e-4, "bf16": 2e-2}[args.precision]
+        err_l = float((lg.cpu() - lg_o).abs().max() / lg_o.abs().max())
+        parity = {"what": "step-0 eval-mode logits and CE loss of slide 0 vs the CPU oracle (same initial parameters)",
+                  "loss_gpu": loss_gpu, "loss_oracle": loss_o, "loss_rel_err": abs(loss_gpu - loss_o) / abs(loss_o),
+                  "logits_rel_err": err_l, "tol": tol}
+        assert parity["loss_rel_err"] <= tol and err_l <= tol, "bench parity probe failed: %s" % parity
+    barrier()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                      # samples from the last warm-up steps through the timed and e2e regions (all under load)
     for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev)
+        wl.step(wl.x_dev, wl.y_dev)
     l0 = sml_b200._lib.launch_count()
-    ms = timed(lambda: step(x_dev, y_dev), args.steps)
+    ms = timed(lambda: wl.step(wl.x_dev, wl.y_dev), args.steps)
     launches = sml_b200._lib.launch_count() - l0
 
     # ---- end to end: every step's bag comes from pinned host memory (H2D inside the timed region) and the loss is read
     #      back (D2H).  Like any loader, the copy of step i+1 is issued on a side stream while step i computes.
+    x_host = wl.x_dev.cpu().pin_memory()
+    y_host = wl.y_dev.cpu().pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    xb = [torch.empty_like(x_dev) for _ in range(2)]
-    yb = [torch.empty_like(y_dev) for _ in range(2)]
+    xb = [torch.empty_like(wl.x_dev) for _ in range(2)]
+    yb = [torch.empty_like(wl.y_dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     state = {"i": 0}
@@ -307,97 +404,56 @@ def run_ours(args):
         state["i"] += 1
         issue_copy(slot ^ 1)                                   # prefetch the next step's bag
         torch.cuda.current_stream().wait_event(ready[slot])
-        loss = step(xb[slot], yb[slot])
+        loss = wl.step(xb[slot], yb[slot])
         freed[slot].record(torch.cuda.current_stream())
         return float(loss.detach())                            # D2H read of the loss
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     sampler.stop_flag = True
+    del xb, yb
 
-    # ---- per-kernel roofline: instrumented pass (CUDA events around every GEMM launch on the launch stream)
-    ops.PROFILE = []
-    step(x_dev, y_dev)
-    torch.cuda.synchronize()
-    prof, ops.PROFILE = ops.PROFILE, None
-    agg = {}
-    shapes = {}
-    for eng, flops, e0, e1, tag in prof:
-        dt = e0.elapsed_time(e1) * 1e-3
-        a = agg.setdefault(eng, [0.0, 0.0, 0])
-        a[0] += flops; a[1] += dt; a[2] += 1
-        sh = shapes.setdefault((eng,) + tag, [0.0, 0.0, 0])
-        sh[0] += flops; sh[1] += dt; sh[2] += 1
-    if args.prof_out and rank == 0:
-        with open(args.prof_out, "w") as f:
-            f.write("# eng M N K batch A_MNmajor B_MNmajor split relu|2softmax C Cb_hi Cb_lo beta : launches total_us avg_us TFLOP/s\n")
-            for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
-                f.write("%s : %d %.1f %.1f %.1f\n" % (" ".join(str(x) for x in k), v[2], v[1] * 1e6, v[1] * 1e6 / v[2], v[0] / v[1] / 1e12))
-    pk, pk_src = peaks()
-    # per-shape roofline of the heaviest tcgen05 GEMM shapes: bound by their outputs (HBM) when K = 64, by the tensor pipe
-    # otherwise.  `traffic` = dram read + write per launch from the round's `ncu --set full` capture (profiles/r01_ncu_summary.txt)
-    ncu_traffic = {(256, 16640, 64, 64, 0): 138.8e6 + 1032.6e6, (16640, 256, 64, 64, 2): 138.6e6 + 492.2e6,
-                   (133120, 1536, 512, 1, 0): 138.0e6 + 1170.8e6, (256, 256, 256, 64, 0): 33.6e6 + 0.9e6}
-    by_shape = []
-    for key, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
-        if key[0] != "tc" or len(by_shape) >= 5:
-            continue
-        M_, N_, K_, nb_, _, _, split_, relu_, c_, hi_, lo_, _ = key[1:]
-        t_avg = v[1] / v[2]
-        bytes_ = nb_ * (2.0 * (1 + split_) * (M_ * K_ + K_ * N_) + M_ * N_ * (4.0 * c_ + 2.0 * hi_ + 2.0 * lo_))
-        hbm_frac = bytes_ / t_avg / 1e9 / pk["hbm_gbs"]
-        tc_frac = v[0] / v[1] / 1e12 / pk["bf16_tflops_sustained"]
-        by_shape.append({"shape": "%dx%dx%d x%d%s%s" % (M_, N_, K_, nb_, " bf16x3" if split_ else "", " +softmax" if relu_ & 2 else ""),
-                         "launches": v[2], "avg_us": t_avg * 1e6,
-                         "bound": "latency (dependent chain, L2-resident operands)" if (K_ == M_ == N_ == 256) else
-                                  ("hbm" if hbm_frac > tc_frac else "tensor"),
-                         "achieved": (bytes_ / t_avg / 1e9) if hbm_frac > tc_frac else v[0] / v[1] / 1e12,
-                         "unit": "GB/s" if hbm_frac > tc_frac else "TFLOP/s", "frac": max(hbm_frac, tc_frac),
-                         "traffic": ncu_traffic.get((M_, N_, K_, nb_, relu_ & 2))})
-    roof = None
-    if deform and "deform_bwd" in agg:
-        f, t, n = agg["deform_bwd"]
-        ach = f / t / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        roof = {"kernel": "deform_attn_bwd_mma_kernel (fused bias-MLP + attention backward, %d launch)" % n, "bound": "tensor",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "peak_source": pk_src + " (sustained, tcgen05 dense bf16)", "share_of_step": t / (ms * 1e-3 / args.steps),
-                "forward_kernel": {"achieved": agg["deform_fwd"][0] / agg["deform_fwd"][1] / 1e12,
-                                   "share_of_step": agg["deform_fwd"][1] / (ms * 1e-3 / args.steps)},
-                "note": "algorithmic FLOPs: 2*(2240 (2-D) | 2176 (1-D) + 256) per (query, key) pair for the backward; the in-kernel "
-                        "forward recomputation and the 3-pass split are not counted.  Warp-level mma.sync (legacy tensor pipe, "
-                        "~576 TFLOP/s), bounded by the per-pair CUDA-core work, not by the tensor pipe"}
-    elif "tc" in agg and agg["tc"][1] > 0:
-        f, t, n = agg["tc"]
-        ach = f / t / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        roof = {"kernel": "gemm_tc_kernel (tcgen05, all %d launches of one step)" % n, "bound": "tensor", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " (sustained)",
-                "share_of_step": t / (ms * 1e-3 / args.steps),
-                "note": "bf16x3 launches count 1x algorithmic FLOPs (3 MMA passes executed)", "by_shape": by_shape}
-    elif "simt" in agg:
-        f, t, n = agg["simt"]
-        roof = {"kernel": "gemm_f32_kernel (SIMT fp32, %d launches)" % n, "bound": "tensor", "achieved": f / t / 1e12,
-                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": f / t / 1e12 / pk["bf16_tflops_sustained"],
-                "traffic": None, "peak_source": pk_src}
+    roof = instrumented_roofline(wl, ms / args.steps, pk, pk_src, args.prof_out if rank == 0 else None)
+
+    # ---- secondary workloads (same N ranks): the north_star model (configs[2]), the loss + gather + sync-BN exchange at
+    #      global batch 64 (configs[3]) and the fp32-grade mode of the headline (configs[1] "fp32 and bf16")
+    secondary = []
+    names = [n for n in args.secondary.split(",") if n] if args.workload == "transmil" else []
+    x_keep = (wl.x_dev, wl.y_dev)
+    del wl
+    torch.cuda.empty_cache()
+    for nm in names:
+        wname, prec, b2 = {"transmil_bf16x3": ("transmil", "bf16x3", B), "pathomic": ("pathomic", args.precision, B),
+                           "batchloss64": ("batchloss64", "fp32", max(64 // world, 1))}[nm]
+        w2 = Workload(wname, prec, b2, N, dev, rank, world, local)
+        if wname != "batchloss64":
+            w2.x_dev, w2.y_dev = x_keep
+        for _ in range(3):
+            w2.step(w2.x_dev, w2.y_dev)
+        k2 = args.secondary_steps * (20 if wname == "batchloss64" else 1)
+        ms2 = timed(lambda: w2.step(w2.x_dev, w2.y_dev), k2)
+        ent = {"workload": ("BatchLoss + PackedGather(all ranks) + BilinearFusion with sync-BN (train) fwd+bwd+Adam, global batch %d"
+                            % (b2 * world)) if wname == "batchloss64" else workload_name(wname, N),
+               "baseline_config": {"transmil_bf16x3": "configs[1] (fp32-grade)", "pathomic": "configs[2]", "batchloss64": "configs[3]"}[nm],
+               "precision": prec, "slides_per_step_per_gpu": b2, "value": b2 * world * k2 / (ms2 * 1e-3), "unit": UNIT,
+               "ms_per_step": ms2 / k2, "steps": k2, "warmup": 3}
+        if wname != "batchloss64":
+            r2 = instrumented_roofline(w2, ms2 / k2, pk, pk_src, None)
+            if r2:
+                ent["roofline"] = {k: r2[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "share_of_step") if k in r2}
+        secondary.append(ent)
+        del w2
+        torch.cuda.empty_cache()
 
     if rank == 0:
         total = B * world * args.steps
         line = {"metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "f32 (bf16x3 split)", "fp32": "f32"}[args.precision],
-                "data": "synthetic",
-                "config": {"workload": ("DeformPathomicNet (2 x MaxNet + 2 x DeformCrossTransMIL attn_dim=2 + concat heads) fwd + weighted CE + "
-                                        "BatchLoss(all ranks) + bwd + Adam on %d-patch x 1024-d bags" % N) if pathomic else
-                                       ("DeformCrossTransMIL(attn_dim=%d: fc1 + genomic fusion + deformable cross-attention + heads) "
-                                        "fwd+CE+bwd+Adam on %d-patch x 1024-d bags" % (2 if args.workload == "deform2d" else 1, N)) if deform
-                           else "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags"
-                                       % N, "slides_per_step_per_gpu": B, "global_batch": B * world, "precision": args.precision,
-                           "parallelism": "dp%d" % world, "l2": "inputs (%d MB/step) and activations exceed the 126 MB L2"
-                                                              % (B * N * 1024 * 4 // 2 ** 20)},
+                "data": "synthetic", "config": workload_config(args, world),
                 "gpu_launches": int(launches),
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8),
                         "d2h_bytes_per_step": 4},
-                "clocks": sampler.summary(), "roofline": roof}
+                "clocks": sampler.summary(), "roofline": roof, "parity": parity, "secondary": secondary}
         if not args.no_cpu_baseline and world == 1 and not deform:
             threads = os.cpu_count() or 1
             cstep = cpu_port_step_fn(N, threads)
@@ -416,6 +472,77 @@ def run_ours(args):
             print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def instrumented_roofline(wl, ms_step, pk, pk_src, prof_out):
+    """per-kernel roofline: one instrumented step (CUDA events around every GEMM / fused-attention launch on the launch stream)"""
+    from sml_b200 import ops
+    ops.PROFILE = []
+    wl.step(wl.x_dev, wl.y_dev)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    agg, shapes = {}, {}
+    for eng, flops, e0, e1, tag in prof:
+        dt = e0.elapsed_time(e1) * 1e-3
+        a = agg.setdefault(eng, [0.0, 0.0, 0])
+        a[0] += flops; a[1] += dt; a[2] += 1
+        sh = shapes.setdefault((eng,) + tag, [0.0, 0.0, 0])
+        sh[0] += flops; sh[1] += dt; sh[2] += 1
+    if prof_out:
+        with open(prof_out, "w") as f:
+            f.write("# eng M N K batch A_MNmajor B_MNmajor split relu|2softmax C Cb_hi Cb_lo beta : launches total_us avg_us TFLOP/s\n")
+            for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                f.write("%s : %d %.1f %.1f %.1f\n" % (" ".join(str(x) for x in k), v[2], v[1] * 1e6, v[1] * 1e6 / v[2], v[0] / v[1] / 1e12))
+    # per-shape roofline of the heaviest tcgen05 GEMM shapes: bound by their outputs (HBM) when K = 64, by the tensor pipe
+    # otherwise.  `traffic` = dram read + write per launch from the round's `ncu --set full` capture (profiles/rNN_ncu_traffic.json)
+    ncu_traffic, traffic_src = load_ncu_traffic()
+    by_shape = []
+    tr_sum, tr_n = 0.0, 0
+    for key, v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+        if key[0] != "tc" or len(key) < 13:
+            continue
+        M_, N_, K_, nb_, _, _, split_, relu_, c_, hi_, lo_, _ = key[1:]
+        tr = ncu_traffic.get((M_, N_, K_, nb_, relu_ & 2))
+        if tr is not None:
+            tr_sum += tr * v[2]; tr_n += v[2]
+        if len(by_shape) >= 5:
+            continue
+        t_avg = v[1] / v[2]
+        bytes_ = nb_ * (2.0 * (1 + split_) * (M_ * K_ + K_ * N_) + M_ * N_ * (4.0 * c_ + 2.0 * hi_ + 2.0 * lo_))
+        hbm_frac = bytes_ / t_avg / 1e9 / pk["hbm_gbs"]
+        tc_frac = v[0] / v[1] / 1e12 / pk["bf16_tflops_sustained"]
+        by_shape.append({"shape": "%dx%dx%d x%d%s%s" % (M_, N_, K_, nb_, " bf16x3" if split_ else "", " +softmax" if relu_ & 2 else ""),
+                         "launches": v[2], "avg_us": t_avg * 1e6,
+                         "bound": "latency (dependent chain, L2-resident operands)" if (K_ == M_ == N_ == 256) else
+                                  ("hbm" if hbm_frac > tc_frac else "tensor"),
+                         "achieved": (bytes_ / t_avg / 1e9) if hbm_frac > tc_frac else v[0] / v[1] / 1e12,
+                         "unit": "GB/s" if hbm_frac > tc_frac else "TFLOP/s", "frac": max(hbm_frac, tc_frac), "traffic": tr})
+    roof = None
+    peak = pk["bf16_tflops_sustained"]
+    if wl.deform and "deform_bwd" in agg:
+        f, t, n = agg["deform_bwd"]
+        ach = f / t / 1e12
+        roof = {"kernel": "deform_attn_bwd kernel (fused bias-MLP + attention backward, %d launch)" % n, "bound": "tensor",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": pk_src + " (sustained, tcgen05 dense bf16)", "share_of_step": t / (ms_step * 1e-3),
+                "forward_kernel": {"achieved": agg["deform_fwd"][0] / agg["deform_fwd"][1] / 1e12,
+                                   "share_of_step": agg["deform_fwd"][1] / (ms_step * 1e-3)},
+                "note": "algorithmic FLOPs: 2*(2240 (2-D) | 2176 (1-D) + 256) per (query, key) pair for the backward; the in-kernel "
+                        "forward recomputation and the 3-pass split are not counted"}
+    elif "tc" in agg and agg["tc"][1] > 0:
+        f, t, n = agg["tc"]
+        ach = f / t / 1e12
+        roof = {"kernel": "gemm_tc_kernel (tcgen05, all %d launches of one step)" % n, "bound": "tensor", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": (tr_sum / tr_n) if tr_n else None, "traffic_note": ("mean dram read + write bytes per launch over the %d of %d "
+                "launches whose shape is in the ncu capture %s" % (tr_n, n, traffic_src)) if tr_n else None,
+                "peak_source": pk_src + " (sustained)", "share_of_step": t / (ms_step * 1e-3),
+                "note": "bf16x3 launches count 1x algorithmic FLOPs (3 MMA passes executed)", "by_shape": by_shape}
+    elif "simt" in agg:
+        f, t, n = agg["simt"]
+        roof = {"kernel": "gemm_f32_kernel (SIMT fp32, %d launches)" % n, "bound": "tensor", "achieved": f / t / 1e12,
+                "peak": peak, "unit": "TFLOP/s", "frac": f / t / 1e12 / peak, "traffic": None, "peak_source": pk_src}
+    return roof
 
 
 def main():

@@ -18,4 +18,4 @@ import is the un-vendored, unpinned PyPI package ``nystrom-attention``
 (models/NystromAttention.py:20-157, models/cmta_utils.py:147-281) and the
 fixtures are generated from the first.
 """
-from . import nystrom, deform, heads, loss, modulation, pwl  # noqa: F401
+from . import nystrom, deform, heads, loss, modulation, pwl, cmta  # noqa: F401

@@ -66,12 +66,14 @@ def _attend(q, k, v, bias_fn, q_chunk):
 
 
 def deform_attn_1d(x1, x2, p, heads=8, dim_head=64, groups=4, ds=4, ksize=6, offset_scale=2.0,
-                   pad_order="reference", q_chunk=0, return_parts=False):
+                   pad_order="reference", q_chunk=0, return_parts=False, rows=None):
     """DeformCrossAttention1D.forward, dropout 0 (DeformableAttention1D.py:156-240).
 
     pad_order="reference" reproduces the degenerate grid_sample_1d of the
     reference (grid padded as (x=vgrid, y=0) on an [n,1] image, :36-43);
     "upstream" is the intended 1-D linear interpolation along the sequence.
+    ``rows`` (LongTensor of query indices): evaluate the attention only for those queries (softmax rows are independent)
+    and return y[:, :, rows] - how BASELINE-size bags (n = 16 385, n_kv = 4096) are checked in seconds.
     """
     b, C, n = x1.shape
     inner = heads * dim_head
@@ -100,6 +102,8 @@ def deform_attn_1d(x1, x2, p, heads=8, dim_head=64, groups=4, ds=4, ksize=6, off
     qh, kh, vh = sp(qs), sp(k), sp(v)
     seq = 2.0 * torch.arange(n, dtype=x1.dtype) / max(n - 1, 1) - 1.0         # :215-216
     hpg = heads // g
+    if rows is not None:
+        qh, seq = qh[:, :, rows], seq[rows]
 
     def bias_fn(s, e):                                                        # :84-102
         pos = slog(seq[s:e].view(1, -1, 1, 1) - vs.view(b * g, 1, nkv, 1))
@@ -107,7 +111,7 @@ def deform_attn_1d(x1, x2, p, heads=8, dim_head=64, groups=4, ds=4, ksize=6, off
         return bb.reshape(b, g, e - s, nkv, hpg).permute(0, 1, 4, 2, 3).reshape(b, heads, e - s, nkv)
 
     out = _attend(qh, kh, vh, bias_fn, q_chunk)                               # :211-231
-    out = out.transpose(-1, -2).reshape(b, inner, n)
+    out = out.transpose(-1, -2).reshape(b, inner, -1)
     y = torch.einsum("oc,bcn->bon", p["to_out.weight"][:, :, 0], out) + p["to_out.bias"].view(1, -1, 1)
     if return_parts:
         return y, dict(vgrid=vgrid, vgrid_scaled=vs, taps=taps, kv=kv, offsets=off)
@@ -115,11 +119,11 @@ def deform_attn_1d(x1, x2, p, heads=8, dim_head=64, groups=4, ds=4, ksize=6, off
 
 
 def deform_attn_2d(x1, x2, p, side, heads=8, dim_head=64, groups=8, ds=4, ksize=6, offset_scale=4.0,
-                   q_chunk=0, return_parts=False):
+                   q_chunk=0, return_parts=False, rows=None):
     """DeformCrossAttention2D.forward, eval-mode dropout (DeformableAttention2D.py:223-325).
 
     x1, x2 [b,C,N] with N = side*side (the reference hard-codes side=50).
-    Returns (out [b,C,N], vgrid [(b g),2,hk,wk]) like return_vgrid=True.
+    Returns (out [b,C,N], vgrid [(b g),2,hk,wk]) like return_vgrid=True.  ``rows``: as in deform_attn_1d.
     """
     b, C, N = x1.shape
     H = W = side
@@ -161,6 +165,8 @@ def deform_attn_2d(x1, x2, p, side, heads=8, dim_head=64, groups=8, ds=4, ksize=
     qgrid = torch.stack([qx.view(1, W).expand(H, W), qy.view(H, 1).expand(H, W)], dim=-1).reshape(N, 2)
     kgrid = torch.stack([vsx.reshape(b * g, nkv), vsy.reshape(b * g, nkv)], dim=-1)     # [(bg), nkv, 2]
     hpg = heads // g
+    if rows is not None:
+        qh, qgrid = qh[:, :, rows], qgrid[rows]
 
     def bias_fn(s, e):                                                        # :143-157
         pos = slog(qgrid[s:e].view(1, e - s, 1, 2) - kgrid.view(b * g, 1, nkv, 2))
@@ -168,7 +174,7 @@ def deform_attn_2d(x1, x2, p, side, heads=8, dim_head=64, groups=8, ds=4, ksize=
         return bb.reshape(b, g, e - s, nkv, hpg).permute(0, 1, 4, 2, 3).reshape(b, heads, e - s, nkv)
 
     out = _attend(qh, kh, vh, bias_fn, q_chunk)                               # :292-312
-    out = out.transpose(-1, -2).reshape(b, inner, N)
+    out = out.transpose(-1, -2).reshape(b, inner, -1)
     y = torch.einsum("oc,bcn->bon", p["to_out.weight"][:, :, 0, 0], out) + p["to_out.bias"].view(1, -1, 1)
     if return_parts:
         return y, vgrid, dict(vgrid_scaled=kgrid, taps=taps, kv=kv, offsets=off)

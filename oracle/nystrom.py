@@ -113,7 +113,7 @@ def ppeg(x, p, prefix, H, W):
 
 def transmil(x, p, dim=512):
     """mil.py:225-259 TransMIL.forward (eval mode).  Returns (encoded, logits)."""
-    h = torch.relu(x.float() @ p["_fc1.0.weight"].t() + p["_fc1.0.bias"])
+    h = torch.relu(x.to(p["_fc1.0.weight"].dtype) @ p["_fc1.0.weight"].t() + p["_fc1.0.bias"])   # .float() in the reference; fp64 when the parameters are
     n = h.shape[1]
     side = int(math.ceil(math.sqrt(n)))
     add = side * side - n

@@ -12,6 +12,7 @@ from .models.DeformCrossTransMIL import DeformCrossTransMIL, FusionNet, DeformCr
 from .models.MultiheadAttention import MultiheadAttention  # noqa: F401
 from .models.fusion import BilinearFusion  # noqa: F401
 from .models.model import MaxNet, DeformPathomicNet  # noqa: F401
+from .models.cmta import CMTA, MCAT_Surv, Transformer_P, Transformer_G  # noqa: F401
 from .utils.loss import BatchLoss, OrthogonalLoss  # noqa: F401
 from .utils.gather import GatherLayer, PackedGather  # noqa: F401
 from .utils.sync_batchnorm import SyncBatchNorm1d, SynchronizedBatchNorm1d, convert_model  # noqa: F401

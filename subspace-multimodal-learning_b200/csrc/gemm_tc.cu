@@ -511,7 +511,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
       if (seen >= target) break;
       __nanosleep(64);
     }
-    if (seen < target) atomicExch(&g_tc_timeout_flag, 2u);
+    if (seen < target) { atomicExch(&g_tc_timeout_flag, 2u); __threadfence_system(); __trap(); }   // fail loudly, never continue
     asm volatile("fence.proxy.async;" ::: "memory");    // later TMA (async proxy) reads see the other CTAs' generic-proxy stores
   }
   __syncthreads();

@@ -27,13 +27,17 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   return ok;
 }
 static __device__ unsigned int g_tc_timeout_flag = 0;   // one per translation unit (no -rdc); see sml_tc_timeout_flag()
-// bounded wait: a protocol bug must never hang the GPU box; on timeout raise a flag the host can read and go on
+// bounded wait: a protocol bug must never hang the GPU box, and must never be silent either.  On timeout the flag is
+// raised (so that the host can tell a pipeline timeout from any other fault) and the kernel TRAPS: the launch fails, the
+// CUDA context reports an error at the next synchronisation and no garbage result is ever consumed.  The flag is only a
+// diagnostic; waits never short-circuit on it.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
     if (mbar_try_wait(bar, parity)) return true;
-    if ((it & 1023u) == 1023u && *((volatile unsigned int*)&g_tc_timeout_flag) != 0u) return false;
   }
   atomicExch(&g_tc_timeout_flag, 1u);
+  __threadfence_system();
+  __trap();
   return false;
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {

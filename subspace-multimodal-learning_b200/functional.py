@@ -8,15 +8,56 @@ from . import ops
 from ._lib import c_i32, check, lib, ptr, stream
 from .ops import F32, gemm, to_bf16
 
-_seed_state = {"seed": 0x5EED, "offset": 0}
+# Counter-based dropout state (Dropout, AlphaDropout, attention dropout, the TransLayer skip): every mask is a pure function of
+# (seed, offset).  Like the reference, which draws from torch's generator, the stream follows ``torch.manual_seed``: on first
+# use (and whenever torch's seed changes) the seed is derived from ``torch.initial_seed()`` and the distributed rank, so seed
+# sweeps differ, DDP ranks draw different masks, and a run resumed with ``set_rng_state(get_rng_state())`` continues the stream.
+_seed_state = {"seed": None, "offset": 0, "torch_seed": None, "explicit": False}
+
+
+def _rank():
+    try:
+        import torch.distributed as dist
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    except Exception:
+        return 0
+
+
+def _sync_with_torch():
+    if _seed_state["explicit"]:
+        return
+    ts = int(torch.initial_seed())
+    if _seed_state["torch_seed"] != ts:
+        _seed_state["torch_seed"] = ts
+        _seed_state["seed"] = (ts * 0x9E3779B97F4A7C15 + 0x5EED + 7919 * _rank()) & 0xFFFFFFFFFFFF
+        _seed_state["offset"] = 0
 
 
 def manual_seed(seed):
-    _seed_state["seed"] = int(seed) & 0xFFFFFFFFFFFF
-    _seed_state["offset"] = 0
+    """pin the dropout stream explicitly (tests, benchmarks); ``manual_seed(None)`` returns to following torch.manual_seed"""
+    if seed is None:
+        _seed_state.update(explicit=False, torch_seed=None)
+        return
+    _seed_state.update(seed=int(seed) & 0xFFFFFFFFFFFF, offset=0, explicit=True)
+
+
+def current_seed():
+    _sync_with_torch()
+    return _seed_state["seed"]
+
+
+def get_rng_state():
+    """checkpointable state of the dropout stream (save next to the optimizer state)"""
+    _sync_with_torch()
+    return dict(_seed_state)
+
+
+def set_rng_state(state):
+    _seed_state.update(state)
 
 
 def _next_offset(n):
+    _sync_with_torch()
     o = _seed_state["offset"]
     _seed_state["offset"] = o + int(n)
     return o
@@ -111,7 +152,7 @@ def dropout_add(x, u, p, training):
     if p == 0.0 and x is None:
         return u
     off = _next_offset(u.numel()) if p > 0 else 0
-    return DropoutAddFn.apply(x, u, p, _seed_state["seed"], off)
+    return DropoutAddFn.apply(x, u, p, current_seed(), off)
 
 
 class AlphaDropoutFn(torch.autograd.Function):
@@ -140,7 +181,7 @@ class AlphaDropoutFn(torch.autograd.Function):
 def alpha_dropout(x, p, training):
     if not training or p == 0.0:
         return x
-    return AlphaDropoutFn.apply(x, float(p), _seed_state["seed"], _next_offset(x.numel()))
+    return AlphaDropoutFn.apply(x, float(p), current_seed(), _next_offset(x.numel()))
 
 
 class PPEGFn(torch.autograd.Function):
@@ -155,7 +196,8 @@ class PPEGFn(torch.autograd.Function):
         assert T == 1 + H * W
         y = torch.empty_like(x)
         w7c = w7.detach().contiguous()
-        check(lib.sml_ppeg_fwd(ptr(x), ptr(w7c), ptr(bias.detach()), ptr(y), c_i32(B), c_i32(H), c_i32(W), c_i32(C), stream()),
+        bc = bias.detach().contiguous()
+        check(lib.sml_ppeg_fwd(ptr(x), ptr(w7c), ptr(bc), ptr(y), c_i32(B), c_i32(H), c_i32(W), c_i32(C), stream()),
               "ppeg_fwd")
         ctx.save_for_backward(x, w7c)
         ctx.cfg = (B, H, W, C)
@@ -185,8 +227,10 @@ class PPEGFoldFn(torch.autograd.Function):
         C = w7.shape[0]
         wf = torch.empty(49, C, device=w7.device, dtype=F32)
         bf = torch.empty(C, device=w7.device, dtype=F32)
-        check(lib.sml_ppeg_fold(ptr(w7.detach().contiguous()), ptr(w5.detach().contiguous()), ptr(w3.detach().contiguous()),
-                                ptr(b7.detach()), ptr(b5.detach()), ptr(b3.detach()), ptr(wf), ptr(bf), c_i32(C), stream()), "ppeg_fold")
+        w7c, w5c, w3c = w7.detach().contiguous(), w5.detach().contiguous(), w3.detach().contiguous()   # locals outlive the launch
+        b7c, b5c, b3c = b7.detach().contiguous(), b5.detach().contiguous(), b3.detach().contiguous()
+        check(lib.sml_ppeg_fold(ptr(w7c), ptr(w5c), ptr(w3c), ptr(b7c), ptr(b5c), ptr(b3c), ptr(wf), ptr(bf), c_i32(C), stream()),
+              "ppeg_fold")
         ctx.shapes = (w7.shape, w5.shape, w3.shape)
         return wf, bf
 
@@ -197,7 +241,8 @@ class PPEGFoldFn(torch.autograd.Function):
         dw7 = torch.empty(s7, device=dwf.device, dtype=F32)
         dw5 = torch.empty(s5, device=dwf.device, dtype=F32)
         dw3 = torch.empty(s3, device=dwf.device, dtype=F32)
-        check(lib.sml_ppeg_unfold(ptr(dwf.contiguous()), ptr(dw7), ptr(dw5), ptr(dw3), c_i32(C), stream()), "ppeg_unfold")
+        dwfc = dwf.contiguous()
+        check(lib.sml_ppeg_unfold(ptr(dwfc), ptr(dw7), ptr(dw5), ptr(dw3), c_i32(C), stream()), "ppeg_unfold")
         return dw7, dbf, dw5, dbf, dw3, dbf
 
 
@@ -255,7 +300,8 @@ class MeanTokensFn(torch.autograd.Function):
     def backward(ctx, dy):
         B, T, C = ctx.shape
         dx = torch.empty(B, T, C, device=dy.device, dtype=F32)
-        check(lib.sml_add_rowvec(ptr(dx), None, ptr(dy.contiguous()), ops.c_f32(1.0 / T), ops.c_i64(B), ops.c_i64(T), c_i32(C),
+        dyc = dy.contiguous()
+        check(lib.sml_add_rowvec(ptr(dx), None, ptr(dyc), ops.c_f32(1.0 / T), ops.c_i64(B), ops.c_i64(T), c_i32(C),
                                  stream()), "add_rowvec")
         return dx
 
@@ -282,7 +328,8 @@ class UnaryFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, y = ctx.saved_tensors
         dx = torch.empty_like(x)
-        check(lib.sml_unary_bwd(c_i32(ctx.op), ptr(x), ptr(y), ptr(dy.contiguous()), ptr(dx), ops.c_i64(x.numel()), stream()), "unary_bwd")
+        dyc = dy.contiguous()
+        check(lib.sml_unary_bwd(c_i32(ctx.op), ptr(x), ptr(y), ptr(dyc), ptr(dx), ops.c_i64(x.numel()), stream()), "unary_bwd")
         return dx, None
 
 

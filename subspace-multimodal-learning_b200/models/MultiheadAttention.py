@@ -35,6 +35,7 @@ class MultiheadAttention(nn.Module):
         self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
         self.bias_k = self.bias_v = None
         self.add_zero_attn = add_zero_attn
+        self.precision = None      # engine of the token-level projections: None / "fp32" (SIMT), "bf16x3", "bf16" (tcgen05)
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -52,9 +53,12 @@ class MultiheadAttention(nn.Module):
         assert key.shape == value.shape and E == self.embed_dim
         w, bias = self.in_proj_weight, self.in_proj_bias
         bq, bk, bv = (None, None, None) if bias is None else (bias[:E], bias[E:2 * E], bias[2 * E:])
-        q = Fn.scale(Fn.linear(query.float(), w[:E], bq), float(hd) ** -0.5)            # :125-205
-        k = Fn.linear(key.float(), w[E:2 * E], bk)
-        v = k if False else Fn.linear(value.float(), w[2 * E:], bv)
+        mode = self.precision or "fp32"
+        mq = mode if L >= 1024 else "fp32"            # the long side (N patch tokens) runs on the tensor-core engine
+        mk = mode if S >= 1024 else "fp32"
+        q = Fn.scale(Fn.linear(query.float(), w[:E], bq, mode=mq), float(hd) ** -0.5)   # :125-205
+        k = Fn.linear(key.float(), w[E:2 * E], bk, mode=mk)
+        v = Fn.linear(value.float(), w[2 * E:], bv, mode=mk)
         qh = q.view(L, B, h, hd).permute(1, 2, 0, 3)                                    # [B,h,L,hd] views (:245-249)
         kh = k.view(S, B, h, hd).permute(1, 2, 0, 3)
         vh = v.view(S, B, h, hd).permute(1, 2, 0, 3)
@@ -63,7 +67,7 @@ class MultiheadAttention(nn.Module):
         attn = Fn.dropout_add(None, attn, self.dropout, self.training)                  # :301
         o = Fn.matmul(attn, vh)                                                         # [B,h,L,hd] :303
         o = o.permute(2, 0, 1, 3).reshape(L, B, E)                                      # :305
-        out = Fn.linear(o, self.out_proj.weight, self.out_proj.bias)                    # :306
+        out = Fn.linear(o, self.out_proj.weight, self.out_proj.bias, mode=mq)           # :306
         if need_weights:
             if need_raw:
                 return out, raw                                                         # :308-312

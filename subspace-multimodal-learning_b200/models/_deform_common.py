@@ -67,7 +67,7 @@ def run_deform(mod, x1, x2, return_vgrid, two_d, side=None, want_taps=False):
     assert mod.log_distance_ok, "cpb_log_distance=False is not on the reference path"
     x1t, x2t = x1.transpose(1, 2), x2.transpose(1, 2)
     p = mod.dropout.p if mod.training else 0.0
-    seed = Fn._seed_state["seed"] + 7919 * Fn._next_offset(1) if p > 0 else 0
+    seed = Fn.current_seed() + 7919 * Fn._next_offset(1) if p > 0 else 0
     cfg = dict(dim2d=two_d, side=side, heads=mod.heads, groups=mod.offset_groups, ds=mod.downsample_factor,
                ksize=mod.offset_kernel_size, scale=float(mod.offset_scale), gq=mod.group_queries, gkv=mod.group_key_values,
                p_drop=float(p), seed=int(seed), mode=mod.pad_order_mode, want_taps=want_taps,

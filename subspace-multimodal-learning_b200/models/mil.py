@@ -25,7 +25,7 @@ class TransLayer(nn.Module):
         # x + dropout(attn(norm(x))) as ONE autograd node: the skip gradient is added inside the LayerNorm-backward kernel
         p = float(a.to_out[1].p) if self.training else 0.0
         x = x.float()
-        skip = (p, Fn._seed_state["seed"], Fn._next_offset(x.numel()) if p > 0 else 0)
+        skip = (p, Fn.current_seed() if p > 0 else 0, Fn._next_offset(x.numel()) if p > 0 else 0)
         return nystrom_attention(x, a.to_qkv.weight, a.to_out[0].weight, a.to_out[0].bias, a.res_conv.weight, a.heads,
                                  a.num_landmarks, a.pinv_iterations, a.precision or NA.DEFAULT_PRECISION,
                                  pre_norm=(self.norm.weight, self.norm.bias, self.norm.eps), skip=skip)

@@ -39,7 +39,8 @@ class _BatchLossFn(torch.autograd.Function):
         O, V, S, T, rn = ctx.saved_tensors
         Ng, NS = O.shape[0], V.shape[0]
         dS, dT = torch.empty_like(S), torch.empty_like(T)
-        check(lib.sml_batchloss_bwd(ptr(S), ptr(T), ptr(rn), ptr(dloss.contiguous()), ptr(dS), ptr(dT), c_i32(Ng), c_i32(NS), stream()),
+        dl = dloss.contiguous()                          # bound to a local: must outlive the launch
+        check(lib.sml_batchloss_bwd(ptr(S), ptr(T), ptr(rn), ptr(dl), ptr(dS), ptr(dT), c_i32(Ng), c_i32(NS), stream()),
               "batchloss_bwd")
         if ctx.big:
             Ngp = (Ng + 7) // 8 * 8                      # TMA wants 16-byte row pitches: pad the tiny [Ng,Ng] operand
@@ -95,7 +96,8 @@ class _OrthFn(torch.autograd.Function):
         P, Ph, G, Gh, stats = ctx.saved_tensors
         B, D = P.shape
         gs = [torch.empty_like(P) for _ in range(4)]
-        check(lib.sml_orthogonal_loss_bwd(ptr(P), ptr(Ph), ptr(G), ptr(Gh), ops.c_f32(ctx.gamma), ptr(stats), ptr(dloss.contiguous()),
+        dl = dloss.contiguous()
+        check(lib.sml_orthogonal_loss_bwd(ptr(P), ptr(Ph), ptr(G), ptr(Gh), ops.c_f32(ctx.gamma), ptr(stats), ptr(dl),
                                           *[ptr(g) for g in gs], c_i32(B), c_i32(D), stream()), "orthogonal_loss_bwd")
         return gs[0], gs[1], gs[2], gs[3], None
 

@@ -20,8 +20,12 @@ def modulate_classifier_grads(classifier, feat_t, feat_i, labels, return_info=Fa
     hs = two_hs // 2
     assert G is not None and G.is_contiguous() and feat_t.shape == feat_i.shape == (labels.shape[0], hs)
     info = torch.empty(4, device=W.device, dtype=torch.float32) if return_info else None
-    check(lib.sml_grad_modulate(ptr(W.detach().contiguous()), ptr(b.detach().contiguous()), ptr(G),
-                                ptr(feat_t.detach().float().contiguous()), ptr(feat_i.detach().float().contiguous()),
-                                ptr(labels.to(torch.int64).contiguous()), c_i32(labels.shape[0]), c_i32(L), c_i32(hs), ptr(info),
-                                stream()), "grad_modulate")
+    # every converted tensor is bound to a local that outlives the launch: a temporary freed right after ptr() could be
+    # recycled by the caching allocator for the next conversion (two arguments aliasing one block)
+    Wc, bc = W.detach().contiguous(), b.detach().contiguous()
+    ft, fi = feat_t.detach().float().contiguous(), feat_i.detach().float().contiguous()
+    lab = labels.to(torch.int64).contiguous()
+    check(lib.sml_grad_modulate(ptr(Wc), ptr(bc), ptr(G), ptr(ft), ptr(fi), ptr(lab), c_i32(labels.shape[0]), c_i32(L), c_i32(hs),
+                                ptr(info), stream()), "grad_modulate")
+    del Wc, bc, ft, fi, lab
     return info

@@ -53,3 +53,22 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
+
+
+def test_bench_reference_arm_does_not_load_the_product():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) must not map libsml_b200.so or import sml_b200,
+    and its JSON line carries the same config / steps / warm-up as our arm would"""
+    import json
+    import subprocess
+    import sys
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--patches', '300', '--steps', '2', '--warmup', '1'];"
+            "runpy.run_path(%r, run_name='__main__');"
+            "assert 'sml_b200' not in sys.modules, 'product package imported by the reference arm';"
+            "assert 'libsml_b200' not in open('/proc/self/maps').read(), 'libsml_b200.so mapped in the reference arm'"
+            % os.path.join(ROOT, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1
+    assert line["config"]["slides_per_step_per_gpu"] == 8 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0

@@ -249,3 +249,35 @@ def test_pwl_table_backward_equals_mlp_backward():
     got = oracle.pwl.param_grads_from_segments(p, "", table, G0, G1)
     for k in q:
         assert float((got[k] - q[k].grad).abs().max()) < 1e-8 * max(1.0, float(q[k].grad.abs().max())), k
+
+
+def test_cmta():
+    """oracle/cmta.py vs the unmodified reference CMTA (tests/golden/make_golden_cmta.py), outputs and gradients"""
+    g = load_golden("cmta")["cmta"]
+    p = _leaf(synth_state_dict(g["shapes"], g["seed"]))
+    with torch.no_grad():
+        for k in p:
+            if k.endswith("cls_token"):
+                p[k].mul_(0.1)
+    x_path = randn((2, 150, 1024), 212); x_omic = randn((2, 431), 213).abs()
+    outs = oracle.cmta.cmta(x_path, x_omic, p)
+    for j, (o, w) in enumerate(zip(outs, g["outs"])):
+        assert rel_err(o, w) < 1e-4, j
+    sum((o * randn(o.shape, 220 + j)).sum() for j, o in enumerate(outs)).backward()
+    grads_close({k: p[k].grad for k in g["gparams"]}, g["gparams"], 2e-3)
+    for k, nv in g["gnorms"].items():
+        assert abs(float(p[k].grad.norm()) - nv) <= 2e-3 * nv + 1e-6, k
+
+
+def test_mcat_front():
+    """the patch-token part of MCAT_Surv (projection + SNNs + co-attention) vs the logits of the unmodified reference is
+    covered on the GPU (torch glue downstream); here: the oracle's co-attention on the fixture's parameters is finite and
+    has the reference's shapes (G queries x N keys, raw scores, F13)"""
+    for tag in ("mcat4", "mcat6"):
+        g = load_golden("cmta")[tag]
+        p = synth_state_dict(g["shapes"], g["seed"])
+        seed = g["seed"] - 1
+        x_path = randn((2, 150, 1024), seed + 2); x_omic = randn((2, 431), seed + 3).abs()
+        o, raw = oracle.cmta.mcat_front(x_path, x_omic, p, g["sizes"])
+        G = len(g["sizes"])
+        assert o.shape == (G, 2, 256) and raw.shape == (2, 1, G, 150) and torch.isfinite(o).all()
