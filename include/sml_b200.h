@@ -222,6 +222,11 @@ int sml_deform_attn_fwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, con
 int sml_deform_attn_bwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
                            const float* vs, const float* cpb, const float* out, const float* lse, const float* dout,
                            float* dq, float* dk, float* dv, float* dvs, float* part, int32_t split, void* stream);
+/* Blackwell-native forward of the 2-D case (CD = 2, one head per offset group): same arguments, outputs and dropout mask as
+ * sml_deform_attn_fwd_tc(split = 0); the bias MLP, q k^T and p v run as tcgen05.mma with accumulators and the ReLU'd
+ * activations in tensor memory (csrc/deform_tc5.cu).  Replaces models/DeformableAttention2D.py:292-312 (+ CPB :120-157). */
+int sml_deform_attn_fwd_tc5(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
+                            const float* vs, const float* cpb, float* out, float* lse, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fusion heads, subspace losses and the batch-norm statistics the ranks exchange.

@@ -12,6 +12,12 @@ from ._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
 from .ops import F32, Split, gemm, to_bf16
 
 
+import os as _os
+# "bf16" mode, 2-D, one head per offset group: run the forward as the tcgen05 / TMEM kernel (csrc/deform_tc5.cu) instead of the
+# warp-level mma.sync kernel; SML_DEFORM_TC5=0 selects the latter (kept parity-tested)
+TC5_FWD = _os.environ.get("SML_DEFORM_TC5", "1") != "0"
+
+
 def _prof_begin():
     if ops.PROFILE is None:
         return None
@@ -144,6 +150,9 @@ class DeformAttnFn(torch.autograd.Function):
         if prec == "fp32":          # SIMT fp32 kernel
             check(lib.sml_deform_attn_fwd(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                           ptr(out), ptr(lse), stream()), "deform_attn_fwd")
+        elif prec == "bf16" and TC5_FWD and two_d and heads == G:     # tcgen05 / TMEM kernel
+            check(lib.sml_deform_attn_fwd_tc5(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
+                                              ptr(out), ptr(lse), stream()), "deform_attn_fwd_tc5")
         else:                       # register-fragment MMA kernel (bf16 hi/lo 3-pass or plain bf16 operands)
             check(lib.sml_deform_attn_fwd_tc(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                              ptr(out), ptr(lse), c_i32(1 if prec == "bf16x3" else 0), stream()), "deform_attn_fwd_tc")

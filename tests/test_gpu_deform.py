@@ -301,3 +301,37 @@ def test_cpb1d_table_matches_mlp(seed, OUT):
     ns = int(nseg.item())
     assert ns == oracle.pwl.build_table(p)[0].numel() + 1
     assert bool((brk[:ns - 1][1:] >= brk[:ns - 1][:-1]).all())
+
+
+@pytest.mark.parametrize("shape", [(1, 2500, 144, 50), (2, 16384, 1024, 128), (1, 1024, 49, 32)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_deform_fwd_tcgen05_matches_warp_mma(shape, p_drop):
+    """the tcgen05 / TMEM forward (csrc/deform_tc5.cu) against the warp-level kernel it replaces in bf16 mode: same inputs, same
+    dropout hash -> outputs and log-sum-exp within bf16 rounding of each other, and against the fp32-grade split kernel at 2e-2"""
+    import sml_b200
+    from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
+    b, T, nkv, side = shape
+    heads = G = 8
+    torch.manual_seed(3)
+    q = torch.randn(b, T, heads * 64, device="cuda") * 0.3
+    k = torch.randn(b, nkv, heads * 64, device="cuda")
+    v = torch.randn(b, nkv, heads * 64, device="cuda")
+    vs = torch.rand(b * G, nkv, 2, device="cuda") * 2.4 - 1.2
+    cpb = torch.randn(lib.sml_deform_cpb_nparams(c_i32(2), c_i32(1)), device="cuda") * 0.4
+    cfg = (c_i32 * 8)(b, heads, T, nkv, G, 2, side, 64)
+    outs = {}
+    for name in ("tc5", "mma", "split"):
+        out = torch.empty(b, T, heads * 64, device="cuda"); lse = torch.empty(b, heads, T, device="cuda")
+        if name == "tc5":
+            check(lib.sml_deform_attn_fwd_tc5(cfg, c_f32(p_drop), c_u64(1234), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse),
+                                              stream()), "deform_attn_fwd_tc5")
+        else:
+            check(lib.sml_deform_attn_fwd_tc(cfg, c_f32(p_drop), c_u64(1234), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse),
+                                             c_i32(1 if name == "split" else 0), stream()), "deform_attn_fwd_tc")
+        torch.cuda.synchronize()
+        outs[name] = (out, lse)
+    assert torch.isfinite(outs["tc5"][0]).all() and torch.isfinite(outs["tc5"][1]).all()
+    assert rel_err(outs["tc5"][1], outs["split"][1]) < 2e-3, rel_err(outs["tc5"][1], outs["split"][1])          # log-sum-exp
+    assert rel_err(outs["tc5"][0], outs["split"][0]) < 2e-2, rel_err(outs["tc5"][0], outs["split"][0])
+    # no worse than the kernel it replaces (both single-pass bf16 inside), with slack for different rounding points
+    assert rel_err(outs["tc5"][0], outs["split"][0]) < 2.0 * rel_err(outs["mma"][0], outs["split"][0]) + 2e-3
