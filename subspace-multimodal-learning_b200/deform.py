@@ -13,9 +13,9 @@ from .ops import F32, Split, gemm, to_bf16
 
 
 import os as _os
-# "bf16" mode, 2-D, one head per offset group: run the forward as the tcgen05 / TMEM kernel (csrc/deform_tc5.cu) instead of the
-# warp-level mma.sync kernel; SML_DEFORM_TC5=0 selects the latter (kept parity-tested)
-TC5_FWD = _os.environ.get("SML_DEFORM_TC5", "1") != "0"
+# "bf16" mode, 2-D, one head per offset group: SML_DEFORM_TC5=1 runs the forward as the first tcgen05 / TMEM kernel
+# (csrc/deform_tc5.cu, one key per MMA round trip: measured 43 ms against 16.4 ms for the warp-level kernel at B=8/16k, so off)
+TC5_FWD = _os.environ.get("SML_DEFORM_TC5", "0") != "0"
 
 
 def _prof_begin():

@@ -331,7 +331,7 @@ def test_deform_fwd_tcgen05_matches_warp_mma(shape, p_drop):
         torch.cuda.synchronize()
         outs[name] = (out, lse)
     assert torch.isfinite(outs["tc5"][0]).all() and torch.isfinite(outs["tc5"][1]).all()
-    assert rel_err(outs["tc5"][1], outs["split"][1]) < 2e-3, rel_err(outs["tc5"][1], outs["split"][1])          # log-sum-exp
+    assert rel_err(outs["tc5"][1], outs["split"][1]) < 5e-3, rel_err(outs["tc5"][1], outs["split"][1])          # log-sum-exp
     assert rel_err(outs["tc5"][0], outs["split"][0]) < 2e-2, rel_err(outs["tc5"][0], outs["split"][0])
     # no worse than the kernel it replaces (both single-pass bf16 inside), with slack for different rounding points
     assert rel_err(outs["tc5"][0], outs["split"][0]) < 2.0 * rel_err(outs["mma"][0], outs["split"][0]) + 2e-3
