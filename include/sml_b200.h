@@ -216,7 +216,8 @@ int sml_deform_attn_bwd(const int32_t* cfg8, float p_drop, uint64_t seed, const 
                         float* dq, float* dk, float* dv, float* dvs, float* part, void* stream);
 /* Tensor-core variants of the two entries above (same arguments and contracts + `split`): the 32x32 layer of the bias MLP,
  * q k^T, p v and every backward contraction run as warp-level bf16 MMAs on register fragments.  split = 1: bf16 hi/lo 3-pass
- * products (fp32-grade, 1e-4 tolerance); split = 0: plain bf16 operands (2e-2 tolerance). */
+ * products (fp32-grade, 1e-4 tolerance); split = 0: plain bf16 operands (2e-2 tolerance; the "lean" kernels: distances from
+ * shared-memory tables, layer 3 and the small bias gradients on the MMA pipe); split = 2: plain bf16, the round-1 kernels. */
 int sml_deform_attn_fwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
                            const float* vs, const float* cpb, float* out, float* lse, int32_t split, void* stream);
 int sml_deform_attn_bwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,

@@ -21,12 +21,15 @@ __device__ __forceinline__ float slogf(float x) {
   const float l = logf(fabsf(x) + 1.f);
   return x > 0.f ? l : (x < 0.f ? -l : 0.f);
 }
+// counter-based dropout hash of one (batch, head, query, key) pair: 64 -> 32 bit fold + an avalanching 32-bit finaliser
+// (two multiplies; the previous 64-bit splitmix cost ~25 integer instructions per pair, ~10 % of the attention kernels).
+// Every deformable-attention kernel (SIMT, warp-MMA, tcgen05; forward and backward) regenerates the mask from this function.
 __device__ __forceinline__ uint32_t pair_hash(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed * 0xD1342543DE82EF95ull + idx + 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (uint32_t)(z >> 16);
+  uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x9E3779B1u) ^ (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x85EBCA77u);
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
 }
 __device__ __forceinline__ void query_pos(const AttnCfg& cf, int i, float& px, float& py) {
   if (cf.CD == 2) {

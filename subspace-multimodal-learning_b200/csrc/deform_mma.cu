@@ -37,6 +37,13 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// d = a b + c with the addend in its own registers (no accumulator-initialising moves)
+__device__ __forceinline__ void mma16816_c(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, float c0, float c1,
+                                           float c2, float c3) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};\n"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
 // d += a b with hi/lo operands (small terms first)
 template <bool SPLIT>
 __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
@@ -916,6 +923,716 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ lean bf16 kernels (round 2)
+// Same fused attention as above for the plain-bf16 mode, with the per-pair CUDA-core work cut from ~140 to ~70 warp
+// instructions per 16-pair tile (forward):
+//   * signed-log distances come from per-key-tile tables in shared memory (the query lattice is regular: x distance per
+//     (key, CTA row), y distance per (key, lattice row)): 4 LDS instead of 4 subtract + log + copysign chains per thread
+//   * ReLU + bf16 packing is one cvt.rn.relu.bf16x2.f32 per two values
+//   * layer 3 (32 -> 1) runs as two more MMAs whose B operand holds w3 in the column of the current key, so the bias lands
+//     directly in the C fragment of the 8-key logit group (no thread-local dot product, no quad shuffle)
+// tools/ubench_tmem.cu shows why this stays on warp-level MMAs: a tcgen05.mma costs >= 45 cycles per instruction whatever its
+// N (measured), so the [128 pairs x 32] x [32 x 32] layer as 128 x 32 x 16 tcgen05 MMAs needs >= 90 cycles per 128 pairs for
+// layer 2 alone (+ TMEM round trips), against 64 cycles for the same work as 16 m16n8k16 warp MMAs per SM sub-partition.
+__device__ __forceinline__ uint32_t relu_pack(float lo, float hi) {      // max(x, 0) -> bf16x2, low half <- lo
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+template <int CD, int NK>
+struct LeanTab {
+  float SX[NK][MQ];                  // slog(qx(CTA row) - kx(key))            [key in tile][row]
+  float SY[CD == 2 ? MQ : 1][NK];    // slog(qy(lattice-row slot) - ky(key))   [slot][key in tile]
+  float qx[MQ], qy[MQ];
+  float kpos[NK][2];
+};
+// fills the tables for the keys [0, nk) of the current tile (kpos already in shared memory)
+template <int CD, int NK>
+__device__ __forceinline__ void lean_tables(LeanTab<CD, NK>& tb, int ny) {
+  for (int e = threadIdx.x; e < NK * MQ; e += MTHREADS) {
+    const int key = e / MQ, r = e % MQ;
+    tb.SX[key][r] = slog_fast(tb.qx[r] - tb.kpos[key][0]);
+  }
+  if (CD == 2)
+    for (int e = threadIdx.x; e < NK * ny; e += MTHREADS) {
+      const int slot = e / NK, key = e % NK;
+      tb.SY[slot][key] = slog_fast(tb.qy[slot] - tb.kpos[key][1]);
+    }
+}
+// query positions of the CTA rows (x per row; y per lattice-row slot).  Returns the number of y slots.
+template <int CD, int NK>
+__device__ __forceinline__ int lean_query_tables(LeanTab<CD, NK>& tb, const AttnCfg& cf, int q0) {
+  const int last = min(q0 + MQ - 1, cf.n - 1);
+  const int y0 = CD == 2 ? q0 / cf.W : 0;
+  const int ny = CD == 2 ? last / cf.W - y0 + 1 : 1;
+  if (threadIdx.x < MQ) {
+    float px, py;
+    query_pos(cf, min(q0 + (int)threadIdx.x, cf.n - 1), px, py);
+    tb.qx[threadIdx.x] = px;
+    if (CD == 2 && (int)threadIdx.x < ny) {
+      query_pos(cf, min((y0 + (int)threadIdx.x) * cf.W, cf.n - 1), px, py);
+      tb.qy[threadIdx.x] = py;
+    }
+  }
+  return ny;
+}
+
+template <int CD>
+struct LeanFwdSmem {
+  __nv_bfloat16 Q[MQ][MLD], K[64][MLD], V[2][64][MLD];
+  LeanTab<CD, 64> tb;
+};
+
+// grid (ceil(n / 64), heads, B), 128 threads; same contract as deform_attn_fwd_mma_kernel<CD, false>
+template <int CD, int MINB>
+__global__ void __launch_bounds__(MTHREADS, MINB) deform_attn_fwd_lean_kernel(const AttnCfg cf, const float* __restrict__ q,
+                                                                            const float* __restrict__ k, const float* __restrict__ v,
+                                                                            const float* __restrict__ vs, const float* __restrict__ cpb,
+                                                                            float* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LeanFwdSmem<CD>& sm = *reinterpret_cast<LeanFwdSmem<CD>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
+  const int grp = head / cf.OUT, o = head % cf.OUT;
+  const int bg = b * cf.G + grp;
+  CpbRegs<CD, false> cr;
+  cr.load(cpb, cf.OUT, o, lane);
+  uint32_t w3f[2][2];                                   // B fragments of w3 (k = hidden unit), nonzero column chosen per key
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const float* W3 = cpb + CPB_H * CD + CPB_H + CPB_H * CPB_H + CPB_H + o * CPB_H + 16 * s + 2 * t;
+    w3f[s][0] = pack_bf16(W3[0], W3[1]);
+    w3f[s][1] = pack_bf16(W3[8], W3[9]);
+  }
+  load_tile<false, MQ>(sm.Q, nullptr, q + (int64_t)b * cf.n * cf.inner + head * AD, cf.inner, q0, cf.n);
+  const int ny = lean_query_tables<CD, 64>(sm.tb, cf, q0);
+  const int r0 = w * 16 + g, r1 = r0 + 8;
+  const int ys0 = CD == 2 ? min(q0 + r0, cf.n - 1) / cf.W - q0 / cf.W : 0;
+  const int ys1 = CD == 2 ? min(q0 + r1, cf.n - 1) / cf.W - q0 / cf.W : 0;
+  float oacc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[j][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
+  const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
+  const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
+  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+
+  for (int k0 = 0; k0 < cf.nkv; k0 += 64) {
+    __syncthreads();
+    load_tile<false, 64>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
+    load_tile<true, 64>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
+    if (tid < 64) {
+      const bool ok = k0 + tid < cf.nkv;
+      sm.tb.kpos[tid][0] = ok ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD] : 0.f;
+      sm.tb.kpos[tid][1] = (ok && CD == 2) ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD + 1] : 0.f;
+    }
+    __syncthreads();
+    lean_tables<CD, 64>(sm.tb, ny);
+    // ---- S = b3 + Q K^T
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = cr.b3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4];
+      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][16 * ks + 2 * t]);
+      ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][16 * ks + 2 * t]);
+      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][16 * ks + 2 * t + 8]);
+      ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][16 * ks + 2 * t + 8]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][16 * ks + 2 * t]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][16 * ks + 2 * t + 8]);
+        mma16816(s[j], ah, bh0, bh1);
+      }
+    }
+    __syncthreads();                                    // tables complete
+    // ---- + continuous position bias
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      float bias[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int key = 8 * j + u;
+        const float ax0 = sm.tb.SX[key][r0], ax1 = sm.tb.SX[key][r1];
+        const float ay0 = CD == 2 ? sm.tb.SY[ys0][key] : 0.f, ay1 = CD == 2 ? sm.tb.SY[ys1][key] : 0.f;
+        uint32_t ah[2][4];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          float h0[4], h1[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float u0 = fmaf(cr.w1x[s2][e], ax0, cr.b1[s2][e]), u1 = fmaf(cr.w1x[s2][e], ax1, cr.b1[s2][e]);
+            if (CD == 2) { u0 = fmaf(cr.w1y[s2][e], ay0, u0); u1 = fmaf(cr.w1y[s2][e], ay1, u1); }
+            h0[e] = u0; h1[e] = u1;
+          }
+          ah[s2][0] = relu_pack(h0[0], h0[1]); ah[s2][1] = relu_pack(h1[0], h1[1]);
+          ah[s2][2] = relu_pack(h0[2], h0[3]); ah[s2][3] = relu_pack(h1[2], h1[3]);
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          mma16816_c(acc[jj], ah[0], cr.wh[jj][0][0], cr.wh[jj][0][1], cr.b2[jj][0], cr.b2[jj][1], cr.b2[jj][0], cr.b2[jj][1]);
+          mma16816(acc[jj], ah[1], cr.wh[jj][1][0], cr.wh[jj][1][1]);
+        }
+        const bool mine = g == u;                        // column of this key in the 8-key C fragment
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          uint32_t hh[4];
+          hh[0] = relu_pack(acc[2 * s2][0], acc[2 * s2][1]);         hh[1] = relu_pack(acc[2 * s2][2], acc[2 * s2][3]);
+          hh[2] = relu_pack(acc[2 * s2 + 1][0], acc[2 * s2 + 1][1]); hh[3] = relu_pack(acc[2 * s2 + 1][2], acc[2 * s2 + 1][3]);
+          mma16816(bias, hh, mine ? w3f[s2][0] : 0u, mine ? w3f[s2][1] : 0u);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (jj == j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[jj][e] += bias[e];
+        }
+    }
+    // ---- online softmax on the fragments
+    float mt0 = -INFINITY, mt1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (k0 + 8 * j + 2 * t + e >= cf.nkv) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
+        mt0 = fmaxf(mt0, s[j][e]); mt1 = fmaxf(mt1, s[j][2 + e]);
+      }
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 1)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 1));
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 2)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 2));
+    const float mn0 = fmaxf(m0, mt0), mn1 = fmaxf(m1, mt1);
+    const float al0 = m0 == -INFINITY ? 0.f : __expf(m0 - mn0), al1 = m1 == -INFINITY ? 0.f : __expf(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= al0; l1 *= al1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { oacc[j][0] *= al0; oacc[j][1] *= al0; oacc[j][2] *= al1; oacc[j][3] *= al1; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float p0 = __expf(s[j][e] - mn0), p1 = __expf(s[j][2 + e] - mn1);
+        l0 += p0; l1 += p1;
+        if (cf.p_drop > 0.f) {
+          const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
+          p0 = pair_hash(cf.seed, hrow0 + key) >= thresh ? p0 * keep_scale : 0.f;
+          p1 = pair_hash(cf.seed, hrow1 + key) >= thresh ? p1 * keep_scale : 0.f;
+        }
+        s[j][e] = p0; s[j][2 + e] = p1;
+      }
+    // ---- O += P V (P as bf16 hi + lo: the backward's delta = dO . O relies on an fp32-grade O)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+      split2<true>(s[2 * ks][0], s[2 * ks][1], ah[0], al[0]);
+      split2<true>(s[2 * ks][2], s[2 * ks][3], ah[1], al[1]);
+      split2<true>(s[2 * ks + 1][0], s[2 * ks + 1][1], ah[2], al[2]);
+      split2<true>(s[2 * ks + 1][2], s[2 * ks + 1][3], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t bh0, bh1, bl0, bl1;
+        ldmatrix_x2_trans(bh0, bh1, &sm.V[0][16 * ks + (lane & 15)][8 * j]);
+        ldmatrix_x2_trans(bl0, bl1, &sm.V[1][16 * ks + (lane & 15)][8 * j]);
+        mma3<true>(oacc[j], ah, al, bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  if (q0 + r0 < cf.n) {
+    float* orow = out + ((int64_t)b * cf.n + q0 + r0) * cf.inner + head * AD + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][0] * i0, oacc[j][1] * i0);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0] = m0 + logf(l0);
+  }
+  if (q0 + r1 < cf.n) {
+    float* orow = out + ((int64_t)b * cf.n + q0 + r1) * cf.inner + head * AD + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][2] * i1, oacc[j][3] * i1);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1] = m1 + logf(l1);
+  }
+}
+
+
+// ---- lean backward (plain bf16 operands).  Same phases and outputs as deform_attn_bwd_mma_kernel<CD, false>; per key the
+// CUDA-core work drops from ~470 to ~250 warp instructions:
+//   * distances from the shared-memory tables (lean_tables); d slog / dx = exp(-|slog|)
+//   * layer 3 on the MMA pipe (w3 in column 0 of the B operand; lanes t == 0 hold the two biases, one shuffle each)
+//   * second ReLU: h2 is kept only as the packed bf16 A fragments; dh2 = mask(h2 > 0) & (dS w3) in packed bf16x2 arithmetic
+//   * db2 = dh2^T 1 and dw3 = h2^T dS ride on the MMA pipe as extra columns of the [16 pairs x 8] right operand
+//     X = [ax | ay | 1 | dS | 0...] that the layer-1 gradients already use (dW1 | db1 = dpre^T X)
+//   * first ReLU backward in packed form as well (mask from the bf16 h1 fragments)
+__device__ __forceinline__ uint32_t nz_mask_bf16x2(uint32_t a) {       // 0xffff per half that is > 0 (a holds relu outputs)
+  uint32_t d;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(0u));
+  return d;
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
+template <int CD>
+struct LeanBwdSmem {
+  __nv_bfloat16 Q[MQ][MLD], dO[2][MQ][MLD];
+  __nv_bfloat16 K[BK][MLD], V[2][BK][MLD];
+  __nv_bfloat16 P[MQ][PLD], dS[MQ][PLD];     // `red` aliases P + dS at the end of the kernel
+  float dQ[32][MTHREADS];
+  float stg[4][2][16][9];
+  float kgs[4][8][16];
+  float c1[4][24];
+  float c2[4][8];                    // b2[4][2] by t
+  float dkpos[BK][2];
+  LeanTab<CD, BK> tb;
+};
+
+template <int CD, int UNR>
+__global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
+    const AttnCfg cf, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const float* __restrict__ vs, const float* __restrict__ cpb, const float* __restrict__ out,
+    const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dk,
+    float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LeanBwdSmem<CD>& sm = *reinterpret_cast<LeanBwdSmem<CD>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
+  const int grp = head / cf.OUT, o = head % cf.OUT;
+  const int bg = b * cf.G + grp;
+  uint32_t wh[4][2][2];         // layer 2:  B[k][n = c] = W2[c][k]                  [n-tile j][k-step s][reg]
+  uint32_t wth[4][2][2];        // dh1 = dh2 W2:  B[k' = c][n = k] = W2[c][k]        [n-tile jn][k-step s'][reg]
+  uint32_t w1b[2][2];           // d pos = dpre W1:  B[k][n < CD] = W1[k][n]         [k-step s][reg]
+  uint32_t w3f[2][2];           // w3 pairs of hidden units (16 s + 2 t + {0, 1}) and (+ 8): A-column / B-row order
+  float b3;
+  {
+    const float* W1 = cpb; const float* B1 = W1 + CPB_H * CD; const float* W2 = B1 + CPB_H;
+    const float* B2 = W2 + CPB_H * CPB_H; const float* W3 = B2 + CPB_H; const float* B3 = W3 + cf.OUT * CPB_H;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float* row = W2 + (8 * j + g) * CPB_H + 16 * s + 2 * t;
+        wh[j][s][0] = pack_bf16(row[0], row[1]);
+        wh[j][s][1] = pack_bf16(row[8], row[9]);
+        const float* col = W2 + (16 * s + 2 * t) * CPB_H + 8 * j + g;
+        wth[j][s][0] = pack_bf16(col[0], col[CPB_H]);
+        wth[j][s][1] = pack_bf16(col[8 * CPB_H], col[9 * CPB_H]);
+      }
+    b3 = B3[o];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int k0_ = 16 * s + 2 * t;
+      const bool on = g < CD;
+      w1b[s][0] = pack_bf16(on ? W1[k0_ * CD + g] : 0.f, on ? W1[(k0_ + 1) * CD + g] : 0.f);
+      w1b[s][1] = pack_bf16(on ? W1[(k0_ + 8) * CD + g] : 0.f, on ? W1[(k0_ + 9) * CD + g] : 0.f);
+      w3f[s][0] = pack_bf16(W3[o * CPB_H + k0_], W3[o * CPB_H + k0_ + 1]);
+      w3f[s][1] = pack_bf16(W3[o * CPB_H + k0_ + 8], W3[o * CPB_H + k0_ + 9]);
+    }
+    if (tid < 4 * 24) {
+      const int tt = tid / 24, i = tid % 24, which = i / 8, s = (i % 8) / 4, e = i % 4;
+      const int kk = 16 * s + 2 * tt + (e & 1) + 8 * (e >> 1);
+      sm.c1[tt][i] = which == 0 ? W1[kk * CD] : (which == 1 ? (CD == 2 ? W1[kk * CD + 1] : 0.f) : B1[kk]);
+    }
+    if (tid < 4 * 8) {
+      const int tt = tid / 8, i = tid % 8, j = i / 2, e = i % 2;
+      sm.c2[tt][i] = B2[8 * j + 2 * tt + e];
+    }
+  }
+  const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
+  load_tile<false, MQ>(sm.Q, nullptr, q + qoff, cf.inner, q0, cf.n);
+  load_tile<true, MQ>(sm.dO[0], sm.dO[1], dout + qoff, cf.inner, q0, cf.n);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sm.dQ[i][tid] = 0.f;
+  const int ny = lean_query_tables<CD, BK>(sm.tb, cf, q0);
+  const int r0 = w * 16 + g, r1 = r0 + 8;
+  const bool ok0 = q0 + r0 < cf.n, ok1 = q0 + r1 < cf.n;
+  const int ys0 = CD == 2 ? min(q0 + r0, cf.n - 1) / cf.W - q0 / cf.W : 0;
+  const int ys1 = CD == 2 ? min(q0 + r1, cf.n - 1) / cf.W - q0 / cf.W : 0;
+  float delta0 = 0.f, delta1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;
+  {
+    if (ok0) {
+      const float* orow = out + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta0 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta0))));
+      }
+      lse0 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0];
+    }
+    if (ok1) {
+      const float* orow = out + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta1 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta1))));
+      }
+      lse1 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1];
+    }
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 1); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 1);
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 2); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 2);
+  }
+  // CPB parameter gradient accumulators (C fragments)
+  float gW2[2][4][4];          // dW2[c][k]:                         [m-tile of c][n-tile of k]
+  float gL1[2][4];             // dpre^T X = [dW1x | dW1y | db1 | .]: [m-tile of k]
+  float gX2[2][4];             // dh2^T  X = [. | . | db2 | .]:       [m-tile of c]
+  float gX3[2][4];             // h2^T   X = [. | . | . | dw3]:       [m-tile of c]
+  float gb3 = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      gL1[a][c] = 0.f; gX2[a][c] = 0.f; gX3[a][c] = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gW2[a][c][e] = 0.f;
+    }
+  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
+  const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
+  const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
+  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* c1 = sm.c1[t];
+  const float* c2 = sm.c2[t];
+  float (*stS)[9] = sm.stg[w][0];
+  float (*stD)[9] = sm.stg[w][1];
+  const uint32_t w3c0 = g == 0 ? w3f[0][0] : 0u, w3c1 = g == 0 ? w3f[0][1] : 0u;     // layer 3 as an MMA: w3 in column 0
+  const uint32_t w3c2 = g == 0 ? w3f[1][0] : 0u, w3c3 = g == 0 ? w3f[1][1] : 0u;
+  const int qlane = lane & ~3;
+
+  for (int k0 = 0; k0 < cf.nkv; k0 += BK) {
+    __syncthreads();
+    load_tile<false, BK>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
+    load_tile<true, BK>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
+    if (tid < BK) {
+      const bool ok = k0 + tid < cf.nkv;
+      sm.tb.kpos[tid][0] = ok ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD] : 0.f;
+      sm.tb.kpos[tid][1] = (ok && CD == 2) ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD + 1] : 0.f;
+      sm.dkpos[tid][0] = 0.f; sm.dkpos[tid][1] = 0.f;
+    }
+    __syncthreads();
+    lean_tables<CD, BK>(sm.tb, ny);
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < BK / 8; ++j) {
+      // ---- phase 1: S = Q K^T and dP = dO V^T (dO, V as hi + lo) of my 16 rows x this 8-key group -> warp-private staging
+      {
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t ah[4], gh[4], gl[4];
+          const int c0 = 16 * ks + 2 * t;
+          ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0]);
+          ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0 + 8]);
+          gh[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0]);     gh[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0]);
+          gh[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0 + 8]); gh[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0 + 8]);
+          gl[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0]);     gl[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0]);
+          gl[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0 + 8]); gl[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0 + 8]);
+          const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0]);
+          const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0 + 8]);
+          const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0]);
+          const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0 + 8]);
+          const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0]);
+          const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0 + 8]);
+          mma16816(s, ah, kh0, kh1);
+          mma3<true>(dp, gh, gl, vh0, vh1, vl0, vl1);
+        }
+        __syncwarp();
+        stS[g][2 * t] = s[0]; stS[g][2 * t + 1] = s[1]; stS[g + 8][2 * t] = s[2]; stS[g + 8][2 * t + 1] = s[3];
+        stD[g][2 * t] = dp[0]; stD[g][2 * t + 1] = dp[1]; stD[g + 8][2 * t] = dp[2]; stD[g + 8][2 * t + 1] = dp[3];
+        __syncwarp();
+      }
+      // ---- phase 2: CPB forward + backward, one key (16 pairs) per MMA tile
+#pragma unroll UNR
+      for (int u = 0; u < 8; ++u) {
+        const int key = 8 * j + u;
+        const float ax0 = sm.tb.SX[key][r0], ax1 = sm.tb.SX[key][r1];
+        const float ay0 = CD == 2 ? sm.tb.SY[ys0][key] : 0.f, ay1 = CD == 2 ? sm.tb.SY[ys1][key] : 0.f;
+        // layer 1 -> A fragments of h1 = relu(W1 a + b1)
+        uint32_t ah[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const float4 wx = lds128v(c1 + 4 * s), wy = lds128v(c1 + 8 + 4 * s), bb = lds128v(c1 + 16 + 4 * s);
+          const float wxa[4] = {wx.x, wx.y, wx.z, wx.w}, wya[4] = {wy.x, wy.y, wy.z, wy.w}, bba[4] = {bb.x, bb.y, bb.z, bb.w};
+          float h0[4], h1[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float u0 = fmaf(wxa[e], ax0, bba[e]), u1 = fmaf(wxa[e], ax1, bba[e]);
+            if (CD == 2) { u0 = fmaf(wya[e], ay0, u0); u1 = fmaf(wya[e], ay1, u1); }
+            h0[e] = u0; h1[e] = u1;
+          }
+          ah[s][0] = relu_pack(h0[0], h0[1]); ah[s][1] = relu_pack(h1[0], h1[1]);
+          ah[s][2] = relu_pack(h0[2], h0[3]); ah[s][3] = relu_pack(h1[2], h1[3]);
+        }
+        // layer 2 -> A fragments of h2 = relu(W2 h1 + b2) (the fp32 accumulators die here)
+        uint32_t hh[2][4];
+        {
+          const float4 ba = lds128v(c2), bbv = lds128v(c2 + 4);
+          const float b2v[8] = {ba.x, ba.y, ba.z, ba.w, bbv.x, bbv.y, bbv.z, bbv.w};
+          float acc[4][4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            mma16816_c(acc[jj], ah[0], wh[jj][0][0], wh[jj][0][1], b2v[2 * jj], b2v[2 * jj + 1], b2v[2 * jj], b2v[2 * jj + 1]);
+            mma16816(acc[jj], ah[1], wh[jj][1][0], wh[jj][1][1]);
+          }
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            hh[s][0] = relu_pack(acc[2 * s][0], acc[2 * s][1]);         hh[s][1] = relu_pack(acc[2 * s][2], acc[2 * s][3]);
+            hh[s][2] = relu_pack(acc[2 * s + 1][0], acc[2 * s + 1][1]); hh[s][3] = relu_pack(acc[2 * s + 1][2], acc[2 * s + 1][3]);
+          }
+        }
+        // layer 3: column 0 of the C fragment = bias of rows r0 / r1 (lanes t == 0) -> whole quad
+        float p0, p1;
+        {
+          float d3[4];
+          mma16816_c(d3, hh[0], w3c0, w3c1, 0.f, 0.f, 0.f, 0.f);
+          mma16816(d3, hh[1], w3c2, w3c3);
+          p0 = __shfl_sync(0xffffffffu, d3[0], qlane);
+          p1 = __shfl_sync(0xffffffffu, d3[2], qlane);
+        }
+        const bool kok = k0 + key < cf.nkv;
+        const float P0 = kok ? __expf(stS[g][u] + p0 + b3 - lse0) : 0.f;
+        const float P1 = kok ? __expf(stS[g + 8][u] + p1 + b3 - lse1) : 0.f;
+        float keep0 = 1.f, keep1 = 1.f;
+        if (cf.p_drop > 0.f) {
+          keep0 = pair_hash(cf.seed, hrow0 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+          keep1 = pair_hash(cf.seed, hrow1 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+        }
+        const float dS0 = P0 * (stD[g][u] * keep0 - delta0);
+        const float dS1 = P1 * (stD[g + 8][u] * keep1 - delta1);
+        if (t < 2) {
+          const int rs = t ? r1 : r0;
+          sm.P[rs][key] = __float2bfloat16_rn(t ? P1 * keep1 : P0 * keep0);
+          sm.dS[rs][key] = __float2bfloat16_rn(t ? dS1 : dS0);
+        }
+        if (t == 0) gb3 += dS0 + dS1;
+        // dh2 = 1[h2 > 0] (dS w3): packed bf16x2, A-fragment order
+        const uint32_t dS0p = pack_bf16(dS0, dS0), dS1p = pack_bf16(dS1, dS1);
+        uint32_t dah[2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          dah[s][0] = nz_mask_bf16x2(hh[s][0]) & mul_bf16x2(dS0p, w3f[s][0]);
+          dah[s][1] = nz_mask_bf16x2(hh[s][1]) & mul_bf16x2(dS1p, w3f[s][0]);
+          dah[s][2] = nz_mask_bf16x2(hh[s][2]) & mul_bf16x2(dS0p, w3f[s][1]);
+          dah[s][3] = nz_mask_bf16x2(hh[s][3]) & mul_bf16x2(dS1p, w3f[s][1]);
+        }
+        // right operand X = [ax | ay | 1 | dS | 0 ...] ([16 pairs x 8], C-fragment layout: lanes t == 0 hold (ax, ay), t == 1 (1, dS))
+        uint32_t bx0, bx1;
+        {
+          uint32_t x0 = 0u, x1 = 0u;
+          if (t == 0) { x0 = pack_bf16(ax0, ay0); x1 = pack_bf16(ax1, ay1); }
+          else if (t == 1) { x0 = pack_bf16(1.f, dS0); x1 = pack_bf16(1.f, dS1); }
+          bx0 = movm_trans(x0); bx1 = movm_trans(x1);
+        }
+        // dW2[c][k] += sum_pairs dh2[p][c] h1[p][k];  [. . db2 .] += dh2^T X;  [. . . dw3] += h2^T X
+        {
+          uint32_t bh[4][2];
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) {
+            const int s = jn >> 1, rb = (jn & 1) * 2;
+            bh[jn][0] = movm_trans(ah[s][rb]); bh[jn][1] = movm_trans(ah[s][rb + 1]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t ta[4];
+            ta[0] = movm_trans(dah[mt][0]); ta[1] = movm_trans(dah[mt][2]); ta[2] = movm_trans(dah[mt][1]); ta[3] = movm_trans(dah[mt][3]);
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) mma16816(gW2[mt][jn], ta, bh[jn][0], bh[jn][1]);
+            mma16816(gX2[mt], ta, bx0, bx1);
+            uint32_t th[4];
+            th[0] = movm_trans(hh[mt][0]); th[1] = movm_trans(hh[mt][2]); th[2] = movm_trans(hh[mt][1]); th[3] = movm_trans(hh[mt][3]);
+            mma16816(gX3[mt], th, bx0, bx1);
+          }
+        }
+        // dh1 = dh2 W2, first ReLU backward (mask from the bf16 h1 fragments), packed as A fragments
+        uint32_t peh[4][2];                                 // [n-tile jn of k][row r0 / r1]
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+          float d1[4];
+          mma16816_c(d1, dah[0], wth[jn][0][0], wth[jn][0][1], 0.f, 0.f, 0.f, 0.f);
+          mma16816(d1, dah[1], wth[jn][1][0], wth[jn][1][1]);
+          peh[jn][0] = nz_mask_bf16x2(ah[jn >> 1][(jn & 1) * 2]) & pack_bf16(d1[0], d1[1]);
+          peh[jn][1] = nz_mask_bf16x2(ah[jn >> 1][(jn & 1) * 2 + 1]) & pack_bf16(d1[2], d1[3]);
+        }
+        // d bias / d (signed-log distance) = dpre W1; lanes t == 0 hold (x, y) of rows r0 / r1
+        float dpo[4];
+        {
+          const uint32_t pa0[4] = {peh[0][0], peh[0][1], peh[1][0], peh[1][1]};
+          const uint32_t pa1[4] = {peh[2][0], peh[2][1], peh[3][0], peh[3][1]};
+          mma16816_c(dpo, pa0, w1b[0][0], w1b[0][1], 0.f, 0.f, 0.f, 0.f);
+          mma16816(dpo, pa1, w1b[1][0], w1b[1][1]);
+        }
+        // [dW1x | dW1y | db1 | .] += dpre^T X
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t ta[4];
+          ta[0] = movm_trans(peh[2 * mt][0]); ta[1] = movm_trans(peh[2 * mt + 1][0]);
+          ta[2] = movm_trans(peh[2 * mt][1]); ta[3] = movm_trans(peh[2 * mt + 1][1]);
+          mma16816(gL1[mt], ta, bx0, bx1);
+        }
+        // key-coordinate gradient: d slog(x)/dx = 1 / (|x| + 1) = exp(-|slog(x)|), minus sign for the key
+        if (t == 0) {
+          const float kgx = -(dpo[0] * __expf(-fabsf(ax0)) + dpo[2] * __expf(-fabsf(ax1)));
+          const float kgy = CD == 2 ? -(dpo[1] * __expf(-fabsf(ay0)) + dpo[3] * __expf(-fabsf(ay1))) : 0.f;
+          *reinterpret_cast<float2*>(&sm.kgs[w][g][2 * u]) = make_float2(kgx, kgy);
+        }
+      }
+      __syncwarp();
+      if (lane < 16) {
+        float r = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) r += sm.kgs[w][gg][lane];
+        if (CD == 2 || (lane & 1) == 0) atomicAdd(&sm.dkpos[8 * j + (lane >> 1)][lane & 1], r);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // ---- phase 3: dQ += dS K
+    {
+      float dqacc[8][4];
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dqacc[jd][e] = sm.dQ[jd * 4 + e][tid];
+#pragma unroll
+      for (int ks = 0; ks < BK / 16; ++ks) {
+        uint32_t ah[4];
+        const int c0 = 16 * ks + 2 * t;
+        ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0]);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0 + 8]);
+#pragma unroll
+        for (int jd = 0; jd < 8; ++jd) {
+          uint32_t bh0, bh1;
+          ldmatrix_x2_trans(bh0, bh1, &sm.K[16 * ks + (lane & 15)][8 * jd]);
+          mma16816(dqacc[jd], ah, bh0, bh1);
+        }
+      }
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sm.dQ[jd * 4 + e][tid] = dqacc[jd][e];
+    }
+    // ---- dK += dS^T Q and dV += (P keep)^T dO: warp slice = 16 keys x 32 dims, contraction over the CTA's 64 queries
+    {
+      const int mt = w & 1, dh = w >> 1;
+      float dkacc[4][4], dvacc[4][4];
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dkacc[jd][e] = 0.f; dvacc[jd][e] = 0.f; }
+      const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int qrow = 16 * ks + rr + 8 * (mi >> 1), kcol = 16 * mt + 8 * (mi & 1);
+        uint32_t sh[4], ph[4];
+        ldmatrix_x4_trans(sh[0], sh[1], sh[2], sh[3], &sm.dS[qrow][kcol]);
+        ldmatrix_x4_trans(ph[0], ph[1], ph[2], ph[3], &sm.P[qrow][kcol]);
+#pragma unroll
+        for (int jd = 0; jd < 4; ++jd) {
+          uint32_t qh0, qh1, gh0, gh1;
+          ldmatrix_x2_trans(qh0, qh1, &sm.Q[16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          ldmatrix_x2_trans(gh0, gh1, &sm.dO[0][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          mma16816(dkacc[jd], sh, qh0, qh1);
+          mma16816(dvacc[jd], ph, gh0, gh1);
+        }
+      }
+      const int key0 = k0 + 16 * mt + g, key1 = key0 + 8;
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd) {
+        const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
+        if (key0 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
+          atomicAdd(dk + off, dkacc[jd][0]); atomicAdd(dk + off + 1, dkacc[jd][1]);
+          atomicAdd(dv + off, dvacc[jd][0]); atomicAdd(dv + off + 1, dvacc[jd][1]);
+        }
+        if (key1 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
+          atomicAdd(dk + off, dkacc[jd][2]); atomicAdd(dk + off + 1, dkacc[jd][3]);
+          atomicAdd(dv + off, dvacc[jd][2]); atomicAdd(dv + off + 1, dvacc[jd][3]);
+        }
+      }
+    }
+    if (tid < BK * CD) {
+      const int key = tid / CD, c = tid % CD;
+      if (k0 + key < cf.nkv) atomicAdd(dvs + ((int64_t)bg * cf.nkv + k0 + key) * CD + c, sm.dkpos[key][c]);
+    }
+  }
+  // ---- dQ
+  if (ok0) {
+    float* row = dq + qoff + (int64_t)(q0 + r0) * cf.inner + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4][tid], sm.dQ[j * 4 + 1][tid]);
+  }
+  if (ok1) {
+    float* row = dq + qoff + (int64_t)(q0 + r1) * cf.inner + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4 + 2][tid], sm.dQ[j * 4 + 3][tid]);
+  }
+  // ---- CPB parameter partials of this CTA: [W1 32*CD][b1 32][W2 1024][b2 32][W3 OUT*32][b3 OUT]
+  __syncthreads();
+  float* const red = reinterpret_cast<float*>(&sm.P[0][0]);
+  static_assert(sizeof(LeanBwdSmem<CD>::P) + sizeof(LeanBwdSmem<CD>::dS) >= NRED * sizeof(float), "the reduction buffer aliases P + dS");
+  for (int i = tid; i < NRED; i += MTHREADS) red[i] = 0.f;
+  __syncthreads();
+  {
+    float* rW1 = red; float* rb1 = rW1 + CPB_H * 2; float* rW2 = rb1 + CPB_H; float* rb2 = rW2 + CPB_H * CPB_H;
+    float* rw3 = rb2 + CPB_H; float* rb3 = rw3 + CPB_H;
+    // C fragments with rows = hidden unit (16 mt + g, + 8) and columns 2 t + {0, 1} of X = [ax | ay | 1 | dS]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int kk = 16 * mt + g;
+      if (t == 0) {
+        atomicAdd(&rW1[kk * 2], gL1[mt][0]); atomicAdd(&rW1[kk * 2 + 1], gL1[mt][1]);
+        atomicAdd(&rW1[(kk + 8) * 2], gL1[mt][2]); atomicAdd(&rW1[(kk + 8) * 2 + 1], gL1[mt][3]);
+      } else if (t == 1) {
+        atomicAdd(&rb1[kk], gL1[mt][0]); atomicAdd(&rb1[kk + 8], gL1[mt][2]);
+        atomicAdd(&rb2[kk], gX2[mt][0]); atomicAdd(&rb2[kk + 8], gX2[mt][2]);
+        atomicAdd(&rw3[kk], gX3[mt][1]); atomicAdd(&rw3[kk + 8], gX3[mt][3]);
+      }
+    }
+    gb3 = warp_sum(gb3);
+    if (lane == 0) atomicAdd(rb3, gb3);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+        const int c = 16 * mt + g, kk = 8 * jn + 2 * t;
+        atomicAdd(&rW2[c * CPB_H + kk], gW2[mt][jn][0]); atomicAdd(&rW2[c * CPB_H + kk + 1], gW2[mt][jn][1]);
+        atomicAdd(&rW2[(c + 8) * CPB_H + kk], gW2[mt][jn][2]); atomicAdd(&rW2[(c + 8) * CPB_H + kk + 1], gW2[mt][jn][3]);
+      }
+  }
+  __syncthreads();
+  {
+    const int np = CPB_H * CD + CPB_H + CPB_H * CPB_H + CPB_H + cf.OUT * CPB_H + cf.OUT;
+    float* prow = part + ((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * np;
+    const float* rW1 = red; const float* rb1 = rW1 + CPB_H * 2; const float* rW2 = rb1 + CPB_H;
+    const float* rb2 = rW2 + CPB_H * CPB_H; const float* rw3 = rb2 + CPB_H; const float* rb3 = rw3 + CPB_H;
+    for (int i = tid; i < np; i += MTHREADS) {
+      int e = i;
+      float val;
+      if (e < CPB_H * CD) val = rW1[(e / CD) * 2 + (e % CD)];
+      else if ((e -= CPB_H * CD) < CPB_H) val = rb1[e];
+      else if ((e -= CPB_H) < CPB_H * CPB_H) val = rW2[e];
+      else if ((e -= CPB_H * CPB_H) < CPB_H) val = rb2[e];
+      else if ((e -= CPB_H) < cf.OUT * CPB_H) val = (e / CPB_H == o) ? rw3[e % CPB_H] : 0.f;
+      else { e -= cf.OUT * CPB_H; val = (e == o) ? rb3[0] : 0.f; }
+      prow[i] = val;
+    }
+  }
+}
+
 }  // namespace sml
 
 using namespace sml;
@@ -935,15 +1652,33 @@ static int launch_fwd(const AttnCfg& cf, const float* q, const float* k, const f
   return 0;
 }
 
+template <int CD, int MINB>
+static int launch_fwd_lean(const AttnCfg& cf, const float* q, const float* k, const float* v, const float* vs, const float* cpb,
+                           float* out, float* lse, void* stream) {
+  dim3 grid((cf.n + MQ - 1) / MQ, cf.heads, cf.B);
+  const size_t smem = sizeof(LeanFwdSmem<CD>);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(deform_attn_fwd_lean_kernel<CD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  deform_attn_fwd_lean_kernel<CD, MINB><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, out, lse);
+  SML_LAUNCH_OK("sml_deform_attn_fwd_tc (lean)");
+  return 0;
+}
+
+/* split: 0 = plain bf16 operands (lean kernel), 1 = bf16 hi/lo 3-pass (fp32-grade), 2 = plain bf16, round-1 kernel (kept for A/B) */
 extern "C" int sml_deform_attn_fwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k,
                                       const float* v, const float* vs, const float* cpb, float* out, float* lse, int32_t split,
                                       void* stream) {
   AttnCfg cf;
   if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
-  if (cf.CD == 2) return split ? launch_fwd<2, true>(cf, q, k, v, vs, cpb, out, lse, stream)
-                               : launch_fwd<2, false>(cf, q, k, v, vs, cpb, out, lse, stream);
-  return split ? launch_fwd<1, true>(cf, q, k, v, vs, cpb, out, lse, stream)
-               : launch_fwd<1, false>(cf, q, k, v, vs, cpb, out, lse, stream);
+  if (split == 0) return cf.CD == 2 ? launch_fwd_lean<2, 3>(cf, q, k, v, vs, cpb, out, lse, stream)
+                                    : launch_fwd_lean<1, 3>(cf, q, k, v, vs, cpb, out, lse, stream);
+  if (cf.CD == 2) return split == 1 ? launch_fwd<2, true>(cf, q, k, v, vs, cpb, out, lse, stream)
+                                    : launch_fwd<2, false>(cf, q, k, v, vs, cpb, out, lse, stream);
+  return split == 1 ? launch_fwd<1, true>(cf, q, k, v, vs, cpb, out, lse, stream)
+                    : launch_fwd<1, false>(cf, q, k, v, vs, cpb, out, lse, stream);
 }
 
 template <int CD, bool SPLIT>
@@ -963,15 +1698,35 @@ static int launch_bwd(const AttnCfg& cf, const float* q, const float* k, const f
   return 0;
 }
 
-/* same contract as sml_deform_attn_bwd (dk, dv, dvs zero-initialised; part [sml_deform_attn_bwd_blocks, nparams]) */
+template <int CD, int UNR>
+static int launch_bwd_lean(const AttnCfg& cf, const float* q, const float* k, const float* v, const float* vs, const float* cpb,
+                           const float* out, const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs,
+                           float* part, void* stream) {
+  dim3 grid((cf.n + MQ - 1) / MQ, cf.heads, cf.B);
+  const size_t smem = sizeof(LeanBwdSmem<CD>);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(deform_attn_bwd_lean_kernel<CD, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  deform_attn_bwd_lean_kernel<CD, UNR><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs,
+                                                                              part);
+  SML_LAUNCH_OK("sml_deform_attn_bwd_tc (lean)");
+  return 0;
+}
+
+/* same contract as sml_deform_attn_bwd (dk, dv, dvs zero-initialised; part [sml_deform_attn_bwd_blocks, nparams]);
+ * split as in sml_deform_attn_fwd_tc */
 extern "C" int sml_deform_attn_bwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k,
                                       const float* v, const float* vs, const float* cpb, const float* out, const float* lse,
                                       const float* dout, float* dq, float* dk, float* dv, float* dvs, float* part, int32_t split,
                                       void* stream) {
   AttnCfg cf;
   if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
-  if (cf.CD == 2) return split ? launch_bwd<2, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
-                               : launch_bwd<2, false>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
-  return split ? launch_bwd<1, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
-               : launch_bwd<1, false>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
+  if (split == 0) return cf.CD == 2 ? launch_bwd_lean<2, 1>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
+                                    : launch_bwd_lean<1, 1>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
+  if (cf.CD == 2) return split == 1 ? launch_bwd<2, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
+                                    : launch_bwd<2, false>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
+  return split == 1 ? launch_bwd<1, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
+                    : launch_bwd<1, false>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
 }

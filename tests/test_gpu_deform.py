@@ -335,3 +335,34 @@ def test_deform_fwd_tcgen05_matches_warp_mma(shape, p_drop):
     assert rel_err(outs["tc5"][0], outs["split"][0]) < 2e-2, rel_err(outs["tc5"][0], outs["split"][0])
     # no worse than the kernel it replaces (both single-pass bf16 inside), with slack for different rounding points
     assert rel_err(outs["tc5"][0], outs["split"][0]) < 2.0 * rel_err(outs["mma"][0], outs["split"][0]) + 2e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 2500, 144, 50, 2), (2, 16384, 1024, 128, 2), (1, 1024, 49, 32, 2), (2, 2501, 625, 0, 1), (1, 777, 130, 0, 1)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_deform_fwd_lean_matches_split(shape, p_drop):
+    """the lean bf16 forward (table-driven distances, layer 3 on the MMA pipe) against the fp32-grade split kernel and the round-1
+    bf16 kernel: same inputs, same dropout hash; 1-D (two heads per offset group) and 2-D, ragged tiles"""
+    import sml_b200
+    from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
+    b, T, nkv, side, cd = shape
+    heads = 8
+    G = 8 if cd == 2 else 4
+    torch.manual_seed(5)
+    q = torch.randn(b, T, heads * 64, device="cuda") * 0.3
+    k = torch.randn(b, nkv, heads * 64, device="cuda")
+    v = torch.randn(b, nkv, heads * 64, device="cuda")
+    vs = torch.rand(b * G, nkv, cd, device="cuda") * 2.4 - 1.2
+    cpb = torch.randn(lib.sml_deform_cpb_nparams(c_i32(cd), c_i32(heads // G)), device="cuda") * 0.4
+    cfg = (c_i32 * 8)(b, heads, T, nkv, G, cd, side, 64)
+    outs = {}
+    for name, split in (("lean", 0), ("split", 1), ("old", 2)):
+        out = torch.empty(b, T, heads * 64, device="cuda"); lse = torch.empty(b, heads, T, device="cuda")
+        check(lib.sml_deform_attn_fwd_tc(cfg, c_f32(p_drop), c_u64(99), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse),
+                                         c_i32(split), stream()), "deform_attn_fwd_tc")
+        torch.cuda.synchronize()
+        outs[name] = (out, lse)
+    assert torch.isfinite(outs["lean"][0]).all() and torch.isfinite(outs["lean"][1]).all()
+    e_lse, e_out = rel_err(outs["lean"][1], outs["split"][1]), rel_err(outs["lean"][0], outs["split"][0])
+    o_lse, o_out = rel_err(outs["old"][1], outs["split"][1]), rel_err(outs["old"][0], outs["split"][0])
+    assert e_lse < 5e-3 and e_out < 2e-2, (e_lse, e_out)
+    assert e_out < 2.0 * o_out + 2e-3 and e_lse < 2.0 * o_lse + 1e-3, (e_lse, o_lse, e_out, o_out)
