@@ -257,30 +257,132 @@ __global__ void __launch_bounds__(256) gather_bwd_kernel(const GatherCfg cf, con
   }
 }
 
+// Vectorised forms (channels per group a multiple of 4, the only case on the reference path: 16 in 2-D, 32 in 1-D): one thread
+// per (sample, 4 channels).  Forward: the four tap rows are fetched with one 128-bit load each, all four in flight before the
+// first FMA (out-of-range taps read a clamped address with weight 0), one 128-bit store.  Same FMA order as the scalar kernel.
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__global__ void __launch_bounds__(256) gather_fwd_vec_kernel(const GatherCfg cf, const float* __restrict__ x2,
+                                                             const float* __restrict__ vs, float* __restrict__ kv,
+                                                             int32_t* __restrict__ taps) {
+  const int qpg = cf.cg >> 2;
+  const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * qpg;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % qpg);
+  const int64_t loc = i / qpg;
+  const int p = (int)(loc % cf.nkv), bg = (int)(loc / cf.nkv);
+  const int b = bg / cf.G, g = bg % cf.G;
+  const Taps t = make_taps(cf, vs, loc);
+  if (taps && c4 == 0) *reinterpret_cast<int2*>(taps + loc * 2) = make_int2(t.x0, t.y0);
+  const float* xb = x2 + (int64_t)b * cf.H * cf.W * cf.C + g * cf.cg + 4 * c4;
+  float w[4];
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+    const bool ok = xx >= 0 && xx < cf.W && yy >= 0 && yy < cf.H;
+    w[k] = ok ? ((k & 1) ? t.wx1 : 1.f - t.wx1) * ((k >> 1) ? t.wy1 : 1.f - t.wy1) : 0.f;
+    const int xc = min(max(xx, 0), cf.W - 1), yc = min(max(yy, 0), cf.H - 1);
+    v[k] = ldg4(xb + (int64_t)(yc * cf.W + xc) * cf.C);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc.x = fmaf(w[k], v[k].x, acc.x); acc.y = fmaf(w[k], v[k].y, acc.y);
+    acc.z = fmaf(w[k], v[k].z, acc.z); acc.w = fmaf(w[k], v[k].w, acc.w);
+  }
+  *reinterpret_cast<float4*>(kv + ((int64_t)b * cf.nkv + p) * cf.C + g * cf.cg + 4 * c4) = acc;
+}
+
+// backward, coordinate gradients (and, when `scatter`, the fp32-atomic d x2 fallback): thread per (sample, 4 channels), the
+// partial sums of a sample's cg / 4 threads are combined with shuffles.
+__global__ void __launch_bounds__(256) gather_bwd_vec_kernel(const GatherCfg cf, const float* __restrict__ x2,
+                                                             const float* __restrict__ vs, const float* __restrict__ dkv,
+                                                             float* __restrict__ dx2, const float* __restrict__ dvs_in,
+                                                             float* __restrict__ dvs_out, const bool scatter) {
+  const int qpg = cf.cg >> 2;
+  const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * qpg;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < total;
+  const int c4 = live ? (int)(i % qpg) : 0;
+  const int64_t loc = live ? i / qpg : 0;
+  float gix = 0.f, giy = 0.f;
+  if (live) {
+    const int p = (int)(loc % cf.nkv), bg = (int)(loc / cf.nkv);
+    const int b = bg / cf.G, g = bg % cf.G;
+    const Taps t = make_taps(cf, vs, loc);
+    const float4 go = ldg4(dkv + ((int64_t)b * cf.nkv + p) * cf.C + g * cf.cg + 4 * c4);
+    const int64_t base = (int64_t)b * cf.H * cf.W * cf.C + g * cf.cg + 4 * c4;
+    float4 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
+      ok[k] = xx >= 0 && xx < cf.W && yy >= 0 && yy < cf.H;
+      const int xc = min(max(xx, 0), cf.W - 1), yc = min(max(yy, 0), cf.H - 1);
+      v[k] = ldg4(x2 + base + (int64_t)(yc * cf.W + xc) * cf.C);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const float wx = (k & 1) ? t.wx1 : 1.f - t.wx1, wy = (k >> 1) ? t.wy1 : 1.f - t.wy1;
+      if (scatter) {
+        float* o = dx2 + base + (int64_t)((t.y0 + (k >> 1)) * cf.W + t.x0 + (k & 1)) * cf.C;
+        const float ww = wx * wy;
+        atomicAdd(o, ww * go.x); atomicAdd(o + 1, ww * go.y); atomicAdd(o + 2, ww * go.z); atomicAdd(o + 3, ww * go.w);
+      }
+      const float d = fmaf(v[k].x, go.x, fmaf(v[k].y, go.y, fmaf(v[k].z, go.z, v[k].w * go.w)));
+      gix += ((k & 1) ? 1.f : -1.f) * wy * d;
+      giy += ((k >> 1) ? 1.f : -1.f) * wx * d;
+    }
+  }
+  for (int o = qpg >> 1; o > 0; o >>= 1) {
+    gix += __shfl_xor_sync(0xffffffffu, gix, o);
+    giy += __shfl_xor_sync(0xffffffffu, giy, o);
+  }
+  if (live && c4 == 0) {
+    const float dgx = gix * 0.5f * (float)cf.W, dgy = giy * 0.5f * (float)cf.H;
+    if (cf.CD == 2) {
+      dvs_out[loc * 2] = (dvs_in ? dvs_in[loc * 2] : 0.f) + dgx;
+      dvs_out[loc * 2 + 1] = (dvs_in ? dvs_in[loc * 2 + 1] : 0.f) + dgy;
+    } else {
+      dvs_out[loc] = (dvs_in ? dvs_in[loc] : 0.f) + (cf.mode == 0 ? dgx : dgy);
+    }
+  }
+}
+
 // Atomic-free, deterministic scatter of d kv into d x2: one block per (b, g) owns every destination pixel of its channel
 // group.  The 4 nkv (sample, tap) entries are sorted by destination in shared memory (bitonic network on the composite key
 // dest * NP + entry, so the order inside a destination is canonical), then every run of equal destinations is reduced by one
 // warp (lanes = the group's channels: coalesced d kv reads, one coalesced store per destination).  dx2 must be zeroed by the
 // caller (pixels no sample touches).
 constexpr int GS_THREADS = 512;
-template <int NP>
+// NP = padded entry count (power of two), EPS = entries per sample: 4 bilinear taps in 2-D; 2 in 1-D, where the sampled image is
+// one pixel wide (F5) and only the tap column xx == 0 can be in range.  skey / wgt live in dynamic shared memory (8 NP bytes:
+// 128 KB for the 1-D path at 16 k tokens with n_kv = 4096 -> NP = 8192 ... 2-D lattices up to n_kv = 4096 -> NP = 16384).
+template <int NP, int EPS>
 __global__ void __launch_bounds__(GS_THREADS) gather_bwd_sorted_kernel(const GatherCfg cf, const float* __restrict__ vs,
                                                                        const float* __restrict__ dkv, float* __restrict__ dx2) {
-  __shared__ uint32_t skey[NP];
-  __shared__ float wgt[NP];
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  uint32_t* skey = reinterpret_cast<uint32_t*>(gs_smem);
+  float* wgt = reinterpret_cast<float*>(gs_smem) + NP;
   const int bg = blockIdx.x, b = bg / cf.G, g = bg % cf.G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t INVALID = 0xffffffffu;
+  constexpr int ESH = EPS == 4 ? 2 : 1;
   for (int e = tid; e < NP; e += GS_THREADS) {
     uint32_t key = INVALID;
     float w = 0.f;
-    if (e < 4 * cf.nkv) {
-      const int p = e >> 2, k = e & 3;
+    if (e < EPS * cf.nkv) {
+      const int p = e >> ESH;
       const Taps t = make_taps(cf, vs, (int64_t)bg * cf.nkv + p);
-      const int xx = t.x0 + (k & 1), yy = t.y0 + (k >> 1);
-      if (xx >= 0 && xx < cf.W && yy >= 0 && yy < cf.H) {
+      // EPS == 2: tap row ky = e & 1, tap column = the one that lands on xx == 0 (x0 == 0 -> kx = 0, x0 == -1 -> kx = 1)
+      const int kx = EPS == 4 ? (e & 1) : -t.x0, ky = EPS == 4 ? ((e >> 1) & 1) : (e & 1);
+      const int xx = t.x0 + kx, yy = t.y0 + ky;
+      if ((kx == 0 || kx == 1) && xx >= 0 && xx < cf.W && yy >= 0 && yy < cf.H) {
         key = (uint32_t)(yy * cf.W + xx) * (uint32_t)NP + (uint32_t)e;
-        w = ((k & 1) ? t.wx1 : 1.f - t.wx1) * ((k >> 1) ? t.wy1 : 1.f - t.wy1);
+        w = (kx ? t.wx1 : 1.f - t.wx1) * (ky ? t.wy1 : 1.f - t.wy1);
       }
     }
     skey[e] = key; wgt[e] = w;
@@ -309,10 +411,20 @@ __global__ void __launch_bounds__(GS_THREADS) gather_bwd_sorted_kernel(const Gat
       const uint32_t kq = skey[qn];
       if (kq == INVALID || kq / NP != dest) break;
       const int e = (int)(kq % NP);
-      if (lane < cf.cg) acc = fmaf(wgt[e], dkv[((int64_t)b * cf.nkv + (e >> 2)) * cf.C + g * cf.cg + lane], acc);
+      if (lane < cf.cg) acc = fmaf(wgt[e], dkv[((int64_t)b * cf.nkv + (e >> ESH)) * cf.C + g * cf.cg + lane], acc);
     }
     if (lane < cf.cg) dx2[((int64_t)b * cf.H * cf.W + dest) * cf.C + g * cf.cg + lane] = acc;
   }
+}
+
+template <int NP, int EPS>
+static void launch_sorted(const GatherCfg& cf, const float* vs, const float* dkv, float* dx2, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gather_bwd_sorted_kernel<NP, EPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP * 8);
+    attr = true;
+  }
+  gather_bwd_sorted_kernel<NP, EPS><<<(unsigned)(cf.B * cf.G), GS_THREADS, NP * 8, st>>>(cf, vs, dkv, dx2);
 }
 
 // ------------------------------------------------------------------------------------------ fused attention
@@ -894,8 +1006,13 @@ static GatherCfg make_gcfg(const int32_t* c) {
 extern "C" int sml_deform_gather_fwd(const int32_t* cfg8, const float* x2, const float* vs, float* kv, int32_t* taps,
                                      void* stream) {
   const GatherCfg cf = make_gcfg(cfg8);
-  const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * cf.cg;
-  gather_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(cf, x2, vs, kv, taps);
+  if (cf.cg % 4 == 0) {
+    const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * (cf.cg / 4);
+    gather_fwd_vec_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(cf, x2, vs, kv, taps);
+  } else {
+    const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * cf.cg;
+    gather_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(cf, x2, vs, kv, taps);
+  }
   SML_LAUNCH_OK("sml_deform_gather_fwd");
   return 0;
 }
@@ -903,17 +1020,36 @@ extern "C" int sml_deform_gather_bwd(const int32_t* cfg8, const float* x2, const
                                      const float* dvs_in, float* dvs_out, void* stream) {
   const GatherCfg cf = make_gcfg(cfg8);
   SML_CHECK(cf.cg <= 32 && (cf.cg & (cf.cg - 1)) == 0, "sml_deform_gather_bwd: channels per group must be a power of two <= 32");
-  const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * cf.cg;
-  // d x2: sorted, atomic-free scatter when the (b, g) entry list fits shared memory and the composite key 32 bits;
-  // else (n_kv > 1024: 1-D bags beyond 4 k tokens, 2-D beyond 128 x 128) fp32 atomics
-  const int entries = 4 * cf.nkv;
-  const bool sorted = entries <= 4096 && (int64_t)cf.H * cf.W < (1 << 20);
-  gather_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(cf, x2, vs, dkv, dx2, dvs_in, dvs_out, !sorted);
+  // d x2: sorted, atomic-free, deterministic scatter whenever the (b, g) entry list fits shared memory (<= 16384 entries:
+  // 2-D lattices up to n_kv = 4096, 1-D bags up to n_kv = 8192) and the composite key fits 32 bits; fp32 atomics beyond that
+  const int eps = cf.CD == 1 ? 2 : 4;
+  const int entries = eps * cf.nkv;
+  int np = 1024;
+  while (np < entries) np <<= 1;
+  const bool sorted = np <= 16384 && (int64_t)cf.H * cf.W * np <= (1ll << 32);
+  cudaStream_t st = as_stream(stream);
+  if (cf.cg % 4 == 0) {
+    const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * (cf.cg / 4);
+    gather_bwd_vec_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cf, x2, vs, dkv, dx2, dvs_in, dvs_out, !sorted);
+  } else {
+    const int64_t total = (int64_t)cf.B * cf.G * cf.nkv * cf.cg;
+    gather_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cf, x2, vs, dkv, dx2, dvs_in, dvs_out, !sorted);
+  }
   SML_LAUNCH_OK("sml_deform_gather_bwd");
   if (sorted) {
-    const unsigned blocks = (unsigned)(cf.B * cf.G);
-    if (entries <= 1024) gather_bwd_sorted_kernel<1024><<<blocks, GS_THREADS, 0, as_stream(stream)>>>(cf, vs, dkv, dx2);
-    else gather_bwd_sorted_kernel<4096><<<blocks, GS_THREADS, 0, as_stream(stream)>>>(cf, vs, dkv, dx2);
+    if (eps == 4) {
+      if (np == 1024) launch_sorted<1024, 4>(cf, vs, dkv, dx2, st);
+      else if (np == 2048) launch_sorted<2048, 4>(cf, vs, dkv, dx2, st);
+      else if (np == 4096) launch_sorted<4096, 4>(cf, vs, dkv, dx2, st);
+      else if (np == 8192) launch_sorted<8192, 4>(cf, vs, dkv, dx2, st);
+      else launch_sorted<16384, 4>(cf, vs, dkv, dx2, st);
+    } else {
+      if (np == 1024) launch_sorted<1024, 2>(cf, vs, dkv, dx2, st);
+      else if (np == 2048) launch_sorted<2048, 2>(cf, vs, dkv, dx2, st);
+      else if (np == 4096) launch_sorted<4096, 2>(cf, vs, dkv, dx2, st);
+      else if (np == 8192) launch_sorted<8192, 2>(cf, vs, dkv, dx2, st);
+      else launch_sorted<16384, 2>(cf, vs, dkv, dx2, st);
+    }
     SML_LAUNCH_OK("sml_deform_gather_bwd(sorted scatter)");
   }
   return 0;

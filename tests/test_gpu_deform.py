@@ -366,3 +366,46 @@ def test_deform_fwd_lean_matches_split(shape, p_drop):
     o_lse, o_out = rel_err(outs["old"][1], outs["split"][1]), rel_err(outs["old"][0], outs["split"][0])
     assert e_lse < 5e-3 and e_out < 2e-2, (e_lse, e_out)
     assert e_out < 2.0 * o_out + 2e-3 and e_lse < 2.0 * o_lse + 1e-3, (e_lse, o_lse, e_out, o_out)
+
+
+@pytest.mark.parametrize("case", ["1d_16k_upstream", "1d_16k_reference", "2d_256x256", "2d_50x50"])
+def test_gather_sorted_scatter_large(case):
+    """the sorted, atomic-free d x2 scatter beyond n_kv = 1024: the 1-D path at 16 385 tokens (n_kv = 4096, both pad orders) and a
+    256 x 256 lattice (n_kv = 4096, 16 384 sorted entries): bitwise identical across launches, equal to autograd of
+    F.grid_sample; the vectorised forward gather against F.grid_sample as well"""
+    from sml_b200._lib import c_i32, check, lib, ptr, stream
+    if case.startswith("1d"):
+        b, G, H, W, cg, nkv, CD, mode = 2, 4, 16385, 1, 32, 4096, 1, (1 if case.endswith("upstream") else 0)
+    elif case == "2d_256x256":
+        b, G, H, W, cg, nkv, CD, mode = 1, 8, 256, 256, 16, 4096, 2, 0
+    else:
+        b, G, H, W, cg, nkv, CD, mode = 2, 8, 50, 50, 16, 144, 2, 0
+    torch.manual_seed(10)
+    x2 = torch.randn(b, H * W, G * cg, device="cuda")
+    vs = (torch.randn(b * G, nkv, CD, device="cuda") * 0.6).clamp(-1.3, 1.3)
+    dkv = torch.randn(b, nkv, G * cg, device="cuda")
+    cfg = (c_i32 * 8)(b, G, cg, H, W, nkv, CD, mode)
+    kv = torch.empty(b, nkv, G * cg, device="cuda")
+    check(lib.sml_deform_gather_fwd(cfg, ptr(x2), ptr(vs), ptr(kv), None, stream()), "gather_fwd")
+    outs = []
+    for _ in range(3):
+        dx2 = torch.zeros_like(x2); dvs = torch.empty_like(vs)
+        check(lib.sml_deform_gather_bwd(cfg, ptr(x2), ptr(vs), ptr(dkv), ptr(dx2), None, ptr(dvs), stream()), "gather_bwd")
+        outs.append((dx2.clone(), dvs.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
+    feat = x2.view(b, H, W, G, cg).permute(0, 3, 4, 1, 2).reshape(b * G, cg, H, W).clone().requires_grad_()
+    if CD == 2:
+        gxy = vs.view(b * G, nkv, 1, 2).clone().requires_grad_()
+        grid = gxy
+    else:
+        gxy = vs.view(b * G, nkv, 1, 1).clone().requires_grad_()
+        z = torch.zeros_like(gxy)
+        grid = torch.cat([gxy, z], -1) if mode == 0 else torch.cat([z, gxy], -1)
+    samp = torch.nn.functional.grid_sample(feat, grid, mode="bilinear", padding_mode="zeros", align_corners=False)   # [bG, cg, nkv, 1]
+    want_kv = samp.detach().view(b, G, cg, nkv).permute(0, 3, 1, 2).reshape(b, nkv, G * cg)
+    assert rel_err(kv, want_kv) < 1e-5
+    gout = dkv.view(b, nkv, G, cg).permute(0, 2, 3, 1).reshape(b * G, cg, nkv, 1)
+    samp.backward(gout)
+    want_dx2 = feat.grad.view(b, G, cg, H, W).permute(0, 3, 4, 1, 2).reshape(b, H * W, G * cg)
+    assert rel_err(outs[0][0], want_dx2) < 1e-5
+    assert rel_err(outs[0][1], gxy.grad.view(b * G, nkv, CD)) < 1e-4
