@@ -18,3 +18,4 @@ from .utils.gather import GatherLayer, PackedGather  # noqa: F401
 from .utils.sync_batchnorm import SyncBatchNorm1d, SynchronizedBatchNorm1d, convert_model  # noqa: F401
 from .utils.modulation import modulate_classifier_grads  # noqa: F401
 from .install import install  # noqa: F401
+from . import data  # noqa: F401

@@ -1364,7 +1364,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
         uint32_t ah[2][4];
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          const float4 wx = lds128v(c1 + 4 * s), wy = lds128v(c1 + 8 + 4 * s), bb = lds128v(c1 + 16 + 4 * s);
+          const float4 wx = *reinterpret_cast<const float4*>(c1 + 4 * s), wy = *reinterpret_cast<const float4*>(c1 + 8 + 4 * s), bb = *reinterpret_cast<const float4*>(c1 + 16 + 4 * s);
           const float wxa[4] = {wx.x, wx.y, wx.z, wx.w}, wya[4] = {wy.x, wy.y, wy.z, wy.w}, bba[4] = {bb.x, bb.y, bb.z, bb.w};
           float h0[4], h1[4];
 #pragma unroll
@@ -1379,7 +1379,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
         // layer 2 -> A fragments of h2 = relu(W2 h1 + b2) (the fp32 accumulators die here)
         uint32_t hh[2][4];
         {
-          const float4 ba = lds128v(c2), bbv = lds128v(c2 + 4);
+          const float4 ba = *reinterpret_cast<const float4*>(c2), bbv = *reinterpret_cast<const float4*>(c2 + 4);
           const float b2v[8] = {ba.x, ba.y, ba.z, ba.w, bbv.x, bbv.y, bbv.z, bbv.w};
           float acc[4][4];
 #pragma unroll
@@ -1412,12 +1412,12 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
         }
         const float dS0 = P0 * (stD[g][u] * keep0 - delta0);
         const float dS1 = P1 * (stD[g + 8][u] * keep1 - delta1);
-        if (t < 2) {
-          const int rs = t ? r1 : r0;
-          sm.P[rs][key] = __float2bfloat16_rn(t ? P1 * keep1 : P0 * keep0);
-          sm.dS[rs][key] = __float2bfloat16_rn(t ? dS1 : dS0);
+        {                                                  // lanes t = 0 / 1 store rows r0 / r1 (branch-free: selects + predicated stores)
+          const __nv_bfloat16 pv = __float2bfloat16_rn(t ? P1 * keep1 : P0 * keep0), sv = __float2bfloat16_rn(t ? dS1 : dS0);
+          __nv_bfloat16* pp = &sm.P[t ? r1 : r0][key];
+          if (t < 2) { *pp = pv; *(pp + (&sm.dS[0][0] - &sm.P[0][0])) = sv; }
         }
-        if (t == 0) gb3 += dS0 + dS1;
+        gb3 += t == 0 ? dS0 + dS1 : 0.f;
         // dh2 = 1[h2 > 0] (dS w3): packed bf16x2, A-fragment order
         const uint32_t dS0p = pack_bf16(dS0, dS0), dS1p = pack_bf16(dS1, dS1);
         uint32_t dah[2][4];
@@ -1431,9 +1431,8 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
         // right operand X = [ax | ay | 1 | dS | 0 ...] ([16 pairs x 8], C-fragment layout: lanes t == 0 hold (ax, ay), t == 1 (1, dS))
         uint32_t bx0, bx1;
         {
-          uint32_t x0 = 0u, x1 = 0u;
-          if (t == 0) { x0 = pack_bf16(ax0, ay0); x1 = pack_bf16(ax1, ay1); }
-          else if (t == 1) { x0 = pack_bf16(1.f, dS0); x1 = pack_bf16(1.f, dS1); }
+          const uint32_t xa0 = pack_bf16(ax0, ay0), xa1 = pack_bf16(ax1, ay1), xb0 = pack_bf16(1.f, dS0), xb1 = pack_bf16(1.f, dS1);
+          const uint32_t x0 = t == 0 ? xa0 : (t == 1 ? xb0 : 0u), x1 = t == 0 ? xa1 : (t == 1 ? xb1 : 0u);
           bx0 = movm_trans(x0); bx1 = movm_trans(x1);
         }
         // dW2[c][k] += sum_pairs dh2[p][c] h1[p][k];  [. . db2 .] += dh2^T X;  [. . . dw3] += h2^T X
@@ -1483,10 +1482,10 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
           mma16816(gL1[mt], ta, bx0, bx1);
         }
         // key-coordinate gradient: d slog(x)/dx = 1 / (|x| + 1) = exp(-|slog(x)|), minus sign for the key
-        if (t == 0) {
+        {
           const float kgx = -(dpo[0] * __expf(-fabsf(ax0)) + dpo[2] * __expf(-fabsf(ax1)));
           const float kgy = CD == 2 ? -(dpo[1] * __expf(-fabsf(ay0)) + dpo[3] * __expf(-fabsf(ay1))) : 0.f;
-          *reinterpret_cast<float2*>(&sm.kgs[w][g][2 * u]) = make_float2(kgx, kgy);
+          if (t == 0) *reinterpret_cast<float2*>(&sm.kgs[w][g][2 * u]) = make_float2(kgx, kgy);
         }
       }
       __syncwarp();

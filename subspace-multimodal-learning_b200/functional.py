@@ -6,7 +6,7 @@ import torch
 
 from . import ops
 from ._lib import c_i32, check, lib, ptr, stream
-from .ops import F32, gemm, to_bf16
+from .ops import BF16, F32, Split, gemm, to_bf16
 
 # Counter-based dropout state (Dropout, AlphaDropout, attention dropout, the TransLayer skip): every mask is a pure function of
 # (seed, offset).  Like the reference, which draws from torch's generator, the stream follows ``torch.manual_seed``: on first
@@ -64,6 +64,13 @@ def _next_offset(n):
 
 
 def _prep(t, mode):
+    """GEMM operand of `t` for the arithmetic mode.  A bf16 tensor (bf16-packed bags, data/bags.py) is its own operand in
+    "bf16" mode -- the rounding the mode would apply to fp32 data has already happened at packing time -- and is widened
+    (exactly) for the fp32-grade modes."""
+    if t.dtype == BF16:
+        if mode == "bf16":
+            return Split(t.contiguous())
+        t = t.float()
     return t if mode == "fp32" else to_bf16(t.contiguous(), split=(mode == "bf16x3"))
 
 
@@ -434,6 +441,8 @@ class Fc1ClsFn(torch.autograd.Function):
         B, n, K = x.shape
         D = w.shape[0]
         x = x.contiguous()
+        if x.dtype == BF16 and mode != "bf16":
+            x = x.float()
         h = torch.empty(B, 1 + n + add, D, device=x.device, dtype=F32)
         xo = _prep(x.view(B * n, K), mode)
         wo = _prep(w.detach().contiguous(), mode)

@@ -85,7 +85,7 @@ class DeformCrossTransMIL(nn.Module):
 
     def forward(self, path, omic):
         mode = dc.gemm_mode(self.precision)                    # engine of the big token-level GEMMs (fc1, fusion)
-        path = Fn.linear(path.float(), self._fc1[0].weight, self._fc1[0].bias, relu=True, mode=mode)      # :99-100
+        path = Fn.linear(path if path.dtype == torch.bfloat16 else path.float(), self._fc1[0].weight, self._fc1[0].bias, relu=True, mode=mode)      # :99-100
         omic = omic.float()
         B, N = path.shape[0], path.shape[1]
         h = self.fusion_layer(path, omic)                                                        # :104-110 (repeat folded)

@@ -75,7 +75,7 @@ class TransMIL(nn.Module):
         side = int(math.ceil(math.sqrt(n)))
         add = side * side - n
         # _fc1 + ReLU, pad-to-square and cls token in one pass: the GEMM writes into the [B, 1+n+add, 512] buffer
-        h = Fn.fc1_cls(x.float(), self._fc1[0].weight, self._fc1[0].bias, self.cls_token, add, mode)   # mil.py:227-240
+        h = Fn.fc1_cls(x if x.dtype == torch.bfloat16 else x.float(), self._fc1[0].weight, self._fc1[0].bias, self.cls_token, add, mode)   # mil.py:227-240
         h = self.layer1(h)
         h = self.pos_layer(h, side, side)
         h = self.layer2(h)

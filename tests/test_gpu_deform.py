@@ -393,19 +393,23 @@ def test_gather_sorted_scatter_large(case):
         check(lib.sml_deform_gather_bwd(cfg, ptr(x2), ptr(vs), ptr(dkv), ptr(dx2), None, ptr(dvs), stream()), "gather_bwd")
         outs.append((dx2.clone(), dvs.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
-    feat = x2.view(b, H, W, G, cg).permute(0, 3, 4, 1, 2).reshape(b * G, cg, H, W).clone().requires_grad_()
+    # F.grid_sample on the CPU.  For the 16 385-row 1-D image ATen itself is not unique: its scalar path and the CUDA kernel
+    # unnormalise as ((c + 1) * size - 1) / 2 (this repo's order, bit-exact taps in test_gather_taps_bit_exact), the vectorised CPU
+    # path as (c + 1) * (size / 2) - 0.5, one ulp of the pixel coordinate (1e-3 px) apart -> 1e-3 on interpolation weights
+    feat = x2.cpu().view(b, H, W, G, cg).permute(0, 3, 4, 1, 2).reshape(b * G, cg, H, W).clone().requires_grad_()
     if CD == 2:
-        gxy = vs.view(b * G, nkv, 1, 2).clone().requires_grad_()
+        gxy = vs.cpu().view(b * G, nkv, 1, 2).clone().requires_grad_()
         grid = gxy
     else:
-        gxy = vs.view(b * G, nkv, 1, 1).clone().requires_grad_()
+        gxy = vs.cpu().view(b * G, nkv, 1, 1).clone().requires_grad_()
         z = torch.zeros_like(gxy)
         grid = torch.cat([gxy, z], -1) if mode == 0 else torch.cat([z, gxy], -1)
     samp = torch.nn.functional.grid_sample(feat, grid, mode="bilinear", padding_mode="zeros", align_corners=False)   # [bG, cg, nkv, 1]
     want_kv = samp.detach().view(b, G, cg, nkv).permute(0, 3, 1, 2).reshape(b, nkv, G * cg)
-    assert rel_err(kv, want_kv) < 1e-5
-    gout = dkv.view(b, nkv, G, cg).permute(0, 2, 3, 1).reshape(b * G, cg, nkv, 1)
+    tol = 2e-3 if case == "1d_16k_upstream" else 1e-5
+    assert rel_err(kv, want_kv) < tol
+    gout = dkv.cpu().view(b, nkv, G, cg).permute(0, 2, 3, 1).reshape(b * G, cg, nkv, 1)
     samp.backward(gout)
     want_dx2 = feat.grad.view(b, G, cg, H, W).permute(0, 3, 4, 1, 2).reshape(b, H * W, G * cg)
-    assert rel_err(outs[0][0], want_dx2) < 1e-5
-    assert rel_err(outs[0][1], gxy.grad.view(b * G, nkv, CD)) < 1e-4
+    assert rel_err(outs[0][0], want_dx2) < tol
+    assert rel_err(outs[0][1], gxy.grad.view(b * G, nkv, CD)) < max(tol, 1e-4)
