@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=5, help="slides in the CPU baseline sample (~2 s each on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-out", default=None, help="write the per-shape GEMM timing table of the instrumented pass here")
-    ap.add_argument("--secondary", default=os.environ.get("SML_BENCH_SECONDARY", "transmil_bf16x3,pathomic,batchloss64"),
+    ap.add_argument("--secondary", default=os.environ.get("SML_BENCH_SECONDARY", "transmil_bf16x3,pathomic,batchloss64,stress100k"),
                     help="comma list of extra workloads measured after the headline and reported under `secondary` "
                          "(transmil_bf16x3 = the fp32-grade mode of configs[1]; pathomic = configs[2]; batchloss64 = configs[3]: "
                          "BatchLoss + cross-rank gather + sync-BN BilinearFusion at global batch 64); empty string = none")
@@ -246,6 +246,11 @@ class Workload:
             model = sml_b200.DeformCrossTransMIL(Namespace(path_dim=128, attn_dim=2 if name == "deform2d" else 1,
                                                            return_vgrid=False)).to(dev).train()
             self.omic = torch.randn(B, 128, generator=torch.Generator(device=dev).manual_seed(7 + rank), device=dev).abs()
+        elif name == "stress100k":
+            # configs[4]: TransMIL inference (the inference.py path: eval, no grad) on one 100 489-patch bag (317^2), 512 landmarks
+            model = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev).eval()
+            for lyr in (model.layer1, model.layer2):
+                lyr.attn.num_landmarks = 512
         elif name == "batchloss64":
             # configs[3]: the subspace loss with its cross-rank gather (utils/loss.py:13-40, utils/gather.py) + the sync-BN
             # statistics exchange of BilinearFusion's two BatchNorm1d (models/fusion.py:29-32), global batch 64
@@ -265,13 +270,19 @@ class Workload:
             model.set_precision(precision)
         Fn.manual_seed(42 + rank)
         self.model = self.net = model
-        if world > 1:
+        if world > 1 and name != "stress100k":
             # DeformCrossTransMIL: the attn1d / attn2d twin module is unused -> find_unused_parameters
             self.net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=self.deform,
                                                                  broadcast_buffers=False, gradient_as_bucket_view=True)
+        if name == "stress100k":
+            self.net = model                                  # replicas only: no collective on this path
         self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
         if name == "batchloss64":
             self.x_dev = torch.zeros(1, device=dev); self.y_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        elif name == "stress100k":
+            self.x_dev = torch.randn(1, 317 * 317, 1024, generator=torch.Generator(device=dev).manual_seed(42 + rank), device=dev)
+            self.x_dev = self.x_dev.to(torch.bfloat16) if precision == "bf16" else self.x_dev
+            self.y_dev = torch.zeros(1, device=dev, dtype=torch.int64)
         else:
             self.x_dev, self.y_dev = synth_bag(B, N, 42 + rank, dev)
             self.x0_f32 = self.x_dev[:1].cpu()                     # fp32 original of slide 0: input of the CPU oracle probe
@@ -291,6 +302,9 @@ class Workload:
             sml_b200.modulate_classifier_grads(self.model.classifier, f_t, f_i, y)       # train_test.py:87-184 (gradient_modulate: True)
             self.opt.step()
             return loss
+        if self.name == "stress100k":
+            with torch.no_grad():
+                return self.net(x)[1].sum()
         if self.name == "batchloss64":
             self.vg.grad = None
             emb = self.net(self.vec1, self.vec2)                                         # BilinearFusion: 2 x sync-BN (train mode)
@@ -448,20 +462,24 @@ def run_ours(args):
     torch.cuda.empty_cache()
     for nm in names:
         wname, prec, b2 = {"transmil_bf16x3": ("transmil", "bf16x3", B), "pathomic": ("pathomic", args.precision, B),
-                           "batchloss64": ("batchloss64", "fp32", max(64 // world, 1))}[nm]
+                           "batchloss64": ("batchloss64", "fp32", max(64 // world, 1)),
+                           "stress100k": ("stress100k", args.precision, 1)}[nm]
         w2 = Workload(wname, prec, b2, N, dev, rank, world, local)
-        if wname != "batchloss64" and prec == args.precision:
+        if wname not in ("batchloss64", "stress100k") and prec == args.precision:
             w2.x_dev, w2.y_dev = x_keep                       # same bags (and feed format) as the headline workload
         for _ in range(3):
             w2.step(w2.x_dev, w2.y_dev)
-        k2 = args.secondary_steps * (20 if wname == "batchloss64" else 1)
+        k2 = args.secondary_steps * (20 if wname == "batchloss64" else (4 if wname == "stress100k" else 1))
         ms2 = timed(lambda: w2.step(w2.x_dev, w2.y_dev), k2)
         ent = {"workload": ("BatchLoss + PackedGather(all ranks) + BilinearFusion with sync-BN (train) fwd+bwd+Adam, global batch %d"
-                            % (b2 * world)) if wname == "batchloss64" else workload_name(wname, N),
-               "baseline_config": {"transmil_bf16x3": "configs[1] (fp32-grade)", "pathomic": "configs[2]", "batchloss64": "configs[3]"}[nm],
+                            % (b2 * world)) if wname == "batchloss64" else
+                           ("TransMIL inference (eval, no grad) on 100 489-patch x 1024-d bags, 512 landmarks, one bag per GPU (replicas)"
+                            if wname == "stress100k" else workload_name(wname, N)),
+               "baseline_config": {"transmil_bf16x3": "configs[1] (fp32-grade)", "pathomic": "configs[2]", "batchloss64": "configs[3]",
+                                   "stress100k": "configs[4]"}[nm],
                "precision": prec, "slides_per_step_per_gpu": b2, "value": b2 * world * k2 / (ms2 * 1e-3), "unit": UNIT,
                "ms_per_step": ms2 / k2, "steps": k2, "warmup": 3}
-        if wname != "batchloss64":
+        if wname not in ("batchloss64", "stress100k"):
             r2 = instrumented_roofline(w2, ms2 / k2, pk, pk_src, None)
             if r2:
                 ent["roofline"] = {k: r2[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "share_of_step") if k in r2}
