@@ -52,6 +52,8 @@ def parse():
                          "(transmil_bf16x3 = the fp32-grade mode of configs[1]; pathomic = configs[2]; batchloss64 = configs[3]: "
                          "BatchLoss + cross-rank gather + sync-BN BilinearFusion at global batch 64); empty string = none")
     ap.add_argument("--secondary-steps", type=int, default=5)
+    ap.add_argument("--graph", type=int, default=int(os.environ.get("SML_BENCH_GRAPH", "1")),
+                    help="1: replay the train step as one CUDA graph (sml_b200.GraphedStep) on single-GPU runs")
     return ap.parse_args()
 
 
@@ -224,7 +226,7 @@ def load_ncu_traffic():
 class Workload:
     """one train-step workload on this rank: model + optimizer + synthetic inputs + step function"""
 
-    def __init__(self, name, precision, batch, patches, dev, rank, world, local):
+    def __init__(self, name, precision, batch, patches, dev, rank, world, local, graph=False):
         import sml_b200
         from argparse import Namespace
         from sml_b200 import functional as Fn
@@ -276,7 +278,9 @@ class Workload:
                                                                  broadcast_buffers=False, gradient_as_bucket_view=True)
         if name == "stress100k":
             self.net = model                                  # replicas only: no collective on this path
-        self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True)
+        self.graphed = None
+        self.want_graph = bool(graph) and world == 1 and name in ("transmil", "pathomic", "deform2d", "deform1d")
+        self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True, capturable=self.want_graph)
         if name == "batchloss64":
             self.x_dev = torch.zeros(1, device=dev); self.y_dev = torch.zeros(1, device=dev, dtype=torch.int64)
         elif name == "stress100k":
@@ -291,7 +295,25 @@ class Workload:
                 # mode's tensor-core GEMM does to its operand anyway, so the step computes bit-identical results from either
                 self.x_dev = self.x_dev.to(torch.bfloat16)
 
+    def enable_graph(self):
+        """capture the step (after the eager warm-up) as one CUDA graph; on failure the workload stays eager and says so"""
+        if not self.want_graph or self.graphed is not None:
+            return
+        import sml_b200
+        try:
+            self.graphed = sml_b200.GraphedStep(self._step, (self.x_dev, self.y_dev), warmup=1)
+            self.graph_note = "one CUDA graph per step (sml_b200.GraphedStep)"
+        except Exception as e:                               # noqa: BLE001
+            self.graphed = None
+            self.want_graph = False
+            self.graph_note = "eager (graph capture failed: %s)" % str(e)[:120]
+
     def step(self, x, y):
+        if self.graphed is not None:
+            return self.graphed(x, y)
+        return self._step(x, y)
+
+    def _step(self, x, y):
         import sml_b200
         F = torch.nn.functional
         self.opt.zero_grad(set_to_none=True)
@@ -363,7 +385,7 @@ def run_ours(args):
 
     pk, pk_src = peaks()
     B, N = args.batch, args.patches
-    wl = Workload(args.workload, args.precision, B, N, dev, rank, world, local)
+    wl = Workload(args.workload, args.precision, B, N, dev, rank, world, local, graph=args.graph)
     deform = wl.deform
 
     # ---- step-0 parity probe (rank 0): eval-mode logits / CE loss of slide 0 from the SAME initial parameters as the CPU
@@ -394,8 +416,14 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         wl.step(wl.x_dev, wl.y_dev)
     l0 = sml_b200._lib.launch_count()
+    wl._step(wl.x_dev, wl.y_dev)                             # kernels of ONE step, counted on an eager step (a graph replay is
+    launches_per_step = sml_b200._lib.launch_count() - l0    # one host call; its nodes are these same kernels)
+    wl.enable_graph()
+    for _ in range(2):
+        wl.step(wl.x_dev, wl.y_dev)
     ms = timed(lambda: wl.step(wl.x_dev, wl.y_dev), args.steps)
-    launches = sml_b200._lib.launch_count() - l0
+    launches = launches_per_step * args.steps
+    launch_note = getattr(wl, "graph_note", "eager")
 
     # ---- end to end through the repo's loader (sml_b200.data.bags): the rank's bags sit in a page-locked host shard in the
     #      feed format of the mode (bf16-packed in "bf16" mode, fp32 otherwise); BagLoader copies every step's batch H2D on a side
@@ -464,11 +492,13 @@ def run_ours(args):
         wname, prec, b2 = {"transmil_bf16x3": ("transmil", "bf16x3", B), "pathomic": ("pathomic", args.precision, B),
                            "batchloss64": ("batchloss64", "fp32", max(64 // world, 1)),
                            "stress100k": ("stress100k", args.precision, 1)}[nm]
-        w2 = Workload(wname, prec, b2, N, dev, rank, world, local)
+        w2 = Workload(wname, prec, b2, N, dev, rank, world, local, graph=args.graph)
         if wname not in ("batchloss64", "stress100k") and prec == args.precision:
             w2.x_dev, w2.y_dev = x_keep                       # same bags (and feed format) as the headline workload
         for _ in range(3):
             w2.step(w2.x_dev, w2.y_dev)
+        w2.enable_graph()
+        w2.step(w2.x_dev, w2.y_dev)
         k2 = args.secondary_steps * (20 if wname == "batchloss64" else (4 if wname == "stress100k" else 1))
         ms2 = timed(lambda: w2.step(w2.x_dev, w2.y_dev), k2)
         ent = {"workload": ("BatchLoss + PackedGather(all ranks) + BilinearFusion with sync-BN (train) fwd+bwd+Adam, global batch %d"
@@ -478,7 +508,7 @@ def run_ours(args):
                "baseline_config": {"transmil_bf16x3": "configs[1] (fp32-grade)", "pathomic": "configs[2]", "batchloss64": "configs[3]",
                                    "stress100k": "configs[4]"}[nm],
                "precision": prec, "slides_per_step_per_gpu": b2, "value": b2 * world * k2 / (ms2 * 1e-3), "unit": UNIT,
-               "ms_per_step": ms2 / k2, "steps": k2, "warmup": 3}
+               "ms_per_step": ms2 / k2, "steps": k2, "warmup": 3, "launch": getattr(w2, "graph_note", "eager")}
         if wname not in ("batchloss64", "stress100k"):
             r2 = instrumented_roofline(w2, ms2 / k2, pk, pk_src, None)
             if r2:
@@ -493,7 +523,7 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "f32 (bf16x3 split)", "fp32": "f32"}[args.precision],
                 "data": "synthetic", "config": workload_config(args, world),
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "launch": launch_note,
                 "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4},
                 "feed": ("bf16-packed bags in a page-locked shard, sml_b200.data.BagLoader (prefetch 2)" if args.precision == "bf16"
@@ -523,7 +553,7 @@ def instrumented_roofline(wl, ms_step, pk, pk_src, prof_out):
     """per-kernel roofline: one instrumented step (CUDA events around every GEMM / fused-attention launch on the launch stream)"""
     from sml_b200 import ops
     ops.PROFILE = []
-    wl.step(wl.x_dev, wl.y_dev)
+    wl._step(wl.x_dev, wl.y_dev)                             # eager pass (a graph replay would bypass the Python-side event hooks)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     agg, shapes = {}, {}

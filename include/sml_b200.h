@@ -24,6 +24,13 @@ const char* sml_last_error(void);
 int sml_version(void);
 /* number of kernels launched through this library by the calling process (bench `gpu_launches`) */
 int64_t sml_launch_count(void);
+/* Dropout salt for CUDA-graph capture of a train step (train_test.py:57-85 as one replayable graph).  Every dropout mask is a
+ * counter-based hash of a (seed, offset) pair passed by value, which a captured graph would freeze; with a salt installed each
+ * mask kernel xors its seed with the 64-bit word salt2[1] read on the device at run time.  sml_seed_salt_advance moves
+ * {salt2[0] counter, salt2[1] salt} to the next value (captured as the first node of the step graph: fresh masks per replay, the
+ * forward and backward kernels of one step still agree).  sml_set_seed_salt(NULL) (default) leaves seeds as passed. */
+int sml_set_seed_salt(const void* salt2);
+int sml_seed_salt_advance(void* salt2, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Dense contractions.  One descriptor drives both engines:

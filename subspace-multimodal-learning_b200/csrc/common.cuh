@@ -10,6 +10,10 @@
 namespace sml {
 
 void set_error(const char* fmt, ...);
+const unsigned long long* seed_salt();      // device address of the current dropout salt, or NULL (api.cu)
+__device__ __forceinline__ unsigned long long salted(unsigned long long seed, const unsigned long long* salt) {
+  return salt ? seed ^ __ldg(salt) : seed;
+}
 extern std::atomic<long long> g_launches;
 
 #define SML_CHECK(cond, ...)                                   \

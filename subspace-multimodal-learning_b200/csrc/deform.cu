@@ -576,8 +576,8 @@ __global__ void __launch_bounds__(ATHREADS) deform_attn_fwd_kernel(const AttnCfg
         float d0 = p0, d1 = p1;
         if (cf.p_drop > 0.f) {
           const unsigned long long base = (((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r)) * cf.nkv) + k0;
-          d0 = pair_hash(cf.seed, base + lane) >= thresh ? p0 * keep_scale : 0.f;
-          d1 = pair_hash(cf.seed, base + lane + 32) >= thresh ? p1 * keep_scale : 0.f;
+          d0 = pair_hash(salted(cf.seed, cf.salt), base + lane) >= thresh ? p0 * keep_scale : 0.f;
+          d1 = pair_hash(salted(cf.seed, cf.salt), base + lane + 32) >= thresh ? p1 * keep_scale : 0.f;
         }
         sm.Pt[lane][r] = d0;
         sm.Pt[lane + 32][r] = d1;
@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(ATHREADS) deform_attn_bwd_kernel(
       float keep = 1.f;
       if (cf.p_drop > 0.f) {
         const unsigned long long idx = (((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + qi)) * cf.nkv) + k0 + j;
-        keep = pair_hash(cf.seed, idx) >= thresh ? keep_scale : 0.f;
+        keep = pair_hash(salted(cf.seed, cf.salt), idx) >= thresh ? keep_scale : 0.f;
       }
       const float dS = P * (sm.dP[qi][j] * keep - sm.delta[qi]);
       sm.S[qi][j] = dS;

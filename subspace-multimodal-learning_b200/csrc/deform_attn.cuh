@@ -13,6 +13,7 @@ struct AttnCfg {
   int W;                          // 2-D query lattice width (CD == 2): token i -> (x = i % W, y = i / W)
   float qden0, qden1;             // query-lattice normalisation denominators max(size-1,1)
   float p_drop; unsigned long long seed;
+  const unsigned long long* salt;   // see api.cu (NULL: seed as passed)
 };
 constexpr int AD = 64;            // head dim (the only configuration on the reference path)
 constexpr int CPB_H = 32;
@@ -56,7 +57,7 @@ static inline int make_acfg(AttnCfg& cf, const int32_t* c, float p_drop, uint64_
   } else {
     cf.qden0 = (float)(cf.n - 1 > 1 ? cf.n - 1 : 1); cf.qden1 = 1.f;
   }
-  cf.p_drop = p_drop; cf.seed = seed;
+  cf.p_drop = p_drop; cf.seed = seed; cf.salt = seed_salt();
   return 0;
 }
 

@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(MTHREADS, SPLIT ? 2 : 3) deform_attn_fwd_mma_k
         if (cf.p_drop > 0.f) {
           const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
           const unsigned long long base = (unsigned long long)(b * cf.heads + head) * cf.n;
-          p0 = pair_hash(cf.seed, (base + (q0 + r0)) * cf.nkv + key) >= thresh ? p0 * keep_scale : 0.f;
-          p1 = pair_hash(cf.seed, (base + (q0 + r1)) * cf.nkv + key) >= thresh ? p1 * keep_scale : 0.f;
+          p0 = pair_hash(salted(cf.seed, cf.salt), (base + (q0 + r0)) * cf.nkv + key) >= thresh ? p0 * keep_scale : 0.f;
+          p1 = pair_hash(salted(cf.seed, cf.salt), (base + (q0 + r1)) * cf.nkv + key) >= thresh ? p1 * keep_scale : 0.f;
         }
         s[j][e] = p0; s[j][2 + e] = p1;
       }
@@ -652,8 +652,8 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_mma_kernel(
         const float P1 = kok ? __expf(stS[g + 8][u] + p1 + b3 - lse1) : 0.f;
         float keep0 = 1.f, keep1 = 1.f;
         if (cf.p_drop > 0.f) {
-          keep0 = pair_hash(cf.seed, (hbase + (q0 + r0)) * cf.nkv + k0 + key) >= thresh ? keep_scale : 0.f;
-          keep1 = pair_hash(cf.seed, (hbase + (q0 + r1)) * cf.nkv + k0 + key) >= thresh ? keep_scale : 0.f;
+          keep0 = pair_hash(salted(cf.seed, cf.salt), (hbase + (q0 + r0)) * cf.nkv + k0 + key) >= thresh ? keep_scale : 0.f;
+          keep1 = pair_hash(salted(cf.seed, cf.salt), (hbase + (q0 + r1)) * cf.nkv + k0 + key) >= thresh ? keep_scale : 0.f;
         }
         const float dS0 = P0 * (stD[g][u] * keep0 - delta0);
         const float dS1 = P1 * (stD[g + 8][u] * keep1 - delta1);
@@ -1125,8 +1125,8 @@ __global__ void __launch_bounds__(MTHREADS, MINB) deform_attn_fwd_lean_kernel(co
         l0 += p0; l1 += p1;
         if (cf.p_drop > 0.f) {
           const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
-          p0 = pair_hash(cf.seed, hrow0 + key) >= thresh ? p0 * keep_scale : 0.f;
-          p1 = pair_hash(cf.seed, hrow1 + key) >= thresh ? p1 * keep_scale : 0.f;
+          p0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + key) >= thresh ? p0 * keep_scale : 0.f;
+          p1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + key) >= thresh ? p1 * keep_scale : 0.f;
         }
         s[j][e] = p0; s[j][2 + e] = p1;
       }
@@ -1407,8 +1407,8 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
         const float P1 = kok ? __expf(stS[g + 8][u] + p1 + b3 - lse1) : 0.f;
         float keep0 = 1.f, keep1 = 1.f;
         if (cf.p_drop > 0.f) {
-          keep0 = pair_hash(cf.seed, hrow0 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
-          keep1 = pair_hash(cf.seed, hrow1 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+          keep0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+          keep1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
         }
         const float dS0 = P0 * (stD[g][u] * keep0 - delta0);
         const float dS1 = P1 * (stD[g + 8][u] * keep1 - delta1);

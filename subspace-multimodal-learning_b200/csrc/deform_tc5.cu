@@ -368,8 +368,8 @@ deform_attn_fwd_tc5_kernel(const AttnCfg cf, const float* __restrict__ q, const 
         lsum += p0 + p1;
         if (cf.p_drop > 0.f) {
           const unsigned long long key = (unsigned long long)(k0 + 32 * g + 2 * c);
-          p0 = pair_hash(cf.seed, hbase + key) >= thresh ? p0 * keep_scale : 0.f;
-          p1 = pair_hash(cf.seed, hbase + key + 1) >= thresh ? p1 * keep_scale : 0.f;
+          p0 = pair_hash(salted(cf.seed, cf.salt), hbase + key) >= thresh ? p0 * keep_scale : 0.f;
+          p1 = pair_hash(salted(cf.seed, cf.salt), hbase + key + 1) >= thresh ? p1 * keep_scale : 0.f;
         }
         ph_[c] = pack_bf16x2(p0, p1);
         pl_[c] = pack_bf16x2(p0 - __uint_as_float(ph_[c] << 16), p1 - __uint_as_float(ph_[c] & 0xffff0000u));

@@ -317,7 +317,8 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {   // splitmix64 finalise
 }
 __global__ void __launch_bounds__(256) dropout_add_kernel(const float* __restrict__ x, const float* __restrict__ u,
                                                           float* __restrict__ y, int64_t n, float p, uint64_t seed,
-                                                          uint64_t offset) {
+                                                          uint64_t offset, const unsigned long long* __restrict__ salt) {
+  seed = salted(seed, salt);
   const float scale = 1.f / (1.f - p);
   const uint32_t thresh = (uint32_t)(p * 4294967296.0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -333,7 +334,8 @@ __global__ void __launch_bounds__(256) dropout_add_kernel(const float* __restric
 // alpha' = -selu_scale * selu_alpha, a = ((1 - p)(1 + p alpha'^2))^-1/2, b = -a alpha' p.  bwd = 1: y = dx given x = dy.
 __global__ void __launch_bounds__(256) alpha_dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p,
                                                             float a, float dropped, float b, int bwd, uint64_t seed,
-                                                            uint64_t offset) {
+                                                            uint64_t offset, const unsigned long long* __restrict__ salt) {
+  seed = salted(seed, salt);
   const uint32_t thresh = (uint32_t)(p * 4294967296.0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const bool keep = mix32(seed * 0xD1342543DE82EF95ull + offset + (uint64_t)i) >= thresh;
@@ -527,7 +529,7 @@ extern "C" int sml_dropout_add(const float* x, const float* u, float* y, int64_t
                                uint64_t offset, void* stream) {
   SML_CHECK(p >= 0.f && p < 1.f, "sml_dropout_add: p=%f out of range", p);
   if (n == 0) return 0;
-  dropout_add_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, u, y, n, p, seed, offset);
+  dropout_add_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, u, y, n, p, seed, offset, seed_salt());
   SML_LAUNCH_OK("sml_dropout_add");
   return 0;
 }
@@ -537,7 +539,7 @@ extern "C" int sml_alpha_dropout(const float* x, float* y, int64_t n, float p, i
   if (n == 0) return 0;
   const double ap = -1.0507009873554804934193349852946 * 1.6732632423543772848170429916717;
   const double a = 1.0 / sqrt((1.0 - p) * (1.0 + p * ap * ap)), b = -a * ap * p;
-  alpha_dropout_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, y, n, p, (float)a, (float)(a * ap + b), (float)b, bwd, seed, offset);
+  alpha_dropout_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, y, n, p, (float)a, (float)(a * ap + b), (float)b, bwd, seed, offset, seed_salt());
   SML_LAUNCH_OK("sml_alpha_dropout");
   return 0;
 }
