@@ -131,7 +131,7 @@ __device__ __forceinline__ TileCoord decode_tile(const EpiParams& ep, int tile, 
 
 // Epilogue of one 128 x BN tile: TMEM accumulator -> registers -> (alpha, beta*C, diag, bias, row-table, ReLU | row softmax)
 // -> fp32 and/or bf16 hi/lo global stores.  Called by the 8 epilogue warps (warp index 2..9).
-template <int BN, bool STAGED>
+template <int BN, bool STAGED, bool LEAN>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoord& t, uint32_t tmem_acc, int warp, int lane,
                                               float2* stats_buf, float* staging) {
   const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -140,6 +140,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
   constexpr int CH = BN / 2;                    // columns per epilogue warp
   const int cbeg = half * CH;
   uint32_t r[32];
+  // LEAN (the Moore-Penrose chain: alpha, beta C, diag I, fp32 + bf16 hi / lo out, full vector chunks): split-K, softmax, bias,
+  // row table, ReLU and the ragged-tail path are compiled out.  The generic kernel is ~9.7 k SASS instructions, more than
+  // the instruction cache holds, and its cold epilogue showed up as instruction-fetch stalls in the 25 us chain launches.
+  const int e_ksplit = LEAN ? 1 : ep.ksplit, e_softmax = LEAN ? 0 : ep.softmax, e_relu = LEAN ? 0 : ep.relu;
+  const float* e_bias = LEAN ? nullptr : ep.bias;
+  const float* e_rowtab = LEAN ? nullptr : ep.rowtab;
+  const int e_vec = LEAN ? 1 : ep.vec_ok;
   {
       const int n0 = t.n0, m0 = t.m0, b1 = t.b1, b2 = t.b2, ks = t.ks;
       const int gm = m0 + row;
@@ -149,7 +156,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
       float* crow = ep.C ? ep.C + coff : nullptr;
       __nv_bfloat16* hrow = ep.Cb_hi ? ep.Cb_hi + coff : nullptr;
       __nv_bfloat16* lrow = ep.Cb_lo ? ep.Cb_lo + coff : nullptr;
-      if (ep.ksplit > 1) {
+      if (e_ksplit > 1) {
         // split-K partial: alpha * acc (+ bias / diag on split 0) accumulated with red.global.add into the zeroed C
         for (int c = cbeg; c < cbeg + CH; c += 32) {
           tc_ld32(trow + c, r);
@@ -159,14 +166,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
             const int gn = n0 + c + j;
             if (gn < ep.N) {
               float x = ep.alpha * __uint_as_float(r[j]);
-              if (ks == 0) { if (gn == gm) x += ep.diag; if (ep.bias) x += __ldg(ep.bias + gn); }
+              if (ks == 0) { if (gn == gm) x += ep.diag; if (e_bias) x += __ldg(e_bias + gn); }
               atomicAdd(crow + (int64_t)gn * ep.sc_n, x);
             }
           }
         }
       } else {
         float mx = -INFINITY, inv = 1.f;
-        if (ep.softmax && !ep.C && !ep.Cb_lo && ep.Cb_hi && ep.vec_ok && n0 + BN <= ep.N) {
+        if (e_softmax && !ep.C && !ep.Cb_lo && ep.Cb_hi && e_vec && n0 + BN <= ep.N) {
           // bf16-only probabilities (bf16 mode): ONE exp per element.  Pass 1 finds the row maximum (no exp), pass 2 forms
           // e = exp(x - max) once, keeps it as packed bf16 pairs in registers and sums it in fp32; the pairs are then
           // scaled by 1 / sum and stored (the two-exp path below costs twice the MUFU work, which bounds this epilogue).
@@ -222,7 +229,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
           }
           return;
         }
-        if (ep.softmax) {
+        if (e_softmax) {
           // Row softmax fused in the epilogue.  A row lives in one TMEM lane; the two warps sharing a lane quarter each
           // scan their own half of the columns ONCE with an online (max, sum) update and swap the pair through shared
           // memory, so the statistics cost one TMEM pass.
@@ -255,9 +262,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
           const int gn0 = n0 + c;
           if (gn0 >= ep.N) break;
           float v[32];
-          if (ep.vec_ok && gn0 + 32 <= ep.N) {
+          if (e_vec && gn0 + 32 <= ep.N) {
             // ---- lean path: full 32-column chunk, 16-byte aligned rows, unit column stride
-            if (ep.softmax) {
+            if (e_softmax) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __expf(ep.alpha * __uint_as_float(r[j]) - mx) * inv;
             } else {
@@ -276,15 +283,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += (j == dj) ? ep.diag : 0.f;
               }
-              if (ep.bias) {
+              if (e_bias) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                  const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + gn0 + j));
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(e_bias + gn0 + j));
                   v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
                 }
               }
-              if (ep.rowtab && row_ok) {                     // rows past M must not index the table
-                const float* tr = ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn0;
+              if (e_rowtab && row_ok) {                     // rows past M must not index the table
+                const float* tr = e_rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                   const float4 tv = __ldg(reinterpret_cast<const float4*>(tr + j));
@@ -292,7 +299,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
                   v[j + 2] = fmaf(ep.rowtab_scale, tv.z, v[j + 2]); v[j + 3] = fmaf(ep.rowtab_scale, tv.w, v[j + 3]);
                 }
               }
-              if (ep.relu) {
+              if (e_relu) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
               }
@@ -328,20 +335,20 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
                 }
               }
             }
-          } else {
+          } else if (!LEAN) {
             // ---- general path (N tail, odd strides)
             if (!row_ok) continue;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int gn = gn0 + j;
               float x = ep.alpha * __uint_as_float(r[j]);
-              if (ep.softmax) x = __expf(x - mx) * inv;
+              if (e_softmax) x = __expf(x - mx) * inv;
               else if (gn < ep.N) {
                 if (ep.beta != 0.f) x = fmaf(ep.beta, crow[(int64_t)gn * ep.sc_n], x);
                 if (gn == gm) x += ep.diag;
-                if (ep.bias) x += __ldg(ep.bias + gn);
-                if (ep.rowtab) x = fmaf(ep.rowtab_scale, __ldg(ep.rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn), x);
-                if (ep.relu) x = fmaxf(x, 0.f);
+                if (e_bias) x += __ldg(e_bias + gn);
+                if (e_rowtab) x = fmaf(ep.rowtab_scale, __ldg(e_rowtab + (int64_t)b1 * ep.rt_b1 + (int64_t)b2 * ep.rt_b2 + (int64_t)(gm / ep.rowdiv) * ep.rt_m + gn), x);
+                if (e_relu) x = fmaxf(x, 0.f);
               }
               v[j] = x;
             }
@@ -354,7 +361,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& ep, const TileCoo
 
 // Persistent kernel: gridDim.x CTAs (<= #SMs) walk the tile list with stride gridDim.x.  The fp32 accumulator is
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the TMA + MMA main loop of tile i+1.
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES, bool LEAN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl, const EpiParams ep) {
@@ -474,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a = lt & 1u;
       mbar_wait(&tmem_full[a], (lt >> 1) & 1u);   // on a (bounded) timeout keep going: all 8 warps must reach the named barrier
       tc_fence_after();
-      epilogue_tile<BN, S::STAGED>(ep, t, tmem_base + a * BN, warp, lane, stats + (lt & 1u) * 2 * TC_BM, staging);
+      epilogue_tile<BN, S::STAGED, LEAN>(ep, t, tmem_base + a * BN, warp, lane, stats + (lt & 1u) * 2 * TC_BM, staging);
       // this accumulator buffer may be overwritten by the MMA of tile lt + 2
       tc_fence_before();
       __syncwarp();
@@ -622,7 +629,7 @@ gemm_tc_program_kernel(const __grid_constant__ Program prog, unsigned int* sync_
         const uint32_t a = lt & 1u;
         mbar_wait(&tmem_full[a], (lt >> 1) & 1u);
         tc_fence_after();
-        epilogue_tile<BN, S::STAGED>(ep, t, tmem_base + a * BN, warp, lane, stats + (lt & 1u) * 2 * TC_BM, staging);
+        epilogue_tile<BN, S::STAGED, false>(ep, t, tmem_base + a * BN, warp, lane, stats + (lt & 1u) * 2 * TC_BM, staging);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[a])) : "memory");
@@ -639,10 +646,10 @@ gemm_tc_program_kernel(const __grid_constant__ Program prog, unsigned int* sync_
 }
 
 // ------------------------------------------------------------------------------------------ host side
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, int STAGES, bool LEAN = false>
 static int launch_tc(const CUtensorMap* tms, const EpiParams& ep, dim3 grid, cudaStream_t st) {
   using S = TcSmem<BN, SPLIT, STAGES>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, SPLIT, STAGES>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, SPLIT, STAGES, LEAN>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -661,12 +668,12 @@ static int launch_tc(const CUtensorMap* tms, const EpiParams& ep, dim3 grid, cud
   return 0;
 }
 
-template <int BN, bool SPLIT, int STAGES>
+template <int BN, bool SPLIT, int STAGES, bool LEAN = false>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* tms, const EpiParams& ep, dim3 grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false, SPLIT, STAGES>(tms, ep, grid, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true, SPLIT, STAGES>(tms, ep, grid, st);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false, SPLIT, STAGES>(tms, ep, grid, st);
-  return launch_tc<BN, true, true, SPLIT, STAGES>(tms, ep, grid, st);
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, SPLIT, STAGES, LEAN>(tms, ep, grid, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, SPLIT, STAGES, LEAN>(tms, ep, grid, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false, SPLIT, STAGES, LEAN>(tms, ep, grid, st);
+  return launch_tc<BN, true, true, SPLIT, STAGES, LEAN>(tms, ep, grid, st);
 }
 
 }  // namespace sml
@@ -784,7 +791,11 @@ extern "C" int sml_gemm_tc(const sml_gemm_desc* d, void* stream) {
     return dispatch_major<64, false, 6>(a_mn, b_mn, tms, ep, grid, st);
   } else {
     if (plan.BN == 256) return dispatch_major<256, true, 2>(a_mn, b_mn, tms, ep, grid, st);   // 192 KB ring: direct stores
-    if (plan.BN == 128) return dispatch_major<128, true, 2>(a_mn, b_mn, tms, ep, grid, st);
+    if (plan.BN == 128) {
+      const bool lean = ep.ksplit <= 1 && !ep.softmax && !ep.bias && !ep.rowtab && !ep.relu && ep.vec_ok && ep.N % 32 == 0;
+      if (lean) return dispatch_major<128, true, 2, true>(a_mn, b_mn, tms, ep, grid, st);
+      return dispatch_major<128, true, 2>(a_mn, b_mn, tms, ep, grid, st);
+    }
     return dispatch_major<64, true, 3>(a_mn, b_mn, tms, ep, grid, st);
   }
 }

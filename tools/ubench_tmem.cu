@@ -128,6 +128,36 @@ __global__ void __launch_bounds__(512, 1) ubench(int mode, int nwarps, int iters
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     t1 = clock64();
+  } else if ((mode == 13 || mode == 14) && warp == 0) {
+    // the GEMM main loop's access pattern: descriptors change every iteration (stage / k offset), runtime N.
+    // mode 13: one thread inside `if (lane == 0)` (gemm_tc.cu today); mode 14: whole warp, warp-uniform operands
+    // (TMEM base through shfl), elected lane issues
+    const uint32_t idn = make_idesc(128, nwarps);
+    const uint32_t sb = smem_u32(smem);
+    if (mode == 13) {
+      if (lane == 0) {
+        t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+          const uint32_t st = (it % 3) * 8192u, kk = (it & 3) * 32u;
+          mma_ss(tb + (it & 1) * 256, make_smem_desc(sb + 16384 + st + kk, 16, 1024), make_smem_desc(sb + st + kk, 16, 1024), idn, (it & 15) ? 1u : 0u);
+        }
+        tc_commit(&bars[1]);
+        mbar_wait(&bars[1], 0);
+        t1 = clock64();
+      }
+    } else {
+      const uint32_t tbu = __shfl_sync(0xffffffffu, tb, 0);
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t st = (it % 3) * 8192u, kk = (it & 3) * 32u;
+        const uint64_t da = make_smem_desc(sb + 16384 + st + kk, 16, 1024), db = make_smem_desc(sb + st + kk, 16, 1024);
+        if (elect_one()) mma_ss(tbu + (it & 1) * 256, da, db, idn, (it & 15) ? 1u : 0u);
+      }
+      if (elect_one()) tc_commit(&bars[1]);
+      __syncwarp();
+      mbar_wait(&bars[1], 0);
+      t1 = clock64();
+    }
   } else if ((mode == 11 || mode == 12) && tid == 0) {
     long long dt = 0;
     if (mode == 11) {
@@ -234,10 +264,10 @@ __global__ void __launch_bounds__(512, 1) ubench(int mode, int nwarps, int iters
 int main() {
   long long* d; cudaMalloc(&d, 128 * sizeof(long long));
   long long h[128];
-  cudaFuncSetAttribute(ubench, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+  cudaFuncSetAttribute(ubench, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000);
   auto run = [&](int mode, int nwarps, int iters, const char* what, double bytes_per_iter_per_warp) {
     cudaMemset(d, 0, 128 * sizeof(long long));
-    ubench<<<1, 512, 40000>>>(mode, nwarps, iters, d);
+    ubench<<<1, 512, 100000>>>(mode, nwarps, iters, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", what, cudaGetErrorString(e)); exit(1); }
     cudaMemcpy(h, d, 128 * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -258,6 +288,8 @@ int main() {
   for (int n : {32, 128, 256}) run(10, n, 2000, "tcgen05.mma M=128 N=<warps> K=16 TS elect", 0);
   for (int n : {16, 32, 64, 128, 256}) run(11, n, 2000, "hoisted operands: mma M=128 N=<warps> K=16 SS", 0);
   for (int n : {16, 32, 64, 128, 256}) run(12, n, 2000, "hoisted operands: mma M=128 N=<warps> K=16 TS", 0);
+  for (int n : {64, 128, 256}) run(13, n, 2000, "GEMM-loop pattern, if (lane == 0): mma M=128 N=<warps>", 0);
+  for (int n : {64, 128, 256}) run(14, n, 2000, "GEMM-loop pattern, uniform + elect: mma M=128 N=<warps>", 0);
   run(4, 4, 1000, "round trip st16->arrive->mma->commit->ld32", 0);
   return 0;
 }
