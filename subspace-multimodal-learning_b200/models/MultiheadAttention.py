@@ -3,7 +3,16 @@ copy at models/cmta_utils.py:354-847): same constructor, forward signature, para
 the RAW pre-softmax score tensor [B, heads, L, S] (need_raw=True, :299-312).  CUDA only.
 
 Only the paths the reference call sites use are implemented (MCAT model.py:587,627; CMTA model.py:748-750,809-818):
-packed in-projection with bias, no masks, no bias_kv / zero_attn, same embedding dim for q/k/v."""
+packed in-projection with bias, no masks, no bias_kv / zero_attn, same embedding dim for q/k/v.
+
+Genomic x WSI direction (a handful of genomic queries over tens of thousands of patch tokens: MCAT model.py:627, CMTA
+model.py:809): the K and V projections of the patch tokens are never materialised.  With the per-head slices
+Wk_h, Wv_h of the packed in-projection,
+    scores_h = q_h (Wk_h x + bk_h)^T = (q_h Wk_h) x^T + q_h . bk_h            -> one [h L, E] x [E, S] product on the raw tokens
+    out_h    = sum_j a_hj (Wv_h x_j + bv_h) = (a_h x) Wv_h^T + (sum_j a_hj) bv_h -> one [h L, S] x [S, E] product, then [L, E] x [E, hd]
+which reads the token matrix twice instead of projecting it (2 x 2 S E^2 FLOPs, two [S, E] tensors written and re-read):
+at S = 16 384, E = 256, 6 queries that is 0.4 instead of 17 GFLOP per slide.  Exact re-association: same outputs, raw scores and
+gradients to rounding (tests/test_gpu_heads.py)."""
 import torch
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
@@ -36,6 +45,7 @@ class MultiheadAttention(nn.Module):
         self.bias_k = self.bias_v = None
         self.add_zero_attn = add_zero_attn
         self.precision = None      # engine of the token-level projections: None / "fp32" (SIMT), "bf16x3", "bf16" (tcgen05)
+        self.fold_kv = None        # None: automatic (few queries over many keys); True / False force the re-associated form
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -57,6 +67,9 @@ class MultiheadAttention(nn.Module):
         mq = mode if L >= 1024 else "fp32"            # the long side (N patch tokens) runs on the tensor-core engine
         mk = mode if S >= 1024 else "fp32"
         q = Fn.scale(Fn.linear(query.float(), w[:E], bq, mode=mq), float(hd) ** -0.5)   # :125-205
+        fold = self.fold_kv if self.fold_kv is not None else (h * L <= 64 and S >= 1024)
+        if fold:
+            return self._forward_folded(q, key.float(), value.float(), w, bk, bv, need_weights, need_raw)
         k = Fn.linear(key.float(), w[E:2 * E], bk, mode=mk)
         v = Fn.linear(value.float(), w[2 * E:], bv, mode=mk)
         qh = q.view(L, B, h, hd).permute(1, 2, 0, 3)                                    # [B,h,L,hd] views (:245-249)
@@ -71,5 +84,33 @@ class MultiheadAttention(nn.Module):
         if need_weights:
             if need_raw:
                 return out, raw                                                         # :308-312
+            return out, Fn.scale(attn.sum(dim=1), 1.0 / h)
+        return out, None
+
+    def _forward_folded(self, q, key, value, w, bk, bv, need_weights, need_raw):
+        """few queries over many keys: K / V projections folded into the query side and the output side (module docstring)"""
+        L, B, E = q.shape
+        S = key.shape[0]
+        h, hd = self.num_heads, self.head_dim
+        qh = q.view(L, B, h, hd).permute(1, 2, 0, 3)                                    # [B,h,L,hd]
+        wk_h = w[E:2 * E].view(1, h, hd, E).expand(B, h, hd, E)                         # per-head slices, broadcast over B
+        wv_h = w[2 * E:].view(1, h, hd, E).expand(B, h, hd, E)
+        qk = Fn.matmul(qh, wk_h)                                                        # [B,h,L,E] = q_h Wk_h
+        kt = key.permute(1, 2, 0)                                                       # [B,E,S] view of the raw tokens
+        raw = Fn.matmul(qk.reshape(B, h * L, E), kt).view(B, h, L, S)                   # (q_h Wk_h) x^T
+        if bk is not None:
+            cb = Fn.matmul(qh, bk.view(1, h, hd, 1).expand(B, h, hd, 1))                # [B,h,L,1] = q_h . bk_h
+            raw = raw + cb
+        attn = Fn.softmax_lastdim(raw)
+        attn = Fn.dropout_add(None, attn, self.dropout, self.training)
+        ctx = Fn.matmul(attn.reshape(B, h * L, S), value.permute(1, 0, 2)).view(B, h, L, E)     # a_h x
+        o = Fn.matmul(ctx, wv_h.transpose(-1, -2))                                      # [B,h,L,hd] = (a_h x) Wv_h^T
+        if bv is not None:
+            o = o + attn.sum(dim=-1, keepdim=True) * bv.view(1, h, 1, hd)               # (sum_j a_hj) bv_h (= bv_h without dropout)
+        o = o.permute(2, 0, 1, 3).reshape(L, B, E)
+        out = Fn.linear(o, self.out_proj.weight, self.out_proj.bias)
+        if need_weights:
+            if need_raw:
+                return out, raw
             return out, Fn.scale(attn.sum(dim=1), 1.0 / h)
         return out, None

@@ -27,6 +27,44 @@ def test_mha_golden():
     assert rel_err(o4, g["out4"]) < 1e-4 and rel_err(raw4, g["raw4"]) < 1e-4
 
 
+@pytest.mark.parametrize("heads", [1, 4])
+def test_mha_folded_kv_equals_projected(heads):
+    """the re-associated co-attention (K / V projections never materialised) against the golden fixture of the
+    reference (forced on its 70-key case) and against the projected form at 6 genomic queries x 16 384 patch tokens: outputs,
+    raw scores and every gradient"""
+    import sml_b200
+    g = load_golden("mha")
+    if heads == 1:
+        mha = sml_b200.MultiheadAttention(256, 1).cuda().eval()
+        mha.load_state_dict(g["state"])
+        mha.fold_kv = True
+        q = g["q"].cuda().requires_grad_(); kv = g["kv"].cuda().requires_grad_()
+        o, raw = mha(q, kv, kv)
+        assert rel_err(o, g["out"]) < 1e-4 and rel_err(raw, g["raw"]) < 1e-4
+        (o * g["go"].cuda()).sum().backward()
+        assert rel_err(q.grad, g["gq"]) < 1e-3 and rel_err(kv.grad, g["gkv"]) < 1e-3
+        grads_close({k: p.grad for k, p in mha.named_parameters()}, g["gparams"], 1e-3)
+    torch.manual_seed(2)
+    mha = sml_b200.MultiheadAttention(256, heads).cuda().eval()
+    with torch.no_grad():
+        mha.in_proj_bias.normal_(0, 0.1)
+    qx = randn((6, 2, 256), 501).cuda(); kx = (randn((16384, 2, 256), 502) * 0.5).cuda(); go = randn((6, 2, 256), 503).cuda()
+    res = {}
+    for fold in (False, True):
+        mha.fold_kv = fold
+        mha.zero_grad(set_to_none=True)
+        q = qx.clone().requires_grad_(); kv = kx.clone().requires_grad_()
+        o, raw = mha(q, kv, kv)
+        (o * go).sum().backward()
+        res[fold] = (o.detach(), raw.detach(), q.grad, kv.grad, {k: p.grad.clone() for k, p in mha.named_parameters()})
+    mha.fold_kv = None
+    assert mha(qx, kx, kx)[0].shape == (6, 2, 256)                                  # automatic choice takes the folded form here
+    a, b = res[False], res[True]
+    assert rel_err(b[0], a[0]) < 1e-4 and rel_err(b[1], a[1]) < 1e-4
+    assert rel_err(b[2], a[2]) < 1e-3 and rel_err(b[3], a[3]) < 1e-3
+    grads_close(b[4], a[4], 1e-3)
+
+
 def test_bilinear_fusion_golden():
     import sml_b200
     g = load_golden("bilinear_fusion")
