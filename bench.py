@@ -272,7 +272,8 @@ class Workload:
             model.set_precision(precision)
         Fn.manual_seed(42 + rank)
         self.model = self.net = model
-        if world > 1 and name != "stress100k":
+        self.gdp = bool(graph) and world > 1 and name == "transmil"   # graph replay + one flat gradient all-reduce instead of DDP
+        if world > 1 and name != "stress100k" and not self.gdp:
             # DeformCrossTransMIL: the attn1d / attn2d twin module is unused -> find_unused_parameters
             self.net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=self.deform,
                                                                  broadcast_buffers=False, gradient_as_bucket_view=True)
@@ -297,9 +298,18 @@ class Workload:
 
     def enable_graph(self):
         """capture the step (after the eager warm-up) as one CUDA graph; on failure the workload stays eager and says so"""
+        import sml_b200
+        if self.gdp and self.graphed is None:
+            F = torch.nn.functional
+
+            def loss_fn(x, y):
+                enc, logits, _ = self.model(x)
+                return F.cross_entropy(logits, y) + 0.0 * enc.sum()
+            self.graphed = sml_b200.GraphedDataParallelStep(self.model, self.opt, loss_fn, (self.x_dev, self.y_dev))
+            self.graph_note = "CUDA graph of forward + backward into a flat gradient buffer, one NCCL all-reduce, fused Adam"
+            return
         if not self.want_graph or self.graphed is not None:
             return
-        import sml_b200
         try:
             self.graphed = sml_b200.GraphedStep(self._step, (self.x_dev, self.y_dev), warmup=1)
             self.graph_note = "one CUDA graph per step (sml_b200.GraphedStep)"
@@ -316,6 +326,17 @@ class Workload:
     def _step(self, x, y):
         import sml_b200
         F = torch.nn.functional
+        if self.gdp:                                         # eager form of the same step (warm-up, launch counting)
+            self.opt.zero_grad(set_to_none=False)
+            enc, logits, _ = self.model(x)
+            loss = F.cross_entropy(logits, y) + 0.0 * enc.sum()
+            loss.backward()
+            import torch.distributed as dist
+            for p_ in self.model.parameters():
+                if p_.grad is not None:
+                    dist.all_reduce(p_.grad, op=dist.ReduceOp.AVG)
+            self.opt.step()
+            return loss
         self.opt.zero_grad(set_to_none=True)
         if self.name == "pathomic":
             _, f_t, f_i, lg, _, _, _ = self.net(x_path=x, x_omic_tumor=self.x_t, x_omic_immune=self.x_i)

@@ -19,4 +19,4 @@ from .utils.sync_batchnorm import SyncBatchNorm1d, SynchronizedBatchNorm1d, conv
 from .utils.modulation import modulate_classifier_grads  # noqa: F401
 from .install import install  # noqa: F401
 from . import data  # noqa: F401
-from .graph import GraphedStep  # noqa: F401
+from .graph import GraphedStep, GraphedDataParallelStep  # noqa: F401

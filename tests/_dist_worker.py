@@ -55,6 +55,42 @@ def run(rank, world, port, mode, out_dir):
         res["bn_x"] = x.detach().cpu(); res["bn_y"] = y.detach().cpu(); res["bn_gy"] = gy.cpu(); res["bn_gx"] = x.grad.cpu()
         res["bn_w"] = bn.weight.detach().cpu(); res["bn_b"] = bn.bias.detach().cpu()
         res["bn_gw"] = bn.weight.grad.cpu(); res["bn_rv"] = bn.running_var.cpu()
+    if mode == "gpu":
+        # ---- GraphedDataParallelStep == the same steps with eager backward + per-parameter gradient averaging
+        from argparse import Namespace
+        from sml_b200 import functional as Fn
+        import copy
+        torch.manual_seed(5)
+        net0 = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev).eval()      # eval: no dropout (offsets are host-side)
+        net0.set_precision("bf16")
+        st0 = copy.deepcopy(net0.state_dict())
+        x = randn((2, 600, 1024), 100 + rank).to(dev); y = torch.tensor([rank, 3 - rank], device=dev)
+        F = torch.nn.functional
+
+        def make():
+            net = sml_b200.TransMIL(Namespace(label_dim=4, path_dim=128)).to(dev).eval()
+            net.set_precision("bf16"); net.load_state_dict(st0)
+            return net, torch.optim.Adam(net.parameters(), lr=1e-3, fused=True, capturable=True)
+        net_a, opt_a = make()
+        la = []
+        for _ in range(3):
+            opt_a.zero_grad(set_to_none=True)
+            enc, lg, _ = net_a(x)
+            loss = F.cross_entropy(lg, y) + 0.0 * enc.sum()
+            loss.backward()
+            for p_ in net_a.parameters():
+                dist.all_reduce(p_.grad); p_.grad.div_(world)
+            opt_a.step()
+            la.append(float(loss))
+        net_b, opt_b = make()
+        step = sml_b200.GraphedDataParallelStep(net_b, opt_b, lambda xx, yy: (lambda o: F.cross_entropy(o[1], yy) + 0.0 * o[0].sum())(net_b(xx)),
+                                                (x, y))
+        with torch.no_grad():                                # the capture's warm-up runs accumulate nothing into the weights
+            for k, v in net_b.state_dict().items():
+                assert torch.equal(v, st0[k].to(dev)), k
+        lb = [float(step(x, y)) for _ in range(3)]
+        res["gdp_eager"] = la; res["gdp_graph"] = lb
+        res["gdp_w"] = net_b._fc2.weight.detach().cpu(); res["gdp_w_eager"] = net_a._fc2.weight.detach().cpu()
     torch.save(res, os.path.join(out_dir, "rank%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()

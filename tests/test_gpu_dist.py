@@ -37,3 +37,10 @@ def test_two_rank_batchloss_and_syncbn():
         assert rel_err(r["bn_rv"], bn.running_var) < 1e-5
         o += n
     assert rel_err(res[0]["bn_gw"] + res[1]["bn_gw"], bn.weight.grad) < 1e-4
+    # GraphedDataParallelStep: same losses as the eager data-parallel loop, identical weights on both ranks
+    for r in res:
+        assert abs(r["gdp_eager"][0] - r["gdp_graph"][0]) <= 1e-6 * abs(r["gdp_eager"][0])
+        for a, b in zip(r["gdp_eager"][1:], r["gdp_graph"][1:]):
+            assert abs(a - b) <= 5e-3 * abs(a), (r["gdp_eager"], r["gdp_graph"])
+    assert torch.equal(res[0]["gdp_w"], res[1]["gdp_w"])
+    assert rel_err(res[0]["gdp_w"], res[0]["gdp_w_eager"]) < 5e-3
