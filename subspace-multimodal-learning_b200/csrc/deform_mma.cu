@@ -1632,6 +1632,580 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
   }
 }
 
+
+// ---- warp-specialised backward (plain bf16 operands, 2-D or 1-D lattices whose 64-query tiles span <= 8 lattice rows).
+// The lean backward above runs 8 warps per SM (220 registers, 56 of them parameter-gradient accumulators) and is bound by
+// dependent-issue latency: each warp walks a ~290-instruction chain per key with two warps per scheduler.  Here a CTA has two
+// warpgroups that pipeline over the keys:
+//   producers (warps 0-3): bias MLP forward (layers 1-3), P, dS, the bf16 P / dS tiles, gb3; then dQ += dS K
+//   consumers (warps 4-7): dh2, dW2 / db2 / dw3, dh1 = dh2 W2, first ReLU backward, dW1 / db1, key-coordinate gradients; then
+//                          dK += dS^T Q, dV += (P keep)^T dO
+// Producer i and consumer i own the same 16 query rows; per key the producer hands over its h1 / h2 A fragments, dS and the
+// signed-log distances (22 registers per lane) through a double-buffered shared-memory slot guarded by two mbarriers.  Both
+// roles fit 128 registers, so two CTAs = 16 warps share an SM and each scheduler interleaves four half-length chains.
+constexpr int WS_THREADS = 256;
+constexpr int WS_NY = 8;             // lattice-row slots of the y table (64 consecutive tokens span <= 8 rows when W >= 10)
+
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(ws_smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();                          // a protocol bug must not hang the GPU
+}
+
+template <int CD>
+struct WsBwdSmem {
+  __nv_bfloat16 Q[MQ][MLD], dO[2][MQ][MLD];
+  __nv_bfloat16 K[BK][MLD], V[2][BK][MLD];
+  __nv_bfloat16 P[MQ][PLD], dS[MQ][PLD];     // `red` aliases P + dS at the end of the kernel
+  float dQ[32][MTHREADS];
+  float stg[4][2][16][9];
+  float kgs[4][8][16];
+  float c1[4][24];
+  float c2[4][8];
+  float dkpos[BK][2];
+  float SX[BK][MQ];
+  float SY[CD == 2 ? WS_NY : 1][BK];
+  float qx[MQ], qy[WS_NY];
+  float kpos[BK][2];
+  uint32_t wth[16][32];              // dh1 = dh2 W2 operand fragments by lane: [(jn * 2 + s) * 2 + reg][lane]
+  uint4 hb[4][2][6][32];             // hand-over slots [pair][slot][4-register group][lane]
+  uint64_t full[4][2], empty[4][2];
+};
+
+template <int CD>
+__global__ void __launch_bounds__(WS_THREADS, 2) deform_attn_bwd_ws_kernel(
+    const AttnCfg cf, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const float* __restrict__ vs, const float* __restrict__ cpb, const float* __restrict__ out,
+    const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq, float* __restrict__ dk,
+    float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WsBwdSmem<CD>& sm = *reinterpret_cast<WsBwdSmem<CD>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const bool producer = warp < 4;
+  const int w = warp & 3;                        // pair index: producer w and consumer w own query rows 16 w .. 16 w + 15
+  const int ptid = tid & 127;                    // thread index inside the warpgroup
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
+  const int grp = head / cf.OUT, o = head % cf.OUT;
+  const int bg = b * cf.G + grp;
+  const float* W1 = cpb; const float* B1 = W1 + CPB_H * CD; const float* W2 = B1 + CPB_H;
+  const float* B2 = W2 + CPB_H * CPB_H; const float* W3 = B2 + CPB_H; const float* B3 = W3 + cf.OUT * CPB_H;
+  // ---- shared constants
+  if (tid < 4 * 24) {
+    const int tt = tid / 24, i = tid % 24, which = i / 8, s = (i % 8) / 4, e = i % 4;
+    const int kk = 16 * s + 2 * tt + (e & 1) + 8 * (e >> 1);
+    sm.c1[tt][i] = which == 0 ? W1[kk * CD] : (which == 1 ? (CD == 2 ? W1[kk * CD + 1] : 0.f) : B1[kk]);
+  }
+  if (tid >= 128 && tid < 128 + 4 * 8) {
+    const int i0 = tid - 128, tt = i0 / 8, i = i0 % 8, j = i / 2, e = i % 2;
+    sm.c2[tt][i] = B2[8 * j + 2 * tt + e];
+  }
+  if (tid >= 160 && tid < 192) {                 // W2 operand fragments of dh1 = dh2 W2 (B[k' = c][n = k] = W2[c][k]), by lane
+    const int ln = tid - 160, gg = ln >> 2, tt = ln & 3;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float* col = W2 + (16 * s + 2 * tt) * CPB_H + 8 * jn + gg;
+        sm.wth[(jn * 2 + s) * 2 + 0][ln] = pack_bf16(col[0], col[CPB_H]);
+        sm.wth[(jn * 2 + s) * 2 + 1][ln] = pack_bf16(col[8 * CPB_H], col[9 * CPB_H]);
+      }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i)
+      for (int s = 0; s < 2; ++s) { ws_mbar_init(&sm.full[i][s], 1); ws_mbar_init(&sm.empty[i][s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
+  if (producer) {
+    load_tile<false, MQ>(sm.Q, nullptr, q + qoff, cf.inner, q0, cf.n);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sm.dQ[i][ptid] = 0.f;
+  } else {
+    // consumer threads load dO (hi / lo) with their warpgroup index
+    for (int e = ptid; e < MQ * 16; e += 128) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < cf.n) x = *reinterpret_cast<const float4*>(dout + qoff + (int64_t)(q0 + r) * cf.inner + c4);
+      uint32_t h0, l0, h1, l1;
+      split2<true>(x.x, x.y, h0, l0);
+      split2<true>(x.z, x.w, h1, l1);
+      *reinterpret_cast<uint2*>(&sm.dO[0][r][c4]) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(&sm.dO[1][r][c4]) = make_uint2(l0, l1);
+    }
+  }
+  {                                              // query positions: x per CTA row, y per lattice-row slot
+    const int last = min(q0 + MQ - 1, cf.n - 1);
+    const int y0 = CD == 2 ? q0 / cf.W : 0;
+    const int nyq = CD == 2 ? last / cf.W - y0 + 1 : 1;
+    if (tid >= 192 && tid < 192 + MQ) {
+      const int r = tid - 192;
+      float px, py;
+      query_pos(cf, min(q0 + r, cf.n - 1), px, py);
+      sm.qx[r] = px;
+      if (CD == 2 && r < nyq) {
+        query_pos(cf, min((y0 + r) * cf.W, cf.n - 1), px, py);
+        sm.qy[r] = py;
+      }
+    }
+  }
+  const int ny = CD == 2 ? min(q0 + MQ - 1, cf.n - 1) / cf.W - q0 / cf.W + 1 : 1;
+  const int r0 = w * 16 + g, r1 = r0 + 8;
+  const bool ok0 = q0 + r0 < cf.n, ok1 = q0 + r1 < cf.n;
+  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  uint32_t kc = 0;                               // keys handed over so far by this pair (slot = kc & 1, phase = (kc >> 1) & 1)
+
+  // ------------------------------------------------------------------------------------------------ role state
+  // producer
+  uint32_t wh[4][2][2];
+  uint32_t w3c[4];
+  float b3 = 0.f, delta0 = 0.f, delta1 = 0.f, lse0 = INFINITY, lse1 = INFINITY, gb3 = 0.f;
+  int ys0 = 0, ys1 = 0;
+  unsigned long long hrow0 = 0, hrow1 = 0;
+  // consumer
+  float gW2[2][4][4], gL1[2][4], gX2[2][4], gX3[2][4];
+  uint32_t w1b[2][2], w3f[2][2];
+  if (producer) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float* row = W2 + (8 * j + g) * CPB_H + 16 * s + 2 * t;
+        wh[j][s][0] = pack_bf16(row[0], row[1]);
+        wh[j][s][1] = pack_bf16(row[8], row[9]);
+      }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int k0_ = 16 * s + 2 * t;
+      w3c[2 * s] = g == 0 ? pack_bf16(W3[o * CPB_H + k0_], W3[o * CPB_H + k0_ + 1]) : 0u;
+      w3c[2 * s + 1] = g == 0 ? pack_bf16(W3[o * CPB_H + k0_ + 8], W3[o * CPB_H + k0_ + 9]) : 0u;
+    }
+    b3 = B3[o];
+    ys0 = CD == 2 ? min(q0 + r0, cf.n - 1) / cf.W - q0 / cf.W : 0;
+    ys1 = CD == 2 ? min(q0 + r1, cf.n - 1) / cf.W - q0 / cf.W : 0;
+    hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
+    hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
+    if (ok0) {
+      const float* orow = out + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta0 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta0))));
+      }
+      lse0 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0];
+    }
+    if (ok1) {
+      const float* orow = out + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta1 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta1))));
+      }
+      lse1 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1];
+    }
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 1); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 1);
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 2); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 2);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        gL1[a][c] = 0.f; gX2[a][c] = 0.f; gX3[a][c] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gW2[a][c][e] = 0.f;
+      }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int k0_ = 16 * s + 2 * t;
+      const bool on = g < CD;
+      w1b[s][0] = pack_bf16(on ? W1[k0_ * CD + g] : 0.f, on ? W1[(k0_ + 1) * CD + g] : 0.f);
+      w1b[s][1] = pack_bf16(on ? W1[(k0_ + 8) * CD + g] : 0.f, on ? W1[(k0_ + 9) * CD + g] : 0.f);
+      w3f[s][0] = pack_bf16(W3[o * CPB_H + k0_], W3[o * CPB_H + k0_ + 1]);
+      w3f[s][1] = pack_bf16(W3[o * CPB_H + k0_ + 8], W3[o * CPB_H + k0_ + 9]);
+    }
+  }
+  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
+  const float* c1 = sm.c1[t];
+  const float* c2 = sm.c2[t];
+  float (*stS)[9] = sm.stg[w][0];
+  float (*stD)[9] = sm.stg[w][1];
+  const int qlane = lane & ~3;
+
+  for (int k0 = 0; k0 < cf.nkv; k0 += BK) {
+    __syncthreads();
+    if (producer) {
+      load_tile<false, BK>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
+      load_tile<true, BK>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
+    } else if (ptid < BK) {
+      const bool ok = k0 + ptid < cf.nkv;
+      sm.kpos[ptid][0] = ok ? vs[((int64_t)bg * cf.nkv + k0 + ptid) * CD] : 0.f;
+      sm.kpos[ptid][1] = (ok && CD == 2) ? vs[((int64_t)bg * cf.nkv + k0 + ptid) * CD + 1] : 0.f;
+      sm.dkpos[ptid][0] = 0.f; sm.dkpos[ptid][1] = 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < BK * MQ; e += WS_THREADS) {
+      const int key = e / MQ, r = e % MQ;
+      sm.SX[key][r] = slog_fast(sm.qx[r] - sm.kpos[key][0]);
+    }
+    if (CD == 2)
+      for (int e = tid; e < BK * ny; e += WS_THREADS) {
+        const int slot = e / BK, key = e % BK;
+        sm.SY[slot][key] = slog_fast(sm.qy[slot] - sm.kpos[key][1]);
+      }
+    __syncthreads();
+    if (producer) {
+      // ================================================================================================ producer
+#pragma unroll 1
+      for (int j = 0; j < BK / 8; ++j) {
+        {                                            // S = Q K^T and dP = dO V^T of my 16 rows x this 8-key group
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t ah[4], gh[4], gl[4];
+            const int c0 = 16 * ks + 2 * t;
+            ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0]);
+            ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0 + 8]);
+            gh[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0]);     gh[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0]);
+            gh[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0 + 8]); gh[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0 + 8]);
+            gl[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0]);     gl[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0]);
+            gl[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0 + 8]); gl[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0 + 8]);
+            const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0]);
+            const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0 + 8]);
+            const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0]);
+            const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0 + 8]);
+            const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0]);
+            const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0 + 8]);
+            mma16816(s, ah, kh0, kh1);
+            mma3<true>(dp, gh, gl, vh0, vh1, vl0, vl1);
+          }
+          __syncwarp();
+          stS[g][2 * t] = s[0]; stS[g][2 * t + 1] = s[1]; stS[g + 8][2 * t] = s[2]; stS[g + 8][2 * t + 1] = s[3];
+          stD[g][2 * t] = dp[0]; stD[g][2 * t + 1] = dp[1]; stD[g + 8][2 * t] = dp[2]; stD[g + 8][2 * t + 1] = dp[3];
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u, ++kc) {
+          const int key = 8 * j + u;
+          const float ax0 = sm.SX[key][r0], ax1 = sm.SX[key][r1];
+          const float ay0 = CD == 2 ? sm.SY[ys0][key] : 0.f, ay1 = CD == 2 ? sm.SY[ys1][key] : 0.f;
+          uint32_t ah[2][4];
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const float4 wx = *reinterpret_cast<const float4*>(c1 + 4 * s), wy = *reinterpret_cast<const float4*>(c1 + 8 + 4 * s),
+                         bb = *reinterpret_cast<const float4*>(c1 + 16 + 4 * s);
+            const float wxa[4] = {wx.x, wx.y, wx.z, wx.w}, wya[4] = {wy.x, wy.y, wy.z, wy.w}, bba[4] = {bb.x, bb.y, bb.z, bb.w};
+            float h0[4], h1[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float u0 = fmaf(wxa[e], ax0, bba[e]), u1 = fmaf(wxa[e], ax1, bba[e]);
+              if (CD == 2) { u0 = fmaf(wya[e], ay0, u0); u1 = fmaf(wya[e], ay1, u1); }
+              h0[e] = u0; h1[e] = u1;
+            }
+            ah[s][0] = relu_pack(h0[0], h0[1]); ah[s][1] = relu_pack(h1[0], h1[1]);
+            ah[s][2] = relu_pack(h0[2], h0[3]); ah[s][3] = relu_pack(h1[2], h1[3]);
+          }
+          uint32_t hh[2][4];
+          {
+            const float4 ba = *reinterpret_cast<const float4*>(c2), bbv = *reinterpret_cast<const float4*>(c2 + 4);
+            const float b2v[8] = {ba.x, ba.y, ba.z, ba.w, bbv.x, bbv.y, bbv.z, bbv.w};
+            float acc[4][4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              mma16816_c(acc[jj], ah[0], wh[jj][0][0], wh[jj][0][1], b2v[2 * jj], b2v[2 * jj + 1], b2v[2 * jj], b2v[2 * jj + 1]);
+              mma16816(acc[jj], ah[1], wh[jj][1][0], wh[jj][1][1]);
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              hh[s][0] = relu_pack(acc[2 * s][0], acc[2 * s][1]);         hh[s][1] = relu_pack(acc[2 * s][2], acc[2 * s][3]);
+              hh[s][2] = relu_pack(acc[2 * s + 1][0], acc[2 * s + 1][1]); hh[s][3] = relu_pack(acc[2 * s + 1][2], acc[2 * s + 1][3]);
+            }
+          }
+          float p0, p1;
+          {
+            float d3[4];
+            mma16816_c(d3, hh[0], w3c[0], w3c[1], 0.f, 0.f, 0.f, 0.f);
+            mma16816(d3, hh[1], w3c[2], w3c[3]);
+            p0 = __shfl_sync(0xffffffffu, d3[0], qlane);
+            p1 = __shfl_sync(0xffffffffu, d3[2], qlane);
+          }
+          const bool kok = k0 + key < cf.nkv;
+          const float P0 = kok ? __expf(stS[g][u] + p0 + b3 - lse0) : 0.f;
+          const float P1 = kok ? __expf(stS[g + 8][u] + p1 + b3 - lse1) : 0.f;
+          float keep0 = 1.f, keep1 = 1.f;
+          if (cf.p_drop > 0.f) {
+            keep0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+            keep1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+          }
+          const float dS0 = P0 * (stD[g][u] * keep0 - delta0);
+          const float dS1 = P1 * (stD[g + 8][u] * keep1 - delta1);
+          {
+            const __nv_bfloat16 pv = __float2bfloat16_rn(t ? P1 * keep1 : P0 * keep0), sv = __float2bfloat16_rn(t ? dS1 : dS0);
+            __nv_bfloat16* pp = &sm.P[t ? r1 : r0][key];
+            if (t < 2) { *pp = pv; *(pp + (&sm.dS[0][0] - &sm.P[0][0])) = sv; }
+          }
+          gb3 += t == 0 ? dS0 + dS1 : 0.f;
+          // hand over to the consumer of this pair
+          const uint32_t slot = kc & 1u;
+          ws_mbar_wait(&sm.empty[w][slot], ((kc >> 1) & 1u) ^ 1u);
+          uint4* hb = &sm.hb[w][slot][0][lane];
+          hb[0 * 32] = make_uint4(ah[0][0], ah[0][1], ah[0][2], ah[0][3]);
+          hb[1 * 32] = make_uint4(ah[1][0], ah[1][1], ah[1][2], ah[1][3]);
+          hb[2 * 32] = make_uint4(hh[0][0], hh[0][1], hh[0][2], hh[0][3]);
+          hb[3 * 32] = make_uint4(hh[1][0], hh[1][1], hh[1][2], hh[1][3]);
+          hb[4 * 32] = make_uint4(__float_as_uint(dS0), __float_as_uint(dS1), __float_as_uint(ax0), __float_as_uint(ay0));
+          hb[5 * 32] = make_uint4(__float_as_uint(ax1), __float_as_uint(ay1), 0u, 0u);
+          __syncwarp();
+          if (lane == 0) ws_mbar_arrive(&sm.full[w][slot]);
+        }
+      }
+    } else {
+      // ================================================================================================ consumer
+#pragma unroll 1
+      for (int j = 0; j < BK / 8; ++j) {
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u, ++kc) {
+          const uint32_t slot = kc & 1u;
+          ws_mbar_wait(&sm.full[w][slot], (kc >> 1) & 1u);
+          uint32_t ah[2][4], hh[2][4];
+          float dS0, dS1, ax0, ay0, ax1, ay1;
+          {
+            const uint4* hb = &sm.hb[w][slot][0][lane];
+            const uint4 a0 = hb[0 * 32], a1 = hb[1 * 32], h0 = hb[2 * 32], h1 = hb[3 * 32], m0 = hb[4 * 32], m1 = hb[5 * 32];
+            ah[0][0] = a0.x; ah[0][1] = a0.y; ah[0][2] = a0.z; ah[0][3] = a0.w;
+            ah[1][0] = a1.x; ah[1][1] = a1.y; ah[1][2] = a1.z; ah[1][3] = a1.w;
+            hh[0][0] = h0.x; hh[0][1] = h0.y; hh[0][2] = h0.z; hh[0][3] = h0.w;
+            hh[1][0] = h1.x; hh[1][1] = h1.y; hh[1][2] = h1.z; hh[1][3] = h1.w;
+            dS0 = __uint_as_float(m0.x); dS1 = __uint_as_float(m0.y); ax0 = __uint_as_float(m0.z); ay0 = __uint_as_float(m0.w);
+            ax1 = __uint_as_float(m1.x); ay1 = __uint_as_float(m1.y);
+          }
+          __syncwarp();
+          if (lane == 0) ws_mbar_arrive(&sm.empty[w][slot]);
+          // dh2 = 1[h2 > 0] (dS w3): packed bf16x2, A-fragment order
+          const uint32_t dS0p = pack_bf16(dS0, dS0), dS1p = pack_bf16(dS1, dS1);
+          uint32_t dah[2][4];
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            dah[s][0] = nz_mask_bf16x2(hh[s][0]) & mul_bf16x2(dS0p, w3f[s][0]);
+            dah[s][1] = nz_mask_bf16x2(hh[s][1]) & mul_bf16x2(dS1p, w3f[s][0]);
+            dah[s][2] = nz_mask_bf16x2(hh[s][2]) & mul_bf16x2(dS0p, w3f[s][1]);
+            dah[s][3] = nz_mask_bf16x2(hh[s][3]) & mul_bf16x2(dS1p, w3f[s][1]);
+          }
+          uint32_t bx0, bx1;
+          {
+            const uint32_t xa0 = pack_bf16(ax0, ay0), xa1 = pack_bf16(ax1, ay1), xb0 = pack_bf16(1.f, dS0), xb1 = pack_bf16(1.f, dS1);
+            const uint32_t x0 = t == 0 ? xa0 : (t == 1 ? xb0 : 0u), x1 = t == 0 ? xa1 : (t == 1 ? xb1 : 0u);
+            bx0 = movm_trans(x0); bx1 = movm_trans(x1);
+          }
+          {
+            uint32_t bh[4][2];
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn) {
+              const int s = jn >> 1, rb = (jn & 1) * 2;
+              bh[jn][0] = movm_trans(ah[s][rb]); bh[jn][1] = movm_trans(ah[s][rb + 1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              uint32_t ta[4];
+              ta[0] = movm_trans(dah[mt][0]); ta[1] = movm_trans(dah[mt][2]); ta[2] = movm_trans(dah[mt][1]); ta[3] = movm_trans(dah[mt][3]);
+#pragma unroll
+              for (int jn = 0; jn < 4; ++jn) mma16816(gW2[mt][jn], ta, bh[jn][0], bh[jn][1]);
+              mma16816(gX2[mt], ta, bx0, bx1);
+              uint32_t th[4];
+              th[0] = movm_trans(hh[mt][0]); th[1] = movm_trans(hh[mt][2]); th[2] = movm_trans(hh[mt][1]); th[3] = movm_trans(hh[mt][3]);
+              mma16816(gX3[mt], th, bx0, bx1);
+            }
+          }
+          uint32_t peh[4][2];
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) {
+            float d1[4];
+            mma16816_c(d1, dah[0], sm.wth[(jn * 2 + 0) * 2][lane], sm.wth[(jn * 2 + 0) * 2 + 1][lane], 0.f, 0.f, 0.f, 0.f);
+            mma16816(d1, dah[1], sm.wth[(jn * 2 + 1) * 2][lane], sm.wth[(jn * 2 + 1) * 2 + 1][lane]);
+            peh[jn][0] = nz_mask_bf16x2(ah[jn >> 1][(jn & 1) * 2]) & pack_bf16(d1[0], d1[1]);
+            peh[jn][1] = nz_mask_bf16x2(ah[jn >> 1][(jn & 1) * 2 + 1]) & pack_bf16(d1[2], d1[3]);
+          }
+          float dpo[4];
+          {
+            const uint32_t pa0[4] = {peh[0][0], peh[0][1], peh[1][0], peh[1][1]};
+            const uint32_t pa1[4] = {peh[2][0], peh[2][1], peh[3][0], peh[3][1]};
+            mma16816_c(dpo, pa0, w1b[0][0], w1b[0][1], 0.f, 0.f, 0.f, 0.f);
+            mma16816(dpo, pa1, w1b[1][0], w1b[1][1]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t ta[4];
+            ta[0] = movm_trans(peh[2 * mt][0]); ta[1] = movm_trans(peh[2 * mt + 1][0]);
+            ta[2] = movm_trans(peh[2 * mt][1]); ta[3] = movm_trans(peh[2 * mt + 1][1]);
+            mma16816(gL1[mt], ta, bx0, bx1);
+          }
+          {
+            const float kgx = -(dpo[0] * __expf(-fabsf(ax0)) + dpo[2] * __expf(-fabsf(ax1)));
+            const float kgy = CD == 2 ? -(dpo[1] * __expf(-fabsf(ay0)) + dpo[3] * __expf(-fabsf(ay1))) : 0.f;
+            if (t == 0) *reinterpret_cast<float2*>(&sm.kgs[w][g][2 * u]) = make_float2(kgx, kgy);
+          }
+        }
+        __syncwarp();
+        if (lane < 16) {
+          float r = 0.f;
+#pragma unroll
+          for (int gg = 0; gg < 8; ++gg) r += sm.kgs[w][gg][lane];
+          if (CD == 2 || (lane & 1) == 0) atomicAdd(&sm.dkpos[8 * j + (lane >> 1)][lane & 1], r);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (producer) {
+      // ---- dQ += dS K
+      float dqacc[8][4];
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dqacc[jd][e] = sm.dQ[jd * 4 + e][ptid];
+#pragma unroll
+      for (int ks = 0; ks < BK / 16; ++ks) {
+        uint32_t ah[4];
+        const int c0 = 16 * ks + 2 * t;
+        ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0]);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0 + 8]);
+#pragma unroll
+        for (int jd = 0; jd < 8; ++jd) {
+          uint32_t bh0, bh1;
+          ldmatrix_x2_trans(bh0, bh1, &sm.K[16 * ks + (lane & 15)][8 * jd]);
+          mma16816(dqacc[jd], ah, bh0, bh1);
+        }
+      }
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sm.dQ[jd * 4 + e][ptid] = dqacc[jd][e];
+      if (ptid < BK * CD) {
+        const int key = ptid / CD, c = ptid % CD;
+        if (k0 + key < cf.nkv) atomicAdd(dvs + ((int64_t)bg * cf.nkv + k0 + key) * CD + c, sm.dkpos[key][c]);
+      }
+    } else {
+      // ---- dK += dS^T Q and dV += (P keep)^T dO: warp slice = 16 keys x 32 dims, contraction over the CTA's 64 queries
+      const int mt = w & 1, dh = w >> 1;
+      float dkacc[4][4], dvacc[4][4];
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dkacc[jd][e] = 0.f; dvacc[jd][e] = 0.f; }
+      const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int qrow = 16 * ks + rr + 8 * (mi >> 1), kcol = 16 * mt + 8 * (mi & 1);
+        uint32_t sh[4], ph[4];
+        ldmatrix_x4_trans(sh[0], sh[1], sh[2], sh[3], &sm.dS[qrow][kcol]);
+        ldmatrix_x4_trans(ph[0], ph[1], ph[2], ph[3], &sm.P[qrow][kcol]);
+#pragma unroll
+        for (int jd = 0; jd < 4; ++jd) {
+          uint32_t qh0, qh1, gh0, gh1;
+          ldmatrix_x2_trans(qh0, qh1, &sm.Q[16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          ldmatrix_x2_trans(gh0, gh1, &sm.dO[0][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          mma16816(dkacc[jd], sh, qh0, qh1);
+          mma16816(dvacc[jd], ph, gh0, gh1);
+        }
+      }
+      const int key0 = k0 + 16 * mt + g, key1 = key0 + 8;
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd) {
+        const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
+        if (key0 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
+          atomicAdd(dk + off, dkacc[jd][0]); atomicAdd(dk + off + 1, dkacc[jd][1]);
+          atomicAdd(dv + off, dvacc[jd][0]); atomicAdd(dv + off + 1, dvacc[jd][1]);
+        }
+        if (key1 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
+          atomicAdd(dk + off, dkacc[jd][2]); atomicAdd(dk + off + 1, dkacc[jd][3]);
+          atomicAdd(dv + off, dvacc[jd][2]); atomicAdd(dv + off + 1, dvacc[jd][3]);
+        }
+      }
+    }
+  }
+  // ---- dQ
+  if (producer) {
+    if (ok0) {
+      float* row = dq + qoff + (int64_t)(q0 + r0) * cf.inner + 2 * t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4][ptid], sm.dQ[j * 4 + 1][ptid]);
+    }
+    if (ok1) {
+      float* row = dq + qoff + (int64_t)(q0 + r1) * cf.inner + 2 * t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4 + 2][ptid], sm.dQ[j * 4 + 3][ptid]);
+    }
+  }
+  // ---- CPB parameter partials of this CTA: [W1 32*CD][b1 32][W2 1024][b2 32][W3 OUT*32][b3 OUT]
+  __syncthreads();
+  float* const red = reinterpret_cast<float*>(&sm.P[0][0]);
+  static_assert(sizeof(WsBwdSmem<CD>::P) + sizeof(WsBwdSmem<CD>::dS) >= NRED * sizeof(float), "the reduction buffer aliases P + dS");
+  for (int i = tid; i < NRED; i += WS_THREADS) red[i] = 0.f;
+  __syncthreads();
+  {
+    float* rW1 = red; float* rb1 = rW1 + CPB_H * 2; float* rW2 = rb1 + CPB_H; float* rb2 = rW2 + CPB_H * CPB_H;
+    float* rw3 = rb2 + CPB_H; float* rb3 = rw3 + CPB_H;
+    if (producer) {
+      gb3 = warp_sum(gb3);
+      if (lane == 0) atomicAdd(rb3, gb3);
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int kk = 16 * mt + g;
+        if (t == 0) {
+          atomicAdd(&rW1[kk * 2], gL1[mt][0]); atomicAdd(&rW1[kk * 2 + 1], gL1[mt][1]);
+          atomicAdd(&rW1[(kk + 8) * 2], gL1[mt][2]); atomicAdd(&rW1[(kk + 8) * 2 + 1], gL1[mt][3]);
+        } else if (t == 1) {
+          atomicAdd(&rb1[kk], gL1[mt][0]); atomicAdd(&rb1[kk + 8], gL1[mt][2]);
+          atomicAdd(&rb2[kk], gX2[mt][0]); atomicAdd(&rb2[kk + 8], gX2[mt][2]);
+          atomicAdd(&rw3[kk], gX3[mt][1]); atomicAdd(&rw3[kk + 8], gX3[mt][3]);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+          const int c = 16 * mt + g, kk = 8 * jn + 2 * t;
+          atomicAdd(&rW2[c * CPB_H + kk], gW2[mt][jn][0]); atomicAdd(&rW2[c * CPB_H + kk + 1], gW2[mt][jn][1]);
+          atomicAdd(&rW2[(c + 8) * CPB_H + kk], gW2[mt][jn][2]); atomicAdd(&rW2[(c + 8) * CPB_H + kk + 1], gW2[mt][jn][3]);
+        }
+    }
+  }
+  __syncthreads();
+  {
+    const int np = CPB_H * CD + CPB_H + CPB_H * CPB_H + CPB_H + cf.OUT * CPB_H + cf.OUT;
+    float* prow = part + ((int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * np;
+    const float* rW1 = red; const float* rb1 = rW1 + CPB_H * 2; const float* rW2 = rb1 + CPB_H;
+    const float* rb2 = rW2 + CPB_H * CPB_H; const float* rw3 = rb2 + CPB_H; const float* rb3 = rw3 + CPB_H;
+    for (int i = tid; i < np; i += WS_THREADS) {
+      int e = i;
+      float val;
+      if (e < CPB_H * CD) val = rW1[(e / CD) * 2 + (e % CD)];
+      else if ((e -= CPB_H * CD) < CPB_H) val = rb1[e];
+      else if ((e -= CPB_H) < CPB_H * CPB_H) val = rW2[e];
+      else if ((e -= CPB_H * CPB_H) < CPB_H) val = rb2[e];
+      else if ((e -= CPB_H) < cf.OUT * CPB_H) val = (e / CPB_H == o) ? rw3[e % CPB_H] : 0.f;
+      else { e -= cf.OUT * CPB_H; val = (e == o) ? rb3[0] : 0.f; }
+      prow[i] = val;
+    }
+  }
+}
+
 }  // namespace sml
 
 using namespace sml;
@@ -1714,16 +2288,39 @@ static int launch_bwd_lean(const AttnCfg& cf, const float* q, const float* k, co
   return 0;
 }
 
+template <int CD>
+static int launch_bwd_ws(const AttnCfg& cf, const float* q, const float* k, const float* v, const float* vs, const float* cpb,
+                         const float* out, const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs,
+                         float* part, void* stream) {
+  dim3 grid((cf.n + MQ - 1) / MQ, cf.heads, cf.B);
+  const size_t smem = sizeof(WsBwdSmem<CD>);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(deform_attn_bwd_ws_kernel<CD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  deform_attn_bwd_ws_kernel<CD><<<grid, WS_THREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part);
+  SML_LAUNCH_OK("sml_deform_attn_bwd_tc (warp-specialised)");
+  return 0;
+}
+
 /* same contract as sml_deform_attn_bwd (dk, dv, dvs zero-initialised; part [sml_deform_attn_bwd_blocks, nparams]);
- * split as in sml_deform_attn_fwd_tc */
+ * split as in sml_deform_attn_fwd_tc; split = 5: plain bf16, warp-specialised producer / consumer variant (experimental) */
 extern "C" int sml_deform_attn_bwd_tc(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k,
                                       const float* v, const float* vs, const float* cpb, const float* out, const float* lse,
                                       const float* dout, float* dq, float* dk, float* dv, float* dvs, float* part, int32_t split,
                                       void* stream) {
   AttnCfg cf;
   if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
-  if (split == 0) return cf.CD == 2 ? launch_bwd_lean<2, 1>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
-                                    : launch_bwd_lean<1, 1>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
+  // split = 5: the warp-specialised producer / consumer variant (correct, parity-tested through this entry; measured 77 ms
+  // against 49.5 ms for the lean kernel at B = 8 / 16 k: at 128 registers per thread both roles spill and the hand-over
+  // costs more than the doubled occupancy returns - see DESIGN.md 3.1)
+  if (split == 5 && (cf.CD == 1 || cf.W >= 10))      // y table: a 64-token tile spans <= 8 lattice rows
+    return cf.CD == 2 ? launch_bwd_ws<2>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
+                      : launch_bwd_ws<1>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
+  if (split == 0 || split == 4 || split == 5)
+    return cf.CD == 2 ? launch_bwd_lean<2, 1>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
+                      : launch_bwd_lean<1, 1>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
   if (cf.CD == 2) return split == 1 ? launch_bwd<2, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)
                                     : launch_bwd<2, false>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream);
   return split == 1 ? launch_bwd<1, true>(cf, q, k, v, vs, cpb, out, lse, dout, dq, dk, dv, dvs, part, stream)

@@ -413,3 +413,33 @@ def test_gather_sorted_scatter_large(case):
     want_dx2 = feat.grad.view(b, G, cg, H, W).permute(0, 3, 4, 1, 2).reshape(b, H * W, G * cg)
     assert rel_err(outs[0][0], want_dx2) < tol
     assert rel_err(outs[0][1], gxy.grad.view(b * G, nkv, CD)) < max(tol, 1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 2500, 144, 50, 2), (1, 16384, 1024, 128, 2), (2, 2501, 625, 0, 1)])
+def test_deform_bwd_warp_specialised_matches_lean(shape):
+    """the producer / consumer backward (split code 5) against the lean backward (split code 0): same inputs, same dropout hash,
+    every output (d q, d k, d v, key-coordinate gradients, summed bias-MLP partials)"""
+    from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
+    b, T, nkv, side, cd = shape
+    heads = 8
+    G = 8 if cd == 2 else 4
+    torch.manual_seed(6)
+    q = torch.randn(b, T, heads * 64, device="cuda") * 0.3
+    k = torch.randn(b, nkv, heads * 64, device="cuda"); v = torch.randn(b, nkv, heads * 64, device="cuda")
+    vs = torch.rand(b * G, nkv, cd, device="cuda") * 2.4 - 1.2
+    npar = lib.sml_deform_cpb_nparams(c_i32(cd), c_i32(heads // G))
+    cpb = torch.randn(npar, device="cuda") * 0.4
+    cfg = (c_i32 * 8)(b, heads, T, nkv, G, cd, side, 64)
+    out = torch.empty(b, T, heads * 64, device="cuda"); lse = torch.empty(b, heads, T, device="cuda")
+    check(lib.sml_deform_attn_fwd_tc(cfg, c_f32(0.1), c_u64(7), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse), c_i32(0), stream()))
+    dout = torch.randn_like(out)
+    res = {}
+    for code in (0, 5):
+        dq = torch.empty_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v); dvs = torch.zeros_like(vs)
+        part = torch.empty(lib.sml_deform_attn_bwd_blocks(cfg), npar, device="cuda")
+        check(lib.sml_deform_attn_bwd_tc(cfg, c_f32(0.1), c_u64(7), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse), ptr(dout),
+                                         ptr(dq), ptr(dk), ptr(dv), ptr(dvs), ptr(part), c_i32(code), stream()))
+        torch.cuda.synchronize()
+        res[code] = (dq, dk, dv, dvs, part.sum(0))
+    for a, bb, tol in zip(res[0], res[5], (1e-5, 1e-4, 1e-4, 1e-3, 2e-3)):
+        assert rel_err(bb, a) < tol, rel_err(bb, a)
