@@ -467,8 +467,8 @@ class Fc1ClsFn(torch.autograd.Function):
             dmain[:, :add] += dh[:, 1 + n:]
         g = torch.empty(B, n, D, device=dh.device, dtype=F32)
         for bi in range(B):
-            hb, db_ = h[bi, 1:1 + n], dmain[bi]
-            check(lib.sml_relu_bwd(ptr(hb), ptr(db_.contiguous()), ptr(g[bi]), ops.c_i64(n * D), stream()), "relu_bwd")
+            hb, db_ = h[bi, 1:1 + n], dmain[bi].contiguous()       # bound to a local: alive until the launch is enqueued
+            check(lib.sml_relu_bwd(ptr(hb), ptr(db_), ptr(g[bi]), ops.c_i64(n * D), stream()), "relu_bwd")
         g2 = g.view(B * n, D)
         g_op = _prep(g2, mode)
         x_op = xo if xo is not None else x.view(B * n, K)
