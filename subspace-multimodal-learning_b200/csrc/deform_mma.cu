@@ -1553,13 +1553,13 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
         const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
         if (key0 < cf.nkv) {
           const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
-          atomicAdd(dk + off, dkacc[jd][0]); atomicAdd(dk + off + 1, dkacc[jd][1]);
-          atomicAdd(dv + off, dvacc[jd][0]); atomicAdd(dv + off + 1, dvacc[jd][1]);
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][0], dkacc[jd][1]));     // red.global.add.v2.f32
+          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][0], dvacc[jd][1]));
         }
         if (key1 < cf.nkv) {
           const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
-          atomicAdd(dk + off, dkacc[jd][2]); atomicAdd(dk + off + 1, dkacc[jd][3]);
-          atomicAdd(dv + off, dvacc[jd][2]); atomicAdd(dv + off + 1, dvacc[jd][3]);
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][2], dkacc[jd][3]));
+          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][2], dvacc[jd][3]));
         }
       }
     }
@@ -2127,13 +2127,13 @@ __global__ void __launch_bounds__(WS_THREADS, 2) deform_attn_bwd_ws_kernel(
         const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
         if (key0 < cf.nkv) {
           const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
-          atomicAdd(dk + off, dkacc[jd][0]); atomicAdd(dk + off + 1, dkacc[jd][1]);
-          atomicAdd(dv + off, dvacc[jd][0]); atomicAdd(dv + off + 1, dvacc[jd][1]);
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][0], dkacc[jd][1]));     // red.global.add.v2.f32
+          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][0], dvacc[jd][1]));
         }
         if (key1 < cf.nkv) {
           const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
-          atomicAdd(dk + off, dkacc[jd][2]); atomicAdd(dk + off + 1, dkacc[jd][3]);
-          atomicAdd(dv + off, dvacc[jd][2]); atomicAdd(dv + off + 1, dvacc[jd][3]);
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][2], dkacc[jd][3]));
+          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][2], dvacc[jd][3]));
         }
       }
     }
