@@ -38,15 +38,19 @@ class NystromAttention(nn.Module):
         self.precision = None      # None -> module-level DEFAULT_PRECISION
 
     def forward(self, x, mask=None, return_attn=False):
-        if mask is not None or return_attn:
-            raise NotImplementedError("sml_b200 NystromAttention: mask / return_attn are never used by the reference "
-                                      "call sites (mil.py:186, cmta_utils.py:872) and are not implemented")
+        if mask is not None:
+            raise NotImplementedError("sml_b200 NystromAttention: mask is never passed by the reference call sites "
+                                      "(mil.py:186, cmta_utils.py:872) and is not implemented")
         if not self.residual:
             raise NotImplementedError("sml_b200 NystromAttention: residual=False is not on the reference path")
         y = nystrom_attention(x.float(), self.to_qkv.weight, self.to_out[0].weight, self.to_out[0].bias,
                               self.res_conv.weight, self.heads, self.num_landmarks, self.pinv_iterations,
                               self.precision or DEFAULT_PRECISION)
-        return Fn.dropout_add(None, y, self.to_out[1].p, self.training)
+        out = Fn.dropout_add(None, y, self.to_out[1].p, self.training)
+        if return_attn:                                     # :153-155 (detached, exact-fp32 engine; inspection only)
+            from ..nystrom import nystrom_attn_map
+            return out, nystrom_attn_map(x.detach().float(), self.to_qkv.weight, self.heads, self.num_landmarks, self.pinv_iterations)
+        return out
 
     def landmark_ids(self, n, device="cuda"):
         """int32 landmark id of each (front-padded) token: t // ceil(n/m) — the bit-exact index contract."""

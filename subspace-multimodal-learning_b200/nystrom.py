@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 from ._lib import c_i32, check, lib, ptr, stream
-from .ops import F32, TB, mm
+from .ops import F32, TB, gemm, mm
 
 PRECISIONS = ("fp32", "bf16x3", "bf16")
 # Run the Moore-Penrose GEMM chains as single persistent cooperative launches (sml_gemm_tc_program).  Measured on B200 at
@@ -379,6 +379,33 @@ class NystromAttentionFn(torch.autograd.Function):
         else:
             dx = dxp[:, pad:]
         return dx, dw_qkv, dw_out, db_out, dw_conv, dln_w, dln_b, None, None, None, None, None, None
+
+
+@torch.no_grad()
+def nystrom_attn_map(x, w_qkv, heads, m, iters):
+    """``return_attn=True`` of NystromAttention.forward (NystromAttention.py:153-155): the dense approximate attention map
+    A1 . A2^+ . A3 [b, h, n', n'] over the front-padded tokens.  Inspection only (no caller in the reference uses it): evaluated
+    on the exact-fp32 engine, detached from autograd; n'^2 floats per head, so meant for small bags."""
+    ops.require_cuda(x, w_qkv)
+    b, n, D = x.shape
+    inner = w_qkv.shape[0] // 3
+    h, d = heads, inner // heads
+    pad = (m - n % m) % m
+    npad = n + pad
+    dev = x.device
+    xp = torch.zeros(b, npad, D, device=dev, dtype=F32)
+    xp[:, pad:] = x
+    weff = w_qkv.detach().clone()
+    ops.axpby_(weff[:inner], w_qkv.detach()[:inner].contiguous(), d ** -0.5, 0.0)
+    qkv = torch.empty(b, npad, 3, h, d, device=dev, dtype=F32)
+    gemm(xp.view(b * npad, D), weff.t(), out=qkv.view(b * npad, 3 * inner))
+    ql, kl = landmarks_fwd(qkv, b, npad, h, d, m)
+    q, k = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(2))
+    a1 = gemm(q, kl.transpose(-1, -2)); ops.softmax_(a1.view(-1, m))
+    a2 = gemm(ql, kl.transpose(-1, -2)); ops.softmax_(a2.view(-1, m))
+    a3 = gemm(ql, k.transpose(-1, -2)); ops.softmax_(a3.view(-1, npad))
+    z, _ = pinv_fwd(a2, iters, "fp32")
+    return gemm(gemm(a1, z.f), a3)
 
 
 def fused_cvt_ok(ksize):

@@ -180,3 +180,19 @@ def test_translayer_training_mode_skip_and_dropout():
     want_db = kept.float().sum(dim=(0, 1)) / 0.9
     assert rel_err(tl.attn.to_out[0].bias.grad, want_db) < 1e-4
     assert torch.isfinite(xg.grad).all() and float((xg.grad - 1).abs().max()) > 0          # skip gradient (1) + attention path
+
+
+def test_return_attn_map():
+    """NystromAttention(..., return_attn=True): second output = A1 A2^+ A3 over the padded tokens (NystromAttention.py:153-155)"""
+    import sml_b200
+    torch.manual_seed(4)
+    mod = sml_b200.NystromAttention(dim=128, dim_head=16, heads=8, num_landmarks=32, pinv_iterations=6).cuda().eval()
+    x = randn((2, 200, 128), 611)
+    p = {k: v.detach().cpu().double() for k, v in mod.state_dict().items()}
+    yo, parts = oracle.nystrom.nystrom_attention(x.double(), p, heads=8, num_landmarks=32, pinv_iterations=6, return_parts=True)
+    want = (parts["a1"] @ parts["z"]) @ parts["a3"]
+    y, attn = mod(x.cuda(), return_attn=True)
+    assert attn.shape == (2, 8, 224, 224)
+    assert rel_err(attn, want) < 1e-4 and rel_err(y, yo) < 1e-4
+    with pytest.raises(NotImplementedError):
+        mod(x.cuda(), mask=torch.ones(2, 200, dtype=torch.bool, device="cuda"))
