@@ -7,6 +7,8 @@ rank statistic, and the host reads seven scalars at the end -- one synchronisati
 return tuple and definitions (macro averages over the labels that occur, one-vs-rest AUC, 0 when a class is absent as the
 reference's ``except ValueError`` branch does), so ``train_test.py:263-290`` can call it unchanged.
 """
+import threading
+
 import torch
 import torch.nn.functional as F
 
@@ -103,3 +105,63 @@ def epochVal(model, dataLoader, args):
     res = compute_avg_metrics(gt[:fill], act[:fill])
     model.train(training)
     return res
+
+
+class AsyncEvaluator:
+    """Periodic evaluation that does not stall the train loop (reference: train_test.py:195-250 evaluates on rank 0
+    every 10 iterations *inside* the loop, so every rank waits for it at the next collective).
+
+    ``submit(model, tag)`` snapshots the weights into a shadow model on a side stream (ordered after everything already
+    enqueued on the training stream) and runs ``epochVal`` over ``make_loader()`` on that stream from a worker thread;
+    training continues on its own stream.  ``poll()`` returns the finished ``(tag, metrics)`` pairs, ``wait()`` blocks for the
+    one in flight.  One evaluation at a time: ``submit`` while one is running returns False (the reference would have blocked).
+    """
+
+    def __init__(self, shadow_model, make_loader, args):
+        self.shadow, self.make_loader, self.args = shadow_model.eval(), make_loader, args
+        self.dev = next(shadow_model.parameters()).device
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.thread, self.done, self.error = None, [], None
+        self._lock = threading.Lock()
+
+    def busy(self):
+        return self.thread is not None and self.thread.is_alive()
+
+    def submit(self, model, tag=None):
+        if self.busy():
+            return False
+        src = (model.module if hasattr(model, "module") else model).state_dict()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            self.stream.wait_event(ev)
+            for k, v in self.shadow.state_dict().items():
+                v.copy_(src[k], non_blocking=True)
+        # the optimizer must not overwrite the weights while the snapshot copies read them
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+
+        def run():
+            try:
+                torch.cuda.set_device(self.dev)
+                with torch.cuda.stream(self.stream):
+                    res = epochVal(self.shadow, self.make_loader(), self.args)
+                with self._lock:
+                    self.done.append((tag, res))
+            except Exception as e:                           # noqa: BLE001 - surfaced by poll() / wait()
+                self.error = e
+        self.thread = threading.Thread(target=run, daemon=True)
+        self.thread.start()
+        return True
+
+    def poll(self):
+        if self.error is not None:
+            e, self.error = self.error, None
+            raise e
+        with self._lock:
+            out, self.done = self.done, []
+        return out
+
+    def wait(self):
+        if self.thread is not None:
+            self.thread.join()
+        return self.poll()

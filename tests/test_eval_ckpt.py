@@ -109,3 +109,45 @@ def test_epoch_val_on_device(tmp_path):
     want = compute_avg_metrics(torch.from_numpy(lab[:, 5]), torch.cat(outs).cpu())
     assert np.allclose(got, want, atol=1e-6), (got, want)
     sh.close()
+
+
+@pytest.mark.gpu
+def test_async_evaluator_runs_beside_training(tmp_path):
+    """AsyncEvaluator: the evaluation of a weight snapshot runs on a side stream while the train loop keeps stepping; its
+    metrics equal the synchronous epochVal of a model holding the snapshot"""
+    import copy
+    import sml_b200
+    from argparse import Namespace
+    from sml_b200.utils.evaluate import AsyncEvaluator, epochVal
+    margs = Namespace(init_type="max", input_size_omic_tumor=59, input_size_omic_immune=361, omic_dim=128, path_dim=128, mmhid=128,
+                      return_grad="False", dropout_rate=0.1, label_dim=4, fusion_type="concat", cut_fuse_grad=False,
+                      return_vgrid=False, attn_dim=2, task_type="diag2021")
+    torch.manual_seed(1)
+    net = sml_b200.DeformPathomicNet(margs).cuda().train(); net.set_precision("bf16")
+    shadow = sml_b200.DeformPathomicNet(margs).cuda(); shadow.set_precision("bf16")
+    rng = np.random.default_rng(3)
+    n = 4
+    lab = rng.integers(0, 4, (n, 12)); lab[:4, 5] = np.arange(4)
+    path = os.path.join(tmp_path, "val.bag")
+    sml_b200.data.pack_bags(path, rng.standard_normal((n, 2500, 1024)).astype(np.float32), omic=rng.random((n, 431)),
+                            omic_tumor=rng.random((n, 59)), omic_immune=rng.random((n, 361)), labels=lab)
+    sh = sml_b200.data.BagShard.open(path)
+    mk = lambda: sml_b200.data.BagLoader(sh, 2, "cuda", shuffle=False, drop_last=False)
+    ev = AsyncEvaluator(shadow, mk, Namespace(task_type="diag2021"))
+    snap = copy.deepcopy(net.state_dict())
+    assert ev.submit(net, tag=0)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    x = torch.randn(2, 2500, 1024, device="cuda"); xt = torch.rand(2, 59, device="cuda"); xi = torch.rand(2, 361, device="cuda")
+    y = torch.tensor([0, 2], device="cuda")
+    for _ in range(3):                                       # training goes on (and changes the weights) while the eval runs
+        opt.zero_grad(set_to_none=True)
+        lg = net(x_path=x, x_omic_tumor=xt, x_omic_immune=xi)[3][2]
+        torch.nn.functional.cross_entropy(lg, y).backward()
+        opt.step()
+    (tag, got), = ev.wait()
+    assert tag == 0 and not ev.busy()
+    ref = sml_b200.DeformPathomicNet(margs).cuda(); ref.set_precision("bf16"); ref.load_state_dict(snap)
+    want = epochVal(ref, mk(), Namespace(task_type="diag2021"))
+    assert np.allclose(got, want, atol=1e-6), (got, want)
+    assert any(float((a - b).abs().max()) > 0 for a, b in zip(net.state_dict().values(), snap.values()))   # weights did move
+    sh.close()
