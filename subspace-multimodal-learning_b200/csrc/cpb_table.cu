@@ -117,6 +117,92 @@ __global__ void __launch_bounds__(PWL_THREADS) cpb1d_table_build_kernel(const fl
   }
 }
 
+// ---- parameter gradients from per-segment sums (oracle/pwl.py:param_grads_from_segments).  On segment s the ReLU pattern
+// (m1 of layer 1, m2 of layer 2) is fixed, so bias_o(t) = sum_c W3[o,c] m2_c (A_c t + C_c) + b3_o with
+// A_c = sum_k W2[c,k] m1_k w1_k, C_c = sum_k W2[c,k] m1_k b1_k + b2_c, and every d bias / d parameter is affine in t.  With
+// G0[s,o] = sum dS and G1[s,o] = sum dS t over the segment's pairs (accumulated by deform_attn_bwd_pwl_kernel):
+//   u0[s,c] = m2_c sum_o W3[o,c] G0[s,o], u1 likewise with G1          (gradient reaching layer 2's pre-activation c)
+//   d b3_o = sum_s G0          d W3[o,c] = sum_s m2_c (A_c G1 + C_c G0)          d b2_c = sum_s u0
+//   acc0[c,k] = sum_s m1_k u0[s,c], acc1 likewise       d W2[c,k] = w1_k acc1 + b1_k acc0
+//   d b1_k = sum_c W2[c,k] acc0[c,k]                    d w1_k = sum_c W2[c,k] acc1[c,k]
+// One block of 1024 threads = the (c, k) pairs; segments are walked in chunks of 32.
+constexpr int PWL_SEG_STRIDE = 1090;         // rows of gseg per output: 32 + 33*32 + 1 segments, + 1 spare
+__global__ void __launch_bounds__(PWL_THREADS) cpb1d_table_bwd_kernel(const float* __restrict__ cpb, int OUT,
+                                                                      const float* __restrict__ brk, const int* __restrict__ nseg,
+                                                                      const float* __restrict__ gseg, float* __restrict__ dcpb) {
+  __shared__ float sw1[PWL_H], sb1[PWL_H], sW2[PWL_H * PWL_H], sb2[PWL_H], sW3[2 * PWL_H];
+  __shared__ float u0[32][PWL_H], u1[32][PWL_H], Au[32][PWL_H], Cu[32][PWL_H];
+  __shared__ float g0[32][2], g1[32][2];
+  __shared__ unsigned m1s[32];
+  __shared__ float red0[PWL_H][PWL_H + 1], red1[PWL_H][PWL_H + 1];
+  const int tid = threadIdx.x;
+  const int c = tid >> 5, k = tid & 31;        // my (layer-2 unit, layer-1 unit) pair; in phase A: (segment of the chunk, unit)
+  const CpbView v = cpb_view(cpb, OUT);
+  sW2[tid] = v.W2[tid];
+  if (tid < PWL_H) { sw1[tid] = v.w1[tid]; sb1[tid] = v.b1[tid]; sb2[tid] = v.b2[tid]; }
+  if (tid < OUT * PWL_H) sW3[tid] = v.W3[tid];
+  const int ns = nseg[0], nb = ns - 1;
+  float acc0 = 0.f, acc1 = 0.f;                // threads (c, k): sums for W2
+  float aux0 = 0.f, aux1 = 0.f;                // threads < 32: d b2; threads 32 .. 32 + OUT*32: d W3; threads 128 .. 128 + OUT: d b3
+  __syncthreads();
+  for (int s0 = 0; s0 < ns; s0 += 32) {
+    {                                          // phase A: thread (sl, cc) = (tid >> 5, tid & 31)
+      const int sl = tid >> 5, cc = tid & 31, s = s0 + sl;
+      float U0 = 0.f, U1 = 0.f, AA = 0.f, CC = 0.f;
+      unsigned m1 = 0u;
+      if (s < ns) {
+        const float lo = s == 0 ? -CUDART_INF_F : brk[s - 1], hi = s == nb ? CUDART_INF_F : brk[s];
+        const float tm = seg_mid(lo, hi);
+        float A, C;
+        affine2(sw1, sb1, sW2 + cc * PWL_H, sb2[cc], tm, A, C);
+        m1 = __ballot_sync(0xffffffffu, fmaf(sw1[cc], tm, sb1[cc]) > 0.f);
+        if (fmaf(A, tm, C) > 0.f) {
+          AA = A; CC = C;
+          for (int o = 0; o < OUT; ++o) {
+            const float G0 = gseg[((int64_t)o * PWL_SEG_STRIDE + s) * 2], G1 = gseg[((int64_t)o * PWL_SEG_STRIDE + s) * 2 + 1];
+            U0 = fmaf(sW3[o * PWL_H + cc], G0, U0); U1 = fmaf(sW3[o * PWL_H + cc], G1, U1);
+          }
+        }
+      }
+      u0[sl][cc] = U0; u1[sl][cc] = U1; Au[sl][cc] = AA; Cu[sl][cc] = CC;
+      if (cc == 0) m1s[sl] = m1;
+      if (cc < 2) {
+        const bool ok = s < ns && cc < OUT;
+        g0[sl][cc] = ok ? gseg[((int64_t)cc * PWL_SEG_STRIDE + s) * 2] : 0.f;
+        g1[sl][cc] = ok ? gseg[((int64_t)cc * PWL_SEG_STRIDE + s) * 2 + 1] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int sl = 0; sl < 32; ++sl) {          // phase B
+      if ((m1s[sl] >> k) & 1u) { acc0 += u0[sl][c]; acc1 += u1[sl][c]; }
+    }
+    if (tid < PWL_H) {
+      for (int sl = 0; sl < 32; ++sl) aux0 += u0[sl][tid];
+    } else if (tid < PWL_H + OUT * PWL_H) {
+      const int o = (tid - PWL_H) >> 5, cc = tid & 31;
+      for (int sl = 0; sl < 32; ++sl) aux0 = fmaf(Au[sl][cc], g1[sl][o], fmaf(Cu[sl][cc], g0[sl][o], aux0));
+    } else if (tid >= 128 && tid < 128 + OUT) {
+      for (int sl = 0; sl < 32; ++sl) aux1 += g0[sl][tid - 128];
+    }
+    __syncthreads();
+  }
+  // parameter order: w1 [32], b1 [32], W2 [32 x 32], b2 [32], W3 [OUT x 32], b3 [OUT]
+  float* dw1 = dcpb; float* db1 = dw1 + PWL_H; float* dW2 = db1 + PWL_H; float* db2 = dW2 + PWL_H * PWL_H;
+  float* dW3 = db2 + PWL_H; float* db3 = dW3 + OUT * PWL_H;
+  dW2[tid] = fmaf(sw1[k], acc1, sb1[k] * acc0);
+  red0[c][k] = sW2[tid] * acc0; red1[c][k] = sW2[tid] * acc1;
+  if (tid < PWL_H) db2[tid] = aux0;
+  else if (tid < PWL_H + OUT * PWL_H) dW3[tid - PWL_H] = aux0;
+  else if (tid >= 128 && tid < 128 + OUT) db3[tid - 128] = aux1;
+  __syncthreads();
+  if (tid < PWL_H) {
+    float a = 0.f, b = 0.f;
+    for (int cc = 0; cc < PWL_H; ++cc) { a += red0[cc][tid]; b += red1[cc][tid]; }
+    db1[tid] = a; dw1[tid] = b;
+  }
+}
+
 // segment index of t: number of breakpoints <= t
 __device__ __forceinline__ int pwl_segment(const float* __restrict__ brk, int nb, float t) {
   int lo = 0, hi = nb;
@@ -144,6 +230,17 @@ extern "C" int sml_cpb1d_table_build(const float* cpb, int32_t OUT, float* brk, 
   SML_CHECK(OUT >= 1 && OUT <= 2, "sml_cpb1d_table_build: heads per group must be 1 or 2 (got %d)", OUT);
   cpb1d_table_build_kernel<<<1, PWL_THREADS, 0, as_stream(stream)>>>(cpb, OUT, brk, coef, nseg);
   SML_LAUNCH_OK("sml_cpb1d_table_build");
+  return 0;
+}
+/* rows per output of the segment-sum buffer gseg [OUT, rows, 2] of sml_deform_attn_bwd_pwl / sml_cpb1d_table_bwd */
+extern "C" int sml_cpb1d_seg_rows(void) { return PWL_SEG_STRIDE; }
+/* dcpb [sml_deform_cpb_nparams(1, OUT)] (overwritten) = gradient of the bias-MLP parameters from the per-segment sums */
+extern "C" int sml_cpb1d_table_bwd(const float* cpb, int32_t OUT, const float* brk, const int32_t* nseg, const float* gseg, float* dcpb,
+                                   void* stream) {
+  SML_CHECK(cpb && brk && nseg && gseg && dcpb, "sml_cpb1d_table_bwd: null pointer");
+  SML_CHECK(OUT >= 1 && OUT <= 2, "sml_cpb1d_table_bwd: heads per group must be 1 or 2 (got %d)", OUT);
+  cpb1d_table_bwd_kernel<<<1, PWL_THREADS, 0, as_stream(stream)>>>(cpb, OUT, brk, nseg, gseg, dcpb);
+  SML_LAUNCH_OK("sml_cpb1d_table_bwd");
   return 0;
 }
 extern "C" int sml_cpb1d_table_eval(const float* t, int64_t n, const float* brk, const float* coef, const int32_t* nseg, int32_t OUT,

@@ -1165,6 +1165,185 @@ __global__ void __launch_bounds__(MTHREADS, MINB) deform_attn_fwd_lean_kernel(co
 }
 
 
+// ---- 1-D bias MLP as an exact piecewise-linear table (csrc/cpb_table.cu; specification oracle/pwl.py): for one coordinate the
+// MLP Linear(1,32) ReLU Linear(32,32) ReLU Linear(32,o) is a continuous piecewise-linear function of the signed-log distance
+// with <= 1089 segments (65-70 for typical parameters), so the per-pair bias is slope[s] p + icpt[s]: no MMA, ~10 instructions
+// per pair instead of ~65 per 16-pair tile x 16.  Forward kernel = the lean forward with the MLP block replaced by the lookup.
+constexpr int PWL_MAXSEG = 1089;
+constexpr int PWL_CELLS = 1024;          // uniform acceleration grid over the reachable distances |p| <= PWL_PMAX
+constexpr float PWL_PMAX = 1.25f;        // log(3 + eps): normalised positions lie in [-1, 1], offsets add a few grid units
+struct PwlTable {
+  float B[PWL_MAXSEG + 1];               // segment s covers [B[s], B[s + 1]); B[0] = -inf, B[nseg] = +inf
+  float2 co[PWL_MAXSEG];                 // (slope, intercept) of this head's output
+  unsigned short cell[PWL_CELLS];        // segment that contains the left edge of grid cell c
+};
+// segment of p: start from the grid cell's segment, then step (cells hold ~0.06 breakpoints on average, so both loops
+// normally exit at once; any p, even outside the grid, ends in the right segment)
+__device__ __forceinline__ int pwl_seek(const PwlTable& tb, float p) {
+  int c = (int)((p + PWL_PMAX) * (PWL_CELLS / (2.f * PWL_PMAX)));
+  c = min(max(c, 0), PWL_CELLS - 1);
+  int s = tb.cell[c];
+  while (p < tb.B[s]) --s;
+  while (p >= tb.B[s + 1]) ++s;
+  return s;
+}
+__device__ __forceinline__ void pwl_load(PwlTable& tb, const float* __restrict__ brk, const float* __restrict__ coef, int nb, int OUT,
+                                         int o, int tid, int nthreads) {
+  for (int i = tid; i <= nb + 1; i += nthreads) tb.B[i] = i == 0 ? -INFINITY : (i <= nb ? brk[i - 1] : INFINITY);
+  for (int i = tid; i <= nb; i += nthreads)
+    tb.co[i] = make_float2(coef[((int64_t)i * OUT + o) * 2], coef[((int64_t)i * OUT + o) * 2 + 1]);
+  for (int c = tid; c < PWL_CELLS; c += nthreads) {           // number of breakpoints <= left edge of the cell
+    const float edge = -PWL_PMAX + c * (2.f * PWL_PMAX / PWL_CELLS);
+    int lo = 0, hi = nb;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (brk[m] <= edge) lo = m + 1; else hi = m; }
+    tb.cell[c] = (unsigned short)lo;
+  }
+}
+struct PwlFwdSmem {
+  __nv_bfloat16 Q[MQ][MLD], K[64][MLD], V[2][64][MLD];
+  LeanTab<1, 64> tb;
+  PwlTable pw;
+};
+__global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const AttnCfg cf, const float* __restrict__ q,
+                                                                            const float* __restrict__ k, const float* __restrict__ v,
+                                                                            const float* __restrict__ vs, const float* __restrict__ cpb, const float* __restrict__ brk,
+                                                                            const float* __restrict__ coef, const int* __restrict__ nseg,
+                                                                            float* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int CD = 1;
+  PwlFwdSmem& sm = *reinterpret_cast<PwlFwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
+  const int grp = head / cf.OUT, o = head % cf.OUT;
+  const int bg = b * cf.G + grp;
+  // piecewise-linear table of the bias MLP for this head's output o (csrc/cpb_table.cu): segment s covers [B[s], B[s + 1])
+  pwl_load(sm.pw, brk, coef, nseg[0] - 1, cf.OUT, o, tid, MTHREADS);
+  load_tile<false, MQ>(sm.Q, nullptr, q + (int64_t)b * cf.n * cf.inner + head * AD, cf.inner, q0, cf.n);
+  const int ny = lean_query_tables<CD, 64>(sm.tb, cf, q0);
+  const int r0 = w * 16 + g, r1 = r0 + 8;
+  const int ys0 = CD == 2 ? min(q0 + r0, cf.n - 1) / cf.W - q0 / cf.W : 0;
+  const int ys1 = CD == 2 ? min(q0 + r1, cf.n - 1) / cf.W - q0 / cf.W : 0;
+  float oacc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[j][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
+  const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
+  const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
+  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+
+  for (int k0 = 0; k0 < cf.nkv; k0 += 64) {
+    __syncthreads();
+    load_tile<false, 64>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
+    load_tile<true, 64>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
+    if (tid < 64) {
+      const bool ok = k0 + tid < cf.nkv;
+      sm.tb.kpos[tid][0] = ok ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD] : 0.f;
+      sm.tb.kpos[tid][1] = (ok && CD == 2) ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD + 1] : 0.f;
+    }
+    __syncthreads();
+    lean_tables<CD, 64>(sm.tb, ny);
+    // ---- S = b3 + Q K^T
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4];
+      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][16 * ks + 2 * t]);
+      ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][16 * ks + 2 * t]);
+      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][16 * ks + 2 * t + 8]);
+      ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][16 * ks + 2 * t + 8]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][16 * ks + 2 * t]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][16 * ks + 2 * t + 8]);
+        mma16816(s[j], ah, bh0, bh1);
+      }
+    }
+    __syncthreads();                                    // tables complete
+    // ---- + continuous position bias from the table: bias = slope[s] p + icpt[s]
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = 8 * j + 2 * t + e;
+        const float p0 = sm.tb.SX[key][r0], p1 = sm.tb.SX[key][r1];
+        const float2 c0 = sm.pw.co[pwl_seek(sm.pw, p0)], c1 = sm.pw.co[pwl_seek(sm.pw, p1)];
+        s[j][e] += fmaf(c0.x, p0, c0.y);
+        s[j][2 + e] += fmaf(c1.x, p1, c1.y);
+      }
+    // ---- online softmax on the fragments
+    float mt0 = -INFINITY, mt1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (k0 + 8 * j + 2 * t + e >= cf.nkv) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
+        mt0 = fmaxf(mt0, s[j][e]); mt1 = fmaxf(mt1, s[j][2 + e]);
+      }
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 1)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 1));
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 2)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 2));
+    const float mn0 = fmaxf(m0, mt0), mn1 = fmaxf(m1, mt1);
+    const float al0 = m0 == -INFINITY ? 0.f : __expf(m0 - mn0), al1 = m1 == -INFINITY ? 0.f : __expf(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= al0; l1 *= al1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { oacc[j][0] *= al0; oacc[j][1] *= al0; oacc[j][2] *= al1; oacc[j][3] *= al1; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float p0 = __expf(s[j][e] - mn0), p1 = __expf(s[j][2 + e] - mn1);
+        l0 += p0; l1 += p1;
+        if (cf.p_drop > 0.f) {
+          const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
+          p0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + key) >= thresh ? p0 * keep_scale : 0.f;
+          p1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + key) >= thresh ? p1 * keep_scale : 0.f;
+        }
+        s[j][e] = p0; s[j][2 + e] = p1;
+      }
+    // ---- O += P V (P as bf16 hi + lo: the backward's delta = dO . O relies on an fp32-grade O)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], al[4];
+      split2<true>(s[2 * ks][0], s[2 * ks][1], ah[0], al[0]);
+      split2<true>(s[2 * ks][2], s[2 * ks][3], ah[1], al[1]);
+      split2<true>(s[2 * ks + 1][0], s[2 * ks + 1][1], ah[2], al[2]);
+      split2<true>(s[2 * ks + 1][2], s[2 * ks + 1][3], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t bh0, bh1, bl0, bl1;
+        ldmatrix_x2_trans(bh0, bh1, &sm.V[0][16 * ks + (lane & 15)][8 * j]);
+        ldmatrix_x2_trans(bl0, bl1, &sm.V[1][16 * ks + (lane & 15)][8 * j]);
+        mma3<true>(oacc[j], ah, al, bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  if (q0 + r0 < cf.n) {
+    float* orow = out + ((int64_t)b * cf.n + q0 + r0) * cf.inner + head * AD + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][0] * i0, oacc[j][1] * i0);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0] = m0 + logf(l0);
+  }
+  if (q0 + r1 < cf.n) {
+    float* orow = out + ((int64_t)b * cf.n + q0 + r1) * cf.inner + head * AD + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][2] * i1, oacc[j][3] * i1);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1] = m1 + logf(l1);
+  }
+}
+
+
 // ---- lean backward (plain bf16 operands).  Same phases and outputs as deform_attn_bwd_mma_kernel<CD, false>; per key the
 // CUDA-core work drops from ~470 to ~250 warp instructions:
 //   * distances from the shared-memory tables (lean_tables); d slog / dx = exp(-|slog|)
@@ -1632,6 +1811,256 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
   }
 }
 
+
+// ---- 1-D backward with the tabulated bias (see PwlTable above).  No per-key MLP tiles: the warp's 16 rows x 32 keys are
+// processed as logit fragments, exactly like the forward.  Per element: p from the distance table, segment s, bias =
+// slope[s] p + icpt[s], P = exp(S + bias - lse), dS = P (dP keep - delta).  Bias-MLP gradients: per segment the sums
+// G0[s] = sum dS and G1[s] = sum dS p (run-length accumulated per query row, flushed to shared-memory bins when the segment
+// changes, added to the global [OUT, segments, 2] buffer at the end); the host maps them to the MLP parameters by
+// differentiating slope / intercept (functions of the parameters with the segment's fixed ReLU pattern).  Key-coordinate
+// gradient: d bias / d p = slope[s], d p / d kx = -exp(-|p|).  dQ / dK / dV as in the lean backward.
+struct PwlBwdSmem {
+  __nv_bfloat16 Q[MQ][MLD], dO[2][MQ][MLD];
+  __nv_bfloat16 K[BK][MLD], V[2][BK][MLD];
+  __nv_bfloat16 P[MQ][PLD], dS[MQ][PLD];
+  float dQ[32][MTHREADS];
+  float dkpos[BK];
+  LeanTab<1, BK> tb;
+  PwlTable pw;
+  float2 bins[PWL_MAXSEG];
+};
+
+__global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
+    const AttnCfg cf, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+    const float* __restrict__ vs, const float* __restrict__ brk, const float* __restrict__ coef, const int* __restrict__ nseg,
+    const float* __restrict__ out, const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq,
+    float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ gseg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PwlBwdSmem& sm = *reinterpret_cast<PwlBwdSmem*>(smem_raw);
+  constexpr int CD = 1;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
+  const int grp = head / cf.OUT, o = head % cf.OUT;
+  const int bg = b * cf.G + grp;
+  const int ns = nseg[0];
+  pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
+  for (int i = tid; i < ns; i += MTHREADS) sm.bins[i] = make_float2(0.f, 0.f);
+  const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
+  load_tile<false, MQ>(sm.Q, nullptr, q + qoff, cf.inner, q0, cf.n);
+  load_tile<true, MQ>(sm.dO[0], sm.dO[1], dout + qoff, cf.inner, q0, cf.n);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) sm.dQ[i][tid] = 0.f;
+  const int ny = lean_query_tables<CD, BK>(sm.tb, cf, q0);
+  const int r0 = w * 16 + g, r1 = r0 + 8;
+  const bool ok0 = q0 + r0 < cf.n, ok1 = q0 + r1 < cf.n;
+  float delta0 = 0.f, delta1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;
+  {
+    if (ok0) {
+      const float* orow = out + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta0 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta0))));
+      }
+      lse0 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0];
+    }
+    if (ok1) {
+      const float* orow = out + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+      const float* grow = dout + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
+        delta1 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta1))));
+      }
+      lse1 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1];
+    }
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 1); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 1);
+    delta0 += __shfl_xor_sync(0xffffffffu, delta0, 2); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 2);
+  }
+  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
+  const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
+  const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
+  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  // run-length accumulators of the per-segment sums, one run per query row
+  int seg0 = 0, seg1 = 0;
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;        // (G0, G1) of the current run of row r0 / r1
+
+  for (int k0 = 0; k0 < cf.nkv; k0 += BK) {
+    __syncthreads();
+    load_tile<false, BK>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
+    load_tile<true, BK>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
+    if (tid < BK) {
+      const bool ok = k0 + tid < cf.nkv;
+      sm.tb.kpos[tid][0] = ok ? vs[(int64_t)bg * cf.nkv + k0 + tid] : 0.f;
+      sm.tb.kpos[tid][1] = 0.f;
+      sm.dkpos[tid] = 0.f;
+    }
+    __syncthreads();
+    lean_tables<CD, BK>(sm.tb, ny);
+    // ---- S = Q K^T and dP = dO V^T (dO, V as hi + lo) of my 16 rows x the 32 keys of the tile
+    float s[4][4], dp[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s[j][e] = 0.f; dp[j][e] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4], gh[4], gl[4];
+      const int c0 = 16 * ks + 2 * t;
+      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0]);
+      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0 + 8]);
+      gh[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0]);     gh[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0]);
+      gh[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0 + 8]); gh[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0 + 8]);
+      gl[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0]);     gl[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0]);
+      gl[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0 + 8]); gl[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0 + 8]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0]);
+        const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0 + 8]);
+        const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0]);
+        const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0 + 8]);
+        const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0]);
+        const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0 + 8]);
+        mma16816(s[j], ah, kh0, kh1);
+        mma3<true>(dp[j], gh, gl, vh0, vh1, vl0, vl1);
+      }
+    }
+    __syncthreads();                                      // distance table complete
+    // ---- per element: bias, P, dS, segment sums, key-coordinate gradient
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float kg[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = 8 * j + 2 * t + e;
+        const bool kok = k0 + key < cf.nkv;
+        const float p0 = sm.tb.SX[key][r0], p1 = sm.tb.SX[key][r1];
+        const int s0 = pwl_seek(sm.pw, p0), s1 = pwl_seek(sm.pw, p1);
+        const float2 c0 = sm.pw.co[s0], c1 = sm.pw.co[s1];
+        const float P0 = kok ? __expf(s[j][e] + fmaf(c0.x, p0, c0.y) - lse0) : 0.f;
+        const float P1 = kok ? __expf(s[j][2 + e] + fmaf(c1.x, p1, c1.y) - lse1) : 0.f;
+        float keep0 = 1.f, keep1 = 1.f;
+        if (cf.p_drop > 0.f) {
+          keep0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+          keep1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+        }
+        const float dS0 = P0 * (dp[j][e] * keep0 - delta0);
+        const float dS1 = P1 * (dp[j][2 + e] * keep1 - delta1);
+        s[j][e] = P0 * keep0; s[j][2 + e] = P1 * keep1;      // fragments now hold P keep and dS
+        dp[j][e] = dS0; dp[j][2 + e] = dS1;
+        if (s0 != seg0) {
+          if (a00 != 0.f || a01 != 0.f) { atomicAdd(&sm.bins[seg0].x, a00); atomicAdd(&sm.bins[seg0].y, a01); }
+          seg0 = s0; a00 = 0.f; a01 = 0.f;
+        }
+        if (s1 != seg1) {
+          if (a10 != 0.f || a11 != 0.f) { atomicAdd(&sm.bins[seg1].x, a10); atomicAdd(&sm.bins[seg1].y, a11); }
+          seg1 = s1; a10 = 0.f; a11 = 0.f;
+        }
+        a00 += dS0; a01 = fmaf(dS0, p0, a01);
+        a10 += dS1; a11 = fmaf(dS1, p1, a11);
+        kg[e] = -(dS0 * c0.x * __expf(-fabsf(p0)) + dS1 * c1.x * __expf(-fabsf(p1)));
+      }
+      // key-coordinate gradients of keys 8 j + 2 t + {0, 1}: sum over the warp's 16 rows (8 lanes share t)
+#pragma unroll
+      for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
+      if (g == 0) { atomicAdd(&sm.dkpos[8 * j + 2 * t], kg[0]); atomicAdd(&sm.dkpos[8 * j + 2 * t + 1], kg[1]); }
+      // bf16 tiles of P keep and dS for the transposed products
+      *reinterpret_cast<uint32_t*>(&sm.P[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
+      *reinterpret_cast<uint32_t*>(&sm.P[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
+      *reinterpret_cast<uint32_t*>(&sm.dS[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+      *reinterpret_cast<uint32_t*>(&sm.dS[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+    }
+    __syncthreads();
+    // ---- dQ += dS K
+    {
+      float dqacc[8][4];
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dqacc[jd][e] = sm.dQ[jd * 4 + e][tid];
+#pragma unroll
+      for (int ks = 0; ks < BK / 16; ++ks) {
+        uint32_t ah[4];
+        const int c0 = 16 * ks + 2 * t;
+        ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0]);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0 + 8]);
+#pragma unroll
+        for (int jd = 0; jd < 8; ++jd) {
+          uint32_t bh0, bh1;
+          ldmatrix_x2_trans(bh0, bh1, &sm.K[16 * ks + (lane & 15)][8 * jd]);
+          mma16816(dqacc[jd], ah, bh0, bh1);
+        }
+      }
+#pragma unroll
+      for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sm.dQ[jd * 4 + e][tid] = dqacc[jd][e];
+    }
+    // ---- dK += dS^T Q and dV += (P keep)^T dO: warp slice = 16 keys x 32 dims, contraction over the CTA's 64 queries
+    {
+      const int mt = w & 1, dh = w >> 1;
+      float dkacc[4][4], dvacc[4][4];
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dkacc[jd][e] = 0.f; dvacc[jd][e] = 0.f; }
+      const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int qrow = 16 * ks + rr + 8 * (mi >> 1), kcol = 16 * mt + 8 * (mi & 1);
+        uint32_t sh[4], ph[4];
+        ldmatrix_x4_trans(sh[0], sh[1], sh[2], sh[3], &sm.dS[qrow][kcol]);
+        ldmatrix_x4_trans(ph[0], ph[1], ph[2], ph[3], &sm.P[qrow][kcol]);
+#pragma unroll
+        for (int jd = 0; jd < 4; ++jd) {
+          uint32_t qh0, qh1, gh0, gh1;
+          ldmatrix_x2_trans(qh0, qh1, &sm.Q[16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          ldmatrix_x2_trans(gh0, gh1, &sm.dO[0][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          mma16816(dkacc[jd], sh, qh0, qh1);
+          mma16816(dvacc[jd], ph, gh0, gh1);
+        }
+      }
+      const int key0 = k0 + 16 * mt + g, key1 = key0 + 8;
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd) {
+        const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
+        if (key0 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][0], dkacc[jd][1]));
+          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][0], dvacc[jd][1]));
+        }
+        if (key1 < cf.nkv) {
+          const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][2], dkacc[jd][3]));
+          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][2], dvacc[jd][3]));
+        }
+      }
+    }
+    if (tid < BK && k0 + tid < cf.nkv) atomicAdd(dvs + (int64_t)bg * cf.nkv + k0 + tid, sm.dkpos[tid]);
+  }
+  // ---- flush the open runs, dQ, and this CTA's segment sums
+  if (a00 != 0.f || a01 != 0.f) { atomicAdd(&sm.bins[seg0].x, a00); atomicAdd(&sm.bins[seg0].y, a01); }
+  if (a10 != 0.f || a11 != 0.f) { atomicAdd(&sm.bins[seg1].x, a10); atomicAdd(&sm.bins[seg1].y, a11); }
+  if (ok0) {
+    float* row = dq + qoff + (int64_t)(q0 + r0) * cf.inner + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4][tid], sm.dQ[j * 4 + 1][tid]);
+  }
+  if (ok1) {
+    float* row = dq + qoff + (int64_t)(q0 + r1) * cf.inner + 2 * t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4 + 2][tid], sm.dQ[j * 4 + 3][tid]);
+  }
+  __syncthreads();
+  for (int i = tid; i < ns; i += MTHREADS) {
+    const float2 bv = sm.bins[i];
+    if (bv.x != 0.f || bv.y != 0.f)
+      atomicAdd(reinterpret_cast<float2*>(gseg + ((int64_t)o * (PWL_MAXSEG + 1) + i) * 2), bv);
+  }
+}
 
 // ---- warp-specialised backward (plain bf16 operands, 2-D or 1-D lattices whose 64-query tiles span <= 8 lattice rows).
 // The lean backward above runs 8 warps per SM (220 registers, 56 of them parameter-gradient accumulators) and is bound by
@@ -2237,6 +2666,47 @@ static int launch_fwd_lean(const AttnCfg& cf, const float* q, const float* k, co
   }
   deform_attn_fwd_lean_kernel<CD, MINB><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, out, lse);
   SML_LAUNCH_OK("sml_deform_attn_fwd_tc (lean)");
+  return 0;
+}
+
+/* 1-D only (CD = 1): forward with the bias MLP replaced by its piecewise-linear table (sml_cpb1d_table_build), plain bf16 operands */
+extern "C" int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
+                                       const float* vs, const float* cpb, const float* brk, const float* coef, const int32_t* nseg,
+                                       float* out, float* lse, void* stream) {
+  AttnCfg cf;
+  if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
+  SML_CHECK(cf.CD == 1, "sml_deform_attn_fwd_pwl: one coordinate dimension only");
+  dim3 grid((cf.n + MQ - 1) / MQ, cf.heads, cf.B);
+  const size_t smem = sizeof(PwlFwdSmem);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(deform_attn_fwd_pwl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  deform_attn_fwd_pwl_kernel<<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, brk, coef, nseg, out, lse);
+  SML_LAUNCH_OK("sml_deform_attn_fwd_pwl");
+  return 0;
+}
+
+/* backward of sml_deform_attn_fwd_pwl.  dk, dv, dvs and gseg [OUT, sml_cpb1d_table_slots() + 2, 2] zero-initialised by the caller;
+ * gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with output o whose distance p lies in segment s */
+extern "C" int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
+                                       const float* vs, const float* brk, const float* coef, const int32_t* nseg, const float* out,
+                                       const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs, float* gseg,
+                                       void* stream) {
+  AttnCfg cf;
+  if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
+  SML_CHECK(cf.CD == 1, "sml_deform_attn_bwd_pwl: one coordinate dimension only");
+  dim3 grid((cf.n + MQ - 1) / MQ, cf.heads, cf.B);
+  const size_t smem = sizeof(PwlBwdSmem);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(deform_attn_bwd_pwl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  deform_attn_bwd_pwl_kernel<<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse, dout, dq, dk, dv,
+                                                                          dvs, gseg);
+  SML_LAUNCH_OK("sml_deform_attn_bwd_pwl");
   return 0;
 }
 

@@ -16,6 +16,18 @@ import os as _os
 # "bf16" mode, 2-D, one head per offset group: SML_DEFORM_TC5=1 runs the forward as the first tcgen05 / TMEM kernel
 # (csrc/deform_tc5.cu, one key per MMA round trip: measured 43 ms against 16.4 ms for the warp-level kernel at B=8/16k, so off)
 TC5_FWD = _os.environ.get("SML_DEFORM_TC5", "0") != "0"
+# "bf16" mode, 1-D: the bias MLP as its exact piecewise-linear table (csrc/cpb_table.cu) inside the fused attention kernels
+PWL_1D = _os.environ.get("SML_DEFORM_PWL", "1") != "0"
+
+
+def cpb1d_table(cpb, OUT):
+    """device-built table of the 1-D bias MLP: (brk [slots], coef [slots + 1, OUT, 2], nseg int32 [1])"""
+    slots = lib.sml_cpb1d_table_slots()
+    brk = torch.empty(slots, device=cpb.device, dtype=F32)
+    coef = torch.empty(slots + 1, OUT, 2, device=cpb.device, dtype=F32)
+    nseg = torch.empty(1, device=cpb.device, dtype=torch.int32)
+    check(lib.sml_cpb1d_table_build(ptr(cpb), c_i32(OUT), ptr(brk), ptr(coef), ptr(nseg), stream()), "cpb1d_table_build")
+    return brk, coef, nseg
 
 
 def _prof_begin():
@@ -168,10 +180,15 @@ class DeformAttnFn(torch.autograd.Function):
         out = torch.empty(b, T, inner, device=dev, dtype=F32)
         lse = torch.empty(b, heads, T, device=dev, dtype=F32)
         pairs = float(b) * heads * T * nkv
+        pwl = None
         prof = _prof_begin()
         if prec == "fp32":          # SIMT fp32 kernel
             check(lib.sml_deform_attn_fwd(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                           ptr(out), ptr(lse), stream()), "deform_attn_fwd")
+        elif prec == "bf16" and PWL_1D and not two_d:                  # 1-D: bias from the piecewise-linear table
+            brk, coef, nseg = pwl = cpb1d_table(cpb, heads // G)
+            check(lib.sml_deform_attn_fwd_pwl(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
+                                              ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), stream()), "deform_attn_fwd_pwl")
         elif prec == "bf16" and TC5_FWD and two_d and heads == G:     # tcgen05 / TMEM kernel
             check(lib.sml_deform_attn_fwd_tc5(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                               ptr(out), ptr(lse), stream()), "deform_attn_fwd_tc5")
@@ -187,6 +204,7 @@ class DeformAttnFn(torch.autograd.Function):
         ctx.cfg = dict(cfg, ocfg=ocfg, gcfg=gcfg, acfg=acfg, nkv=nkv, OC=OC, gd=gd, gq=gq, gkv=gkv, inner=inner,
                        shapes=[t.shape for t in (wq, wk, wv, wout, wc, w2, cw1, cb1, cw2, cb2, cw3, cb3)])
         ctx.taps = taps
+        ctx.pwl = pwl
         ctx.mark_non_differentiable(*([] if taps is None else []))
         return y, vgrid
 
@@ -210,9 +228,19 @@ class DeformAttnFn(torch.autograd.Function):
         dvs_b = torch.zeros_like(vs)
         nblk = lib.sml_deform_attn_bwd_blocks(cfg["acfg"])
         npar = lib.sml_deform_cpb_nparams(c_i32(OC), c_i32(heads // G))
-        part = torch.empty(nblk, npar, device=dev, dtype=F32)
+        pwl = ctx.pwl
+        part = torch.empty(nblk, npar, device=dev, dtype=F32) if pwl is None else None
         prof = _prof_begin()
-        if prec == "fp32":
+        if pwl is not None:         # 1-D, bias from the table: per-segment sums, mapped to the MLP parameters afterwards
+            brk, coef, nseg = pwl
+            gseg = torch.zeros(heads // G, lib.sml_cpb1d_seg_rows(), 2, device=dev, dtype=F32)
+            dcpb = torch.empty(npar, device=dev, dtype=F32)
+            check(lib.sml_deform_attn_bwd_pwl(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
+                                              ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk),
+                                              ptr(dv), ptr(dvs_b), ptr(gseg), stream()), "deform_attn_bwd_pwl")
+            check(lib.sml_cpb1d_table_bwd(ptr(cpb), c_i32(heads // G), ptr(brk), ptr(nseg), ptr(gseg), ptr(dcpb), stream()),
+                  "cpb1d_table_bwd")
+        elif prec == "fp32":
             check(lib.sml_deform_attn_bwd(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
                                           ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b), ptr(part),
                                           stream()), "deform_attn_bwd")
@@ -223,7 +251,8 @@ class DeformAttnFn(torch.autograd.Function):
         # backward = 2x the forward contractions (the forward recomputation inside the kernel is not counted)
         _prof_end(prof, "deform_bwd", float(b) * heads * T * nkv * 2 * (2 * (OC * 32 + 32 * 32 + 32) + 4 * 64),
                   (b, heads, T, nkv, OC, prec))
-        dcpb = ops.colsum(part)
+        if pwl is None:
+            dcpb = ops.colsum(part)
         # k, v projections
         dkv, dwk = gconv_bwd(kv, wk2, cfg["gkv"], dk, mode=prec)
         _, dwv = gconv_bwd(kv, wv2, cfg["gkv"], dv, dx_out=dkv, dx_beta=1.0, mode=prec)

@@ -443,3 +443,82 @@ def test_deform_bwd_warp_specialised_matches_lean(shape):
         res[code] = (dq, dk, dv, dvs, part.sum(0))
     for a, bb, tol in zip(res[0], res[5], (1e-5, 1e-4, 1e-4, 1e-3, 2e-3)):
         assert rel_err(bb, a) < tol, rel_err(bb, a)
+
+
+@pytest.mark.parametrize("shape", [(2, 2501, 625), (1, 16385, 4096), (1, 777, 130)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_deform1d_fwd_pwl_matches_split(shape, p_drop):
+    """1-D forward with the bias MLP tabulated as a piecewise-linear function (sml_deform_attn_fwd_pwl) against the fp32-grade
+    split kernel that evaluates the MLP per pair: same inputs, same dropout hash"""
+    from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
+    from sml_b200.deform import cpb1d_table
+    b, T, nkv = shape
+    heads, G = 8, 4
+    torch.manual_seed(8)
+    q = torch.randn(b, T, heads * 64, device="cuda") * 0.3
+    k = torch.randn(b, nkv, heads * 64, device="cuda"); v = torch.randn(b, nkv, heads * 64, device="cuda")
+    vs = (torch.linspace(-1, 1, nkv, device="cuda").repeat(b * G, 1) + torch.randn(b * G, nkv, device="cuda") * 2e-3).unsqueeze(-1).contiguous()
+    cpb = torch.randn(lib.sml_deform_cpb_nparams(c_i32(1), c_i32(2)), device="cuda") * 0.4
+    cfg = (c_i32 * 8)(b, heads, T, nkv, G, 1, 0, 64)
+    outs = {}
+    for name in ("pwl", "split", "lean"):
+        out = torch.empty(b, T, heads * 64, device="cuda"); lse = torch.empty(b, heads, T, device="cuda")
+        if name == "pwl":
+            brk, coef, nseg = cpb1d_table(cpb, 2)
+            check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(brk), ptr(coef),
+                                              ptr(nseg), ptr(out), ptr(lse), stream()), "fwd_pwl")
+        else:
+            check(lib.sml_deform_attn_fwd_tc(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse),
+                                             c_i32(1 if name == "split" else 0), stream()), "fwd_tc")
+        torch.cuda.synchronize()
+        outs[name] = (out, lse)
+    e_lse, e_out = rel_err(outs["pwl"][1], outs["split"][1]), rel_err(outs["pwl"][0], outs["split"][0])
+    o_lse, o_out = rel_err(outs["lean"][1], outs["split"][1]), rel_err(outs["lean"][0], outs["split"][0])
+    assert e_lse < 5e-3 and e_out < 2e-2, (e_lse, e_out)
+    assert e_out < 2.0 * o_out + 2e-3 and e_lse < 2.0 * o_lse + 1e-3, (e_lse, o_lse, e_out, o_out)
+
+
+@pytest.mark.parametrize("shape", [(2, 2501, 625), (1, 16385, 4096), (1, 777, 130)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_deform1d_bwd_pwl_matches_split(shape, p_drop):
+    """1-D backward with the tabulated bias (sml_deform_attn_bwd_pwl + sml_cpb1d_table_bwd: per-segment sums mapped to the MLP
+    parameters) against the fp32-grade split kernel that differentiates the MLP per pair; the plain-bf16 per-pair kernel on the
+    same inputs sets the scale of the allowed error."""
+    from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
+    from sml_b200.deform import cpb1d_table
+    b, T, nkv = shape
+    heads, G = 8, 4
+    torch.manual_seed(9)
+    q = torch.randn(b, T, heads * 64, device="cuda") * 0.3
+    k = torch.randn(b, nkv, heads * 64, device="cuda"); v = torch.randn(b, nkv, heads * 64, device="cuda")
+    vs = (torch.linspace(-1, 1, nkv, device="cuda").repeat(b * G, 1) + torch.randn(b * G, nkv, device="cuda") * 2e-3).unsqueeze(-1).contiguous()
+    npar = lib.sml_deform_cpb_nparams(c_i32(1), c_i32(2))
+    cpb = torch.randn(npar, device="cuda") * 0.4
+    cfg = (c_i32 * 8)(b, heads, T, nkv, G, 1, 0, 64)
+    dout = torch.randn(b, T, heads * 64, device="cuda")
+    res = {}
+    for name in ("pwl", "split", "lean"):
+        out = torch.empty(b, T, heads * 64, device="cuda"); lse = torch.empty(b, heads, T, device="cuda")
+        dq = torch.empty_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v); dvs = torch.zeros_like(vs)
+        if name == "pwl":
+            brk, coef, nseg = cpb1d_table(cpb, 2)
+            check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(brk), ptr(coef),
+                                              ptr(nseg), ptr(out), ptr(lse), stream()), "fwd_pwl")
+            gseg = torch.zeros(2, lib.sml_cpb1d_seg_rows(), 2, device="cuda")
+            dcpb = torch.empty(npar, device="cuda")
+            check(lib.sml_deform_attn_bwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(brk), ptr(coef), ptr(nseg),
+                                              ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(dvs), ptr(gseg), stream()), "bwd_pwl")
+            check(lib.sml_cpb1d_table_bwd(ptr(cpb), c_i32(2), ptr(brk), ptr(nseg), ptr(gseg), ptr(dcpb), stream()), "table_bwd")
+        else:
+            split = c_i32(1 if name == "split" else 0)
+            check(lib.sml_deform_attn_fwd_tc(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse),
+                                             split, stream()), "fwd_tc")
+            part = torch.empty(lib.sml_deform_attn_bwd_blocks(cfg), npar, device="cuda")
+            check(lib.sml_deform_attn_bwd_tc(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse),
+                                             ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(dvs), ptr(part), split, stream()), "bwd_tc")
+            dcpb = part.sum(0)
+        torch.cuda.synchronize()
+        res[name] = (dq, dk, dv, dvs, dcpb)
+    for i, (nm, floor) in enumerate((("dq", 2e-2), ("dk", 2e-2), ("dv", 2e-2), ("dvs", 3e-2), ("dcpb", 3e-2))):
+        e_pwl, e_lean = rel_err(res["pwl"][i], res["split"][i]), rel_err(res["lean"][i], res["split"][i])
+        assert e_pwl < max(2.0 * e_lean, floor), (nm, e_pwl, e_lean)
