@@ -1167,69 +1167,111 @@ __global__ void __launch_bounds__(MTHREADS, MINB) deform_attn_fwd_lean_kernel(co
 
 // ---- 1-D bias MLP as an exact piecewise-linear table (csrc/cpb_table.cu; specification oracle/pwl.py): for one coordinate the
 // MLP Linear(1,32) ReLU Linear(32,32) ReLU Linear(32,o) is a continuous piecewise-linear function of the signed-log distance
-// with <= 1089 segments (65-70 for typical parameters), so the per-pair bias is slope[s] p + icpt[s]: no MMA, ~10 instructions
-// per pair instead of ~65 per 16-pair tile x 16.  Forward kernel = the lean forward with the MLP block replaced by the lookup.
+// with <= 1089 segments (65-70 for typical parameters), so the per-pair bias is slope[s] p + icpt[s]: no MMA per pair.
+// Along one query row the distance moves by ~2 / n_kv per key, far less than a segment, so a (row, key tile) range contains
+// zero or one breakpoint almost always: its two lines (slope, intercept) x 2 and the breakpoint live in REGISTERS for the
+// tile and the per-pair bias is compare + select + FMA, with no table access.  Tiles whose range holds two or more
+// breakpoints take a (warp-uniform) slow path that searches the shared-memory table per pair.
+// Everything is kept in the base-2 domain: p2 = sign log2(|d| + 1) = p log2(e), logits scaled by log2(e) (the Q tile is
+// scaled when it is converted to bf16), so that slope p + icpt becomes slope p2 + icpt log2(e) with an UNCHANGED slope, the
+// distance costs one MUFU.LG2 and the softmax one MUFU.EX2 without multiplies.
 constexpr int PWL_MAXSEG = 1089;
-constexpr int PWL_CELLS = 1024;          // uniform acceleration grid over the reachable distances |p| <= PWL_PMAX
-constexpr float PWL_PMAX = 1.25f;        // log(3 + eps): normalised positions lie in [-1, 1], offsets add a few grid units
+constexpr float PWL_LOG2E = 1.4426950408889634f, PWL_LN2 = 0.6931471805599453f;
 struct PwlTable {
-  float B[PWL_MAXSEG + 1];               // segment s covers [B[s], B[s + 1]); B[0] = -inf, B[nseg] = +inf
-  float2 co[PWL_MAXSEG];                 // (slope, intercept) of this head's output
-  unsigned short cell[PWL_CELLS];        // segment that contains the left edge of grid cell c
+  float B[PWL_MAXSEG + 1];               // segment s covers [B[s], B[s + 1]) in p2 units; B[0] = -inf, B[nseg] = +inf
+  float2 co[PWL_MAXSEG];                 // (slope, intercept log2(e)) of this head's output
 };
-// segment of p: start from the grid cell's segment, then step (cells hold ~0.06 breakpoints on average, so both loops
-// normally exit at once; any p, even outside the grid, ends in the right segment)
-__device__ __forceinline__ int pwl_seek(const PwlTable& tb, float p) {
-  int c = (int)((p + PWL_PMAX) * (PWL_CELLS / (2.f * PWL_PMAX)));
-  c = min(max(c, 0), PWL_CELLS - 1);
-  int s = tb.cell[c];
+// segment of p, searched from the guess s (any p ends in the right segment)
+__device__ __forceinline__ int pwl_seek(const PwlTable& tb, float p, int s) {
   while (p < tb.B[s]) --s;
   while (p >= tb.B[s + 1]) ++s;
   return s;
 }
 __device__ __forceinline__ void pwl_load(PwlTable& tb, const float* __restrict__ brk, const float* __restrict__ coef, int nb, int OUT,
                                          int o, int tid, int nthreads) {
-  for (int i = tid; i <= nb + 1; i += nthreads) tb.B[i] = i == 0 ? -INFINITY : (i <= nb ? brk[i - 1] : INFINITY);
+  for (int i = tid; i <= nb + 1; i += nthreads) tb.B[i] = i == 0 ? -INFINITY : (i <= nb ? brk[i - 1] * PWL_LOG2E : INFINITY);
   for (int i = tid; i <= nb; i += nthreads)
-    tb.co[i] = make_float2(coef[((int64_t)i * OUT + o) * 2], coef[((int64_t)i * OUT + o) * 2 + 1]);
-  for (int c = tid; c < PWL_CELLS; c += nthreads) {           // number of breakpoints <= left edge of the cell
-    const float edge = -PWL_PMAX + c * (2.f * PWL_PMAX / PWL_CELLS);
-    int lo = 0, hi = nb;
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (brk[m] <= edge) lo = m + 1; else hi = m; }
-    tb.cell[c] = (unsigned short)lo;
+    tb.co[i] = make_float2(coef[((int64_t)i * OUT + o) * 2], coef[((int64_t)i * OUT + o) * 2 + 1] * PWL_LOG2E);
+}
+__device__ __forceinline__ float slog2_fast(float x) { return copysignf(__log2f(fabsf(x) + 1.f), x); }
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+// The two lines of one query row over one key tile: bias2(p) = p < b ? sl p + il : sh p + ih
+struct PwlRow {
+  float b, sl, il, sh, ih;
+  int seg;                               // segment of the lower line (search guess of the next tile)
+};
+// kmin / kmax = range of the tile's key positions; returns true when the row's range holds more than one breakpoint
+__device__ __forceinline__ bool pwl_row_setup(const PwlTable& tb, int ns, float qx, float kmin, float kmax, PwlRow& rw) {
+  const float plo = slog2_fast(qx - kmax), phi = slog2_fast(qx - kmin);
+  const int sL = pwl_seek(tb, plo, rw.seg), sH = pwl_seek(tb, phi, sL);
+  const float2 cl = tb.co[sL], ch = tb.co[min(sL + 1, ns - 1)];
+  rw.seg = sL; rw.b = tb.B[sL + 1];
+  rw.sl = cl.x; rw.il = cl.y; rw.sh = ch.x; rw.ih = ch.y;
+  return sH - sL > 1;
+}
+__device__ __forceinline__ float pwl_bias(const PwlRow& rw, float p) {
+  const bool lo = p < rw.b;
+  return fmaf(p, lo ? rw.sl : rw.sh, lo ? rw.il : rw.ih);
+}
+// min / max of the valid key positions of a tile (threads 0 .. NK - 1 of warp 0 / 1 hold one key each): result in red[0 .. 1]
+template <int NK>
+__device__ __forceinline__ void pwl_key_range(float kx, bool ok, float* red, int tid) {
+  if (tid < NK) {
+    float mn = ok ? kx : INFINITY, mx = ok ? kx : -INFINITY;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    }
+    if ((tid & 31) == 0) { red[2 * (tid >> 5)] = mn; red[2 * (tid >> 5) + 1] = mx; }
   }
 }
 struct PwlFwdSmem {
   __nv_bfloat16 Q[MQ][MLD], K[64][MLD], V[2][64][MLD];
-  LeanTab<1, 64> tb;
+  float kx[64];
+  float red[4];
   PwlTable pw;
 };
+template <bool DROP>
 __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const AttnCfg cf, const float* __restrict__ q,
                                                                             const float* __restrict__ k, const float* __restrict__ v,
-                                                                            const float* __restrict__ vs, const float* __restrict__ cpb, const float* __restrict__ brk,
+                                                                            const float* __restrict__ vs, const float* __restrict__ brk,
                                                                             const float* __restrict__ coef, const int* __restrict__ nseg,
                                                                             float* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int CD = 1;
   PwlFwdSmem& sm = *reinterpret_cast<PwlFwdSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
   const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
   const int grp = head / cf.OUT, o = head % cf.OUT;
   const int bg = b * cf.G + grp;
-  // piecewise-linear table of the bias MLP for this head's output o (csrc/cpb_table.cu): segment s covers [B[s], B[s + 1])
-  pwl_load(sm.pw, brk, coef, nseg[0] - 1, cf.OUT, o, tid, MTHREADS);
-  load_tile<false, MQ>(sm.Q, nullptr, q + (int64_t)b * cf.n * cf.inner + head * AD, cf.inner, q0, cf.n);
-  const int ny = lean_query_tables<CD, 64>(sm.tb, cf, q0);
+  const int ns = nseg[0];
+  pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
+  {                                                     // Q tile, scaled by log2(e)
+    const float* src = q + (int64_t)b * cf.n * cf.inner + head * AD;
+    for (int e = tid; e < MQ * 16; e += MTHREADS) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < cf.n) x = *reinterpret_cast<const float4*>(src + (int64_t)(q0 + r) * cf.inner + c4);
+      *reinterpret_cast<uint2*>(&sm.Q[r][c4]) = make_uint2(pack_bf16(x.x * PWL_LOG2E, x.y * PWL_LOG2E), pack_bf16(x.z * PWL_LOG2E, x.w * PWL_LOG2E));
+    }
+  }
   const int r0 = w * 16 + g, r1 = r0 + 8;
-  const int ys0 = CD == 2 ? min(q0 + r0, cf.n - 1) / cf.W - q0 / cf.W : 0;
-  const int ys1 = CD == 2 ? min(q0 + r1, cf.n - 1) / cf.W - q0 / cf.W : 0;
+  float qx0, qx1, qdum;
+  query_pos(cf, min(q0 + r0, cf.n - 1), qx0, qdum);
+  query_pos(cf, min(q0 + r1, cf.n - 1), qx1, qdum);
+  PwlRow rw0, rw1;
+  rw0.seg = rw1.seg = ns >> 1;
   float oacc[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) oacc[j][e] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;          // base-2 running max, running sum
+  const float keep_scale = DROP ? 1.f / (1.f - cf.p_drop) : 1.f;
   const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
   const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
   const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
@@ -1240,14 +1282,18 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
     __syncthreads();
     load_tile<false, 64>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
     load_tile<true, 64>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
-    if (tid < 64) {
-      const bool ok = k0 + tid < cf.nkv;
-      sm.tb.kpos[tid][0] = ok ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD] : 0.f;
-      sm.tb.kpos[tid][1] = (ok && CD == 2) ? vs[((int64_t)bg * cf.nkv + k0 + tid) * CD + 1] : 0.f;
+    {
+      const bool ok = tid < 64 && k0 + tid < cf.nkv;
+      const float kx = ok ? vs[(int64_t)bg * cf.nkv + k0 + tid] : 0.f;
+      if (tid < 64) sm.kx[tid] = kx;
+      pwl_key_range<64>(kx, ok, sm.red, tid);
     }
     __syncthreads();
-    lean_tables<CD, 64>(sm.tb, ny);
-    // ---- S = b3 + Q K^T
+    const float kmin = fminf(sm.red[0], sm.red[2]), kmax = fmaxf(sm.red[1], sm.red[3]);
+    const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
+    const bool many1 = pwl_row_setup(sm.pw, ns, qx1, kmin, kmax, rw1);
+    const bool slow = __any_sync(0xffffffffu, many0 || many1);
+    // ---- S2 = log2(e) Q K^T
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -1267,31 +1313,42 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
         mma16816(s[j], ah, bh0, bh1);
       }
     }
-    __syncthreads();                                    // tables complete
-    // ---- + continuous position bias from the table: bias = slope[s] p + icpt[s]
+    // ---- + continuous position bias
+    if (!slow) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int key = 8 * j + 2 * t + e;
-        const float p0 = sm.tb.SX[key][r0], p1 = sm.tb.SX[key][r1];
-        const float2 c0 = sm.pw.co[pwl_seek(sm.pw, p0)], c1 = sm.pw.co[pwl_seek(sm.pw, p1)];
-        s[j][e] += fmaf(c0.x, p0, c0.y);
-        s[j][2 + e] += fmaf(c1.x, p1, c1.y);
+      for (int j = 0; j < 8; ++j) {
+        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+        s[j][0] += pwl_bias(rw0, slog2_fast(qx0 - kx.x)); s[j][1] += pwl_bias(rw0, slog2_fast(qx0 - kx.y));
+        s[j][2] += pwl_bias(rw1, slog2_fast(qx1 - kx.x)); s[j][3] += pwl_bias(rw1, slog2_fast(qx1 - kx.y));
       }
-    // ---- online softmax on the fragments
+    } else {
+      for (int j = 0; j < 8; ++j) {
+        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p = slog2_fast(((e & 2) ? qx1 : qx0) - ((e & 1) ? kx.y : kx.x));
+          const float2 c = sm.pw.co[pwl_seek(sm.pw, p, (e & 2) ? rw1.seg : rw0.seg)];
+          s[j][e] += fmaf(c.x, p, c.y);
+        }
+      }
+    }
+    if (k0 + 64 > cf.nkv) {                             // ragged last tile
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (k0 + 8 * j + 2 * t + e >= cf.nkv) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
+    }
+    // ---- online softmax on the fragments (base 2)
     float mt0 = -INFINITY, mt1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (k0 + 8 * j + 2 * t + e >= cf.nkv) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
-        mt0 = fmaxf(mt0, s[j][e]); mt1 = fmaxf(mt1, s[j][2 + e]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      mt0 = fmaxf(mt0, fmaxf(s[j][0], s[j][1])); mt1 = fmaxf(mt1, fmaxf(s[j][2], s[j][3]));
+    }
     mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 1)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 1));
     mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 2)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 2));
     const float mn0 = fmaxf(m0, mt0), mn1 = fmaxf(m1, mt1);
-    const float al0 = m0 == -INFINITY ? 0.f : __expf(m0 - mn0), al1 = m1 == -INFINITY ? 0.f : __expf(m1 - mn1);
+    const float al0 = m0 == -INFINITY ? 0.f : ex2_fast(m0 - mn0), al1 = m1 == -INFINITY ? 0.f : ex2_fast(m1 - mn1);
     m0 = mn0; m1 = mn1;
     l0 *= al0; l1 *= al1;
 #pragma unroll
@@ -1300,9 +1357,9 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        float p0 = __expf(s[j][e] - mn0), p1 = __expf(s[j][2 + e] - mn1);
+        float p0 = ex2_fast(s[j][e] - mn0), p1 = ex2_fast(s[j][2 + e] - mn1);
         l0 += p0; l1 += p1;
-        if (cf.p_drop > 0.f) {
+        if (DROP) {
           const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
           p0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + key) >= thresh ? p0 * keep_scale : 0.f;
           p1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + key) >= thresh ? p1 * keep_scale : 0.f;
@@ -1333,13 +1390,13 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
     float* orow = out + ((int64_t)b * cf.n + q0 + r0) * cf.inner + head * AD + 2 * t;
 #pragma unroll
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][0] * i0, oacc[j][1] * i0);
-    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0] = m0 + logf(l0);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0] = (m0 + log2f(l0)) * PWL_LN2;
   }
   if (q0 + r1 < cf.n) {
     float* orow = out + ((int64_t)b * cf.n + q0 + r1) * cf.inner + head * AD + 2 * t;
 #pragma unroll
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(orow + 8 * j) = make_float2(oacc[j][2] * i1, oacc[j][3] * i1);
-    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1] = m1 + logf(l1);
+    if (t == 0) lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1] = (m1 + log2f(l1)) * PWL_LN2;
   }
 }
 
@@ -1813,47 +1870,67 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
 
 
 // ---- 1-D backward with the tabulated bias (see PwlTable above).  No per-key MLP tiles: the warp's 16 rows x 32 keys are
-// processed as logit fragments, exactly like the forward.  Per element: p from the distance table, segment s, bias =
-// slope[s] p + icpt[s], P = exp(S + bias - lse), dS = P (dP keep - delta).  Bias-MLP gradients: per segment the sums
-// G0[s] = sum dS and G1[s] = sum dS p (run-length accumulated per query row, flushed to shared-memory bins when the segment
-// changes, added to the global [OUT, segments, 2] buffer at the end); the host maps them to the MLP parameters by
-// differentiating slope / intercept (functions of the parameters with the segment's fixed ReLU pattern).  Key-coordinate
-// gradient: d bias / d p = slope[s], d p / d kx = -exp(-|p|).  dQ / dK / dV as in the lean backward.
+// processed as logit fragments, exactly like the forward.  Per element: p2 = sign log2(|d| + 1), the row's two lines from
+// registers (PwlRow), P = 2^(S2 + bias2 - lse2), dS = P (dP keep - delta).  Bias-MLP gradients: per segment the sums
+// G0[s] = sum dS and G1[s] = sum dS p.  A (row, key tile) range touches the segments {seg, seg + 1} only, so the tile's sums
+// are four register accumulators (total and upper-line part); they are merged into per-row running sums that are flushed to
+// shared-memory bins only when the row's lower segment changes (~ once per segment per row), and the bins go to the global
+// [OUT, rows, 2] buffer at the end; sml_cpb1d_table_bwd maps them to the MLP parameters.  Tiles with >= 2 breakpoints in range
+// search the table and bin per pair (warp-uniform slow path).  Key-coordinate gradient: d bias / d p = slope,
+// d p / d kx = -1 / (|d| + 1) = -2^(-|p2|).  dQ / dK / dV as in the lean backward (dK is rescaled by ln 2: the Q tile carries log2 e).
 struct PwlBwdSmem {
   __nv_bfloat16 Q[MQ][MLD], dO[2][MQ][MLD];
   __nv_bfloat16 K[BK][MLD], V[2][BK][MLD];
   __nv_bfloat16 P[MQ][PLD], dS[MQ][PLD];
-  float dQ[32][MTHREADS];
   float dkpos[BK];
-  LeanTab<1, BK> tb;
+  float kx[BK];
+  float red[2];
   PwlTable pw;
   float2 bins[PWL_MAXSEG];
 };
+// running per-row sums of the segments {seg, seg + 1}; the four lanes of a quad hold the same row: they are reduced at flush time
+struct PwlAcc { int seg; float a0, b0, a1, b1; };
+__device__ __forceinline__ void pwl_flush(float2* bins, PwlAcc& ac, int lane) {
+  const unsigned quad = 0xFu << (lane & 28);
+  float v0 = ac.a0, v1 = ac.b0, v2 = ac.a1, v3 = ac.b1;
+  v0 += __shfl_xor_sync(quad, v0, 1); v1 += __shfl_xor_sync(quad, v1, 1); v2 += __shfl_xor_sync(quad, v2, 1); v3 += __shfl_xor_sync(quad, v3, 1);
+  v0 += __shfl_xor_sync(quad, v0, 2); v1 += __shfl_xor_sync(quad, v1, 2); v2 += __shfl_xor_sync(quad, v2, 2); v3 += __shfl_xor_sync(quad, v3, 2);
+  if ((lane & 3) == 0) {
+    if (v0 != 0.f || v1 != 0.f) { atomicAdd(&bins[ac.seg].x, v0); atomicAdd(&bins[ac.seg].y, v1 * PWL_LN2); }
+    if (v2 != 0.f || v3 != 0.f) { atomicAdd(&bins[ac.seg + 1].x, v2); atomicAdd(&bins[ac.seg + 1].y, v3 * PWL_LN2); }
+  }
+  ac.a0 = ac.b0 = ac.a1 = ac.b1 = 0.f;
+}
 
-__global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
+template <bool DROP>
+__global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
     const AttnCfg cf, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
     const float* __restrict__ vs, const float* __restrict__ brk, const float* __restrict__ coef, const int* __restrict__ nseg,
     const float* __restrict__ out, const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq,
     float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ gseg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PwlBwdSmem& sm = *reinterpret_cast<PwlBwdSmem*>(smem_raw);
-  constexpr int CD = 1;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
   const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * MQ;
   const int grp = head / cf.OUT, o = head % cf.OUT;
   const int bg = b * cf.G + grp;
   const int ns = nseg[0];
   pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
-  for (int i = tid; i < ns; i += MTHREADS) sm.bins[i] = make_float2(0.f, 0.f);
+  for (int i = tid; i <= ns; i += MTHREADS) sm.bins[min(i, PWL_MAXSEG - 1)] = make_float2(0.f, 0.f);
   const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
-  load_tile<false, MQ>(sm.Q, nullptr, q + qoff, cf.inner, q0, cf.n);
+  for (int e = tid; e < MQ * 16; e += MTHREADS) {          // Q tile, scaled by log2(e)
+    const int r = e >> 4, c4 = (e & 15) * 4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < cf.n) x = *reinterpret_cast<const float4*>(q + qoff + (int64_t)(q0 + r) * cf.inner + c4);
+    *reinterpret_cast<uint2*>(&sm.Q[r][c4]) = make_uint2(pack_bf16(x.x * PWL_LOG2E, x.y * PWL_LOG2E), pack_bf16(x.z * PWL_LOG2E, x.w * PWL_LOG2E));
+  }
   load_tile<true, MQ>(sm.dO[0], sm.dO[1], dout + qoff, cf.inner, q0, cf.n);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) sm.dQ[i][tid] = 0.f;
-  const int ny = lean_query_tables<CD, BK>(sm.tb, cf, q0);
   const int r0 = w * 16 + g, r1 = r0 + 8;
   const bool ok0 = q0 + r0 < cf.n, ok1 = q0 + r1 < cf.n;
-  float delta0 = 0.f, delta1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;
+  float qx0, qx1, qdum;
+  query_pos(cf, min(q0 + r0, cf.n - 1), qx0, qdum);
+  query_pos(cf, min(q0 + r1, cf.n - 1), qx1, qdum);
+  float delta0 = 0.f, delta1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;      // lse in base-2 units
   {
     if (ok0) {
       const float* orow = out + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
@@ -1863,7 +1940,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
         delta0 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta0))));
       }
-      lse0 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0];
+      lse0 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0] * PWL_LOG2E;
     }
     if (ok1) {
       const float* orow = out + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
@@ -1873,34 +1950,45 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
         delta1 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta1))));
       }
-      lse1 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1];
+      lse1 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1] * PWL_LOG2E;
     }
     delta0 += __shfl_xor_sync(0xffffffffu, delta0, 1); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 1);
     delta0 += __shfl_xor_sync(0xffffffffu, delta0, 2); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 2);
   }
-  const float keep_scale = cf.p_drop > 0.f ? 1.f / (1.f - cf.p_drop) : 1.f;
+  const float keep_scale = DROP ? 1.f / (1.f - cf.p_drop) : 1.f;
   const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
   const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
   const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
   const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
   const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
-  // run-length accumulators of the per-segment sums, one run per query row
-  int seg0 = 0, seg1 = 0;
-  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;        // (G0, G1) of the current run of row r0 / r1
+  PwlRow rw0, rw1;
+  rw0.seg = rw1.seg = ns >> 1;
+  PwlAcc ac0, ac1;
+  ac0.seg = ac1.seg = ns >> 1;
+  ac0.a0 = ac0.b0 = ac0.a1 = ac0.b1 = 0.f;
+  ac1.a0 = ac1.b0 = ac1.a1 = ac1.b1 = 0.f;
+  float dqacc[8][4];
+#pragma unroll
+  for (int jd = 0; jd < 8; ++jd)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dqacc[jd][e] = 0.f;
 
   for (int k0 = 0; k0 < cf.nkv; k0 += BK) {
     __syncthreads();
     load_tile<false, BK>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
     load_tile<true, BK>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
-    if (tid < BK) {
-      const bool ok = k0 + tid < cf.nkv;
-      sm.tb.kpos[tid][0] = ok ? vs[(int64_t)bg * cf.nkv + k0 + tid] : 0.f;
-      sm.tb.kpos[tid][1] = 0.f;
-      sm.dkpos[tid] = 0.f;
+    {
+      const bool ok = tid < BK && k0 + tid < cf.nkv;
+      const float kx = ok ? vs[(int64_t)bg * cf.nkv + k0 + tid] : 0.f;
+      if (tid < BK) { sm.kx[tid] = kx; sm.dkpos[tid] = 0.f; }
+      pwl_key_range<BK>(kx, ok, sm.red, tid);
     }
     __syncthreads();
-    lean_tables<CD, BK>(sm.tb, ny);
-    // ---- S = Q K^T and dP = dO V^T (dO, V as hi + lo) of my 16 rows x the 32 keys of the tile
+    const float kmin = sm.red[0], kmax = sm.red[1];
+    const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
+    const bool many1 = pwl_row_setup(sm.pw, ns, qx1, kmin, kmax, rw1);
+    const bool slow = __any_sync(0xffffffffu, many0 || many1);
+    // ---- S2 = log2(e) Q K^T and dP = dO V^T (dO, V as hi + lo) of my 16 rows x the 32 keys of the tile
     float s[4][4], dp[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -1928,76 +2016,102 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         mma3<true>(dp[j], gh, gl, vh0, vh1, vl0, vl1);
       }
     }
-    __syncthreads();                                      // distance table complete
     // ---- per element: bias, P, dS, segment sums, key-coordinate gradient
+    const bool ragged = k0 + BK > cf.nkv;
+    if (!slow) {
+      float aT0 = 0.f, bT0 = 0.f, aH0 = 0.f, bH0 = 0.f, aT1 = 0.f, bT1 = 0.f, aH1 = 0.f, bH1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float kg[2];
+      for (int j = 0; j < 4; ++j) {
+        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+        float kg[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int key = 8 * j + 2 * t + e;
-        const bool kok = k0 + key < cf.nkv;
-        const float p0 = sm.tb.SX[key][r0], p1 = sm.tb.SX[key][r1];
-        const int s0 = pwl_seek(sm.pw, p0), s1 = pwl_seek(sm.pw, p1);
-        const float2 c0 = sm.pw.co[s0], c1 = sm.pw.co[s1];
-        const float P0 = kok ? __expf(s[j][e] + fmaf(c0.x, p0, c0.y) - lse0) : 0.f;
-        const float P1 = kok ? __expf(s[j][2 + e] + fmaf(c1.x, p1, c1.y) - lse1) : 0.f;
-        float keep0 = 1.f, keep1 = 1.f;
-        if (cf.p_drop > 0.f) {
-          keep0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
-          keep1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + (unsigned long long)(k0 + key)) >= thresh ? keep_scale : 0.f;
+        for (int e = 0; e < 2; ++e) {
+          const float kxe = e ? kx.y : kx.x;
+          const float p0 = slog2_fast(qx0 - kxe), p1 = slog2_fast(qx1 - kxe);
+          const bool lo0 = p0 < rw0.b, lo1 = p1 < rw1.b;
+          const float sl0 = lo0 ? rw0.sl : rw0.sh, sl1 = lo1 ? rw1.sl : rw1.sh;
+          float P0 = ex2_fast(s[j][e] + fmaf(p0, sl0, lo0 ? rw0.il : rw0.ih) - lse0);
+          float P1 = ex2_fast(s[j][2 + e] + fmaf(p1, sl1, lo1 ? rw1.il : rw1.ih) - lse1);
+          if (ragged && k0 + 8 * j + 2 * t + e >= cf.nkv) { P0 = 0.f; P1 = 0.f; }
+          float keep0 = 1.f, keep1 = 1.f;
+          if (DROP) {
+            const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
+            keep0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + key) >= thresh ? keep_scale : 0.f;
+            keep1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + key) >= thresh ? keep_scale : 0.f;
+          }
+          const float dS0 = P0 * (DROP ? dp[j][e] * keep0 - delta0 : dp[j][e] - delta0);
+          const float dS1 = P1 * (DROP ? dp[j][2 + e] * keep1 - delta1 : dp[j][2 + e] - delta1);
+          s[j][e] = DROP ? P0 * keep0 : P0; s[j][2 + e] = DROP ? P1 * keep1 : P1;      // fragments now hold P keep and dS
+          dp[j][e] = dS0; dp[j][2 + e] = dS1;
+          const float h0 = lo0 ? 0.f : dS0, h1 = lo1 ? 0.f : dS1;
+          aT0 += dS0; bT0 = fmaf(dS0, p0, bT0); aH0 += h0; bH0 = fmaf(h0, p0, bH0);
+          aT1 += dS1; bT1 = fmaf(dS1, p1, bT1); aH1 += h1; bH1 = fmaf(h1, p1, bH1);
+          kg[e] = -fmaf(dS0 * sl0, ex2_fast(-fabsf(p0)), dS1 * sl1 * ex2_fast(-fabsf(p1)));
         }
-        const float dS0 = P0 * (dp[j][e] * keep0 - delta0);
-        const float dS1 = P1 * (dp[j][2 + e] * keep1 - delta1);
-        s[j][e] = P0 * keep0; s[j][2 + e] = P1 * keep1;      // fragments now hold P keep and dS
-        dp[j][e] = dS0; dp[j][2 + e] = dS1;
-        if (s0 != seg0) {
-          if (a00 != 0.f || a01 != 0.f) { atomicAdd(&sm.bins[seg0].x, a00); atomicAdd(&sm.bins[seg0].y, a01); }
-          seg0 = s0; a00 = 0.f; a01 = 0.f;
-        }
-        if (s1 != seg1) {
-          if (a10 != 0.f || a11 != 0.f) { atomicAdd(&sm.bins[seg1].x, a10); atomicAdd(&sm.bins[seg1].y, a11); }
-          seg1 = s1; a10 = 0.f; a11 = 0.f;
-        }
-        a00 += dS0; a01 = fmaf(dS0, p0, a01);
-        a10 += dS1; a11 = fmaf(dS1, p1, a11);
-        kg[e] = -(dS0 * c0.x * __expf(-fabsf(p0)) + dS1 * c1.x * __expf(-fabsf(p1)));
+        // key-coordinate gradients of keys 8 j + 2 t + {0, 1}: sum over the warp's 16 rows (8 lanes share t)
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
+        if (g == 0) { atomicAdd(&sm.dkpos[8 * j + 2 * t], kg[0]); atomicAdd(&sm.dkpos[8 * j + 2 * t + 1], kg[1]); }
+        *reinterpret_cast<uint32_t*>(&sm.P[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
+        *reinterpret_cast<uint32_t*>(&sm.P[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
+        *reinterpret_cast<uint32_t*>(&sm.dS[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+        *reinterpret_cast<uint32_t*>(&sm.dS[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
       }
-      // key-coordinate gradients of keys 8 j + 2 t + {0, 1}: sum over the warp's 16 rows (8 lanes share t)
+      // merge the tile's sums into the rows' running sums (flush when the lower segment moved)
+      if (rw0.seg != ac0.seg) { pwl_flush(sm.bins, ac0, lane); ac0.seg = rw0.seg; }
+      if (rw1.seg != ac1.seg) { pwl_flush(sm.bins, ac1, lane); ac1.seg = rw1.seg; }
+      ac0.a0 += aT0 - aH0; ac0.b0 += bT0 - bH0; ac0.a1 += aH0; ac0.b1 += bH0;
+      ac1.a0 += aT1 - aH1; ac1.b0 += bT1 - bH1; ac1.a1 += aH1; ac1.b1 += bH1;
+    } else {
+      for (int j = 0; j < 4; ++j) {
+        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+        float kg[2];
 #pragma unroll
-      for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
-      if (g == 0) { atomicAdd(&sm.dkpos[8 * j + 2 * t], kg[0]); atomicAdd(&sm.dkpos[8 * j + 2 * t + 1], kg[1]); }
-      // bf16 tiles of P keep and dS for the transposed products
-      *reinterpret_cast<uint32_t*>(&sm.P[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
-      *reinterpret_cast<uint32_t*>(&sm.P[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
-      *reinterpret_cast<uint32_t*>(&sm.dS[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
-      *reinterpret_cast<uint32_t*>(&sm.dS[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+        for (int e = 0; e < 2; ++e) {
+          const float kxe = e ? kx.y : kx.x;
+          const bool kok = k0 + 8 * j + 2 * t + e < cf.nkv;
+          const float p0 = slog2_fast(qx0 - kxe), p1 = slog2_fast(qx1 - kxe);
+          const int s0 = pwl_seek(sm.pw, p0, rw0.seg), s1 = pwl_seek(sm.pw, p1, rw1.seg);
+          const float2 c0 = sm.pw.co[s0], c1 = sm.pw.co[s1];
+          const float P0 = kok ? ex2_fast(s[j][e] + fmaf(c0.x, p0, c0.y) - lse0) : 0.f;
+          const float P1 = kok ? ex2_fast(s[j][2 + e] + fmaf(c1.x, p1, c1.y) - lse1) : 0.f;
+          float keep0 = 1.f, keep1 = 1.f;
+          if (DROP) {
+            const unsigned long long key = (unsigned long long)(k0 + 8 * j + 2 * t + e);
+            keep0 = pair_hash(salted(cf.seed, cf.salt), hrow0 + key) >= thresh ? keep_scale : 0.f;
+            keep1 = pair_hash(salted(cf.seed, cf.salt), hrow1 + key) >= thresh ? keep_scale : 0.f;
+          }
+          const float dS0 = P0 * (dp[j][e] * keep0 - delta0);
+          const float dS1 = P1 * (dp[j][2 + e] * keep1 - delta1);
+          s[j][e] = P0 * keep0; s[j][2 + e] = P1 * keep1;
+          dp[j][e] = dS0; dp[j][2 + e] = dS1;
+          if (dS0 != 0.f) { atomicAdd(&sm.bins[s0].x, dS0); atomicAdd(&sm.bins[s0].y, dS0 * p0 * PWL_LN2); }
+          if (dS1 != 0.f) { atomicAdd(&sm.bins[s1].x, dS1); atomicAdd(&sm.bins[s1].y, dS1 * p1 * PWL_LN2); }
+          kg[e] = -fmaf(dS0 * c0.x, ex2_fast(-fabsf(p0)), dS1 * c1.x * ex2_fast(-fabsf(p1)));
+        }
+#pragma unroll
+        for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
+        if (g == 0) { atomicAdd(&sm.dkpos[8 * j + 2 * t], kg[0]); atomicAdd(&sm.dkpos[8 * j + 2 * t + 1], kg[1]); }
+        *reinterpret_cast<uint32_t*>(&sm.P[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
+        *reinterpret_cast<uint32_t*>(&sm.P[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
+        *reinterpret_cast<uint32_t*>(&sm.dS[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+        *reinterpret_cast<uint32_t*>(&sm.dS[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+      }
     }
     __syncthreads();
     // ---- dQ += dS K
-    {
-      float dqacc[8][4];
 #pragma unroll
-      for (int jd = 0; jd < 8; ++jd)
+    for (int ks = 0; ks < BK / 16; ++ks) {
+      uint32_t ah[4];
+      const int c0 = 16 * ks + 2 * t;
+      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0]);
+      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0 + 8]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) dqacc[jd][e] = sm.dQ[jd * 4 + e][tid];
-#pragma unroll
-      for (int ks = 0; ks < BK / 16; ++ks) {
-        uint32_t ah[4];
-        const int c0 = 16 * ks + 2 * t;
-        ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0]);
-        ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0 + 8]);
-#pragma unroll
-        for (int jd = 0; jd < 8; ++jd) {
-          uint32_t bh0, bh1;
-          ldmatrix_x2_trans(bh0, bh1, &sm.K[16 * ks + (lane & 15)][8 * jd]);
-          mma16816(dqacc[jd], ah, bh0, bh1);
-        }
+      for (int jd = 0; jd < 8; ++jd) {
+        uint32_t bh0, bh1;
+        ldmatrix_x2_trans(bh0, bh1, &sm.K[16 * ks + (lane & 15)][8 * jd]);
+        mma16816(dqacc[jd], ah, bh0, bh1);
       }
-#pragma unroll
-      for (int jd = 0; jd < 8; ++jd)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) sm.dQ[jd * 4 + e][tid] = dqacc[jd][e];
     }
     // ---- dK += dS^T Q and dV += (P keep)^T dO: warp slice = 16 keys x 32 dims, contraction over the CTA's 64 queries
     {
@@ -2029,30 +2143,30 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
         if (key0 < cf.nkv) {
           const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
-          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][0], dkacc[jd][1]));
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][0] * PWL_LN2, dkacc[jd][1] * PWL_LN2));
           atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][0], dvacc[jd][1]));
         }
         if (key1 < cf.nkv) {
           const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
-          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][2], dkacc[jd][3]));
+          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][2] * PWL_LN2, dkacc[jd][3] * PWL_LN2));
           atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][2], dvacc[jd][3]));
         }
       }
     }
     if (tid < BK && k0 + tid < cf.nkv) atomicAdd(dvs + (int64_t)bg * cf.nkv + k0 + tid, sm.dkpos[tid]);
   }
-  // ---- flush the open runs, dQ, and this CTA's segment sums
-  if (a00 != 0.f || a01 != 0.f) { atomicAdd(&sm.bins[seg0].x, a00); atomicAdd(&sm.bins[seg0].y, a01); }
-  if (a10 != 0.f || a11 != 0.f) { atomicAdd(&sm.bins[seg1].x, a10); atomicAdd(&sm.bins[seg1].y, a11); }
+  // ---- flush the running sums, dQ, and this CTA's segment sums
+  pwl_flush(sm.bins, ac0, lane);
+  pwl_flush(sm.bins, ac1, lane);
   if (ok0) {
     float* row = dq + qoff + (int64_t)(q0 + r0) * cf.inner + 2 * t;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4][tid], sm.dQ[j * 4 + 1][tid]);
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(dqacc[j][0], dqacc[j][1]);
   }
   if (ok1) {
     float* row = dq + qoff + (int64_t)(q0 + r1) * cf.inner + 2 * t;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(sm.dQ[j * 4 + 2][tid], sm.dQ[j * 4 + 3][tid]);
+    for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(dqacc[j][2], dqacc[j][3]);
   }
   __syncthreads();
   for (int i = tid; i < ns; i += MTHREADS) {
@@ -2680,10 +2794,12 @@ extern "C" int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64
   const size_t smem = sizeof(PwlFwdSmem);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(deform_attn_fwd_pwl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deform_attn_fwd_pwl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deform_attn_fwd_pwl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  deform_attn_fwd_pwl_kernel<<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, cpb, brk, coef, nseg, out, lse);
+  if (p_drop > 0.f) deform_attn_fwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse);
+  else deform_attn_fwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse);
   SML_LAUNCH_OK("sml_deform_attn_fwd_pwl");
   return 0;
 }
@@ -2701,11 +2817,16 @@ extern "C" int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64
   const size_t smem = sizeof(PwlBwdSmem);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(deform_attn_bwd_pwl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deform_attn_bwd_pwl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deform_attn_bwd_pwl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  deform_attn_bwd_pwl_kernel<<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse, dout, dq, dk, dv,
-                                                                          dvs, gseg);
+  if (p_drop > 0.f)
+    deform_attn_bwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse, dout, dq, dk,
+                                                                                  dv, dvs, gseg);
+  else
+    deform_attn_bwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse, dout, dq, dk,
+                                                                                   dv, dvs, gseg);
   SML_LAUNCH_OK("sml_deform_attn_bwd_pwl");
   return 0;
 }
