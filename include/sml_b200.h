@@ -114,17 +114,18 @@ int sml_cpb1d_table_slots(void);
 int sml_cpb1d_table_build(const float* cpb, int32_t OUT, float* brk, float* coef, int32_t* nseg, void* stream);
 int sml_cpb1d_table_eval(const float* t, int64_t n, const float* brk, const float* coef, const int32_t* nseg, int32_t OUT,
                          float* out, void* stream);
-/* 1-D fused deformable attention forward with the bias taken from that table instead of the per-pair MLP (same contract as
- * sml_deform_attn_fwd_tc with split = 0 and CD = 1; models/DeformableAttention1D.py:211-231 with :60-102 tabulated). */
-int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
-                            const float* vs, const float* cpb, const float* brk, const float* coef, const int32_t* nseg,
-                            float* out, float* lse, void* stream);
-/* Backward of sml_deform_attn_fwd_pwl.  dq is written; dk, dv, dvs and gseg [OUT, sml_cpb1d_seg_rows(), 2] are accumulated
- * into (zero them first).  gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with output o whose signed-log
- * distance p lies in segment s of the table; sml_cpb1d_table_bwd maps the sums to the gradient of the MLP parameters
- * (dcpb [sml_deform_cpb_nparams(1, OUT)], overwritten; specification oracle/pwl.py:param_grads_from_segments). */
+/* 1-D fused deformable attention with the bias taken from that table instead of the per-pair MLP (CD = 1;
+ * models/DeformableAttention1D.py:211-231 with :60-102 tabulated).  q fp32 [B, n, heads 64]; kh, vh = bf16 planes of K and V
+ * [B, nkv, heads 64] (the "bf16" mode's operand rounding, applied once by the caller); vs [(B G), nkv] key positions. */
+int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
+                            const float* vs, const float* brk, const float* coef, const int32_t* nseg, float* out, float* lse,
+                            void* stream);
+/* Backward.  dq is written; dk, dv, dvs and gseg [OUT, sml_cpb1d_seg_rows(), 2] are accumulated into (zero them first).
+ * gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with output o whose signed-log distance p lies in segment s
+ * of the table; sml_cpb1d_table_bwd maps the sums to the gradient of the MLP parameters (dcpb [sml_deform_cpb_nparams(1,
+ * OUT)], overwritten; specification oracle/pwl.py:param_grads_from_segments). */
 int sml_cpb1d_seg_rows(void);
-int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
+int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
                             const float* vs, const float* brk, const float* coef, const int32_t* nseg, const float* out,
                             const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs, float* gseg,
                             void* stream);

@@ -1217,28 +1217,72 @@ __device__ __forceinline__ float pwl_bias(const PwlRow& rw, float p) {
   const bool lo = p < rw.b;
   return fmaf(p, lo ? rw.sl : rw.sh, lo ? rw.il : rw.ih);
 }
-// min / max of the valid key positions of a tile (threads 0 .. NK - 1 of warp 0 / 1 hold one key each): result in red[0 .. 1]
-template <int NK>
-__device__ __forceinline__ void pwl_key_range(float kx, bool ok, float* red, int tid) {
-  if (tid < NK) {
-    float mn = ok ? kx : INFINITY, mx = ok ? kx : -INFINITY;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
-    }
-    if ((tid & 31) == 0) { red[2 * (tid >> 5)] = mn; red[2 * (tid >> 5) + 1] = mx; }
-  }
+// 16-byte global -> shared copies without register staging (rows past the end are zero-filled: src-size 0)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(src), "r"(sz));
 }
+__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int sz = ok ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" :: "r"(d), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+// one stage of the key ring: NK keys x 64 dims of the bf16 K and V planes + the keys' positions
+// Rows are 128 bytes, unpadded; the 16-byte chunk c of row r sits at chunk c ^ (r & 7), which keeps the fragment loads
+// (8 rows x 4 words) and ldmatrix (8 rows x 16 bytes) free of bank conflicts.
+template <int NK>
+struct PwlStage {
+  __nv_bfloat16 K[NK][AD], V[NK][AD];
+  float kx[NK];
+};
+__device__ __forceinline__ const __nv_bfloat16* pwl_sw(const __nv_bfloat16 (*T)[AD], int row, int col) {
+  return &T[row][((((col >> 3) ^ row) & 7) << 3) | (col & 7)];
+}
+template <int NK>
+__device__ __forceinline__ void pwl_stage_load(PwlStage<NK>& st, const __nv_bfloat16* __restrict__ kb, const __nv_bfloat16* __restrict__ vb,
+                                               const float* __restrict__ vsb, int64_t row_stride, int k0, int nkv, int tid) {
+  for (int e = tid; e < NK * 8; e += MTHREADS) {
+    const int r = e >> 3, c8 = (e & 7) * 8;
+    const bool ok = k0 + r < nkv;
+    const int64_t off = (int64_t)(ok ? k0 + r : 0) * row_stride + c8;
+    const int cs = (((c8 >> 3) ^ r) & 7) << 3;
+    cp_async16(&st.K[r][cs], kb + off, ok);
+    cp_async16(&st.V[r][cs], vb + off, ok);
+  }
+  if (tid < NK) { const bool ok = k0 + tid < nkv; cp_async4(&st.kx[tid], vsb + (ok ? k0 + tid : 0), ok); }
+}
+// range of the valid key positions of a stage, computed redundantly by every warp (no extra barrier)
+template <int NK>
+__device__ __forceinline__ void pwl_stage_range(const PwlStage<NK>& st, int k0, int nkv, int lane, float& kmin, float& kmax) {
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NK / 32; ++i) {
+    const float x = st.kx[lane + 32 * i];
+    if (k0 + lane + 32 * i < nkv) { mn = fminf(mn, x); mx = fmaxf(mx, x); }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  }
+  kmin = mn; kmax = mx;
+}
+constexpr int PWL_FK = 64;                // keys per forward tile
 struct PwlFwdSmem {
-  __nv_bfloat16 Q[MQ][MLD], K[64][MLD], V[2][64][MLD];
-  float kx[64];
-  float red[4];
+  __nv_bfloat16 Q[MQ][MLD];
+  PwlStage<PWL_FK> st[3];
   PwlTable pw;
 };
+// K and V arrive as bf16 planes (the mode's operand rounding, done once by the caller instead of once per query tile);
+// tiles move through a three-stage cp.async ring with one barrier per tile.  P is rounded to bf16 for P V (as in every
+// bf16 flash attention; the row sum l is accumulated from the unrounded values).
 template <bool DROP>
 __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const AttnCfg cf, const float* __restrict__ q,
-                                                                            const float* __restrict__ k, const float* __restrict__ v,
+                                                                            const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
                                                                             const float* __restrict__ vs, const float* __restrict__ brk,
                                                                             const float* __restrict__ coef, const int* __restrict__ nseg,
                                                                             float* __restrict__ out, float* __restrict__ lse) {
@@ -1249,6 +1293,14 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
   const int grp = head / cf.OUT, o = head % cf.OUT;
   const int bg = b * cf.G + grp;
   const int ns = nseg[0];
+  const __nv_bfloat16* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const __nv_bfloat16* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vsb = vs + (int64_t)bg * cf.nkv;
+  const int ntiles = (cf.nkv + PWL_FK - 1) / PWL_FK;
+  pwl_stage_load(sm.st[0], kb, vb, vsb, cf.inner, 0, cf.nkv, tid);
+  cp_async_commit();
+  if (ntiles > 1) pwl_stage_load(sm.st[1], kb, vb, vsb, cf.inner, PWL_FK, cf.nkv, tid);
+  cp_async_commit();
   pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
   {                                                     // Q tile, scaled by log2(e)
     const float* src = q + (int64_t)b * cf.n * cf.inner + head * AD;
@@ -1275,21 +1327,16 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
   const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
   const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
   const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
-  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
-  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
 
-  for (int k0 = 0; k0 < cf.nkv; k0 += 64) {
-    __syncthreads();
-    load_tile<false, 64>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
-    load_tile<true, 64>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
-    {
-      const bool ok = tid < 64 && k0 + tid < cf.nkv;
-      const float kx = ok ? vs[(int64_t)bg * cf.nkv + k0 + tid] : 0.f;
-      if (tid < 64) sm.kx[tid] = kx;
-      pwl_key_range<64>(kx, ok, sm.red, tid);
-    }
-    __syncthreads();
-    const float kmin = fminf(sm.red[0], sm.red[2]), kmax = fmaxf(sm.red[1], sm.red[3]);
+  for (int it = 0; it < ntiles; ++it) {
+    const int k0 = it * PWL_FK;
+    cp_async_wait<1>();                                 // my copies of tile `it` have landed
+    __syncthreads();                                    // ... everyone's have, and everyone is done with tile it - 1
+    if (it + 2 < ntiles) pwl_stage_load(sm.st[(it + 2) % 3], kb, vb, vsb, cf.inner, k0 + 2 * PWL_FK, cf.nkv, tid);
+    cp_async_commit();
+    const PwlStage<PWL_FK>& st = sm.st[it % 3];
+    float kmin, kmax;
+    pwl_stage_range(st, k0, cf.nkv, lane, kmin, kmax);
     const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
     const bool many1 = pwl_row_setup(sm.pw, ns, qx1, kmin, kmax, rw1);
     const bool slow = __any_sync(0xffffffffu, many0 || many1);
@@ -1308,8 +1355,8 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
       ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][16 * ks + 2 * t + 8]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][16 * ks + 2 * t]);
-        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][16 * ks + 2 * t + 8]);
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, 16 * ks + 2 * t));
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, 16 * ks + 2 * t + 8));
         mma16816(s[j], ah, bh0, bh1);
       }
     }
@@ -1317,13 +1364,13 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
     if (!slow) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+        const float2 kx = *reinterpret_cast<const float2*>(&st.kx[8 * j + 2 * t]);
         s[j][0] += pwl_bias(rw0, slog2_fast(qx0 - kx.x)); s[j][1] += pwl_bias(rw0, slog2_fast(qx0 - kx.y));
         s[j][2] += pwl_bias(rw1, slog2_fast(qx1 - kx.x)); s[j][3] += pwl_bias(rw1, slog2_fast(qx1 - kx.y));
       }
     } else {
       for (int j = 0; j < 8; ++j) {
-        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+        const float2 kx = *reinterpret_cast<const float2*>(&st.kx[8 * j + 2 * t]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float p = slog2_fast(((e & 2) ? qx1 : qx0) - ((e & 1) ? kx.y : kx.x));
@@ -1332,7 +1379,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
         }
       }
     }
-    if (k0 + 64 > cf.nkv) {                             // ragged last tile
+    if (k0 + PWL_FK > cf.nkv) {                         // ragged last tile
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -1366,20 +1413,19 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
         }
         s[j][e] = p0; s[j][2 + e] = p1;
       }
-    // ---- O += P V (P as bf16 hi + lo: the backward's delta = dO . O relies on an fp32-grade O)
+    // ---- O += P V
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      uint32_t ah[4], al[4];
-      split2<true>(s[2 * ks][0], s[2 * ks][1], ah[0], al[0]);
-      split2<true>(s[2 * ks][2], s[2 * ks][3], ah[1], al[1]);
-      split2<true>(s[2 * ks + 1][0], s[2 * ks + 1][1], ah[2], al[2]);
-      split2<true>(s[2 * ks + 1][2], s[2 * ks + 1][3], ah[3], al[3]);
+      uint32_t ah[4];
+      ah[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+      ah[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+      ah[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      ah[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        uint32_t bh0, bh1, bl0, bl1;
-        ldmatrix_x2_trans(bh0, bh1, &sm.V[0][16 * ks + (lane & 15)][8 * j]);
-        ldmatrix_x2_trans(bl0, bl1, &sm.V[1][16 * ks + (lane & 15)][8 * j]);
-        mma3<true>(oacc[j], ah, al, bh0, bh1, bl0, bl1);
+        uint32_t bh0, bh1;
+        ldmatrix_x2_trans(bh0, bh1, pwl_sw(st.V, 16 * ks + (lane & 15), 8 * j));
+        mma16816(oacc[j], ah, bh0, bh1);
       }
     }
   }
@@ -1879,12 +1925,10 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
 // search the table and bin per pair (warp-uniform slow path).  Key-coordinate gradient: d bias / d p = slope,
 // d p / d kx = -1 / (|d| + 1) = -2^(-|p2|).  dQ / dK / dV as in the lean backward (dK is rescaled by ln 2: the Q tile carries log2 e).
 struct PwlBwdSmem {
-  __nv_bfloat16 Q[MQ][MLD], dO[2][MQ][MLD];
-  __nv_bfloat16 K[BK][MLD], V[2][BK][MLD];
-  __nv_bfloat16 P[MQ][PLD], dS[MQ][PLD];
-  float dkpos[BK];
-  float kx[BK];
-  float red[2];
+  __nv_bfloat16 Q[MQ][MLD], dO[MQ][MLD];
+  PwlStage<BK> st[4];
+  __nv_bfloat16 P[2][MQ][PLD], dS[2][MQ][PLD];
+  float dkpos[2][BK];
   PwlTable pw;
   float2 bins[PWL_MAXSEG];
 };
@@ -1902,9 +1946,13 @@ __device__ __forceinline__ void pwl_flush(float2* bins, PwlAcc& ac, int lane) {
   ac.a0 = ac.b0 = ac.a1 = ac.b1 = 0.f;
 }
 
+// Operands: K, V as bf16 planes from the caller; dO is rounded to bf16 once and delta = bf16(dO) . O uses the same rounded
+// values, so that sum_j P_ij dP_ij = delta holds to fp32 rounding with single-pass products (dP = bf16(dO) bf16(V)^T,
+// O = sum_j P_ij bf16(V_j)).  Key tiles move through a four-stage cp.async ring, P / dS tiles are double-buffered: one
+// barrier per tile.
 template <bool DROP>
-__global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
-    const AttnCfg cf, const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+__global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
+    const AttnCfg cf, const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     const float* __restrict__ vs, const float* __restrict__ brk, const float* __restrict__ coef, const int* __restrict__ nseg,
     const float* __restrict__ out, const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq,
     float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ gseg) {
@@ -1915,16 +1963,29 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
   const int grp = head / cf.OUT, o = head % cf.OUT;
   const int bg = b * cf.G + grp;
   const int ns = nseg[0];
+  const __nv_bfloat16* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const __nv_bfloat16* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
+  const float* vsb = vs + (int64_t)bg * cf.nkv;
+  const int ntiles = (cf.nkv + BK - 1) / BK;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (i < ntiles) pwl_stage_load(sm.st[i], kb, vb, vsb, cf.inner, i * BK, cf.nkv, tid);
+    cp_async_commit();
+  }
   pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
   for (int i = tid; i <= ns; i += MTHREADS) sm.bins[min(i, PWL_MAXSEG - 1)] = make_float2(0.f, 0.f);
+  if (tid < 2 * BK) sm.dkpos[tid / BK][tid % BK] = 0.f;
   const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
-  for (int e = tid; e < MQ * 16; e += MTHREADS) {          // Q tile, scaled by log2(e)
+  for (int e = tid; e < MQ * 16; e += MTHREADS) {          // Q tile scaled by log2(e); dO tile
     const int r = e >> 4, c4 = (e & 15) * 4;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + r < cf.n) x = *reinterpret_cast<const float4*>(q + qoff + (int64_t)(q0 + r) * cf.inner + c4);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+    if (q0 + r < cf.n) {
+      x = *reinterpret_cast<const float4*>(q + qoff + (int64_t)(q0 + r) * cf.inner + c4);
+      y = *reinterpret_cast<const float4*>(dout + qoff + (int64_t)(q0 + r) * cf.inner + c4);
+    }
     *reinterpret_cast<uint2*>(&sm.Q[r][c4]) = make_uint2(pack_bf16(x.x * PWL_LOG2E, x.y * PWL_LOG2E), pack_bf16(x.z * PWL_LOG2E, x.w * PWL_LOG2E));
+    *reinterpret_cast<uint2*>(&sm.dO[r][c4]) = make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
   }
-  load_tile<true, MQ>(sm.dO[0], sm.dO[1], dout + qoff, cf.inner, q0, cf.n);
   const int r0 = w * 16 + g, r1 = r0 + 8;
   const bool ok0 = q0 + r0 < cf.n, ok1 = q0 + r1 < cf.n;
   float qx0, qx1, qdum;
@@ -1932,25 +1993,20 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
   query_pos(cf, min(q0 + r1, cf.n - 1), qx1, qdum);
   float delta0 = 0.f, delta1 = 0.f, lse0 = INFINITY, lse1 = INFINITY;      // lse in base-2 units
   {
-    if (ok0) {
-      const float* orow = out + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
-      const float* grow = dout + qoff + (int64_t)(q0 + r0) * cf.inner + 16 * t;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
-        delta0 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta0))));
-      }
-      lse0 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r0] * PWL_LOG2E;
-    }
-    if (ok1) {
-      const float* orow = out + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
-      const float* grow = dout + qoff + (int64_t)(q0 + r1) * cf.inner + 16 * t;
+    for (int rr = 0; rr < 2; ++rr) {
+      if (rr ? ok1 : ok0) {
+        const int64_t ro = qoff + (int64_t)(q0 + (rr ? r1 : r0)) * cf.inner + 16 * t;
+        float d = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(orow + 4 * i), c = *reinterpret_cast<const float4*>(grow + 4 * i);
-        delta1 = fmaf(a.x, c.x, fmaf(a.y, c.y, fmaf(a.z, c.z, fmaf(a.w, c.w, delta1))));
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = *reinterpret_cast<const float4*>(out + ro + 4 * i), c = *reinterpret_cast<const float4*>(dout + ro + 4 * i);
+          const uint32_t c01 = pack_bf16(c.x, c.y), c23 = pack_bf16(c.z, c.w);
+          d = fmaf(a.x, bf16_lo_f(c01), fmaf(a.y, bf16_hi_f(c01), fmaf(a.z, bf16_lo_f(c23), fmaf(a.w, bf16_hi_f(c23), d))));
+        }
+        const float l2 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + (rr ? r1 : r0)] * PWL_LOG2E;
+        if (rr) { delta1 = d; lse1 = l2; } else { delta0 = d; lse0 = l2; }
       }
-      lse1 = lse[((int64_t)b * cf.heads + head) * cf.n + q0 + r1] * PWL_LOG2E;
     }
     delta0 += __shfl_xor_sync(0xffffffffu, delta0, 1); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 1);
     delta0 += __shfl_xor_sync(0xffffffffu, delta0, 2); delta1 += __shfl_xor_sync(0xffffffffu, delta1, 2);
@@ -1959,8 +2015,6 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
   const uint32_t thresh = (uint32_t)(cf.p_drop * 4294967296.0);
   const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
   const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
-  const float* kb = k + (int64_t)b * cf.nkv * cf.inner + head * AD;
-  const float* vb = v + (int64_t)b * cf.nkv * cf.inner + head * AD;
   PwlRow rw0, rw1;
   rw0.seg = rw1.seg = ns >> 1;
   PwlAcc ac0, ac1;
@@ -1972,23 +2026,21 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
   for (int jd = 0; jd < 8; ++jd)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dqacc[jd][e] = 0.f;
+  cp_async_wait<2>();                                   // tile 0
+  __syncthreads();
 
-  for (int k0 = 0; k0 < cf.nkv; k0 += BK) {
-    __syncthreads();
-    load_tile<false, BK>(sm.K, nullptr, kb, cf.inner, k0, cf.nkv);
-    load_tile<true, BK>(sm.V[0], sm.V[1], vb, cf.inner, k0, cf.nkv);
-    {
-      const bool ok = tid < BK && k0 + tid < cf.nkv;
-      const float kx = ok ? vs[(int64_t)bg * cf.nkv + k0 + tid] : 0.f;
-      if (tid < BK) { sm.kx[tid] = kx; sm.dkpos[tid] = 0.f; }
-      pwl_key_range<BK>(kx, ok, sm.red, tid);
-    }
-    __syncthreads();
-    const float kmin = sm.red[0], kmax = sm.red[1];
+  for (int it = 0; it < ntiles; ++it) {
+    const int k0 = it * BK;
+    const PwlStage<BK>& st = sm.st[it & 3];
+    __nv_bfloat16 (*Pt)[PLD] = sm.P[it & 1];
+    __nv_bfloat16 (*dSt)[PLD] = sm.dS[it & 1];
+    float* dkp = sm.dkpos[it & 1];
+    float kmin, kmax;
+    pwl_stage_range(st, k0, cf.nkv, lane, kmin, kmax);
     const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
     const bool many1 = pwl_row_setup(sm.pw, ns, qx1, kmin, kmax, rw1);
     const bool slow = __any_sync(0xffffffffu, many0 || many1);
-    // ---- S2 = log2(e) Q K^T and dP = dO V^T (dO, V as hi + lo) of my 16 rows x the 32 keys of the tile
+    // ---- S2 = log2(e) Q K^T and dP = dO V^T of my 16 rows x the 32 keys of the tile
     float s[4][4], dp[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -1996,24 +2048,20 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
       for (int e = 0; e < 4; ++e) { s[j][e] = 0.f; dp[j][e] = 0.f; }
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      uint32_t ah[4], gh[4], gl[4];
+      uint32_t ah[4], gh[4];
       const int c0 = 16 * ks + 2 * t;
       ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0]);
       ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0 + 8]);
-      gh[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0]);     gh[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0]);
-      gh[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r0][c0 + 8]); gh[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[0][r1][c0 + 8]);
-      gl[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0]);     gl[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0]);
-      gl[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r0][c0 + 8]); gl[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[1][r1][c0 + 8]);
+      gh[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[r0][c0]);     gh[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[r1][c0]);
+      gh[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[r0][c0 + 8]); gh[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[r1][c0 + 8]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0]);
-        const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(&sm.K[8 * j + g][c0 + 8]);
-        const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0]);
-        const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(&sm.V[0][8 * j + g][c0 + 8]);
-        const uint32_t vl0 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0]);
-        const uint32_t vl1 = *reinterpret_cast<const uint32_t*>(&sm.V[1][8 * j + g][c0 + 8]);
+        const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, c0));
+        const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, c0 + 8));
+        const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.V, 8 * j + g, c0));
+        const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.V, 8 * j + g, c0 + 8));
         mma16816(s[j], ah, kh0, kh1);
-        mma3<true>(dp[j], gh, gl, vh0, vh1, vl0, vl1);
+        mma16816(dp[j], gh, vh0, vh1);
       }
     }
     // ---- per element: bias, P, dS, segment sums, key-coordinate gradient
@@ -2022,7 +2070,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
       float aT0 = 0.f, bT0 = 0.f, aH0 = 0.f, bH0 = 0.f, aT1 = 0.f, bT1 = 0.f, aH1 = 0.f, bH1 = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+        const float2 kx = *reinterpret_cast<const float2*>(&st.kx[8 * j + 2 * t]);
         float kg[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -2051,11 +2099,11 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
         // key-coordinate gradients of keys 8 j + 2 t + {0, 1}: sum over the warp's 16 rows (8 lanes share t)
 #pragma unroll
         for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
-        if (g == 0) { atomicAdd(&sm.dkpos[8 * j + 2 * t], kg[0]); atomicAdd(&sm.dkpos[8 * j + 2 * t + 1], kg[1]); }
-        *reinterpret_cast<uint32_t*>(&sm.P[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
-        *reinterpret_cast<uint32_t*>(&sm.P[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
-        *reinterpret_cast<uint32_t*>(&sm.dS[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
-        *reinterpret_cast<uint32_t*>(&sm.dS[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+        if (g == 0) { atomicAdd(&dkp[8 * j + 2 * t], kg[0]); atomicAdd(&dkp[8 * j + 2 * t + 1], kg[1]); }
+        *reinterpret_cast<uint32_t*>(&Pt[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
+        *reinterpret_cast<uint32_t*>(&Pt[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
+        *reinterpret_cast<uint32_t*>(&dSt[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+        *reinterpret_cast<uint32_t*>(&dSt[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
       }
       // merge the tile's sums into the rows' running sums (flush when the lower segment moved)
       if (rw0.seg != ac0.seg) { pwl_flush(sm.bins, ac0, lane); ac0.seg = rw0.seg; }
@@ -2064,7 +2112,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
       ac1.a0 += aT1 - aH1; ac1.b0 += bT1 - bH1; ac1.a1 += aH1; ac1.b1 += bH1;
     } else {
       for (int j = 0; j < 4; ++j) {
-        const float2 kx = *reinterpret_cast<const float2*>(&sm.kx[8 * j + 2 * t]);
+        const float2 kx = *reinterpret_cast<const float2*>(&st.kx[8 * j + 2 * t]);
         float kg[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -2091,25 +2139,28 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
         }
 #pragma unroll
         for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
-        if (g == 0) { atomicAdd(&sm.dkpos[8 * j + 2 * t], kg[0]); atomicAdd(&sm.dkpos[8 * j + 2 * t + 1], kg[1]); }
-        *reinterpret_cast<uint32_t*>(&sm.P[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
-        *reinterpret_cast<uint32_t*>(&sm.P[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
-        *reinterpret_cast<uint32_t*>(&sm.dS[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
-        *reinterpret_cast<uint32_t*>(&sm.dS[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+        if (g == 0) { atomicAdd(&dkp[8 * j + 2 * t], kg[0]); atomicAdd(&dkp[8 * j + 2 * t + 1], kg[1]); }
+        *reinterpret_cast<uint32_t*>(&Pt[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
+        *reinterpret_cast<uint32_t*>(&Pt[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
+        *reinterpret_cast<uint32_t*>(&dSt[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+        *reinterpret_cast<uint32_t*>(&dSt[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
       }
     }
-    __syncthreads();
+    cp_async_wait<1>();                                 // my copies of tile it + 1 have landed
+    __syncthreads();                                    // P / dS of this tile and tile it + 1 visible; everyone is past tile it - 1
+    if (it + 3 < ntiles) pwl_stage_load(sm.st[(it + 3) & 3], kb, vb, vsb, cf.inner, k0 + 3 * BK, cf.nkv, tid);
+    cp_async_commit();
     // ---- dQ += dS K
 #pragma unroll
     for (int ks = 0; ks < BK / 16; ++ks) {
       uint32_t ah[4];
       const int c0 = 16 * ks + 2 * t;
-      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0]);
-      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.dS[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.dS[r1][c0 + 8]);
+      ah[0] = *reinterpret_cast<const uint32_t*>(&dSt[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&dSt[r1][c0]);
+      ah[2] = *reinterpret_cast<const uint32_t*>(&dSt[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&dSt[r1][c0 + 8]);
 #pragma unroll
       for (int jd = 0; jd < 8; ++jd) {
         uint32_t bh0, bh1;
-        ldmatrix_x2_trans(bh0, bh1, &sm.K[16 * ks + (lane & 15)][8 * jd]);
+        ldmatrix_x2_trans(bh0, bh1, pwl_sw(st.K, 16 * ks + (lane & 15), 8 * jd));
         mma16816(dqacc[jd], ah, bh0, bh1);
       }
     }
@@ -2126,13 +2177,13 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
       for (int ks = 0; ks < 4; ++ks) {
         const int qrow = 16 * ks + rr + 8 * (mi >> 1), kcol = 16 * mt + 8 * (mi & 1);
         uint32_t sh[4], ph[4];
-        ldmatrix_x4_trans(sh[0], sh[1], sh[2], sh[3], &sm.dS[qrow][kcol]);
-        ldmatrix_x4_trans(ph[0], ph[1], ph[2], ph[3], &sm.P[qrow][kcol]);
+        ldmatrix_x4_trans(sh[0], sh[1], sh[2], sh[3], &dSt[qrow][kcol]);
+        ldmatrix_x4_trans(ph[0], ph[1], ph[2], ph[3], &Pt[qrow][kcol]);
 #pragma unroll
         for (int jd = 0; jd < 4; ++jd) {
           uint32_t qh0, qh1, gh0, gh1;
           ldmatrix_x2_trans(qh0, qh1, &sm.Q[16 * ks + (lane & 15)][32 * dh + 8 * jd]);
-          ldmatrix_x2_trans(gh0, gh1, &sm.dO[0][16 * ks + (lane & 15)][32 * dh + 8 * jd]);
+          ldmatrix_x2_trans(gh0, gh1, &sm.dO[16 * ks + (lane & 15)][32 * dh + 8 * jd]);
           mma16816(dkacc[jd], sh, qh0, qh1);
           mma16816(dvacc[jd], ph, gh0, gh1);
         }
@@ -2153,7 +2204,10 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
         }
       }
     }
-    if (tid < BK && k0 + tid < cf.nkv) atomicAdd(dvs + (int64_t)bg * cf.nkv + k0 + tid, sm.dkpos[tid]);
+    if (tid < BK) {
+      if (k0 + tid < cf.nkv) atomicAdd(dvs + (int64_t)bg * cf.nkv + k0 + tid, dkp[tid]);
+      dkp[tid] = 0.f;
+    }
   }
   // ---- flush the running sums, dQ, and this CTA's segment sums
   pwl_flush(sm.bins, ac0, lane);
@@ -2783,10 +2837,11 @@ static int launch_fwd_lean(const AttnCfg& cf, const float* q, const float* k, co
   return 0;
 }
 
-/* 1-D only (CD = 1): forward with the bias MLP replaced by its piecewise-linear table (sml_cpb1d_table_build), plain bf16 operands */
-extern "C" int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
-                                       const float* vs, const float* cpb, const float* brk, const float* coef, const int32_t* nseg,
-                                       float* out, float* lse, void* stream) {
+/* 1-D only (CD = 1): forward with the bias MLP replaced by its piecewise-linear table (sml_cpb1d_table_build).  kh, vh = bf16
+ * planes of K and V (same [B, nkv, heads * 64] layout), q fp32 */
+extern "C" int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
+                                       const float* vs, const float* brk, const float* coef, const int32_t* nseg, float* out, float* lse,
+                                       void* stream) {
   AttnCfg cf;
   if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
   SML_CHECK(cf.CD == 1, "sml_deform_attn_fwd_pwl: one coordinate dimension only");
@@ -2798,15 +2853,17 @@ extern "C" int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64
     cudaFuncSetAttribute(deform_attn_fwd_pwl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  if (p_drop > 0.f) deform_attn_fwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse);
-  else deform_attn_fwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse);
+  const __nv_bfloat16 *kp = (const __nv_bfloat16*)kh, *vp = (const __nv_bfloat16*)vh;
+  if (p_drop > 0.f) deform_attn_fwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse);
+  else deform_attn_fwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse);
   SML_LAUNCH_OK("sml_deform_attn_fwd_pwl");
   return 0;
 }
 
-/* backward of sml_deform_attn_fwd_pwl.  dk, dv, dvs and gseg [OUT, sml_cpb1d_table_slots() + 2, 2] zero-initialised by the caller;
- * gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with output o whose distance p lies in segment s */
-extern "C" int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const float* k, const float* v,
+/* backward of sml_deform_attn_fwd_pwl (kh, vh = the same bf16 planes).  dk, dv, dvs and gseg [OUT, sml_cpb1d_seg_rows(), 2]
+ * zero-initialised by the caller; gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with output o whose distance p
+ * lies in segment s */
+extern "C" int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
                                        const float* vs, const float* brk, const float* coef, const int32_t* nseg, const float* out,
                                        const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs, float* gseg,
                                        void* stream) {
@@ -2821,11 +2878,12 @@ extern "C" int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64
     cudaFuncSetAttribute(deform_attn_bwd_pwl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
+  const __nv_bfloat16 *kp = (const __nv_bfloat16*)kh, *vp = (const __nv_bfloat16*)vh;
   if (p_drop > 0.f)
-    deform_attn_bwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse, dout, dq, dk,
+    deform_attn_bwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse, dout, dq, dk,
                                                                                   dv, dvs, gseg);
   else
-    deform_attn_bwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, k, v, vs, brk, coef, nseg, out, lse, dout, dq, dk,
+    deform_attn_bwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse, dout, dq, dk,
                                                                                    dv, dvs, gseg);
   SML_LAUNCH_OK("sml_deform_attn_bwd_pwl");
   return 0;

@@ -186,8 +186,10 @@ class DeformAttnFn(torch.autograd.Function):
             check(lib.sml_deform_attn_fwd(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                           ptr(out), ptr(lse), stream()), "deform_attn_fwd")
         elif prec == "bf16" and PWL_1D and not two_d:                  # 1-D: bias from the piecewise-linear table
-            brk, coef, nseg = pwl = cpb1d_table(cpb, heads // G)
-            check(lib.sml_deform_attn_fwd_pwl(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
+            brk, coef, nseg = cpb1d_table(cpb, heads // G)
+            kh, vh = ops.to_bf16(k).hi, ops.to_bf16(v).hi              # the mode's operand rounding, once per call
+            pwl = (brk, coef, nseg, kh, vh)
+            check(lib.sml_deform_attn_fwd_pwl(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(kh), ptr(vh), ptr(vs),
                                               ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), stream()), "deform_attn_fwd_pwl")
         elif prec == "bf16" and TC5_FWD and two_d and heads == G:     # tcgen05 / TMEM kernel
             check(lib.sml_deform_attn_fwd_tc5(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
@@ -232,10 +234,10 @@ class DeformAttnFn(torch.autograd.Function):
         part = torch.empty(nblk, npar, device=dev, dtype=F32) if pwl is None else None
         prof = _prof_begin()
         if pwl is not None:         # 1-D, bias from the table: per-segment sums, mapped to the MLP parameters afterwards
-            brk, coef, nseg = pwl
+            brk, coef, nseg, kh, vh = pwl
             gseg = torch.zeros(heads // G, lib.sml_cpb1d_seg_rows(), 2, device=dev, dtype=F32)
             dcpb = torch.empty(npar, device=dev, dtype=F32)
-            check(lib.sml_deform_attn_bwd_pwl(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs),
+            check(lib.sml_deform_attn_bwd_pwl(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(kh), ptr(vh), ptr(vs),
                                               ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk),
                                               ptr(dv), ptr(dvs_b), ptr(gseg), stream()), "deform_attn_bwd_pwl")
             check(lib.sml_cpb1d_table_bwd(ptr(cpb), c_i32(heads // G), ptr(brk), ptr(nseg), ptr(gseg), ptr(dcpb), stream()),
