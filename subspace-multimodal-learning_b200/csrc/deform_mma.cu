@@ -1928,22 +1928,37 @@ struct PwlBwdSmem {
   __nv_bfloat16 Q[MQ][MLD], dO[MQ][MLD];
   PwlStage<BK> st[4];
   __nv_bfloat16 P[2][MQ][PLD], dS[2][MQ][PLD];
-  float dkpos[2][BK];
+  float dkpos[2][MTHREADS / 32][BK];      // per-warp partial key-coordinate gradients (no shared-memory atomics)
   PwlTable pw;
   float2 bins[PWL_MAXSEG];
 };
 // running per-row sums of the segments {seg, seg + 1}; the four lanes of a quad hold the same row: they are reduced at flush time
 struct PwlAcc { int seg; float a0, b0, a1, b1; };
-__device__ __forceinline__ void pwl_flush(float2* bins, PwlAcc& ac, int lane) {
-  const unsigned quad = 0xFu << (lane & 28);
-  float v0 = ac.a0, v1 = ac.b0, v2 = ac.a1, v3 = ac.b1;
-  v0 += __shfl_xor_sync(quad, v0, 1); v1 += __shfl_xor_sync(quad, v1, 1); v2 += __shfl_xor_sync(quad, v2, 1); v3 += __shfl_xor_sync(quad, v3, 1);
-  v0 += __shfl_xor_sync(quad, v0, 2); v1 += __shfl_xor_sync(quad, v1, 2); v2 += __shfl_xor_sync(quad, v2, 2); v3 += __shfl_xor_sync(quad, v3, 2);
-  if ((lane & 3) == 0) {
-    if (v0 != 0.f || v1 != 0.f) { atomicAdd(&bins[ac.seg].x, v0); atomicAdd(&bins[ac.seg].y, v1 * PWL_LN2); }
-    if (v2 != 0.f || v3 != 0.f) { atomicAdd(&bins[ac.seg + 1].x, v2); atomicAdd(&bins[ac.seg + 1].y, v3 * PWL_LN2); }
+// Adds the running sums of the lanes with `need` to the bins and clears them.  The 16 rows of a warp sit in nearly the same
+// place of the table, so they almost always leave the same segment in the same tile: then the warp reduces the four sums
+// with shuffles and one lane issues the four shared-memory atomics (fp32 shared atomics are compare-and-swap loops: 8 rows
+// hitting one bin cost ~15 spins each).  Rows that disagree fall back to one atomic set per row.  Warp-uniform call;
+// `need` is the same in the four lanes of a quad.
+__device__ __forceinline__ void pwl_flush(float2* bins, PwlAcc& ac, bool need, int lane) {
+  const unsigned who = __ballot_sync(0xffffffffu, need);
+  if (who == 0u) return;
+  const int segref = __shfl_sync(0xffffffffu, ac.seg, __ffs(who) - 1);
+  const bool same = __all_sync(0xffffffffu, !need || ac.seg == segref);
+  // the four lanes of a quad hold partial sums (different keys) of the same row: always reduced; all rows only when they agree
+  float v0 = need ? ac.a0 : 0.f, v1 = need ? ac.b0 : 0.f, v2 = need ? ac.a1 : 0.f, v3 = need ? ac.b1 : 0.f;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    if (m < 4 || same) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, m); v1 += __shfl_xor_sync(0xffffffffu, v1, m);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, m); v3 += __shfl_xor_sync(0xffffffffu, v3, m);
+    }
   }
-  ac.a0 = ac.b0 = ac.a1 = ac.b1 = 0.f;
+  if (same ? lane == 0 : (need && (lane & 3) == 0)) {
+    const int sg = same ? segref : ac.seg;
+    if (v0 != 0.f || v1 != 0.f) { atomicAdd(&bins[sg].x, v0); atomicAdd(&bins[sg].y, v1 * PWL_LN2); }
+    if (v2 != 0.f || v3 != 0.f) { atomicAdd(&bins[sg + 1].x, v2); atomicAdd(&bins[sg + 1].y, v3 * PWL_LN2); }
+  }
+  if (need) ac.a0 = ac.b0 = ac.a1 = ac.b1 = 0.f;
 }
 
 // Operands: K, V as bf16 planes from the caller; dO is rounded to bf16 once and delta = bf16(dO) . O uses the same rounded
@@ -1974,7 +1989,6 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
   }
   pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
   for (int i = tid; i <= ns; i += MTHREADS) sm.bins[min(i, PWL_MAXSEG - 1)] = make_float2(0.f, 0.f);
-  if (tid < 2 * BK) sm.dkpos[tid / BK][tid % BK] = 0.f;
   const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
   for (int e = tid; e < MQ * 16; e += MTHREADS) {          // Q tile scaled by log2(e); dO tile
     const int r = e >> 4, c4 = (e & 15) * 4;
@@ -2034,7 +2048,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
     const PwlStage<BK>& st = sm.st[it & 3];
     __nv_bfloat16 (*Pt)[PLD] = sm.P[it & 1];
     __nv_bfloat16 (*dSt)[PLD] = sm.dS[it & 1];
-    float* dkp = sm.dkpos[it & 1];
+    float* dkp = sm.dkpos[it & 1][w];
     float kmin, kmax;
     pwl_stage_range(st, k0, cf.nkv, lane, kmin, kmax);
     const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
@@ -2099,15 +2113,15 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         // key-coordinate gradients of keys 8 j + 2 t + {0, 1}: sum over the warp's 16 rows (8 lanes share t)
 #pragma unroll
         for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
-        if (g == 0) { atomicAdd(&dkp[8 * j + 2 * t], kg[0]); atomicAdd(&dkp[8 * j + 2 * t + 1], kg[1]); }
+        if (g == 0) *reinterpret_cast<float2*>(&dkp[8 * j + 2 * t]) = make_float2(kg[0], kg[1]);
         *reinterpret_cast<uint32_t*>(&Pt[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
         *reinterpret_cast<uint32_t*>(&Pt[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
         *reinterpret_cast<uint32_t*>(&dSt[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
         *reinterpret_cast<uint32_t*>(&dSt[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
       }
       // merge the tile's sums into the rows' running sums (flush when the lower segment moved)
-      if (rw0.seg != ac0.seg) { pwl_flush(sm.bins, ac0, lane); ac0.seg = rw0.seg; }
-      if (rw1.seg != ac1.seg) { pwl_flush(sm.bins, ac1, lane); ac1.seg = rw1.seg; }
+      pwl_flush(sm.bins, ac0, rw0.seg != ac0.seg, lane); ac0.seg = rw0.seg;
+      pwl_flush(sm.bins, ac1, rw1.seg != ac1.seg, lane); ac1.seg = rw1.seg;
       ac0.a0 += aT0 - aH0; ac0.b0 += bT0 - bH0; ac0.a1 += aH0; ac0.b1 += bH0;
       ac1.a0 += aT1 - aH1; ac1.b0 += bT1 - bH1; ac1.a1 += aH1; ac1.b1 += bH1;
     } else {
@@ -2139,7 +2153,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         }
 #pragma unroll
         for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
-        if (g == 0) { atomicAdd(&dkp[8 * j + 2 * t], kg[0]); atomicAdd(&dkp[8 * j + 2 * t + 1], kg[1]); }
+        if (g == 0) *reinterpret_cast<float2*>(&dkp[8 * j + 2 * t]) = make_float2(kg[0], kg[1]);
         *reinterpret_cast<uint32_t*>(&Pt[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
         *reinterpret_cast<uint32_t*>(&Pt[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
         *reinterpret_cast<uint32_t*>(&dSt[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
@@ -2204,14 +2218,13 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         }
       }
     }
-    if (tid < BK) {
-      if (k0 + tid < cf.nkv) atomicAdd(dvs + (int64_t)bg * cf.nkv + k0 + tid, dkp[tid]);
-      dkp[tid] = 0.f;
-    }
+    if (tid < BK && k0 + tid < cf.nkv)
+      atomicAdd(dvs + (int64_t)bg * cf.nkv + k0 + tid, (sm.dkpos[it & 1][0][tid] + sm.dkpos[it & 1][1][tid]) +
+                                                         (sm.dkpos[it & 1][2][tid] + sm.dkpos[it & 1][3][tid]));
   }
   // ---- flush the running sums, dQ, and this CTA's segment sums
-  pwl_flush(sm.bins, ac0, lane);
-  pwl_flush(sm.bins, ac1, lane);
+  pwl_flush(sm.bins, ac0, true, lane);
+  pwl_flush(sm.bins, ac1, true, lane);
   if (ok0) {
     float* row = dq + qoff + (int64_t)(q0 + r0) * cf.inner + 2 * t;
 #pragma unroll
