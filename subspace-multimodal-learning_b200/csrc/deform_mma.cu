@@ -1179,7 +1179,12 @@ constexpr int PWL_MAXSEG = 1089;
 constexpr float PWL_LOG2E = 1.4426950408889634f, PWL_LN2 = 0.6931471805599453f;
 struct PwlTable {
   float B[PWL_MAXSEG + 1];               // segment s covers [B[s], B[s + 1]) in p2 units; B[0] = -inf, B[nseg] = +inf
-  float2 co[PWL_MAXSEG];                 // (slope, intercept log2(e)) of this head's output
+  const float2* co;                      // (slope, intercept) of this head's output: global memory, row stride `cs` float2
+  int cs;
+  __device__ __forceinline__ float2 line(int sg) const {          // (slope, intercept log2(e))
+    const float2 c = __ldg(co + (int64_t)sg * cs);
+    return make_float2(c.x, c.y * PWL_LOG2E);
+  }
 };
 // segment of p, searched from the guess s (any p ends in the right segment)
 __device__ __forceinline__ int pwl_seek(const PwlTable& tb, float p, int s) {
@@ -1190,8 +1195,7 @@ __device__ __forceinline__ int pwl_seek(const PwlTable& tb, float p, int s) {
 __device__ __forceinline__ void pwl_load(PwlTable& tb, const float* __restrict__ brk, const float* __restrict__ coef, int nb, int OUT,
                                          int o, int tid, int nthreads) {
   for (int i = tid; i <= nb + 1; i += nthreads) tb.B[i] = i == 0 ? -INFINITY : (i <= nb ? brk[i - 1] * PWL_LOG2E : INFINITY);
-  for (int i = tid; i <= nb; i += nthreads)
-    tb.co[i] = make_float2(coef[((int64_t)i * OUT + o) * 2], coef[((int64_t)i * OUT + o) * 2 + 1] * PWL_LOG2E);
+  if (tid == 0) { tb.co = reinterpret_cast<const float2*>(coef) + o; tb.cs = OUT; }
 }
 __device__ __forceinline__ float slog2_fast(float x) { return copysignf(__log2f(fabsf(x) + 1.f), x); }
 __device__ __forceinline__ float ex2_fast(float x) {
@@ -1207,11 +1211,13 @@ struct PwlRow {
 // kmin / kmax = range of the tile's key positions; returns true when the row's range holds more than one breakpoint
 __device__ __forceinline__ bool pwl_row_setup(const PwlTable& tb, int ns, float qx, float kmin, float kmax, PwlRow& rw) {
   const float plo = slog2_fast(qx - kmax), phi = slog2_fast(qx - kmin);
-  const int sL = pwl_seek(tb, plo, rw.seg), sH = pwl_seek(tb, phi, sL);
-  const float2 cl = tb.co[sL], ch = tb.co[min(sL + 1, ns - 1)];
-  rw.seg = sL; rw.b = tb.B[sL + 1];
-  rw.sl = cl.x; rw.il = cl.y; rw.sh = ch.x; rw.ih = ch.y;
-  return sH - sL > 1;
+  const int sL = pwl_seek(tb, plo, rw.seg);
+  if (sL != rw.seg || rw.b != tb.B[sL + 1]) {            // the lines change ~ once per segment: mostly skipped
+    const float2 cl = tb.line(sL), ch = tb.line(min(sL + 1, ns - 1));
+    rw.seg = sL; rw.b = tb.B[sL + 1];
+    rw.sl = cl.x; rw.il = cl.y; rw.sh = ch.x; rw.ih = ch.y;
+  }
+  return phi >= tb.B[min(sL + 2, ns)];
 }
 __device__ __forceinline__ float pwl_bias(const PwlRow& rw, float p) {
   const bool lo = p < rw.b;
@@ -1317,6 +1323,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
   query_pos(cf, min(q0 + r1, cf.n - 1), qx1, qdum);
   PwlRow rw0, rw1;
   rw0.seg = rw1.seg = ns >> 1;
+  rw0.b = rw1.b = __int_as_float(0x7fc00000);          // NaN: forces the first line load
   float oacc[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -1374,7 +1381,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float p = slog2_fast(((e & 2) ? qx1 : qx0) - ((e & 1) ? kx.y : kx.x));
-          const float2 c = sm.pw.co[pwl_seek(sm.pw, p, (e & 2) ? rw1.seg : rw0.seg)];
+          const float2 c = sm.pw.line(pwl_seek(sm.pw, p, (e & 2) ? rw1.seg : rw0.seg));
           s[j][e] += fmaf(c.x, p, c.y);
         }
       }
@@ -1926,11 +1933,10 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_lean_kernel(
 // d p / d kx = -1 / (|d| + 1) = -2^(-|p2|).  dQ / dK / dV as in the lean backward (dK is rescaled by ln 2: the Q tile carries log2 e).
 struct PwlBwdSmem {
   __nv_bfloat16 Q[MQ][MLD], dO[MQ][MLD];
-  PwlStage<BK> st[4];
+  PwlStage<BK> st[3];
   __nv_bfloat16 P[2][MQ][PLD], dS[2][MQ][PLD];
   float dkpos[2][MTHREADS / 32][BK];      // per-warp partial key-coordinate gradients (no shared-memory atomics)
   PwlTable pw;
-  float2 bins[PWL_MAXSEG];
 };
 // running per-row sums of the segments {seg, seg + 1}; the four lanes of a quad hold the same row: they are reduced at flush time
 struct PwlAcc { int seg; float a0, b0, a1, b1; };
@@ -1960,13 +1966,19 @@ __device__ __forceinline__ void pwl_flush(float2* bins, PwlAcc& ac, bool need, i
   }
   if (need) ac.a0 = ac.b0 = ac.a1 = ac.b1 = 0.f;
 }
+// one lane's sums (slow path: no assumption on the other lanes)
+__device__ __forceinline__ void pwl_flush_lane(float2* bins, PwlAcc& ac) {
+  if (ac.a0 != 0.f || ac.b0 != 0.f) { atomicAdd(&bins[ac.seg].x, ac.a0); atomicAdd(&bins[ac.seg].y, ac.b0 * PWL_LN2); }
+  if (ac.a1 != 0.f || ac.b1 != 0.f) { atomicAdd(&bins[ac.seg + 1].x, ac.a1); atomicAdd(&bins[ac.seg + 1].y, ac.b1 * PWL_LN2); }
+  ac.a0 = ac.b0 = ac.a1 = ac.b1 = 0.f;
+}
 
 // Operands: K, V as bf16 planes from the caller; dO is rounded to bf16 once and delta = bf16(dO) . O uses the same rounded
 // values, so that sum_j P_ij dP_ij = delta holds to fp32 rounding with single-pass products (dP = bf16(dO) bf16(V)^T,
-// O = sum_j P_ij bf16(V_j)).  Key tiles move through a four-stage cp.async ring, P / dS tiles are double-buffered: one
-// barrier per tile.
+// O = sum_j P_ij bf16(V_j)).  Key tiles move through a three-stage cp.async ring, P / dS tiles are double-buffered: one
+// barrier per tile; 69 KB of shared memory and <= 168 registers: three CTAs per SM.
 template <bool DROP>
-__global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
+__global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
     const AttnCfg cf, const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
     const float* __restrict__ vs, const float* __restrict__ brk, const float* __restrict__ coef, const int* __restrict__ nseg,
     const float* __restrict__ out, const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq,
@@ -1983,12 +1995,12 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
   const float* vsb = vs + (int64_t)bg * cf.nkv;
   const int ntiles = (cf.nkv + BK - 1) / BK;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 2; ++i) {
     if (i < ntiles) pwl_stage_load(sm.st[i], kb, vb, vsb, cf.inner, i * BK, cf.nkv, tid);
     cp_async_commit();
   }
   pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
-  for (int i = tid; i <= ns; i += MTHREADS) sm.bins[min(i, PWL_MAXSEG - 1)] = make_float2(0.f, 0.f);
+  float2* bins = reinterpret_cast<float2*>(gseg) + (int64_t)o * (PWL_MAXSEG + 1);      // global: ~4 reductions per warp and segment
   const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
   for (int e = tid; e < MQ * 16; e += MTHREADS) {          // Q tile scaled by log2(e); dO tile
     const int r = e >> 4, c4 = (e & 15) * 4;
@@ -2031,6 +2043,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
   const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
   PwlRow rw0, rw1;
   rw0.seg = rw1.seg = ns >> 1;
+  rw0.b = rw1.b = __int_as_float(0x7fc00000);          // NaN: forces the first line load
   PwlAcc ac0, ac1;
   ac0.seg = ac1.seg = ns >> 1;
   ac0.a0 = ac0.b0 = ac0.a1 = ac0.b1 = 0.f;
@@ -2040,12 +2053,14 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
   for (int jd = 0; jd < 8; ++jd)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dqacc[jd][e] = 0.f;
-  cp_async_wait<2>();                                   // tile 0
+  // element offset of this thread's dK / dV slice (key 16 mt + g of tile 0, dims 32 dh + 2 t ...)
+  const int64_t goff = ((int64_t)b * cf.nkv + 16 * (w & 1) + g) * cf.inner + head * AD + 32 * (w >> 1) + 2 * t;
+  cp_async_wait<1>();                                   // tile 0
   __syncthreads();
 
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * BK;
-    const PwlStage<BK>& st = sm.st[it & 3];
+    const PwlStage<BK>& st = sm.st[it % 3];
     __nv_bfloat16 (*Pt)[PLD] = sm.P[it & 1];
     __nv_bfloat16 (*dSt)[PLD] = sm.dS[it & 1];
     float* dkp = sm.dkpos[it & 1][w];
@@ -2120,8 +2135,8 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         *reinterpret_cast<uint32_t*>(&dSt[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
       }
       // merge the tile's sums into the rows' running sums (flush when the lower segment moved)
-      pwl_flush(sm.bins, ac0, rw0.seg != ac0.seg, lane); ac0.seg = rw0.seg;
-      pwl_flush(sm.bins, ac1, rw1.seg != ac1.seg, lane); ac1.seg = rw1.seg;
+      pwl_flush(bins, ac0, rw0.seg != ac0.seg, lane); ac0.seg = rw0.seg;
+      pwl_flush(bins, ac1, rw1.seg != ac1.seg, lane); ac1.seg = rw1.seg;
       ac0.a0 += aT0 - aH0; ac0.b0 += bT0 - bH0; ac0.a1 += aH0; ac0.b1 += bH0;
       ac1.a0 += aT1 - aH1; ac1.b0 += bT1 - bH1; ac1.a1 += aH1; ac1.b1 += bH1;
     } else {
@@ -2134,7 +2149,7 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
           const bool kok = k0 + 8 * j + 2 * t + e < cf.nkv;
           const float p0 = slog2_fast(qx0 - kxe), p1 = slog2_fast(qx1 - kxe);
           const int s0 = pwl_seek(sm.pw, p0, rw0.seg), s1 = pwl_seek(sm.pw, p1, rw1.seg);
-          const float2 c0 = sm.pw.co[s0], c1 = sm.pw.co[s1];
+          const float2 c0 = sm.pw.line(s0), c1 = sm.pw.line(s1);
           const float P0 = kok ? ex2_fast(s[j][e] + fmaf(c0.x, p0, c0.y) - lse0) : 0.f;
           const float P1 = kok ? ex2_fast(s[j][2 + e] + fmaf(c1.x, p1, c1.y) - lse1) : 0.f;
           float keep0 = 1.f, keep1 = 1.f;
@@ -2147,8 +2162,10 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
           const float dS1 = P1 * (dp[j][2 + e] * keep1 - delta1);
           s[j][e] = P0 * keep0; s[j][2 + e] = P1 * keep1;
           dp[j][e] = dS0; dp[j][2 + e] = dS1;
-          if (dS0 != 0.f) { atomicAdd(&sm.bins[s0].x, dS0); atomicAdd(&sm.bins[s0].y, dS0 * p0 * PWL_LN2); }
-          if (dS1 != 0.f) { atomicAdd(&sm.bins[s1].x, dS1); atomicAdd(&sm.bins[s1].y, dS1 * p1 * PWL_LN2); }
+          if (s0 != ac0.seg) { pwl_flush_lane(bins, ac0); ac0.seg = s0; }          // run-length accumulation per lane
+          if (s1 != ac1.seg) { pwl_flush_lane(bins, ac1); ac1.seg = s1; }
+          ac0.a0 += dS0; ac0.b0 = fmaf(dS0, p0, ac0.b0);
+          ac1.a0 += dS1; ac1.b0 = fmaf(dS1, p1, ac1.b0);
           kg[e] = -fmaf(dS0 * c0.x, ex2_fast(-fabsf(p0)), dS1 * c1.x * ex2_fast(-fabsf(p1)));
         }
 #pragma unroll
@@ -2160,9 +2177,9 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         *reinterpret_cast<uint32_t*>(&dSt[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
       }
     }
-    cp_async_wait<1>();                                 // my copies of tile it + 1 have landed
+    cp_async_wait<0>();                                 // my copies of tile it + 1 have landed
     __syncthreads();                                    // P / dS of this tile and tile it + 1 visible; everyone is past tile it - 1
-    if (it + 3 < ntiles) pwl_stage_load(sm.st[(it + 3) & 3], kb, vb, vsb, cf.inner, k0 + 3 * BK, cf.nkv, tid);
+    if (it + 2 < ntiles) pwl_stage_load(sm.st[(it + 2) % 3], kb, vb, vsb, cf.inner, k0 + 2 * BK, cf.nkv, tid);
     cp_async_commit();
     // ---- dQ += dS K
 #pragma unroll
@@ -2203,18 +2220,19 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
         }
       }
       const int key0 = k0 + 16 * mt + g, key1 = key0 + 8;
+      const int64_t off0 = goff + (int64_t)k0 * cf.inner, off1 = off0 + 8 * (int64_t)cf.inner;
+      if (key0 < cf.nkv) {
 #pragma unroll
-      for (int jd = 0; jd < 4; ++jd) {
-        const int col = head * AD + 32 * dh + 8 * jd + 2 * t;
-        if (key0 < cf.nkv) {
-          const int64_t off = ((int64_t)b * cf.nkv + key0) * cf.inner + col;
-          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][0] * PWL_LN2, dkacc[jd][1] * PWL_LN2));
-          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][0], dvacc[jd][1]));
+        for (int jd = 0; jd < 4; ++jd) {
+          atomicAdd(reinterpret_cast<float2*>(dk + off0 + 8 * jd), make_float2(dkacc[jd][0] * PWL_LN2, dkacc[jd][1] * PWL_LN2));
+          atomicAdd(reinterpret_cast<float2*>(dv + off0 + 8 * jd), make_float2(dvacc[jd][0], dvacc[jd][1]));
         }
-        if (key1 < cf.nkv) {
-          const int64_t off = ((int64_t)b * cf.nkv + key1) * cf.inner + col;
-          atomicAdd(reinterpret_cast<float2*>(dk + off), make_float2(dkacc[jd][2] * PWL_LN2, dkacc[jd][3] * PWL_LN2));
-          atomicAdd(reinterpret_cast<float2*>(dv + off), make_float2(dvacc[jd][2], dvacc[jd][3]));
+      }
+      if (key1 < cf.nkv) {
+#pragma unroll
+        for (int jd = 0; jd < 4; ++jd) {
+          atomicAdd(reinterpret_cast<float2*>(dk + off1 + 8 * jd), make_float2(dkacc[jd][2] * PWL_LN2, dkacc[jd][3] * PWL_LN2));
+          atomicAdd(reinterpret_cast<float2*>(dv + off1 + 8 * jd), make_float2(dvacc[jd][2], dvacc[jd][3]));
         }
       }
     }
@@ -2223,8 +2241,8 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
                                                          (sm.dkpos[it & 1][2][tid] + sm.dkpos[it & 1][3][tid]));
   }
   // ---- flush the running sums, dQ, and this CTA's segment sums
-  pwl_flush(sm.bins, ac0, true, lane);
-  pwl_flush(sm.bins, ac1, true, lane);
+  pwl_flush(bins, ac0, true, lane);
+  pwl_flush(bins, ac1, true, lane);
   if (ok0) {
     float* row = dq + qoff + (int64_t)(q0 + r0) * cf.inner + 2 * t;
 #pragma unroll
@@ -2234,12 +2252,6 @@ __global__ void __launch_bounds__(MTHREADS, 2) deform_attn_bwd_pwl_kernel(
     float* row = dq + qoff + (int64_t)(q0 + r1) * cf.inner + 2 * t;
 #pragma unroll
     for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(row + 8 * j) = make_float2(dqacc[j][2], dqacc[j][3]);
-  }
-  __syncthreads();
-  for (int i = tid; i < ns; i += MTHREADS) {
-    const float2 bv = sm.bins[i];
-    if (bv.x != 0.f || bv.y != 0.f)
-      atomicAdd(reinterpret_cast<float2*>(gseg + ((int64_t)o * (PWL_MAXSEG + 1) + i) * 2), bv);
   }
 }
 
