@@ -640,7 +640,8 @@ def instrumented_roofline(wl, ms_step, pk, pk_src, prof_out):
                 "forward_kernel": {"achieved": agg["deform_fwd"][0] / agg["deform_fwd"][1] / 1e12,
                                    "share_of_step": agg["deform_fwd"][1] / (ms_step * 1e-3)},
                 "note": "algorithmic FLOPs: 2*(2240 (2-D) | 2176 (1-D) + 256) per (query, key) pair for the backward; the in-kernel "
-                        "forward recomputation and the 3-pass split are not counted"}
+                        "forward recomputation and the 3-pass split are not counted.  1-D bf16 mode: the bias MLP is an exact "
+                        "piecewise-linear table (no per-pair MLP), counted as 10*64 + 24 FLOP per pair backward, 4*64 + 8 forward"}
     elif "tc" in agg and agg["tc"][1] > 0:
         f, t, n = agg["tc"]
         ach = f / t / 1e12

@@ -198,7 +198,9 @@ class DeformAttnFn(torch.autograd.Function):
             check(lib.sml_deform_attn_fwd_tc(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                              ptr(out), ptr(lse), c_i32(1 if prec == "bf16x3" else 0), stream()), "deform_attn_fwd_tc")
         # algorithmic work per (query, key) pair: bias MLP 2 (CD 32 + 32 32 + 32) + q.k and p.v 4 d  
-        _prof_end(prof, "deform_fwd", pairs * (2 * (OC * 32 + 32 * 32 + 32) + 4 * 64), (b, heads, T, nkv, OC, prec))
+        # (1-D table path: the MLP is not evaluated per pair; count q.k, p.v and ~8 table operations)
+        _prof_end(prof, "deform_fwd", pairs * ((8 if pwl is not None else 2 * (OC * 32 + 32 * 32 + 32)) + 4 * 64),
+                  (b, heads, T, nkv, OC, prec))
         y = torch.empty(b, T, C, device=dev, dtype=F32)
         gemm(_op(out.view(b * T, inner), prec), _v(_op(wo2, prec), lambda t: t.t()), out=y.view(b * T, C),
              bias=bout.detach())                                                               # 1D.py:233 / 2D.py:314
@@ -251,7 +253,9 @@ class DeformAttnFn(torch.autograd.Function):
                                              ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk), ptr(dv), ptr(dvs_b),
                                              ptr(part), c_i32(1 if prec == "bf16x3" else 0), stream()), "deform_attn_bwd_tc")
         # backward = 2x the forward contractions (the forward recomputation inside the kernel is not counted)
-        _prof_end(prof, "deform_bwd", float(b) * heads * T * nkv * 2 * (2 * (OC * 32 + 32 * 32 + 32) + 4 * 64),
+        # (1-D table path: five 64-deep products (S, dP, dQ, dK, dV) + ~24 table / segment-sum operations per pair)
+        _prof_end(prof, "deform_bwd", float(b) * heads * T * nkv * (10 * 64 + 24 if pwl is not None else
+                                                                     2 * (2 * (OC * 32 + 32 * 32 + 32) + 4 * 64)),
                   (b, heads, T, nkv, OC, prec))
         if pwl is None:
             dcpb = ops.colsum(part)
