@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SML_PRECISION", "bf16"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=8, help="slides per step per GPU (config_mine.yaml batch_size: 8)")
     ap.add_argument("--patches", type=int, default=16384)
-    ap.add_argument("--workload", default="transmil", choices=["transmil", "deform2d", "deform1d", "pathomic"],
+    ap.add_argument("--workload", default="transmil", choices=["transmil", "deform2d", "deform1d", "pathomic", "pathomic1d"],
                     help="transmil = BASELINE.json configs[1] (the headline); deform2d / deform1d = configs[2], the full "
                          "DeformCrossTransMIL (attn_dim 2 / 1) train step; pathomic = DeformPathomicNet (two genomic encoders + two "
                          "DeformCrossTransMIL branches + heads) with the reference's loss: weighted CE + BatchLoss over all ranks "
@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=5, help="slides in the CPU baseline sample (~2 s each on 16 host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-out", default=None, help="write the per-shape GEMM timing table of the instrumented pass here")
-    ap.add_argument("--secondary", default=os.environ.get("SML_BENCH_SECONDARY", "transmil_bf16x3,pathomic,batchloss64,stress100k"),
+    ap.add_argument("--secondary", default=os.environ.get("SML_BENCH_SECONDARY", "transmil_bf16x3,pathomic,pathomic1d,batchloss64,stress100k"),
                     help="comma list of extra workloads measured after the headline and reported under `secondary` "
                          "(transmil_bf16x3 = the fp32-grade mode of configs[1]; pathomic = configs[2]; batchloss64 = configs[3]: "
                          "BatchLoss + cross-rank gather + sync-BN BilinearFusion at global batch 64); empty string = none")
@@ -61,6 +61,8 @@ def workload_name(workload, patches):
     return {"transmil": "TransMIL(Nystrom m=256, 6 pinv iters, PPEG, 2 layers) fwd+CE+bwd+Adam on %d-patch x 1024-d bags" % patches,
             "pathomic": "DeformPathomicNet (2 x MaxNet + 2 x DeformCrossTransMIL attn_dim=2 + concat heads) fwd + weighted CE + "
                         "BatchLoss(all ranks) + bwd + Adam on %d-patch x 1024-d bags" % patches,
+            "pathomic1d": "DeformPathomicNet (2 x MaxNet + 2 x DeformCrossTransMIL attn_dim=1 [DeformableAttention1D] + concat heads) "
+                          "fwd + weighted CE + bwd + classifier gradient modulation + Adam",
             "deform2d": "DeformCrossTransMIL(attn_dim=2: fc1 + genomic fusion + deformable cross-attention + heads) fwd+CE+bwd+Adam "
                         "on %d-patch x 1024-d bags" % patches,
             "deform1d": "DeformCrossTransMIL(attn_dim=1: fc1 + genomic fusion + deformable cross-attention + heads) fwd+CE+bwd+Adam "
@@ -231,15 +233,18 @@ class Workload:
         from argparse import Namespace
         from sml_b200 import functional as Fn
         self.name, self.precision, self.B, self.N = name, precision, batch, patches
-        self.deform = name in ("deform2d", "deform1d", "pathomic")
+        self.deform = name in ("deform2d", "deform1d", "pathomic", "pathomic1d")
         torch.manual_seed(42)
         B, N = batch, patches
-        if name == "pathomic":
+        if name in ("pathomic", "pathomic1d"):
+            # pathomic1d = BASELINE configs[2] as written (DeformableAttention1D): attn_dim=1 cannot return vgrid in the reference
+            # (SURVEY F11), so that configuration trains on the weighted CE alone; pathomic = the YAML default (attn_dim=2 + BatchLoss)
+            one_d = name == "pathomic1d"
             margs = Namespace(init_type="max", input_size_omic_tumor=59, input_size_omic_immune=361, omic_dim=128, path_dim=128,
                               mmhid=128, return_grad="False", dropout_rate=0.1, label_dim=4, fusion_type="concat", cut_fuse_grad=False,
-                              return_vgrid=True, attn_dim=2, task_type="diag2021")          # config/config_mine.yaml
+                              return_vgrid=not one_d, attn_dim=1 if one_d else 2, task_type="diag2021")   # config/config_mine.yaml
             model = sml_b200.DeformPathomicNet(margs).to(dev).train()
-            self.bloss = sml_b200.BatchLoss(B, world)
+            self.bloss = None if one_d else sml_b200.BatchLoss(B, world)
             self.ce_w = torch.tensor([1.0, 4.15, 2.93, 2.43], device=dev)                   # train_test.py:25
             gen = torch.Generator(device=dev).manual_seed(9 + rank)
             self.x_t = torch.randn(B, 59, generator=gen, device=dev).abs()
@@ -280,7 +285,7 @@ class Workload:
         if name == "stress100k":
             self.net = model                                  # replicas only: no collective on this path
         self.graphed = None
-        self.want_graph = bool(graph) and world == 1 and name in ("transmil", "pathomic", "deform2d", "deform1d")
+        self.want_graph = bool(graph) and world == 1 and name in ("transmil", "pathomic", "pathomic1d", "deform2d", "deform1d")
         self.opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.1, fused=True, capturable=self.want_graph)
         if name == "batchloss64":
             self.x_dev = torch.zeros(1, device=dev); self.y_dev = torch.zeros(1, device=dev, dtype=torch.int64)
@@ -338,9 +343,11 @@ class Workload:
             self.opt.step()
             return loss
         self.opt.zero_grad(set_to_none=True)
-        if self.name == "pathomic":
+        if self.name in ("pathomic", "pathomic1d"):
             _, f_t, f_i, lg, _, _, _ = self.net(x_path=x, x_omic_tumor=self.x_t, x_omic_immune=self.x_i)
-            loss = F.cross_entropy(lg[2], y, weight=self.ce_w) + 0.5 * self.bloss(lg[3], lg[4]).sum() + 0.5 * self.bloss(lg[5], lg[6]).sum()
+            loss = F.cross_entropy(lg[2], y, weight=self.ce_w)
+            if self.bloss is not None:
+                loss = loss + 0.5 * self.bloss(lg[3], lg[4]).sum() + 0.5 * self.bloss(lg[5], lg[6]).sum()
             loss.backward()
             sml_b200.modulate_classifier_grads(self.model.classifier, f_t, f_i, y)       # train_test.py:87-184 (gradient_modulate: True)
             self.opt.step()
@@ -527,6 +534,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
     for nm in names:
         wname, prec, b2 = {"transmil_bf16x3": ("transmil", "bf16x3", B), "pathomic": ("pathomic", args.precision, B),
+                           "pathomic1d": ("pathomic1d", args.precision, B),
                            "batchloss64": ("batchloss64", "fp32", max(64 // world, 1)),
                            "stress100k": ("stress100k", args.precision, 1)}[nm]
         w2 = Workload(wname, prec, b2, N, dev, rank, world, local, graph=args.graph)
@@ -542,7 +550,8 @@ def run_ours(args):
                             % (b2 * world)) if wname == "batchloss64" else
                            ("TransMIL inference (eval, no grad) on 100 489-patch x 1024-d bags, 512 landmarks, one bag per GPU (replicas)"
                             if wname == "stress100k" else workload_name(wname, N)),
-               "baseline_config": {"transmil_bf16x3": "configs[1] (fp32-grade)", "pathomic": "configs[2]", "batchloss64": "configs[3]",
+               "baseline_config": {"transmil_bf16x3": "configs[1] (fp32-grade)", "pathomic": "configs[2] (YAML default: attn_dim 2 + BatchLoss)",
+                                   "pathomic1d": "configs[2] (as written: DeformableAttention1D)", "batchloss64": "configs[3]",
                                    "stress100k": "configs[4]"}[nm],
                "precision": prec, "slides_per_step_per_gpu": b2, "value": b2 * world * k2 / (ms2 * 1e-3), "unit": UNIT,
                "ms_per_step": ms2 / k2, "steps": k2, "warmup": 3, "launch": getattr(w2, "graph_note", "eager")}
