@@ -116,19 +116,23 @@ int sml_cpb1d_table_eval(const float* t, int64_t n, const float* brk, const floa
                          float* out, void* stream);
 /* 1-D fused deformable attention with the bias taken from that table instead of the per-pair MLP (CD = 1;
  * models/DeformableAttention1D.py:211-231 with :60-102 tabulated).  q fp32 [B, n, heads 64]; kh, vh = bf16 planes of K and V
- * [B, nkv, heads 64] (the "bf16" mode's operand rounding, applied once by the caller); vs [(B G), nkv] key positions. */
+ * [B, nkv, heads 64] (the "bf16" mode's operand rounding, applied once by the caller); vs [(B G), nkv] key positions;
+ * krange [sml_deform_pwl_krange_floats(cfg8)] = (min, max) key position of every 32-key tile, filled by
+ * sml_deform_pwl_key_ranges once per forward and reused by the backward. */
+int64_t sml_deform_pwl_krange_floats(const int32_t* cfg8);
+int sml_deform_pwl_key_ranges(const int32_t* cfg8, const float* vs, float* krange, void* stream);
 int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
-                            const float* vs, const float* brk, const float* coef, const int32_t* nseg, float* out, float* lse,
-                            void* stream);
+                            const float* vs, const float* krange, const float* brk, const float* coef, const int32_t* nseg,
+                            float* out, float* lse, void* stream);
 /* Backward.  dq is written; dk, dv, dvs and gseg [OUT, sml_cpb1d_seg_rows(), 2] are accumulated into (zero them first).
  * gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with output o whose signed-log distance p lies in segment s
  * of the table; sml_cpb1d_table_bwd maps the sums to the gradient of the MLP parameters (dcpb [sml_deform_cpb_nparams(1,
  * OUT)], overwritten; specification oracle/pwl.py:param_grads_from_segments). */
 int sml_cpb1d_seg_rows(void);
 int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
-                            const float* vs, const float* brk, const float* coef, const int32_t* nseg, const float* out,
-                            const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs, float* gseg,
-                            void* stream);
+                            const float* vs, const float* krange, const float* brk, const float* coef, const int32_t* nseg,
+                            const float* out, const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs,
+                            float* gseg, void* stream);
 int sml_cpb1d_table_bwd(const float* cpb, int32_t OUT, const float* brk, const int32_t* nseg, const float* gseg, float* dcpb,
                         void* stream);
 /* Gradient modulation of the fusion classifier after backward (train_test.py:87-184; diag2021 / grade / subtype tasks):

@@ -37,6 +37,7 @@ def _load():
     lib = ctypes.CDLL(_LIB_PATH)
     lib.sml_last_error.restype = ctypes.c_char_p
     lib.sml_launch_count.restype = c_i64
+    lib.sml_deform_pwl_krange_floats.restype = c_i64
     return lib
 
 

@@ -79,6 +79,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, ui
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
 __device__ __forceinline__ uint32_t movm_trans(uint32_t a) {
   uint32_t d;
   asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;\n" : "=r"(d) : "r"(a));
@@ -1261,21 +1266,22 @@ __device__ __forceinline__ void pwl_stage_load(PwlStage<NK>& st, const __nv_bflo
   }
   if (tid < NK) { const bool ok = k0 + tid < nkv; cp_async4(&st.kx[tid], vsb + (ok ? k0 + tid : 0), ok); }
 }
-// range of the valid key positions of a stage, computed redundantly by every warp (no extra barrier)
-template <int NK>
-__device__ __forceinline__ void pwl_stage_range(const PwlStage<NK>& st, int k0, int nkv, int lane, float& kmin, float& kmax) {
-  float mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < NK / 32; ++i) {
-    const float x = st.kx[lane + 32 * i];
-    if (k0 + lane + 32 * i < nkv) { mn = fminf(mn, x); mx = fmaxf(mx, x); }
-  }
+// range (min, max) of the key positions of every 32-key tile, written once per call by a small kernel: the attention
+// kernels read their tile's range one tile ahead instead of reducing it inside the key loop (a 10-step dependent shuffle chain)
+__global__ void __launch_bounds__(256) pwl_key_range_kernel(const float* __restrict__ vs, int nkv, int nt, int64_t total, float2* __restrict__ kr) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= total) return;
+  const int64_t bg = wid / nt;
+  const int k = (int)(wid % nt) * 32 + lane;
+  const float x = k < nkv ? vs[bg * nkv + k] : 0.f;
+  float mn = k < nkv ? x : INFINITY, mx = k < nkv ? x : -INFINITY;
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
   }
-  kmin = mn; kmax = mx;
+  if (lane == 0) kr[wid] = make_float2(mn, mx);
 }
 constexpr int PWL_FK = 64;                // keys per forward tile
 struct PwlFwdSmem {
@@ -1289,7 +1295,8 @@ struct PwlFwdSmem {
 template <bool DROP>
 __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const AttnCfg cf, const float* __restrict__ q,
                                                                             const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-                                                                            const float* __restrict__ vs, const float* __restrict__ brk,
+                                                                            const float* __restrict__ vs, const float2* __restrict__ kr,
+                                                                            const float* __restrict__ brk,
                                                                             const float* __restrict__ coef, const int* __restrict__ nseg,
                                                                             float* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1335,15 +1342,19 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
   const unsigned long long hrow0 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r0)) * cf.nkv;
   const unsigned long long hrow1 = ((unsigned long long)(b * cf.heads + head) * cf.n + (q0 + r1)) * cf.nkv;
 
+  const int nt32 = (cf.nkv + 31) >> 5;
+  const float2* krb = kr + (int64_t)bg * nt32;
+  float2 ra = krb[0], rb = krb[min(1, nt32 - 1)];       // ranges of the two 32-key halves of the next tile
+
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * PWL_FK;
+    const float kmin = fminf(ra.x, rb.x), kmax = fmaxf(ra.y, rb.y);
+    ra = krb[min(2 * it + 2, nt32 - 1)]; rb = krb[min(2 * it + 3, nt32 - 1)];
     cp_async_wait<1>();                                 // my copies of tile `it` have landed
     __syncthreads();                                    // ... everyone's have, and everyone is done with tile it - 1
     if (it + 2 < ntiles) pwl_stage_load(sm.st[(it + 2) % 3], kb, vb, vsb, cf.inner, k0 + 2 * PWL_FK, cf.nkv, tid);
     cp_async_commit();
     const PwlStage<PWL_FK>& st = sm.st[it % 3];
-    float kmin, kmax;
-    pwl_stage_range(st, k0, cf.nkv, lane, kmin, kmax);
     const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
     const bool many1 = pwl_row_setup(sm.pw, ns, qx1, kmin, kmax, rw1);
     const bool slow = __any_sync(0xffffffffu, many0 || many1);
@@ -1353,18 +1364,17 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+    // (fragments by ldmatrix: A = 16 rows x 16 dims of Q, B = two 8-key blocks x 16 dims of K per instruction)
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t ah[4];
-      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][16 * ks + 2 * t]);
-      ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][16 * ks + 2 * t]);
-      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][16 * ks + 2 * t + 8]);
-      ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][16 * ks + 2 * t + 8]);
+      ldmatrix_x4(ah[0], ah[1], ah[2], ah[3], &sm.Q[w * 16 + (lane & 15)][16 * ks + 8 * (lane >> 4)]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, 16 * ks + 2 * t));
-        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, 16 * ks + 2 * t + 8));
-        mma16816(s[j], ah, bh0, bh1);
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t b00, b01, b10, b11;
+        ldmatrix_x4(b00, b01, b10, b11, pwl_sw(st.K, 8 * j + (lane & 7) + 8 * (lane >> 4), 16 * ks + 8 * ((lane >> 3) & 1)));
+        mma16816(s[j], ah, b00, b01);
+        mma16816(s[j + 1], ah, b10, b11);
       }
     }
     // ---- + continuous position bias
@@ -1980,9 +1990,9 @@ __device__ __forceinline__ void pwl_flush_lane(float2* bins, PwlAcc& ac) {
 template <bool DROP>
 __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
     const AttnCfg cf, const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-    const float* __restrict__ vs, const float* __restrict__ brk, const float* __restrict__ coef, const int* __restrict__ nseg,
-    const float* __restrict__ out, const float* __restrict__ lse, const float* __restrict__ dout, float* __restrict__ dq,
-    float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ gseg) {
+    const float* __restrict__ vs, const float2* __restrict__ kr, const float* __restrict__ brk, const float* __restrict__ coef,
+    const int* __restrict__ nseg, const float* __restrict__ out, const float* __restrict__ lse, const float* __restrict__ dout,
+    float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, float* __restrict__ dvs, float* __restrict__ gseg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PwlBwdSmem& sm = *reinterpret_cast<PwlBwdSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -2058,14 +2068,17 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
   cp_async_wait<1>();                                   // tile 0
   __syncthreads();
 
+  const float2* krb = kr + (int64_t)bg * ntiles;
+  float2 rng = krb[0];
+
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * BK;
+    const float kmin = rng.x, kmax = rng.y;
+    rng = krb[min(it + 1, ntiles - 1)];
     const PwlStage<BK>& st = sm.st[it % 3];
     __nv_bfloat16 (*Pt)[PLD] = sm.P[it & 1];
     __nv_bfloat16 (*dSt)[PLD] = sm.dS[it & 1];
     float* dkp = sm.dkpos[it & 1][w];
-    float kmin, kmax;
-    pwl_stage_range(st, k0, cf.nkv, lane, kmin, kmax);
     const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
     const bool many1 = pwl_row_setup(sm.pw, ns, qx1, kmin, kmax, rw1);
     const bool slow = __any_sync(0xffffffffu, many0 || many1);
@@ -2078,19 +2091,18 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t ah[4], gh[4];
-      const int c0 = 16 * ks + 2 * t;
-      ah[0] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0]);
-      ah[2] = *reinterpret_cast<const uint32_t*>(&sm.Q[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&sm.Q[r1][c0 + 8]);
-      gh[0] = *reinterpret_cast<const uint32_t*>(&sm.dO[r0][c0]);     gh[1] = *reinterpret_cast<const uint32_t*>(&sm.dO[r1][c0]);
-      gh[2] = *reinterpret_cast<const uint32_t*>(&sm.dO[r0][c0 + 8]); gh[3] = *reinterpret_cast<const uint32_t*>(&sm.dO[r1][c0 + 8]);
+      ldmatrix_x4(ah[0], ah[1], ah[2], ah[3], &sm.Q[w * 16 + (lane & 15)][16 * ks + 8 * (lane >> 4)]);
+      ldmatrix_x4(gh[0], gh[1], gh[2], gh[3], &sm.dO[w * 16 + (lane & 15)][16 * ks + 8 * (lane >> 4)]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t kh0 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, c0));
-        const uint32_t kh1 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.K, 8 * j + g, c0 + 8));
-        const uint32_t vh0 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.V, 8 * j + g, c0));
-        const uint32_t vh1 = *reinterpret_cast<const uint32_t*>(pwl_sw(st.V, 8 * j + g, c0 + 8));
-        mma16816(s[j], ah, kh0, kh1);
-        mma16816(dp[j], gh, vh0, vh1);
+      for (int j = 0; j < 4; j += 2) {
+        const int krow = 8 * j + (lane & 7) + 8 * (lane >> 4), kcol = 16 * ks + 8 * ((lane >> 3) & 1);
+        uint32_t k00, k01, k10, k11, v00, v01, v10, v11;
+        ldmatrix_x4(k00, k01, k10, k11, pwl_sw(st.K, krow, kcol));
+        ldmatrix_x4(v00, v01, v10, v11, pwl_sw(st.V, krow, kcol));
+        mma16816(s[j], ah, k00, k01);
+        mma16816(dp[j], gh, v00, v01);
+        mma16816(s[j + 1], ah, k10, k11);
+        mma16816(dp[j + 1], gh, v10, v11);
       }
     }
     // ---- per element: bias, P, dS, segment sums, key-coordinate gradient
@@ -2185,9 +2197,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
 #pragma unroll
     for (int ks = 0; ks < BK / 16; ++ks) {
       uint32_t ah[4];
-      const int c0 = 16 * ks + 2 * t;
-      ah[0] = *reinterpret_cast<const uint32_t*>(&dSt[r0][c0]);     ah[1] = *reinterpret_cast<const uint32_t*>(&dSt[r1][c0]);
-      ah[2] = *reinterpret_cast<const uint32_t*>(&dSt[r0][c0 + 8]); ah[3] = *reinterpret_cast<const uint32_t*>(&dSt[r1][c0 + 8]);
+      ldmatrix_x4(ah[0], ah[1], ah[2], ah[3], &dSt[w * 16 + (lane & 15)][16 * ks + 8 * (lane >> 4)]);
 #pragma unroll
       for (int jd = 0; jd < 8; ++jd) {
         uint32_t bh0, bh1;
@@ -2862,11 +2872,27 @@ static int launch_fwd_lean(const AttnCfg& cf, const float* q, const float* k, co
   return 0;
 }
 
+/* floats of the key-range scratch of the table kernels: (min, max) per 32-key tile and (batch, group) */
+extern "C" int64_t sml_deform_pwl_krange_floats(const int32_t* cfg8) {
+  return 2 * (int64_t)cfg8[0] * cfg8[4] * ((cfg8[3] + 31) / 32);
+}
+/* krange [sml_deform_pwl_krange_floats] <- per-tile ranges of the key positions vs [(B G), nkv]; once per forward, reused by the backward */
+extern "C" int sml_deform_pwl_key_ranges(const int32_t* cfg8, const float* vs, float* krange, void* stream) {
+  AttnCfg cf;
+  if (make_acfg(cf, cfg8, 0.f, 0)) return 1;
+  SML_CHECK(cf.CD == 1 && vs && krange, "sml_deform_pwl_key_ranges: one coordinate dimension, non-null pointers");
+  static_assert(BK == 32, "the key-range scratch is indexed by 32-key tiles");
+  const int nt = (cf.nkv + 31) / 32;
+  const int64_t total = (int64_t)cf.B * cf.G * nt;
+  pwl_key_range_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(vs, cf.nkv, nt, total, reinterpret_cast<float2*>(krange));
+  SML_LAUNCH_OK("sml_deform_pwl_key_ranges");
+  return 0;
+}
 /* 1-D only (CD = 1): forward with the bias MLP replaced by its piecewise-linear table (sml_cpb1d_table_build).  kh, vh = bf16
- * planes of K and V (same [B, nkv, heads * 64] layout), q fp32 */
+ * planes of K and V (same [B, nkv, heads * 64] layout), q fp32; krange from sml_deform_pwl_key_ranges */
 extern "C" int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
-                                       const float* vs, const float* brk, const float* coef, const int32_t* nseg, float* out, float* lse,
-                                       void* stream) {
+                                       const float* vs, const float* krange, const float* brk, const float* coef, const int32_t* nseg,
+                                       float* out, float* lse, void* stream) {
   AttnCfg cf;
   if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
   SML_CHECK(cf.CD == 1, "sml_deform_attn_fwd_pwl: one coordinate dimension only");
@@ -2879,19 +2905,20 @@ extern "C" int sml_deform_attn_fwd_pwl(const int32_t* cfg8, float p_drop, uint64
     attr = true;
   }
   const __nv_bfloat16 *kp = (const __nv_bfloat16*)kh, *vp = (const __nv_bfloat16*)vh;
-  if (p_drop > 0.f) deform_attn_fwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse);
-  else deform_attn_fwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse);
+  const float2* kr = reinterpret_cast<const float2*>(krange);
+  if (p_drop > 0.f) deform_attn_fwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, kr, brk, coef, nseg, out, lse);
+  else deform_attn_fwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, kr, brk, coef, nseg, out, lse);
   SML_LAUNCH_OK("sml_deform_attn_fwd_pwl");
   return 0;
 }
 
-/* backward of sml_deform_attn_fwd_pwl (kh, vh = the same bf16 planes).  dk, dv, dvs and gseg [OUT, sml_cpb1d_seg_rows(), 2]
- * zero-initialised by the caller; gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with output o whose distance p
- * lies in segment s */
+/* backward of sml_deform_attn_fwd_pwl (kh, vh, krange = the same planes and scratch).  dk, dv, dvs and gseg [OUT,
+ * sml_cpb1d_seg_rows(), 2] zero-initialised by the caller; gseg[o][s] = (sum dS, sum dS p) over the pairs of the heads with
+ * output o whose distance p lies in segment s */
 extern "C" int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64_t seed, const float* q, const void* kh, const void* vh,
-                                       const float* vs, const float* brk, const float* coef, const int32_t* nseg, const float* out,
-                                       const float* lse, const float* dout, float* dq, float* dk, float* dv, float* dvs, float* gseg,
-                                       void* stream) {
+                                       const float* vs, const float* krange, const float* brk, const float* coef, const int32_t* nseg,
+                                       const float* out, const float* lse, const float* dout, float* dq, float* dk, float* dv,
+                                       float* dvs, float* gseg, void* stream) {
   AttnCfg cf;
   if (make_acfg(cf, cfg8, p_drop, seed)) return 1;
   SML_CHECK(cf.CD == 1, "sml_deform_attn_bwd_pwl: one coordinate dimension only");
@@ -2904,12 +2931,13 @@ extern "C" int sml_deform_attn_bwd_pwl(const int32_t* cfg8, float p_drop, uint64
     attr = true;
   }
   const __nv_bfloat16 *kp = (const __nv_bfloat16*)kh, *vp = (const __nv_bfloat16*)vh;
+  const float2* kr = reinterpret_cast<const float2*>(krange);
   if (p_drop > 0.f)
-    deform_attn_bwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse, dout, dq, dk,
-                                                                                  dv, dvs, gseg);
+    deform_attn_bwd_pwl_kernel<true><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, kr, brk, coef, nseg, out, lse, dout, dq,
+                                                                                  dk, dv, dvs, gseg);
   else
-    deform_attn_bwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, brk, coef, nseg, out, lse, dout, dq, dk,
-                                                                                   dv, dvs, gseg);
+    deform_attn_bwd_pwl_kernel<false><<<grid, MTHREADS, smem, as_stream(stream)>>>(cf, q, kp, vp, vs, kr, brk, coef, nseg, out, lse, dout, dq,
+                                                                                   dk, dv, dvs, gseg);
   SML_LAUNCH_OK("sml_deform_attn_bwd_pwl");
   return 0;
 }

@@ -30,6 +30,13 @@ def cpb1d_table(cpb, OUT):
     return brk, coef, nseg
 
 
+def key_ranges(acfg, vs):
+    """(min, max) key position of every 32-key tile: scratch of the 1-D table kernels (one small launch per forward)"""
+    kr = torch.empty(lib.sml_deform_pwl_krange_floats(acfg), device=vs.device, dtype=F32)
+    check(lib.sml_deform_pwl_key_ranges(acfg, ptr(vs), ptr(kr), stream()), "deform_pwl_key_ranges")
+    return kr
+
+
 def _prof_begin():
     if ops.PROFILE is None:
         return None
@@ -188,9 +195,10 @@ class DeformAttnFn(torch.autograd.Function):
         elif prec == "bf16" and PWL_1D and not two_d:                  # 1-D: bias from the piecewise-linear table
             brk, coef, nseg = cpb1d_table(cpb, heads // G)
             kh, vh = ops.to_bf16(k).hi, ops.to_bf16(v).hi              # the mode's operand rounding, once per call
-            pwl = (brk, coef, nseg, kh, vh)
+            kr = key_ranges(acfg, vs)
+            pwl = (brk, coef, nseg, kh, vh, kr)
             check(lib.sml_deform_attn_fwd_pwl(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(kh), ptr(vh), ptr(vs),
-                                              ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), stream()), "deform_attn_fwd_pwl")
+                                              ptr(kr), ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), stream()), "deform_attn_fwd_pwl")
         elif prec == "bf16" and TC5_FWD and two_d and heads == G:     # tcgen05 / TMEM kernel
             check(lib.sml_deform_attn_fwd_tc5(acfg, c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(k), ptr(v), ptr(vs), ptr(cpb),
                                               ptr(out), ptr(lse), stream()), "deform_attn_fwd_tc5")
@@ -236,11 +244,11 @@ class DeformAttnFn(torch.autograd.Function):
         part = torch.empty(nblk, npar, device=dev, dtype=F32) if pwl is None else None
         prof = _prof_begin()
         if pwl is not None:         # 1-D, bias from the table: per-segment sums, mapped to the MLP parameters afterwards
-            brk, coef, nseg, kh, vh = pwl
+            brk, coef, nseg, kh, vh, kr = pwl
             gseg = torch.zeros(heads // G, lib.sml_cpb1d_seg_rows(), 2, device=dev, dtype=F32)
             dcpb = torch.empty(npar, device=dev, dtype=F32)
             check(lib.sml_deform_attn_bwd_pwl(cfg["acfg"], c_f32(cfg["p_drop"]), c_u64(cfg["seed"]), ptr(qs), ptr(kh), ptr(vh), ptr(vs),
-                                              ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk),
+                                              ptr(kr), ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), ptr(dout), ptr(dqs), ptr(dk),
                                               ptr(dv), ptr(dvs_b), ptr(gseg), stream()), "deform_attn_bwd_pwl")
             check(lib.sml_cpb1d_table_bwd(ptr(cpb), c_i32(heads // G), ptr(brk), ptr(nseg), ptr(gseg), ptr(dcpb), stream()),
                   "cpb1d_table_bwd")

@@ -451,7 +451,7 @@ def test_deform1d_fwd_pwl_matches_split(shape, p_drop):
     """1-D forward with the bias MLP tabulated as a piecewise-linear function (sml_deform_attn_fwd_pwl) against the fp32-grade
     split kernel that evaluates the MLP per pair: same inputs, same dropout hash"""
     from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
-    from sml_b200.deform import cpb1d_table
+    from sml_b200.deform import cpb1d_table, key_ranges
     b, T, nkv = shape
     heads, G = 8, 4
     torch.manual_seed(8)
@@ -465,8 +465,8 @@ def test_deform1d_fwd_pwl_matches_split(shape, p_drop):
         out = torch.empty(b, T, heads * 64, device="cuda"); lse = torch.empty(b, heads, T, device="cuda")
         if name == "pwl":
             brk, coef, nseg = cpb1d_table(cpb, 2)
-            kh, vh = k.bfloat16(), v.bfloat16()
-            check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(brk), ptr(coef),
+            kh, vh, kr = k.bfloat16(), v.bfloat16(), key_ranges(cfg, vs)
+            check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(kr), ptr(brk), ptr(coef),
                                               ptr(nseg), ptr(out), ptr(lse), stream()), "fwd_pwl")
         else:
             check(lib.sml_deform_attn_fwd_tc(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse),
@@ -486,7 +486,7 @@ def test_deform1d_bwd_pwl_matches_split(shape, p_drop):
     parameters) against the fp32-grade split kernel that differentiates the MLP per pair; the plain-bf16 per-pair kernel on the
     same inputs sets the scale of the allowed error."""
     from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
-    from sml_b200.deform import cpb1d_table
+    from sml_b200.deform import cpb1d_table, key_ranges
     b, T, nkv = shape
     heads, G = 8, 4
     torch.manual_seed(9)
@@ -503,12 +503,12 @@ def test_deform1d_bwd_pwl_matches_split(shape, p_drop):
         dq = torch.empty_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v); dvs = torch.zeros_like(vs)
         if name == "pwl":
             brk, coef, nseg = cpb1d_table(cpb, 2)
-            kh, vh = k.bfloat16(), v.bfloat16()
-            check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(brk), ptr(coef),
+            kh, vh, kr = k.bfloat16(), v.bfloat16(), key_ranges(cfg, vs)
+            check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(kr), ptr(brk), ptr(coef),
                                               ptr(nseg), ptr(out), ptr(lse), stream()), "fwd_pwl")
             gseg = torch.zeros(2, lib.sml_cpb1d_seg_rows(), 2, device="cuda")
             dcpb = torch.empty(npar, device="cuda")
-            check(lib.sml_deform_attn_bwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(brk), ptr(coef), ptr(nseg),
+            check(lib.sml_deform_attn_bwd_pwl(cfg, c_f32(p_drop), c_u64(5), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(kr), ptr(brk), ptr(coef), ptr(nseg),
                                               ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(dvs), ptr(gseg), stream()), "bwd_pwl")
             check(lib.sml_cpb1d_table_bwd(ptr(cpb), c_i32(2), ptr(brk), ptr(nseg), ptr(gseg), ptr(dcpb), stream()), "table_bwd")
         else:

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import torch
 import sml_b200
 from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
-from sml_b200.deform import cpb1d_table
+from sml_b200.deform import cpb1d_table, key_ranges
 
 b = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 8
 heads, G, T, nkv = 8, 4, 16385, 4096
@@ -26,13 +26,13 @@ gseg = torch.zeros(2, lib.sml_cpb1d_seg_rows(), 2, device="cuda")
 
 
 def fwd_lean(): check(lib.sml_deform_attn_fwd_tc(cfg, c_f32(0.0), c_u64(1), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse), c_i32(0), stream()))
-kh, vh = k.bfloat16(), v.bfloat16()
-def fwd_pwl(): check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(0.0), c_u64(1), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), stream()))
+kh, vh, kr = k.bfloat16(), v.bfloat16(), key_ranges(cfg, vs)
+def fwd_pwl(): check(lib.sml_deform_attn_fwd_pwl(cfg, c_f32(0.0), c_u64(1), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(kr), ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), stream()))
 def bwd_lean(): check(lib.sml_deform_attn_bwd_tc(cfg, c_f32(0.0), c_u64(1), ptr(q), ptr(k), ptr(v), ptr(vs), ptr(cpb), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(dvs), ptr(part), c_i32(0), stream()))
 fns = [("fwd table", fwd_pwl)]
 if "--lean" in sys.argv: fns += [("fwd lean (MLP per pair)", fwd_lean), ("bwd lean (MLP per pair)", bwd_lean)]
 if hasattr(lib, "sml_deform_attn_bwd_pwl"):
-    def bwd_pwl(): check(lib.sml_deform_attn_bwd_pwl(cfg, c_f32(0.0), c_u64(1), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(dvs), ptr(gseg), stream()))
+    def bwd_pwl(): check(lib.sml_deform_attn_bwd_pwl(cfg, c_f32(0.0), c_u64(1), ptr(q), ptr(kh), ptr(vh), ptr(vs), ptr(kr), ptr(brk), ptr(coef), ptr(nseg), ptr(out), ptr(lse), ptr(dout), ptr(dq), ptr(dk), ptr(dv), ptr(dvs), ptr(gseg), stream()))
     fns.append(("bwd table", bwd_pwl))
 pairs = float(b) * heads * T * nkv
 for name, fn in fns:
