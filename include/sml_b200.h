@@ -191,6 +191,18 @@ int sml_nystrom_resconv_bwd(const float* qkv, const float* w, const float* dout,
 int sml_nystrom_a1_bwd(const void* dout_bf16, const void* wm_bf16, const void* a1_bf16, const void* kl_bf16,
                        const void* qkv_bf16, const float* dql, float* dqkv, void* dqkv_hi, float* dkl, int32_t B,
                        int32_t npad, int32_t h, int32_t d, int32_t m, void* stream);
+/* Landmark-by-token product without its probability matrix (models/NystromAttention.py:124, 130-137, 140: sim3, attn3,
+ * attn3 @ v), "bf16" mode, 256 landmarks, head dim 64.  cfg11 = (B, H, 256, 64, n', row stride, batch stride lo, hi, k offset,
+ * v offset, nchunks): K / V are bf16 views into the packed qkv tensor [B, n', 3, H, 64] (element strides / offsets).
+ * fwd: opart [B H nchunks 256 64] and ml [B H nchunks 256 2] fp32 scratch; a3v [B, H, 256, 64] fp32 (+ optional bf16 copy),
+ * lse [B, H, 256] row log-sum-exp (saved for the backward).
+ * bwd: dql [B, H, 256, 64] accumulated; dk -> bf16 K slice of dqkv_bf16 (+ dkl[t / lsz] / lsz if dkl is given, else call
+ * sml_nystrom_a3_dk_landmarks once dkl is complete); dv -> fp32 V slice of dqkv_f32. */
+int sml_nystrom_a3_fwd(const int32_t* cfg11, const void* ql_bf16, const void* qkv_bf16, float* opart, float* ml, float* a3v,
+                       void* a3v_hi, float* lse, void* stream);
+int sml_nystrom_a3_bwd(const int32_t* cfg11, const void* ql_bf16, const void* qkv_bf16, const float* da3v, const float* a3v,
+                       const float* lse, const float* dkl, int32_t lsz, float* dql, void* dqkv_bf16, float* dqkv_f32, void* stream);
+int sml_nystrom_a3_dk_landmarks(const int32_t* cfg11, const float* dkl, int32_t lsz, void* dqkv_bf16, void* stream);
 /* PPEG parameter folding and its backward: w7 [C,49], w5 [C,25], w3 [C,9] depthwise kernels + biases [C] (models/mil.py:195-198)
  * -> wf [49,C] tap-major stencil incl. the identity, bf [C]; unfold scatters d wf back to the three kernels (d bias is shared) */
 int sml_ppeg_fold(const float* w7, const float* w5, const float* w3, const float* b7, const float* b5, const float* b3,

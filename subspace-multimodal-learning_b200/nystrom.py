@@ -31,6 +31,9 @@ FUSE_A1_BWD = True
 import os as _os
 FUSE_A1_BWD = _os.environ.get("SML_FUSE_A1_BWD", "1") != "0"
 FUSE_PINV_CHAIN = _os.environ.get("SML_FUSE_PINV_CHAIN", "0") == "1"
+# bf16 mode, d = 64, m = 256: A3 V = softmax(ql k^T) v as a flash attention over key chunks (csrc/nystrom_a3.cu) - the [m, n']
+# logits / probabilities and their gradients never touch HBM; the backward recomputes P from the saved row log-sum-exp
+FUSE_A3 = _os.environ.get("SML_FUSE_A3", "1") != "0"
 # "bf16" mode: run the Moore-Penrose chain with hi/lo split operands (True, fp32-grade) or in plain bf16 (False)
 PINV_HP = _os.environ.get("SML_PINV_HP", "1") != "0"
 # bf16 mode: keep q, k, v as bf16 only (landmark / residual-conv kernels read the bf16 copy).  Measured neutral on the 16 k
@@ -47,6 +50,22 @@ def landmarks_fwd(qkv, b, npad, h, d, m, qkv_bf16=None):
     check(lib.sml_nystrom_landmarks_fwd(ptr(qkv), ptr(ql), ptr(kl), c_i32(b), c_i32(npad), c_i32(h), c_i32(d), c_i32(m),
                                         None if qkv is not None else ptr(qkv_bf16), stream()), "landmarks_fwd")
     return ql, kl
+
+
+def _a3_cfg(b, h, m, d, npad, nchunks):
+    """cfg11 of sml_nystrom_a3_*: K / V as views into the packed [b, n', 3, h, d] tensor (element strides)"""
+    bs = npad * 3 * h * d
+    lo = bs & 0xffffffff
+    return (c_i32 * 11)(b, h, m, d, npad, 3 * h * d, lo - 2 ** 32 if lo >= 2 ** 31 else lo, bs >> 32, h * d, 2 * h * d, nchunks)
+
+
+def _a3_chunks(b, h, npad, tile, ctas_per_wave, rows_per_cta=1):
+    """number of key chunks: enough CTAs for a few full waves, every chunk non-empty"""
+    ntot = npad // tile
+    want = max(1, (4 * ctas_per_wave) // max(b * h * rows_per_cta, 1))
+    n = max(1, min(want, ntot))
+    tpc = -(-ntot // n)
+    return -(-ntot // tpc)
 
 
 def landmark_ids(npad, m, device):
@@ -197,18 +216,34 @@ class NystromAttentionFn(torch.autograd.Function):
         lowp = mode == "bf16" and fuse          # keep the big probability tensors (A1, A3) in bf16 only
         a1 = TB.new((b, h, npad, m), dev, mode, f32=not lowp)
         a2 = TB.new((b, h, m, m), dev, mode, hp=PINV_HP)
-        a3 = TB.new((b, h, m, npad), dev, mode, f32=not lowp)
-        s3 = a3.f if a3.f is not None else torch.empty(b, h, m, npad, device=dev, dtype=F32)   # logits scratch
+        fuse_a3 = FUSE_A3 and lowp and m == 256 and d == 64 and ksize == 33 and npad % 64 == 0 and qkv.hi is not None
         mm(q_b, kl_b.T(), a1, softmax=fuse)
         mm(ql_b, kl_b.T(), a2, softmax=fuse)
-        mm(ql_b, k_b.T(), TB(s3))
+        lse3 = None
+        if fuse_a3:
+            # sim3 -> softmax over tokens -> . v in one flash pass over key chunks: no [m, n'] tensor (csrc/nystrom_a3.cu)
+            a3 = TB(None, None, None)
+            a3v = TB.new((b, h, m, d), dev, mode)
+            lse3 = torch.empty(b, h, m, device=dev, dtype=F32)
+            nch = _a3_chunks(b, h, npad, 64, 3 * 148, rows_per_cta=m // 64)
+            opart = torch.empty(b * h, nch, m, d, device=dev, dtype=F32)
+            ml = torch.empty(b * h, nch, m, 2, device=dev, dtype=F32)
+            check(lib.sml_nystrom_a3_fwd(_a3_cfg(b, h, m, d, npad, nch), ptr(ql_b.hi), ptr(qkv.hi), ptr(opart), ptr(ml), ptr(a3v.f),
+                                         ptr(a3v.hi), ptr(lse3), stream()), "nystrom_a3_fwd")
+            del opart, ml
+        else:
+            a3 = TB.new((b, h, m, npad), dev, mode, f32=not lowp)
+            s3 = a3.f if a3.f is not None else torch.empty(b, h, m, npad, device=dev, dtype=F32)   # logits scratch
+            mm(ql_b, k_b.T(), TB(s3))
         if not fuse:
             ops.softmax_(a1.f.view(-1, m), a1.hi, a1.lo)
             ops.softmax_(a2.f.view(-1, m), a2.hi, a2.lo)
-        ops.softmax_(s3.view(-1, npad), a3.hi, a3.lo, write_f32=not lowp)            # softmax over tokens
-        del s3
+        if not fuse_a3:
+            ops.softmax_(s3.view(-1, npad), a3.hi, a3.lo, write_f32=not lowp)            # softmax over tokens
+            del s3
         z, pinv_saved = pinv_fwd(a2.f, iters, mode, a2, keep_steps=any(ctx.needs_input_grad))     # :138
-        a3v = mm(a3, v_b, TB.new((b, h, m, d), dev, mode))                           # [b,h,m,d]
+        if not fuse_a3:
+            a3v = mm(a3, v_b, TB.new((b, h, m, d), dev, mode))                       # [b,h,m,d]
         z_op = z if mode != "bf16" else TB(z.f, z.hi, None)
         wm = mm(z_op, a3v, TB.new((b, h, m, d), dev, mode))                          # Z (A3 V)
         merged = TB.new((b, npad, inner), dev, mode)
@@ -232,13 +267,14 @@ class NystromAttentionFn(torch.autograd.Function):
             for bnd in (ql_b, kl_b, wm, a3v, z, a2, weff_b, wout_b, *pinv_saved[4]):
                 extras += [bnd.hi, bnd.lo]
         ctx.save_for_backward(x, ln_w, ln_b, xp.f, xp.hi, xp.lo, weff, w_out, qkv.f, qkv.hi, qkv.lo, ql, kl, a1.f, a1.hi, a1.lo,
-                              a2.f, a3.f, a3.hi, a3.lo, z.f, a3v.f, wm.f, merged.f, merged.hi, merged.lo, wc,
+                              a2.f, lse3 if fuse_a3 else a3.f, a3.hi, a3.lo, z.f, a3v.f, wm.f, merged.f, merged.hi, merged.lo, wc,
                               *(ln_saved or ()), *pinv_saved[0], pinv_saved[1], pinv_saved[2],
                               *([t for st in pinv_saved[3] for bnd in st for t in (bnd.hi, bnd.lo)] if len(pinv_saved) > 3 else []),
                               *extras)
         ctx.n_extras = len(extras)
         ctx.cfg = (b, n, D, h, d, m, iters, pad, npad, inner, ksize, mode, ln_w is not None)
         ctx.skip = skip
+        ctx.fuse_a3 = fuse_a3
         if skip is not None:
             assert ln_w is not None, "the fused skip connection needs the fused LayerNorm"
             return ops.dropout_add(x, y, skip[0], skip[1], skip[2])
@@ -313,8 +349,18 @@ class NystromAttentionFn(torch.autograd.Function):
         dwm = mm(a1.T(), dout_b, TB.new((b, h, m, d), dev, mode))                               # [b,h,m,d]
         dz = mm(dwm, kept_or_of(3, a3v_f).T()).f                                                # [b,h,m,m]
         da3v = mm(kept_or_of(4, z_f).T(), dwm, TB.new((b, h, m, d), dev, mode))                 # [b,h,m,d]
-        da3 = mm(da3v, v_b.T(), TB(torch.empty(b, h, m, npad, device=dev, dtype=F32)))
-        mm(a3.T(), da3v, TB(dv))                                                                # dv = A3^T dA3V
+        fuse_a3 = ctx.fuse_a3
+        if fuse_a3:
+            # dS3 recomputed tile by tile from the saved log-sum-exp: dql (+=), dk (bf16 slice, landmark term added below) and
+            # dv (fp32 slice) in one kernel, nothing of size [m, n'] in HBM
+            lse3 = a3_f
+            dql = TB(torch.zeros(b, h, m, d, device=dev, dtype=F32))
+            a3cfg = _a3_cfg(b, h, m, d, npad, _a3_chunks(b, h, npad, 32, 148))
+            check(lib.sml_nystrom_a3_bwd(a3cfg, ptr(ql_b.hi), ptr(qkv.hi), ptr(da3v.f), ptr(a3v_f), ptr(lse3), None, c_i32(npad // m),
+                                         ptr(dql.f), ptr(dqkv.hi), ptr(dqkv.f), stream()), "nystrom_a3_bwd")
+        else:
+            da3 = mm(da3v, v_b.T(), TB(torch.empty(b, h, m, npad, device=dev, dtype=F32)))
+            mm(a3.T(), da3v, TB(dv))                                                            # dv = A3^T dA3V
         dwc_part = torch.zeros(lib.sml_nystrom_resconv_bwd_blocks(c_i32(b), c_i32(npad), c_i32(h * d)), h * ksize, device=dev,
                                dtype=F32)      # upper bound on the partial rows; unused rows stay zero
         fused_cvt = ksize == 33
@@ -330,17 +376,20 @@ class NystromAttentionFn(torch.autograd.Function):
             da2 = pinv_bwd(a2_f, (zs, scal, arg, steps, zbs_kept, pa2), dz, mode)
         else:
             da2 = pinv_bwd(a2_f, (zs, scal, arg, steps) if steps else (zs, scal, arg), dz, mode)
-        ds3 = TB.new((b, h, m, npad), dev, mode, f32=False); ds3.f = da3.f
         lowp = a1.f is None                     # bf16-only probabilities: dS also only needs its bf16 copy
         p1 = a1.f if a1.f is not None else a1.hi
-        p3 = a3.f if a3.f is not None else a3.hi
+        if not fuse_a3:
+            ds3 = TB.new((b, h, m, npad), dev, mode, f32=False); ds3.f = da3.f
+            p3 = a3.f if a3.f is not None else a3.hi
         if not fuse_a1:
             ds1 = TB.new((b, h, npad, m), dev, mode, f32=False); ds1.f = da1.f
             ops.softmax_bwd_(p1.view(-1, m), ds1.f.view(-1, m), ds1.hi, ds1.lo, write_f32=not lowp)
         ops.softmax_bwd_(a2_f.view(-1, m), da2.view(-1, m))
-        ops.softmax_bwd_(p3.view(-1, npad), ds3.f.view(-1, npad), ds3.hi, ds3.lo, write_f32=not lowp)
+        if not fuse_a3:
+            ops.softmax_bwd_(p3.view(-1, npad), ds3.f.view(-1, npad), ds3.hi, ds3.lo, write_f32=not lowp)
         if lowp:
-            ds3.f = None
+            if not fuse_a3:
+                ds3.f = None
             if not fuse_a1:
                 ds1.f = None
         ds2 = TB.of(da2, mode)
@@ -348,8 +397,11 @@ class NystromAttentionFn(torch.autograd.Function):
         #      the dq / dk contractions, which also emit the bf16 copy of dqkv for the projection backward
         l = npad // m
         dkl = mm(ds2.T(), ql_b)                                                                 # dkl = dS2^T ql (+ dS1^T q below)
-        dql = mm(ds2, kl_b)
-        mm(ds3, k_b, dql, beta=1.0)
+        if fuse_a3:
+            mm(ds2, kl_b, dql, beta=1.0)                                                        # dql = dS3 k (above) + dS2 kl
+        else:
+            dql = mm(ds2, kl_b)
+            mm(ds3, k_b, dql, beta=1.0)
         # bf16 mode: only the bf16 copies of dq / dk are ever read (projection backward), so their fp32 halves are not written
         skip_f32 = mode == "bf16" and fused_cvt
         dq_b = TB(None if skip_f32 else dq, *(hv(t, 0) if t is not None else None for t in (dqkv.hi, dqkv.lo)))
@@ -362,7 +414,10 @@ class NystromAttentionFn(torch.autograd.Function):
         else:
             mm(ds1.T(), q_b, dkl, beta=1.0)                                                     # dkl += dS1^T q
             mm(ds1, kl_b, dq_b, rowtab=dql.f, rowdiv=l, rowtab_scale=1.0 / l)                   # dq = dS1 kl + bcast(dql)/l
-        mm(ds3.T(), ql_b, dk_b, rowtab=dkl.f, rowdiv=l, rowtab_scale=1.0 / l)                   # dk = dS3^T ql + bcast(dkl)/l
+        if fuse_a3:
+            check(lib.sml_nystrom_a3_dk_landmarks(a3cfg, ptr(dkl.f), c_i32(l), ptr(dqkv.hi), stream()), "nystrom_a3_dk_landmarks")
+        else:
+            mm(ds3.T(), ql_b, dk_b, rowtab=dkl.f, rowdiv=l, rowtab_scale=1.0 / l)               # dk = dS3^T ql + bcast(dkl)/l
         if tc and not fused_cvt:
             s = ops.to_bf16(dqkv.f, split=(mode == "bf16x3"))
             dqkv.hi, dqkv.lo = s.hi, s.lo

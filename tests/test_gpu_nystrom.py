@@ -196,3 +196,60 @@ def test_return_attn_map():
     assert rel_err(attn, want) < 1e-4 and rel_err(y, yo) < 1e-4
     with pytest.raises(NotImplementedError):
         mod(x.cuda(), mask=torch.ones(2, 200, dtype=torch.bool, device="cuda"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 8, 1280, 3), (1, 2, 16640, 5), (1, 1, 256, 1)])
+def test_nystrom_a3_fused_matches_torch(shape):
+    """sml_nystrom_a3_fwd / _bwd (flash form of softmax(ql k^T) v over key chunks, NystromAttention.py:124, 130-137, 140) against
+    fp32 torch on the same bf16-rounded operands: a3v, row log-sum-exp, dql, dk (+ landmark-mean term), dv."""
+    from sml_b200._lib import c_i32, check, lib, ptr, stream
+    from sml_b200.nystrom import _a3_cfg
+    b, h, npad, nch = shape
+    m, d = 256, 64
+    torch.manual_seed(3)
+    dev = "cuda"
+    qkv = (torch.randn(b, npad, 3, h, d, device=dev) * 0.7).bfloat16()
+    ql = (torch.randn(b, h, m, d, device=dev) * 0.5).bfloat16()
+    cfg = _a3_cfg(b, h, m, d, npad, nch)
+    a3v = torch.empty(b, h, m, d, device=dev); a3v_hi = torch.empty(b, h, m, d, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(b, h, m, device=dev)
+    opart = torch.empty(b * h, nch, m, d, device=dev); ml = torch.empty(b * h, nch, m, 2, device=dev)
+    check(lib.sml_nystrom_a3_fwd(cfg, ptr(ql), ptr(qkv), ptr(opart), ptr(ml), ptr(a3v), ptr(a3v_hi), ptr(lse), stream()), "a3_fwd")
+    # reference
+    qf = ql.float().requires_grad_()
+    kf = qkv[:, :, 1].permute(0, 2, 1, 3).float().requires_grad_()
+    vf = qkv[:, :, 2].permute(0, 2, 1, 3).float().requires_grad_()
+    sref = qf @ kf.transpose(-1, -2)
+    want = torch.softmax(sref, -1) @ vf
+    assert rel_err(a3v, want.detach()) < 1e-2, rel_err(a3v, want.detach())
+    assert rel_err(a3v_hi.float(), want.detach()) < 1.5e-2
+    assert (lse - torch.logsumexp(sref.detach(), -1)).abs().max() < 2e-3
+    # backward
+    g = torch.randn(b, h, m, d, device=dev)
+    want.backward(g)
+    lsz = max(npad // m, 1)
+    dkl = torch.randn(b, h, m, d, device=dev)
+    dql = torch.full((b, h, m, d), 0.25, device=dev)                 # accumulated into
+    dqkv_hi = torch.zeros(b, npad, 3, h, d, device=dev, dtype=torch.bfloat16)
+    dqkv_f = torch.zeros(b, npad, 3, h, d, device=dev)
+    nchb = min(nch + 1, npad // 32)
+    cfgb = _a3_cfg(b, h, m, d, npad, nchb)
+    check(lib.sml_nystrom_a3_bwd(cfgb, ptr(ql), ptr(qkv), ptr(g), ptr(a3v), ptr(lse), None, c_i32(lsz), ptr(dql), ptr(dqkv_hi), ptr(dqkv_f),
+                                 stream()), "a3_bwd")
+    assert rel_err(dql - 0.25, qf.grad) < 2e-2, rel_err(dql - 0.25, qf.grad)
+    dk = dqkv_hi[:, :, 1].permute(0, 2, 1, 3).float()
+    assert rel_err(dk, kf.grad) < 2e-2, rel_err(dk, kf.grad)
+    dv = dqkv_f[:, :, 2].permute(0, 2, 1, 3)
+    assert rel_err(dv, vf.grad) < 2e-2, rel_err(dv, vf.grad)
+    assert float(dqkv_hi[:, :, 0].abs().max()) == 0 and float(dqkv_f[:, :, :2].abs().max()) == 0      # other slices untouched
+    check(lib.sml_nystrom_a3_dk_landmarks(cfgb, ptr(dkl), c_i32(lsz), ptr(dqkv_hi), stream()), "a3_dk_landmarks")
+    idx = torch.arange(npad, device=dev) // lsz
+    want_dk = kf.grad + dkl[:, :, idx.clamp(max=m - 1)] / lsz
+    dk2 = dqkv_hi[:, :, 1].permute(0, 2, 1, 3).float()
+    assert rel_err(dk2, want_dk) < 2e-2, rel_err(dk2, want_dk)
+    # the landmark term inside the backward kernel gives the same result
+    dqkv_hi2 = torch.zeros_like(dqkv_hi); dql2 = torch.zeros_like(dql)
+    check(lib.sml_nystrom_a3_bwd(cfgb, ptr(ql), ptr(qkv), ptr(g), ptr(a3v), ptr(lse), ptr(dkl), c_i32(lsz), ptr(dql2), ptr(dqkv_hi2),
+                                 ptr(dqkv_f), stream()), "a3_bwd")
+    assert rel_err(dqkv_hi2[:, :, 1].float(), want_dk.permute(0, 2, 1, 3)) < 2e-2
