@@ -322,6 +322,8 @@ class Workload:
             self.graphed = None
             self.want_graph = False
             self.graph_note = "eager (graph capture failed: %s)" % str(e)[:120]
+            import traceback
+            print("graph capture of %s failed:\n%s" % (self.name, traceback.format_exc()), file=sys.stderr)
 
     def step(self, x, y):
         if self.graphed is not None:
@@ -529,9 +531,11 @@ def run_ours(args):
     #      global batch 64 (configs[3]) and the fp32-grade mode of the headline (configs[1] "fp32 and bf16")
     secondary = []
     names = [n for n in args.secondary.split(",") if n] if args.workload == "transmil" else []
+    import gc
     x_keep = (wl.x_dev, wl.y_dev)
     del wl
-    torch.cuda.empty_cache()
+    gc.collect()                       # the graphed step holds the workload in a reference cycle: without the collection the
+    torch.cuda.empty_cache()           # graph's private pool of every earlier workload stays allocated (OOM during a later capture)
     for nm in names:
         wname, prec, b2 = {"transmil_bf16x3": ("transmil", "bf16x3", B), "pathomic": ("pathomic", args.precision, B),
                            "pathomic1d": ("pathomic1d", args.precision, B),
@@ -561,6 +565,7 @@ def run_ours(args):
                 ent["roofline"] = {k: r2[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "share_of_step") if k in r2}
         secondary.append(ent)
         del w2
+        gc.collect()
         torch.cuda.empty_cache()
 
     if rank == 0:
