@@ -342,22 +342,31 @@ __global__ void __launch_bounds__(BT, 1) a3_bwd_kernel(const Cfg cf, const __nv_
     }
     // ---- my 16-key x 16-dim slice of dK = dS^T ql (warps 0-7) or dV = P^T dO (warps 8-15): contraction over the 256 rows
     {
-      float acc[2][4];
+      // two accumulator sets (even / odd 16-row steps): four independent MMA chains of 8 instead of two chains of 16 - with
+      // two chains this loop was bound by the MMA latency (40 % of the kernel's stall samples)
+      float acc2[2][2][4];
 #pragma unroll
-      for (int jd = 0; jd < 2; ++jd)
+      for (int p = 0; p < 2; ++p)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[jd][e] = 0.f;
+        for (int jd = 0; jd < 2; ++jd)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc2[p][jd][e] = 0.f;
       __nv_bfloat16 (*T)[PLD] = which ? Pt : dSt;
       const __nv_bfloat16 (*Bq)[LDQ] = which ? sm.dO : sm.Q;
       const int mi = lane >> 3, rr = lane & 7;
-#pragma unroll 4
+#pragma unroll
       for (int ks = 0; ks < M / 16; ++ks) {
         uint32_t a[4], b00, b01, b10, b11;
         ldsm_x4_t(a[0], a[1], a[2], a[3], &T[16 * ks + rr + 8 * (mi >> 1)][16 * mt + 8 * (mi & 1)]);
         ldsm_x4_t(b00, b01, b10, b11, &Bq[16 * ks + (lane & 15)][16 * dh + 8 * (lane >> 4)]);
-        mma16816(acc[0], a, b00, b01);
-        mma16816(acc[1], a, b10, b11);
+        mma16816(acc2[ks & 1][0], a, b00, b01);
+        mma16816(acc2[ks & 1][1], a, b10, b11);
       }
+      float acc[2][4];
+#pragma unroll
+      for (int jd = 0; jd < 2; ++jd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[jd][e] = acc2[0][jd][e] + acc2[1][jd][e];
       const int key0 = k0 + 16 * mt + g, key1 = key0 + 8;
       const int64_t e0 = (int64_t)b * cf.bs + (int64_t)key0 * cf.rs + head * D + 16 * dh + 2 * t;
       const int64_t e1 = e0 + 8 * cf.rs;
