@@ -445,9 +445,20 @@ def test_deform_bwd_warp_specialised_matches_lean(shape):
         assert rel_err(bb, a) < tol, rel_err(bb, a)
 
 
+def _cpb1d_params(npar, dense):
+    """random bias-MLP parameters; ``dense`` clusters the 32 layer-1 kinks inside |t| < 0.1, so that the range of one
+    (query row, key tile) holds several breakpoints and the table kernels take their per-pair search path"""
+    cpb = torch.randn(npar, device="cuda") * 0.4
+    if dense:
+        w1 = torch.randn(32, device="cuda") * 5.0
+        cpb[:32] = w1
+        cpb[32:64] = -w1 * torch.randn(32, device="cuda") * 0.03
+    return cpb
+
+
 @pytest.mark.parametrize("shape", [(2, 2501, 625), (1, 16385, 4096), (1, 777, 130)])
-@pytest.mark.parametrize("p_drop", [0.0, 0.1])
-def test_deform1d_fwd_pwl_matches_split(shape, p_drop):
+@pytest.mark.parametrize("p_drop,dense", [(0.0, False), (0.1, False), (0.0, True)])
+def test_deform1d_fwd_pwl_matches_split(shape, p_drop, dense):
     """1-D forward with the bias MLP tabulated as a piecewise-linear function (sml_deform_attn_fwd_pwl) against the fp32-grade
     split kernel that evaluates the MLP per pair: same inputs, same dropout hash"""
     from sml_b200._lib import c_f32, c_i32, c_u64, check, lib, ptr, stream
@@ -458,7 +469,7 @@ def test_deform1d_fwd_pwl_matches_split(shape, p_drop):
     q = torch.randn(b, T, heads * 64, device="cuda") * 0.3
     k = torch.randn(b, nkv, heads * 64, device="cuda"); v = torch.randn(b, nkv, heads * 64, device="cuda")
     vs = (torch.linspace(-1, 1, nkv, device="cuda").repeat(b * G, 1) + torch.randn(b * G, nkv, device="cuda") * 2e-3).unsqueeze(-1).contiguous()
-    cpb = torch.randn(lib.sml_deform_cpb_nparams(c_i32(1), c_i32(2)), device="cuda") * 0.4
+    cpb = _cpb1d_params(lib.sml_deform_cpb_nparams(c_i32(1), c_i32(2)), dense)
     cfg = (c_i32 * 8)(b, heads, T, nkv, G, 1, 0, 64)
     outs = {}
     for name in ("pwl", "split", "lean"):
@@ -480,8 +491,8 @@ def test_deform1d_fwd_pwl_matches_split(shape, p_drop):
 
 
 @pytest.mark.parametrize("shape", [(2, 2501, 625), (1, 16385, 4096), (1, 777, 130)])
-@pytest.mark.parametrize("p_drop", [0.0, 0.1])
-def test_deform1d_bwd_pwl_matches_split(shape, p_drop):
+@pytest.mark.parametrize("p_drop,dense", [(0.0, False), (0.1, False), (0.0, True)])
+def test_deform1d_bwd_pwl_matches_split(shape, p_drop, dense):
     """1-D backward with the tabulated bias (sml_deform_attn_bwd_pwl + sml_cpb1d_table_bwd: per-segment sums mapped to the MLP
     parameters) against the fp32-grade split kernel that differentiates the MLP per pair; the plain-bf16 per-pair kernel on the
     same inputs sets the scale of the allowed error."""
@@ -494,7 +505,7 @@ def test_deform1d_bwd_pwl_matches_split(shape, p_drop):
     k = torch.randn(b, nkv, heads * 64, device="cuda"); v = torch.randn(b, nkv, heads * 64, device="cuda")
     vs = (torch.linspace(-1, 1, nkv, device="cuda").repeat(b * G, 1) + torch.randn(b * G, nkv, device="cuda") * 2e-3).unsqueeze(-1).contiguous()
     npar = lib.sml_deform_cpb_nparams(c_i32(1), c_i32(2))
-    cpb = torch.randn(npar, device="cuda") * 0.4
+    cpb = _cpb1d_params(npar, dense)
     cfg = (c_i32 * 8)(b, heads, T, nkv, G, 1, 0, 64)
     dout = torch.randn(b, T, heads * 64, device="cuda")
     res = {}
