@@ -1439,10 +1439,11 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
       ah[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
       ah[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t bh0, bh1;
-        ldmatrix_x2_trans(bh0, bh1, pwl_sw(st.V, 16 * ks + (lane & 15), 8 * j));
-        mma16816(oacc[j], ah, bh0, bh1);
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t b00, b01, b10, b11;
+        ldmatrix_x4_trans(b00, b01, b10, b11, pwl_sw(st.V, 16 * ks + (lane & 15), 8 * j + 8 * (lane >> 4)));
+        mma16816(oacc[j], ah, b00, b01);
+        mma16816(oacc[j + 1], ah, b10, b11);
       }
     }
   }
@@ -2199,10 +2200,11 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
       uint32_t ah[4];
       ldmatrix_x4(ah[0], ah[1], ah[2], ah[3], &dSt[w * 16 + (lane & 15)][16 * ks + 8 * (lane >> 4)]);
 #pragma unroll
-      for (int jd = 0; jd < 8; ++jd) {
-        uint32_t bh0, bh1;
-        ldmatrix_x2_trans(bh0, bh1, pwl_sw(st.K, 16 * ks + (lane & 15), 8 * jd));
-        mma16816(dqacc[jd], ah, bh0, bh1);
+      for (int jd = 0; jd < 8; jd += 2) {
+        uint32_t b00, b01, b10, b11;
+        ldmatrix_x4_trans(b00, b01, b10, b11, pwl_sw(st.K, 16 * ks + (lane & 15), 8 * jd + 8 * (lane >> 4)));
+        mma16816(dqacc[jd], ah, b00, b01);
+        mma16816(dqacc[jd + 1], ah, b10, b11);
       }
     }
     // ---- dK += dS^T Q and dV += (P keep)^T dO: warp slice = 16 keys x 32 dims, contraction over the CTA's 64 queries

@@ -16,6 +16,11 @@ k = torch.randn(b, nkv, heads * 64, device="cuda"); v = torch.randn(b, nkv, head
 vs = (torch.linspace(-1, 1, nkv, device="cuda").repeat(b * G, 1) + torch.randn(b * G, nkv, device="cuda") * 2e-3).unsqueeze(-1).contiguous()
 npar = lib.sml_deform_cpb_nparams(c_i32(1), c_i32(2))
 cpb = torch.randn(npar, device="cuda") * 0.4
+if "--dense" in sys.argv:           # layer-1 kinks clustered in |t| < 0.1: many (row, key tile) ranges hold >= 2 breakpoints
+    w1 = torch.randn(32, device="cuda") * 5.0
+    cpb[:32] = w1; cpb[32:64] = -w1 * torch.randn(32, device="cuda") * 0.03
+if "--wide" in sys.argv:            # large first-layer weights: ~1000 breakpoints spread over the whole distance range
+    cpb[:32] *= 8.0; cpb[64:64 + 1024] *= 3.0
 cfg = (c_i32 * 8)(b, heads, T, nkv, G, 1, 0, 64)
 out = torch.empty(b, T, heads * 64, device="cuda"); lse = torch.empty(b, heads, T, device="cuda")
 dout = torch.randn_like(out); dq = torch.empty_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v); dvs = torch.zeros_like(vs)
