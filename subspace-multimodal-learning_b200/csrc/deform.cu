@@ -417,6 +417,157 @@ __global__ void __launch_bounds__(GS_THREADS) gather_bwd_sorted_kernel(const Gat
   }
 }
 
+// Same contract, with the bitonic network (78 block-wide passes at 4096 entries) replaced by a stable least-significant-digit
+// radix sort on the destination: two 8-bit passes (destinations < 65536), each = per-warp digit counts (match.any groups, no
+// atomics), one exclusive scan of the [256 digits x 16 warps] table, and a ranked scatter.  Entries start in ascending entry
+// order and the sort is stable, so the order inside a destination is canonical (deterministic sums) without sorting on it.
+// Shared memory: two key buffers + weights (12 NP bytes) + the 16 KB count table: 64 KB at NP = 4096 (three blocks per SM).
+constexpr int GR_THREADS = 512, GR_WARPS = GR_THREADS / 32, GR_RADIX = 256;
+template <int NP, int EPS>
+__global__ void __launch_bounds__(GR_THREADS) gather_bwd_radix_kernel(const GatherCfg cf, const float* __restrict__ vs,
+                                                                      const float* __restrict__ dkv, float* __restrict__ dx2) {
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  uint32_t* keyA = reinterpret_cast<uint32_t*>(gs_smem);              // (dest << 16) | entry
+  uint32_t* keyB = keyA + NP;
+  float* wgt = reinterpret_cast<float*>(keyB + NP);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(wgt + NP);             // [digit][warp]
+  __shared__ uint32_t wsum[GR_WARPS];
+  const int bg = blockIdx.x, b = bg / cf.G, g = bg % cf.G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t INVALID = 0xffffffffu;
+  constexpr int ESH = EPS == 4 ? 2 : 1;
+  static_assert(NP % GR_THREADS == 0 && NP <= 65536, "entry ids are 16 bits");
+  for (int e = tid; e < NP; e += GR_THREADS) {
+    uint32_t key = INVALID;
+    float w = 0.f;
+    if (e < EPS * cf.nkv) {
+      const int p = e >> ESH;
+      const Taps t = make_taps(cf, vs, (int64_t)bg * cf.nkv + p);
+      const int kx = EPS == 4 ? (e & 1) : -t.x0, ky = EPS == 4 ? ((e >> 1) & 1) : (e & 1);
+      const int xx = t.x0 + kx, yy = t.y0 + ky;
+      if ((kx == 0 || kx == 1) && xx >= 0 && xx < cf.W && yy >= 0 && yy < cf.H) {
+        key = ((uint32_t)(yy * cf.W + xx) << 16) | (uint32_t)e;
+        w = (kx ? t.wx1 : 1.f - t.wx1) * (ky ? t.wy1 : 1.f - t.wy1);
+      }
+    }
+    keyA[e] = key; wgt[e] = w;
+  }
+  // warp w owns the contiguous entries [w E, (w + 1) E) of the source buffer and walks them in order, 32 at a time
+  constexpr int E = NP / GR_WARPS;
+  uint32_t* src = keyA;
+  uint32_t* dst = keyB;
+#pragma unroll 1
+  for (int shift = 16; shift < 32; shift += 8) {
+    for (int i = tid; i < GR_RADIX * GR_WARPS; i += GR_THREADS) hist[i] = 0u;
+    __syncthreads();
+    for (int r = 0; r < E; r += 32) {
+      const uint32_t d = (src[warp * E + r + lane] >> shift) & 0xffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (lane == __ffs(peers) - 1) hist[d * GR_WARPS + warp] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    {                                                               // exclusive scan of hist (digit-major): 8 values per thread
+      constexpr int PER = GR_RADIX * GR_WARPS / GR_THREADS;
+      uint32_t v[PER], sum = 0u;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { v[i] = hist[tid * PER + i]; sum += v[i]; }
+      uint32_t inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      uint32_t base = 0u;
+      for (int w2 = 0; w2 < warp; ++w2) base += wsum[w2];
+      uint32_t run = base + inc - sum;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { hist[tid * PER + i] = run; run += v[i]; }
+    }
+    __syncthreads();
+    for (int r = 0; r < E; r += 32) {
+      const uint32_t k = src[warp * E + r + lane];
+      const uint32_t d = (k >> shift) & 0xffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t pos = hist[d * GR_WARPS + warp] + __popc(peers & ((1u << lane) - 1u));
+      dst[pos] = k;
+      __syncwarp();
+      if (lane == __ffs(peers) - 1) hist[d * GR_WARPS + warp] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    uint32_t* tmp = src; src = dst; dst = tmp;
+  }
+  const uint32_t* skey = src;                                         // sorted by destination, entry order inside
+  // runs of equal destination: one group of cg / 4 lanes (a float4 of channels per lane) per sorted position, 32 / (cg / 4)
+  // positions in flight per warp; the group whose position starts a run reduces the run (1-2 entries for bounded offsets;
+  // the degenerate 1-D reference pad order puts every sample on one destination and is walked by a single group)
+  constexpr int PER_WARP = NP / GR_WARPS;
+  if ((cf.cg & 3) == 0) {
+    const int qpg = cf.cg >> 2, gpw = 32 / qpg;
+    const int sub = lane / qpg, c4 = (lane % qpg) * 4;
+    // four positions per group and step: the d kv rows of their first entries are requested together (the loop is bound by
+    // the latency of that load, not by bandwidth)
+    constexpr int UN = 4;
+    const float* dkvb = dkv + (int64_t)b * cf.nkv * cf.C + g * cf.cg + c4;
+    for (int pos0 = warp * PER_WARP; pos0 < (warp + 1) * PER_WARP; pos0 += gpw * UN) {
+      uint32_t ck[UN];
+      bool start[UN];
+      float4 gv[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int pos = pos0 + u * gpw + sub;
+        ck[u] = pos < (warp + 1) * PER_WARP ? skey[pos] : INVALID;
+        start[u] = ck[u] != INVALID && (pos == 0 || (skey[pos - 1] >> 16) != (ck[u] >> 16));
+      }
+      if (__all_sync(0xffffffffu, ck[0] == INVALID)) break;
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+        gv[u] = start[u] ? ldg4(dkvb + (int64_t)((int)(ck[u] & 0xffffu) >> ESH) * cf.C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (!start[u]) continue;
+        const uint32_t dest = ck[u] >> 16;
+        const float w0 = wgt[ck[u] & 0xffffu];
+        float4 acc = make_float4(w0 * gv[u].x, w0 * gv[u].y, w0 * gv[u].z, w0 * gv[u].w);     // = fma(w, g, 0)
+        for (int qn = pos0 + u * gpw + sub + 1; qn < NP; ++qn) {
+          const uint32_t kq = skey[qn];
+          if (kq == INVALID || (kq >> 16) != dest) break;
+          const int e = (int)(kq & 0xffffu);
+          const float w = wgt[e];
+          const float4 g2 = ldg4(dkvb + (int64_t)(e >> ESH) * cf.C);
+          acc.x = fmaf(w, g2.x, acc.x); acc.y = fmaf(w, g2.y, acc.y); acc.z = fmaf(w, g2.z, acc.z); acc.w = fmaf(w, g2.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(dx2 + ((int64_t)b * cf.H * cf.W + dest) * cf.C + g * cf.cg + c4) = acc;
+      }
+    }
+    return;
+  }
+  for (int pos = warp * PER_WARP; pos < (warp + 1) * PER_WARP; ++pos) {
+    const uint32_t ck = skey[pos];
+    if (ck == INVALID) break;
+    const uint32_t dest = ck >> 16;
+    if (pos > 0 && (skey[pos - 1] >> 16) == dest) continue;
+    float acc = 0.f;
+    for (int qn = pos; qn < NP; ++qn) {
+      const uint32_t kq = skey[qn];
+      if (kq == INVALID || (kq >> 16) != dest) break;
+      const int e = (int)(kq & 0xffffu);
+      if (lane < cf.cg) acc = fmaf(wgt[e], dkv[((int64_t)b * cf.nkv + (e >> ESH)) * cf.C + g * cf.cg + lane], acc);
+    }
+    if (lane < cf.cg) dx2[((int64_t)b * cf.H * cf.W + dest) * cf.C + g * cf.cg + lane] = acc;
+  }
+}
+template <int NP, int EPS>
+static void launch_radix(const GatherCfg& cf, const float* vs, const float* dkv, float* dx2, cudaStream_t st) {
+  const int smem = NP * 12 + GR_RADIX * GR_WARPS * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gather_bwd_radix_kernel<NP, EPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  gather_bwd_radix_kernel<NP, EPS><<<(unsigned)(cf.B * cf.G), GR_THREADS, smem, st>>>(cf, vs, dkv, dx2);
+}
+
 template <int NP, int EPS>
 static void launch_sorted(const GatherCfg& cf, const float* vs, const float* dkv, float* dx2, cudaStream_t st) {
   static bool attr = false;
@@ -1036,7 +1187,23 @@ extern "C" int sml_deform_gather_bwd(const int32_t* cfg8, const float* x2, const
     gather_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cf, x2, vs, dkv, dx2, dvs_in, dvs_out, !sorted);
   }
   SML_LAUNCH_OK("sml_deform_gather_bwd");
-  if (sorted) {
+  if (sorted && (int64_t)cf.H * cf.W < 65535) {
+    // destinations and entry ids fit 16 bits each: radix-sorted scatter
+    if (eps == 4) {
+      if (np == 1024) launch_radix<1024, 4>(cf, vs, dkv, dx2, st);
+      else if (np == 2048) launch_radix<2048, 4>(cf, vs, dkv, dx2, st);
+      else if (np == 4096) launch_radix<4096, 4>(cf, vs, dkv, dx2, st);
+      else if (np == 8192) launch_radix<8192, 4>(cf, vs, dkv, dx2, st);
+      else launch_radix<16384, 4>(cf, vs, dkv, dx2, st);
+    } else {
+      if (np == 1024) launch_radix<1024, 2>(cf, vs, dkv, dx2, st);
+      else if (np == 2048) launch_radix<2048, 2>(cf, vs, dkv, dx2, st);
+      else if (np == 4096) launch_radix<4096, 2>(cf, vs, dkv, dx2, st);
+      else if (np == 8192) launch_radix<8192, 2>(cf, vs, dkv, dx2, st);
+      else launch_radix<16384, 2>(cf, vs, dkv, dx2, st);
+    }
+    SML_LAUNCH_OK("sml_deform_gather_bwd(radix-sorted scatter)");
+  } else if (sorted) {
     if (eps == 4) {
       if (np == 1024) launch_sorted<1024, 4>(cf, vs, dkv, dx2, st);
       else if (np == 2048) launch_sorted<2048, 4>(cf, vs, dkv, dx2, st);
