@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(GS_THREADS) gather_bwd_sorted_kernel(const Gat
 // order and the sort is stable, so the order inside a destination is canonical (deterministic sums) without sorting on it.
 // Shared memory: two key buffers + weights (12 NP bytes) + the 16 KB count table: 64 KB at NP = 4096 (three blocks per SM).
 constexpr int GR_THREADS = 512, GR_WARPS = GR_THREADS / 32, GR_RADIX = 256;
+constexpr int GR_LONG = 128;          // runs longer than this are reduced by the whole block
+constexpr int GR_MAXLONG = 128;       // NP / GR_LONG such runs at most (16384 / 128)
 template <int NP, int EPS>
 __global__ void __launch_bounds__(GR_THREADS) gather_bwd_radix_kernel(const GatherCfg cf, const float* __restrict__ vs,
                                                                       const float* __restrict__ dkv, float* __restrict__ dx2) {
@@ -432,11 +434,13 @@ __global__ void __launch_bounds__(GR_THREADS) gather_bwd_radix_kernel(const Gath
   float* wgt = reinterpret_cast<float*>(keyB + NP);
   uint32_t* hist = reinterpret_cast<uint32_t*>(wgt + NP);             // [digit][warp]
   __shared__ uint32_t wsum[GR_WARPS];
+  __shared__ int nlong, longpos[GR_MAXLONG];
   const int bg = blockIdx.x, b = bg / cf.G, g = bg % cf.G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr uint32_t INVALID = 0xffffffffu;
   constexpr int ESH = EPS == 4 ? 2 : 1;
   static_assert(NP % GR_THREADS == 0 && NP <= 65536, "entry ids are 16 bits");
+  if (tid == 0) nlong = 0;
   for (int e = tid; e < NP; e += GR_THREADS) {
     uint32_t key = INVALID;
     float w = 0.f;
@@ -529,15 +533,57 @@ __global__ void __launch_bounds__(GR_THREADS) gather_bwd_radix_kernel(const Gath
         const uint32_t dest = ck[u] >> 16;
         const float w0 = wgt[ck[u] & 0xffffu];
         float4 acc = make_float4(w0 * gv[u].x, w0 * gv[u].y, w0 * gv[u].z, w0 * gv[u].w);     // = fma(w, g, 0)
-        for (int qn = pos0 + u * gpw + sub + 1; qn < NP; ++qn) {
+        const int first = pos0 + u * gpw + sub;
+        bool longrun = false;
+        for (int qn = first + 1; qn < NP; ++qn) {
           const uint32_t kq = skey[qn];
           if (kq == INVALID || (kq >> 16) != dest) break;
+          if (qn - first >= GR_LONG) { longrun = true; break; }
           const int e = (int)(kq & 0xffffu);
           const float w = wgt[e];
           const float4 g2 = ldg4(dkvb + (int64_t)(e >> ESH) * cf.C);
           acc.x = fmaf(w, g2.x, acc.x); acc.y = fmaf(w, g2.y, acc.y); acc.z = fmaf(w, g2.z, acc.z); acc.w = fmaf(w, g2.w, acc.w);
         }
-        *reinterpret_cast<float4*>(dx2 + ((int64_t)b * cf.H * cf.W + dest) * cf.C + g * cf.cg + c4) = acc;
+        if (!longrun) *reinterpret_cast<float4*>(dx2 + ((int64_t)b * cf.H * cf.W + dest) * cf.C + g * cf.cg + c4) = acc;
+        else if (c4 == 0) { const int slot = atomicAdd(&nlong, 1); if (slot < GR_MAXLONG) longpos[slot] = first; }
+      }
+    }
+    // Long runs (the degenerate 1-D reference pad order puts every sample of a group on the one or two middle tokens, SURVEY
+    // F5): reduced by the whole block - warp w sums a fixed slice of the run, its lane groups fixed strided subsets of the
+    // slice, partials are combined in a fixed order, so the result stays deterministic.
+    __syncthreads();
+    const int nl = min(nlong, GR_MAXLONG);
+    for (int li = 0; li < nl; ++li) {
+      int first = longpos[0];                                   // process in ascending position order (list order is arbitrary)
+      {
+        int best = -1;
+        for (int q = 0; q < nl; ++q) { const int v = longpos[q]; int rank = 0; for (int r = 0; r < nl; ++r) rank += longpos[r] < v; if (rank == li) best = v; }
+        first = best;
+      }
+      const uint32_t dest = skey[first] >> 16;
+      int lo = first, hi = NP;                                   // end of the run: first position with another destination
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if ((skey[mid] >> 16) <= dest && skey[mid] != INVALID) lo = mid + 1; else hi = mid; }
+      const int len = lo - first, per = (len + GR_WARPS - 1) / GR_WARPS;
+      const int s0 = first + warp * per, s1 = min(s0 + per, first + len);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int qn = s0 + sub; qn < s1; qn += gpw) {
+        const int e = (int)(skey[qn] & 0xffffu);
+        const float w = wgt[e];
+        const float4 g2 = ldg4(dkvb + (int64_t)(e >> ESH) * cf.C);
+        acc.x = fmaf(w, g2.x, acc.x); acc.y = fmaf(w, g2.y, acc.y); acc.z = fmaf(w, g2.z, acc.z); acc.w = fmaf(w, g2.w, acc.w);
+      }
+      for (int o = qpg; o < 32; o <<= 1) {                       // lane groups of the warp, fixed tree
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      float4* part = reinterpret_cast<float4*>(hist);            // the count table is free now: [warp][cg / 4] float4
+      __syncthreads();
+      if (sub == 0) part[warp * qpg + lane] = acc;
+      __syncthreads();
+      if (warp == 0 && sub == 0) {
+        float4 t = part[lane];
+        for (int w2 = 1; w2 < GR_WARPS; ++w2) { const float4 v = part[w2 * qpg + lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        *reinterpret_cast<float4*>(dx2 + ((int64_t)b * cf.H * cf.W + dest) * cf.C + g * cf.cg + c4) = t;
       }
     }
     return;
