@@ -58,7 +58,7 @@ __device__ __forceinline__ float ex2(float x) {
 // token-major bf16 K / V planes inside the packed qkv tensor [b, n', 3, h, 64]: element (b, t, head, c) of K at
 // kv + b * bs + t * rs + k_off + head * 64 + c  (V: v_off)
 struct Cfg {
-  int B, H, npad;
+  int B, H, npad, m;                 // m = landmark rows per (b, h): a multiple of 64 (forward), 256 (backward)
   int64_t rs, bs;
   int k_off, v_off;
   int tiles_per_chunk, nchunks;      // in tiles of the kernel's key tile (forward 64 keys, backward 32)
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(FT, 3) a3_fwd_kernel(const Cfg cf, const __nv_
   const int t0 = chunk * cf.tiles_per_chunk, t1 = min(t0 + cf.tiles_per_chunk, ntot);
   const int ntiles = t1 - t0;
   {
-    const __nv_bfloat16* qb = ql + ((int64_t)bh * M + q0) * D;
+    const __nv_bfloat16* qb = ql + ((int64_t)bh * cf.m + q0) * D;
     for (int e = tid; e < 64 * 8; e += FT) cp16(&sm.Q[e >> 3][(e & 7) * 8], qb + (e >> 3) * D + (e & 7) * 8);
   }
   if (ntiles > 0) stage_load<FK, FT>(sm.st[0], kb, vb, cf.rs, t0 * FK, tid);
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(FT, 3) a3_fwd_kernel(const Cfg cf, const __nv_
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const int r0 = q0 + w * 16 + g, r1 = r0 + 8;
-  const int64_t pb = ((int64_t)bh * cf.nchunks + chunk) * M;
+  const int64_t pb = ((int64_t)bh * cf.nchunks + chunk) * cf.m;
   float* o0 = opart + (pb + r0) * D + 2 * t;
   float* o1 = opart + (pb + r1) * D + 2 * t;
 #pragma unroll
@@ -189,11 +189,11 @@ __global__ void __launch_bounds__(FT, 3) a3_fwd_kernel(const Cfg cf, const __nv_
 
 // a3v [B H, 256, 64] (fp32 + bf16 copy), lse [B H, 256] (natural log) from the chunk partials; one thread per (row, 4 dims)
 __global__ void __launch_bounds__(256) a3_combine_kernel(const float* __restrict__ opart, const float2* __restrict__ ml, int nchunks,
-                                                         int64_t rows, float* __restrict__ a3v, __nv_bfloat16* __restrict__ a3v_hi,
+                                                         int64_t rows, int M, float* __restrict__ a3v, __nv_bfloat16* __restrict__ a3v_hi,
                                                          float* __restrict__ lse) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * 16) return;
-  const int64_t row = i >> 4;                 // bh * 256 + r
+  const int64_t row = i >> 4;                 // bh * m + r
   const int c4 = (int)(i & 15) * 4;
   const int64_t bh = row / M, r = row % M;
   float mx = -INFINITY;
@@ -433,8 +433,9 @@ using namespace sml;
 
 static int a3_cfg(a3::Cfg& cf, const int32_t* c, int tile, const char* who) {
   // c = (B, H, m, d, npad, row stride, batch stride (elements, as two int32: lo, hi), k_off, v_off, nchunks)
-  cf.B = c[0]; cf.H = c[1];
-  SML_CHECK(c[2] == a3::M && c[3] == a3::D, "%s: needs 256 landmarks and head dim 64 (got %d, %d)", who, c[2], c[3]);
+  cf.B = c[0]; cf.H = c[1]; cf.m = c[2];
+  SML_CHECK(c[3] == a3::D && c[2] > 0 && c[2] % 64 == 0 && (tile == a3::FK || c[2] == a3::M),
+            "%s: needs head dim 64 and a multiple of 64 landmarks (256 for the backward) (got %d, %d)", who, c[2], c[3]);
   cf.npad = c[4];
   SML_CHECK(cf.npad % 64 == 0 && cf.npad > 0, "%s: padded length must be a multiple of 64 (got %d)", who, cf.npad);
   cf.rs = c[5];
@@ -460,13 +461,13 @@ extern "C" int sml_nystrom_a3_fwd(const int32_t* cfg11, const void* ql_bf16, con
   const size_t smem = sizeof(a3::FwdSmem);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(a3::a3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  dim3 grid(cf.nchunks, a3::M / 64, cf.B * cf.H);
+  dim3 grid(cf.nchunks, cf.m / 64, cf.B * cf.H);
   a3::a3_fwd_kernel<<<grid, a3::FT, smem, as_stream(stream)>>>(cf, (const __nv_bfloat16*)ql_bf16, (const __nv_bfloat16*)qkv_bf16, opart,
                                                                reinterpret_cast<float2*>(ml));
   SML_LAUNCH_OK("sml_nystrom_a3_fwd");
-  const int64_t rows = (int64_t)cf.B * cf.H * a3::M;
+  const int64_t rows = (int64_t)cf.B * cf.H * cf.m;
   a3::a3_combine_kernel<<<(unsigned)((rows * 16 + 255) / 256), 256, 0, as_stream(stream)>>>(opart, reinterpret_cast<const float2*>(ml), cf.nchunks,
-                                                                                            rows, a3v, (__nv_bfloat16*)a3v_hi, lse);
+                                                                                            rows, cf.m, a3v, (__nv_bfloat16*)a3v_hi, lse);
   SML_LAUNCH_OK("sml_nystrom_a3_fwd(combine)");
   return 0;
 }

@@ -167,7 +167,7 @@ class NystromAttentionFn(torch.autograd.Function):
     written straight into the front-padded buffer (and its bf16 copy)."""
 
     @staticmethod
-    def forward(ctx, x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, m, iters, mode, ln_eps, skip=None):
+    def forward(ctx, x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, m, iters, mode, ln_eps, skip=None, inference=False):
         """skip = (p, seed, offset): return x + dropout(attention(LN(x)), p) (TransLayer, mil.py:186) - the skip gradient is then
         added inside the LayerNorm-backward kernel instead of by autograd's accumulation pass."""
         assert mode in PRECISIONS
@@ -216,7 +216,9 @@ class NystromAttentionFn(torch.autograd.Function):
         lowp = mode == "bf16" and fuse          # keep the big probability tensors (A1, A3) in bf16 only
         a1 = TB.new((b, h, npad, m), dev, mode, f32=not lowp)
         a2 = TB.new((b, h, m, m), dev, mode, hp=PINV_HP)
-        fuse_a3 = FUSE_A3 and lowp and m == 256 and d == 64 and ksize == 33 and npad % 64 == 0 and qkv.hi is not None
+        # (the forward kernel takes any multiple of 64 landmarks, the backward 256: 512-landmark bags fuse when no gradient is needed)
+        fuse_a3 = (FUSE_A3 and mode == "bf16" and d == 64 and ksize == 33 and npad % 64 == 0 and qkv.hi is not None and
+                   (m == 256 or (m % 64 == 0 and inference)))
         mm(q_b, kl_b.T(), a1, softmax=fuse)
         mm(ql_b, kl_b.T(), a2, softmax=fuse)
         lse3 = None
@@ -241,7 +243,7 @@ class NystromAttentionFn(torch.autograd.Function):
         if not fuse_a3:
             ops.softmax_(s3.view(-1, npad), a3.hi, a3.lo, write_f32=not lowp)            # softmax over tokens
             del s3
-        z, pinv_saved = pinv_fwd(a2.f, iters, mode, a2, keep_steps=any(ctx.needs_input_grad))     # :138
+        z, pinv_saved = pinv_fwd(a2.f, iters, mode, a2, keep_steps=any(ctx.needs_input_grad) and not inference)     # :138
         if not fuse_a3:
             a3v = mm(a3, v_b, TB.new((b, h, m, d), dev, mode))                       # [b,h,m,d]
         z_op = z if mode != "bf16" else TB(z.f, z.hi, None)
@@ -433,7 +435,7 @@ class NystromAttentionFn(torch.autograd.Function):
             dx = dx2.view(b, n, D)
         else:
             dx = dxp[:, pad:]
-        return dx, dw_qkv, dw_out, db_out, dw_conv, dln_w, dln_b, None, None, None, None, None, None
+        return dx, dw_qkv, dw_out, db_out, dw_conv, dln_w, dln_b, None, None, None, None, None, None, None
 
 
 @torch.no_grad()
@@ -470,5 +472,6 @@ def fused_cvt_ok(ksize):
 def nystrom_attention(x, w_qkv, w_out, b_out, w_conv, heads, num_landmarks, pinv_iterations, precision="fp32",
                       pre_norm=None, skip=None):
     ln_w, ln_b, eps = pre_norm if pre_norm is not None else (None, None, 1e-5)
+    # inference = called under torch.no_grad() (ctx.needs_input_grad does not tell: it stays True for parameters)
     return NystromAttentionFn.apply(x, w_qkv, w_out, b_out, w_conv, ln_w, ln_b, heads, num_landmarks, pinv_iterations,
-                                    precision, eps, skip)
+                                    precision, eps, skip, not torch.is_grad_enabled())

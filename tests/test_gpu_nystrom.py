@@ -253,3 +253,23 @@ def test_nystrom_a3_fused_matches_torch(shape):
     check(lib.sml_nystrom_a3_bwd(cfgb, ptr(ql), ptr(qkv), ptr(g), ptr(a3v), ptr(lse), ptr(dkl), c_i32(lsz), ptr(dql2), ptr(dqkv_hi2),
                                  ptr(dqkv_f), stream()), "a3_bwd")
     assert rel_err(dqkv_hi2[:, :, 1].float(), want_dk.permute(0, 2, 1, 3)) < 2e-2
+
+
+@pytest.mark.gpu
+def test_nystrom_a3_forward_512_landmarks():
+    """the fused forward with 512 landmark rows (BASELINE configs[4]: 100 k-patch inference) against fp32 torch"""
+    from sml_b200._lib import check, lib, ptr, stream
+    from sml_b200.nystrom import _a3_cfg
+    b, h, npad, nch, m, d = 1, 3, 2560, 4, 512, 64
+    torch.manual_seed(5)
+    dev = "cuda"
+    qkv = (torch.randn(b, npad, 3, h, d, device=dev) * 0.7).bfloat16()
+    ql = (torch.randn(b, h, m, d, device=dev) * 0.5).bfloat16()
+    a3v = torch.empty(b, h, m, d, device=dev); lse = torch.empty(b, h, m, device=dev)
+    opart = torch.empty(b * h, nch, m, d, device=dev); ml = torch.empty(b * h, nch, m, 2, device=dev)
+    check(lib.sml_nystrom_a3_fwd(_a3_cfg(b, h, m, d, npad, nch), ptr(ql), ptr(qkv), ptr(opart), ptr(ml), ptr(a3v), None, ptr(lse), stream()),
+          "a3_fwd")
+    s = ql.float() @ qkv[:, :, 1].permute(0, 2, 1, 3).float().transpose(-1, -2)
+    want = torch.softmax(s, -1) @ qkv[:, :, 2].permute(0, 2, 1, 3).float()
+    assert rel_err(a3v, want) < 1e-2, rel_err(a3v, want)
+    assert (lse - torch.logsumexp(s, -1)).abs().max() < 2e-3
