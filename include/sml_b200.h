@@ -203,6 +203,10 @@ int sml_nystrom_a3_fwd(const int32_t* cfg11, const void* ql_bf16, const void* qk
 int sml_nystrom_a3_bwd(const int32_t* cfg11, const void* ql_bf16, const void* qkv_bf16, const float* da3v, const float* a3v,
                        const float* lse, const float* dkl, int32_t lsz, float* dql, void* dqkv_bf16, float* dqkv_f32, void* stream);
 int sml_nystrom_a3_dk_landmarks(const int32_t* cfg11, const float* dkl, int32_t lsz, void* dqkv_bf16, void* stream);
+/* Inference only (no saved probabilities): out [B, n', H 64] fp32 = softmax_j(q_t . kl_j) wm_j per head, q = the packed bf16 qkv
+ * tensor at offset 0, kl / wm bf16 [B, H, m, 64], m a multiple of 64 (models/NystromAttention.py:122, 130, 140). */
+int sml_nystrom_a1_fwd_nograd(const int32_t* cfg11, const void* qkv_bf16, const void* kl_bf16, const void* wm_bf16, float* out,
+                              void* stream);
 /* PPEG parameter folding and its backward: w7 [C,49], w5 [C,25], w3 [C,9] depthwise kernels + biases [C] (models/mil.py:195-198)
  * -> wf [49,C] tap-major stencil incl. the identity, bf [C]; unfold scatters d wf back to the three kernels (d bias is shared) */
 int sml_ppeg_fold(const float* w7, const float* w5, const float* w3, const float* b7, const float* b5, const float* b3,

@@ -187,6 +187,105 @@ __global__ void __launch_bounds__(FT, 3) a3_fwd_kernel(const Cfg cf, const __nv_
   if (t == 0) { ml[pb + r0] = make_float2(m0, l0); ml[pb + r1] = make_float2(m1, l1); }
 }
 
+// ------------------------------------------------------------------ token-by-landmark side, inference only
+// out[t] = softmax_j(q_t . kl_j) W_j  (NystromAttention.py:122, 130, 140 with W = Z (A3 V) folded: A1 @ W) for 64 token rows per CTA
+// and ALL m landmarks (m / 64 key tiles through the same ring): the [n', m] probabilities are not written.  Only usable when no
+// gradient is needed (the training backward, sml_nystrom_a1_bwd, reads the saved bf16 A1).  q = strided bf16 view of the packed
+// qkv tensor (offset 0), kl / wm contiguous bf16 [B H, m, 64]; out = fp32 [B, n', H 64] (head slice of the merged tensor).
+__global__ void __launch_bounds__(FT, 3) a1_fwd_kernel(const Cfg cf, const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ kl,
+                                                        const __nv_bfloat16* __restrict__ wm, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * 64, bh = blockIdx.y, b = bh / cf.H, head = bh % cf.H;
+  const __nv_bfloat16* kb = kl + (int64_t)bh * cf.m * D;
+  const __nv_bfloat16* vb = wm + (int64_t)bh * cf.m * D;
+  const int ntiles = cf.m / FK;
+  {
+    const __nv_bfloat16* qb = qkv + (int64_t)b * cf.bs + (int64_t)q0 * cf.rs + head * D;
+    for (int e = tid; e < 64 * 8; e += FT) cp16(&sm.Q[e >> 3][(e & 7) * 8], qb + (int64_t)(e >> 3) * cf.rs + (e & 7) * 8);
+  }
+  stage_load<FK, FT>(sm.st[0], kb, vb, D, 0, tid);
+  cp_commit();
+  if (ntiles > 1) stage_load<FK, FT>(sm.st[1], kb, vb, D, FK, tid);
+  cp_commit();
+  float oacc[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oacc[j][e] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int it = 0; it < ntiles; ++it) {
+    cp_wait<1>();
+    __syncthreads();
+    if (it + 2 < ntiles) stage_load<FK, FT>(sm.st[(it + 2) % 3], kb, vb, D, (it + 2) * FK, tid);
+    cp_commit();
+    const Stage<FK>& st = sm.st[it % 3];
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4];
+      ldsm_x4(ah[0], ah[1], ah[2], ah[3], &sm.Q[w * 16 + (lane & 15)][16 * ks + 8 * (lane >> 4)]);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t b00, b01, b10, b11;
+        ldsm_x4(b00, b01, b10, b11, sw(st.K, 8 * j + (lane & 7) + 8 * (lane >> 4), 16 * ks + 8 * ((lane >> 3) & 1)));
+        mma16816(s[j], ah, b00, b01);
+        mma16816(s[j + 1], ah, b10, b11);
+      }
+    }
+    float mt0 = -INFINITY, mt1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mt0 = fmaxf(mt0, fmaxf(s[j][0], s[j][1])); mt1 = fmaxf(mt1, fmaxf(s[j][2], s[j][3]));
+    }
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 1)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 1));
+    mt0 = fmaxf(mt0, __shfl_xor_sync(0xffffffffu, mt0, 2)); mt1 = fmaxf(mt1, __shfl_xor_sync(0xffffffffu, mt1, 2));
+    const float mn0 = fmaxf(m0, mt0 * LOG2E), mn1 = fmaxf(m1, mt1 * LOG2E);
+    const float al0 = ex2(m0 - mn0), al1 = ex2(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= al0; l1 *= al1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { oacc[j][0] *= al0; oacc[j][1] *= al0; oacc[j][2] *= al1; oacc[j][3] *= al1; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = ex2(fmaf(s[j][0], LOG2E, -mn0)); s[j][1] = ex2(fmaf(s[j][1], LOG2E, -mn0));
+      s[j][2] = ex2(fmaf(s[j][2], LOG2E, -mn1)); s[j][3] = ex2(fmaf(s[j][3], LOG2E, -mn1));
+      l0 += s[j][0] + s[j][1]; l1 += s[j][2] + s[j][3];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ah[4];
+      ah[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+      ah[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+      ah[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      ah[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        uint32_t b00, b01, b10, b11;
+        ldsm_x4_t(b00, b01, b10, b11, sw(st.V, 16 * ks + (lane & 15), 8 * j + 8 * (lane >> 4)));
+        mma16816(oacc[j], ah, b00, b01);
+        mma16816(oacc[j + 1], ah, b10, b11);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = q0 + w * 16 + g, r1 = r0 + 8;
+  float* o0 = out + ((int64_t)b * cf.npad + r0) * (cf.H * D) + head * D + 2 * t;
+  float* o1 = out + ((int64_t)b * cf.npad + r1) * (cf.H * D) + head * D + 2 * t;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<float2*>(o0 + 8 * j) = make_float2(oacc[j][0] * i0, oacc[j][1] * i0);
+    *reinterpret_cast<float2*>(o1 + 8 * j) = make_float2(oacc[j][2] * i1, oacc[j][3] * i1);
+  }
+}
+
 // a3v [B H, 256, 64] (fp32 + bf16 copy), lse [B H, 256] (natural log) from the chunk partials; one thread per (row, 4 dims)
 __global__ void __launch_bounds__(256) a3_combine_kernel(const float* __restrict__ opart, const float2* __restrict__ ml, int nchunks,
                                                          int64_t rows, int M, float* __restrict__ a3v, __nv_bfloat16* __restrict__ a3v_hi,
@@ -501,5 +600,23 @@ extern "C" int sml_nystrom_a3_dk_landmarks(const int32_t* cfg11, const float* dk
   const int64_t total = (int64_t)cf.B * cf.npad * cf.H * 8;
   a3::a3_bcast_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(cf, (__nv_bfloat16*)dqkv_bf16, dkl, lsz);
   SML_LAUNCH_OK("sml_nystrom_a3_dk_landmarks");
+  return 0;
+}
+
+/* Inference only: out[b, t, head 64 ..] = softmax_j(q_t . kl_j) wm_j without the [n', m] probabilities (models/NystromAttention.py:
+ * 122, 130, 140 with wm = Z (A3 V)).  cfg11 as above (q = the packed tensor at offset 0); kl, wm bf16 [B, H, m, 64]; out fp32
+ * [B, n', H 64]. */
+extern "C" int sml_nystrom_a1_fwd_nograd(const int32_t* cfg11, const void* qkv_bf16, const void* kl_bf16, const void* wm_bf16, float* out,
+                                         void* stream) {
+  a3::Cfg cf;
+  if (a3_cfg(cf, cfg11, a3::FK, "sml_nystrom_a1_fwd_nograd")) return 1;
+  SML_CHECK(qkv_bf16 && kl_bf16 && wm_bf16 && out, "sml_nystrom_a1_fwd_nograd: null pointer");
+  const size_t smem = sizeof(a3::FwdSmem);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(a3::a1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  dim3 grid(cf.npad / 64, cf.B * cf.H);
+  a3::a1_fwd_kernel<<<grid, a3::FT, smem, as_stream(stream)>>>(cf, (const __nv_bfloat16*)qkv_bf16, (const __nv_bfloat16*)kl_bf16,
+                                                               (const __nv_bfloat16*)wm_bf16, out);
+  SML_LAUNCH_OK("sml_nystrom_a1_fwd_nograd");
   return 0;
 }

@@ -214,12 +214,15 @@ class NystromAttentionFn(torch.autograd.Function):
         # ---- similarities + softmaxes (:122-137)
         fuse = tc and m <= 256
         lowp = mode == "bf16" and fuse          # keep the big probability tensors (A1, A3) in bf16 only
-        a1 = TB.new((b, h, npad, m), dev, mode, f32=not lowp)
+        # inference: the token-by-landmark product is fused too (no A1): see below, after W = Z (A3 V) is known
+        fuse_a1_inf = FUSE_A3 and inference and mode == "bf16" and d == 64 and m % 64 == 0 and npad % 64 == 0 and qkv.hi is not None
+        a1 = TB(None, None, None) if fuse_a1_inf else TB.new((b, h, npad, m), dev, mode, f32=not lowp)
         a2 = TB.new((b, h, m, m), dev, mode, hp=PINV_HP)
         # (the forward kernel takes any multiple of 64 landmarks, the backward 256: 512-landmark bags fuse when no gradient is needed)
         fuse_a3 = (FUSE_A3 and mode == "bf16" and d == 64 and ksize == 33 and npad % 64 == 0 and qkv.hi is not None and
                    (m == 256 or (m % 64 == 0 and inference)))
-        mm(q_b, kl_b.T(), a1, softmax=fuse)
+        if not fuse_a1_inf:
+            mm(q_b, kl_b.T(), a1, softmax=fuse)
         mm(ql_b, kl_b.T(), a2, softmax=fuse)
         lse3 = None
         if fuse_a3:
@@ -238,7 +241,8 @@ class NystromAttentionFn(torch.autograd.Function):
             s3 = a3.f if a3.f is not None else torch.empty(b, h, m, npad, device=dev, dtype=F32)   # logits scratch
             mm(ql_b, k_b.T(), TB(s3))
         if not fuse:
-            ops.softmax_(a1.f.view(-1, m), a1.hi, a1.lo)
+            if not fuse_a1_inf:
+                ops.softmax_(a1.f.view(-1, m), a1.hi, a1.lo)
             ops.softmax_(a2.f.view(-1, m), a2.hi, a2.lo)
         if not fuse_a3:
             ops.softmax_(s3.view(-1, npad), a3.hi, a3.lo, write_f32=not lowp)            # softmax over tokens
@@ -249,7 +253,11 @@ class NystromAttentionFn(torch.autograd.Function):
         z_op = z if mode != "bf16" else TB(z.f, z.hi, None)
         wm = mm(z_op, a3v, TB.new((b, h, m, d), dev, mode))                          # Z (A3 V)
         merged = TB.new((b, npad, inner), dev, mode)
-        mm(a1, wm, TB(merged.f.view(b, npad, h, d).permute(0, 2, 1, 3)))             # A1 (Z A3 V)  :140
+        if fuse_a1_inf:
+            check(lib.sml_nystrom_a1_fwd_nograd(_a3_cfg(b, h, m, d, npad, 1), ptr(qkv.hi), ptr(kl_b.hi), ptr(wm.hi), ptr(merged.f), stream()),
+                  "nystrom_a1_fwd_nograd")
+        else:
+            mm(a1, wm, TB(merged.f.view(b, npad, h, d).permute(0, 2, 1, 3)))         # A1 (Z A3 V)  :140
         ksize = w_conv.shape[2]
         wc = w_conv.detach().reshape(h, ksize).contiguous()
         fused_cvt = ksize == 33
