@@ -1181,6 +1181,7 @@ __global__ void __launch_bounds__(MTHREADS, MINB) deform_attn_fwd_lean_kernel(co
 // scaled when it is converted to bf16), so that slope p + icpt becomes slope p2 + icpt log2(e) with an UNCHANGED slope, the
 // distance costs one MUFU.LG2 and the softmax one MUFU.EX2 without multiplies.
 constexpr int PWL_MAXSEG = 1089;
+constexpr int PWL_MAXTILES = 512;        // 32-key tiles whose ranges are staged in shared memory (n_kv <= 16 384; beyond: global reads)
 constexpr float PWL_LOG2E = 1.4426950408889634f, PWL_LN2 = 0.6931471805599453f;
 struct PwlTable {
   float B[PWL_MAXSEG + 1];               // segment s covers [B[s], B[s + 1]) in p2 units; B[0] = -inf, B[nseg] = +inf
@@ -1216,12 +1217,13 @@ struct PwlRow {
 // kmin / kmax = range of the tile's key positions; returns true when the row's range holds more than one breakpoint
 __device__ __forceinline__ bool pwl_row_setup(const PwlTable& tb, int ns, float qx, float kmin, float kmax, PwlRow& rw) {
   const float plo = slog2_fast(qx - kmax), phi = slog2_fast(qx - kmin);
+  // common case: the lower end is still in the segment of the previous tile - three independent loads, no search
+  const float b0 = tb.B[rw.seg], b1 = tb.B[rw.seg + 1], b2 = tb.B[min(rw.seg + 2, ns)];
+  if (plo >= b0 && plo < b1 && rw.b == b1) return phi >= b2;
   const int sL = pwl_seek(tb, plo, rw.seg);
-  if (sL != rw.seg || rw.b != tb.B[sL + 1]) {            // the lines change ~ once per segment: mostly skipped
-    const float2 cl = tb.line(sL), ch = tb.line(min(sL + 1, ns - 1));
-    rw.seg = sL; rw.b = tb.B[sL + 1];
-    rw.sl = cl.x; rw.il = cl.y; rw.sh = ch.x; rw.ih = ch.y;
-  }
+  const float2 cl = tb.line(sL), ch = tb.line(min(sL + 1, ns - 1));
+  rw.seg = sL; rw.b = tb.B[sL + 1];
+  rw.sl = cl.x; rw.il = cl.y; rw.sh = ch.x; rw.ih = ch.y;
   return phi >= tb.B[min(sL + 2, ns)];
 }
 __device__ __forceinline__ float pwl_bias(const PwlRow& rw, float p) {
@@ -1947,6 +1949,7 @@ struct PwlBwdSmem {
   PwlStage<BK> st[3];
   __nv_bfloat16 P[2][MQ][PLD], dS[2][MQ][PLD];
   float dkpos[2][MTHREADS / 32][BK];      // per-warp partial key-coordinate gradients (no shared-memory atomics)
+  float2 krng[PWL_MAXTILES];              // key-position range of every tile of this (b, g) row
   PwlTable pw;
 };
 // running per-row sums of the segments {seg, seg + 1}; the four lanes of a quad hold the same row: they are reduced at flush time
@@ -2011,6 +2014,8 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
     cp_async_commit();
   }
   pwl_load(sm.pw, brk, coef, ns - 1, cf.OUT, o, tid, MTHREADS);
+  if (ntiles <= PWL_MAXTILES)
+    for (int i = tid; i < ntiles; i += MTHREADS) sm.krng[i] = kr[(int64_t)bg * ntiles + i];
   float2* bins = reinterpret_cast<float2*>(gseg) + (int64_t)o * (PWL_MAXSEG + 1);      // global: ~4 reductions per warp and segment
   const int64_t qoff = (int64_t)b * cf.n * cf.inner + head * AD;
   for (int e = tid; e < MQ * 16; e += MTHREADS) {          // Q tile scaled by log2(e); dO tile
@@ -2070,12 +2075,12 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
   __syncthreads();
 
   const float2* krb = kr + (int64_t)bg * ntiles;
-  float2 rng = krb[0];
+  const bool rng_smem = ntiles <= PWL_MAXTILES;      // (staged before the first barrier below)
 
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * BK;
+    const float2 rng = rng_smem ? sm.krng[it] : krb[it];
     const float kmin = rng.x, kmax = rng.y;
-    rng = krb[min(it + 1, ntiles - 1)];
     const PwlStage<BK>& st = sm.st[it % 3];
     __nv_bfloat16 (*Pt)[PLD] = sm.P[it & 1];
     __nv_bfloat16 (*dSt)[PLD] = sm.dS[it & 1];
@@ -2110,6 +2115,7 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
     const bool ragged = k0 + BK > cf.nkv;
     if (!slow) {
       float aT0 = 0.f, bT0 = 0.f, aH0 = 0.f, bH0 = 0.f, aT1 = 0.f, bT1 = 0.f, aH1 = 0.f, bH1 = 0.f;
+      float kgs[4][2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 kx = *reinterpret_cast<const float2*>(&st.kx[8 * j + 2 * t]);
@@ -2138,14 +2144,23 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_bwd_pwl_kernel(
           aT1 += dS1; bT1 = fmaf(dS1, p1, bT1); aH1 += h1; bH1 = fmaf(h1, p1, bH1);
           kg[e] = -fmaf(dS0 * sl0, ex2_fast(-fabsf(p0)), dS1 * sl1 * ex2_fast(-fabsf(p1)));
         }
-        // key-coordinate gradients of keys 8 j + 2 t + {0, 1}: sum over the warp's 16 rows (8 lanes share t)
-#pragma unroll
-        for (int m = 4; m < 32; m <<= 1) { kg[0] += __shfl_xor_sync(0xffffffffu, kg[0], m); kg[1] += __shfl_xor_sync(0xffffffffu, kg[1], m); }
-        if (g == 0) *reinterpret_cast<float2*>(&dkp[8 * j + 2 * t]) = make_float2(kg[0], kg[1]);
+        kgs[j][0] = kg[0]; kgs[j][1] = kg[1];
         *reinterpret_cast<uint32_t*>(&Pt[r0][8 * j + 2 * t]) = pack_bf16(s[j][0], s[j][1]);
         *reinterpret_cast<uint32_t*>(&Pt[r1][8 * j + 2 * t]) = pack_bf16(s[j][2], s[j][3]);
         *reinterpret_cast<uint32_t*>(&dSt[r0][8 * j + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
         *reinterpret_cast<uint32_t*>(&dSt[r1][8 * j + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+      }
+      // key-coordinate gradients of keys 8 j + 2 t + {0, 1}: sum over the warp's 16 rows (8 lanes share t); the eight chains
+      // are reduced together (three shuffle rounds of eight independent values instead of four separate 3-step chains)
+#pragma unroll
+      for (int m = 4; m < 32; m <<= 1)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          kgs[j][0] += __shfl_xor_sync(0xffffffffu, kgs[j][0], m); kgs[j][1] += __shfl_xor_sync(0xffffffffu, kgs[j][1], m);
+        }
+      if (g == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(&dkp[8 * j + 2 * t]) = make_float2(kgs[j][0], kgs[j][1]);
       }
       // merge the tile's sums into the rows' running sums (flush when the lower segment moved)
       pwl_flush(bins, ac0, rw0.seg != ac0.seg, lane); ac0.seg = rw0.seg;
