@@ -1289,6 +1289,7 @@ constexpr int PWL_FK = 64;                // keys per forward tile
 struct PwlFwdSmem {
   __nv_bfloat16 Q[MQ][MLD];
   PwlStage<PWL_FK> st[3];
+  float2 krng[PWL_MAXTILES];              // key-position range of every 32-key tile of this (b, g) row
   PwlTable pw;
 };
 // K and V arrive as bf16 planes (the mode's operand rounding, done once by the caller instead of once per query tile);
@@ -1346,17 +1347,20 @@ __global__ void __launch_bounds__(MTHREADS, 3) deform_attn_fwd_pwl_kernel(const 
 
   const int nt32 = (cf.nkv + 31) >> 5;
   const float2* krb = kr + (int64_t)bg * nt32;
-  float2 ra = krb[0], rb = krb[min(1, nt32 - 1)];       // ranges of the two 32-key halves of the next tile
+  const bool rng_smem = nt32 <= PWL_MAXTILES;
+  if (rng_smem)
+    for (int i = tid; i < nt32; i += MTHREADS) sm.krng[i] = krb[i];
 
   for (int it = 0; it < ntiles; ++it) {
     const int k0 = it * PWL_FK;
-    const float kmin = fminf(ra.x, rb.x), kmax = fmaxf(ra.y, rb.y);
-    ra = krb[min(2 * it + 2, nt32 - 1)]; rb = krb[min(2 * it + 3, nt32 - 1)];
     cp_async_wait<1>();                                 // my copies of tile `it` have landed
     __syncthreads();                                    // ... everyone's have, and everyone is done with tile it - 1
     if (it + 2 < ntiles) pwl_stage_load(sm.st[(it + 2) % 3], kb, vb, vsb, cf.inner, k0 + 2 * PWL_FK, cf.nkv, tid);
     cp_async_commit();
     const PwlStage<PWL_FK>& st = sm.st[it % 3];
+    const int ia = 2 * it, ib = min(2 * it + 1, nt32 - 1);      // the two 32-key halves of the tile
+    const float2 ra = rng_smem ? sm.krng[ia] : krb[ia], rb = rng_smem ? sm.krng[ib] : krb[ib];
+    const float kmin = fminf(ra.x, rb.x), kmax = fmaxf(ra.y, rb.y);
     const bool many0 = pwl_row_setup(sm.pw, ns, qx0, kmin, kmax, rw0);
     const bool many1 = pwl_row_setup(sm.pw, ns, qx1, kmin, kmax, rw1);
     const bool slow = __any_sync(0xffffffffu, many0 || many1);
