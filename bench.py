@@ -665,6 +665,16 @@ def instrumented_roofline(wl, ms_step, pk, pk_src, prof_out):
                 "launches whose shape is in the ncu capture %s" % (tr_n, n, traffic_src)) if tr_n else None,
                 "peak_source": pk_src + " (sustained)", "share_of_step": t / (ms_step * 1e-3),
                 "note": "bf16x3 launches count 1x algorithmic FLOPs (3 MMA passes executed)", "by_shape": by_shape}
+        # the flash-fused landmark-by-token kernels (csrc/nystrom_a3.cu: warp-level mma.sync, not part of the GEMM engine's sum)
+        fused = {}
+        for eng in ("a3_fwd", "a3_bwd"):
+            if eng in agg and agg[eng][1] > 0:
+                f2, t2, n2 = agg[eng]
+                fused[eng] = {"launches": n2, "avg_us": t2 / n2 * 1e6, "achieved": f2 / t2 / 1e12, "unit": "TFLOP/s",
+                              "frac": f2 / t2 / 1e12 / peak, "share_of_step": t2 / (ms_step * 1e-3),
+                              "flop_per_pair": 256 if eng == "a3_fwd" else 640}
+        if fused:
+            roof["fused_attention"] = fused
     elif "simt" in agg:
         f, t, n = agg["simt"]
         roof = {"kernel": "gemm_f32_kernel (SIMT fp32, %d launches)" % n, "bound": "tensor", "achieved": f / t / 1e12,

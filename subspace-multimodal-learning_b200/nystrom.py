@@ -52,6 +52,18 @@ def landmarks_fwd(qkv, b, npad, h, d, m, qkv_bf16=None):
     return ql, kl
 
 
+def _prof(eng, flops, tag, fn):
+    """run fn() between CUDA events when bench.py's instrumented pass is on (ops.PROFILE is a list)"""
+    if ops.PROFILE is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    ops.PROFILE.append((eng, flops, e0, e1, tag))
+    return r
+
+
 def _a3_cfg(b, h, m, d, npad, nchunks):
     """cfg11 of sml_nystrom_a3_*: K / V as views into the packed [b, n', 3, h, d] tensor (element strides)"""
     bs = npad * 3 * h * d
@@ -233,8 +245,9 @@ class NystromAttentionFn(torch.autograd.Function):
             nch = _a3_chunks(b, h, npad, 64, 3 * 148, rows_per_cta=m // 64)
             opart = torch.empty(b * h, nch, m, d, device=dev, dtype=F32)
             ml = torch.empty(b * h, nch, m, 2, device=dev, dtype=F32)
-            check(lib.sml_nystrom_a3_fwd(_a3_cfg(b, h, m, d, npad, nch), ptr(ql_b.hi), ptr(qkv.hi), ptr(opart), ptr(ml), ptr(a3v.f),
-                                         ptr(a3v.hi), ptr(lse3), stream()), "nystrom_a3_fwd")
+            _prof("a3_fwd", 4.0 * d * b * h * m * npad, (b, h, m, npad),
+                  lambda: check(lib.sml_nystrom_a3_fwd(_a3_cfg(b, h, m, d, npad, nch), ptr(ql_b.hi), ptr(qkv.hi), ptr(opart), ptr(ml),
+                                                       ptr(a3v.f), ptr(a3v.hi), ptr(lse3), stream()), "nystrom_a3_fwd"))
             del opart, ml
         else:
             a3 = TB.new((b, h, m, npad), dev, mode, f32=not lowp)
@@ -366,8 +379,9 @@ class NystromAttentionFn(torch.autograd.Function):
             lse3 = a3_f
             dql = TB(torch.zeros(b, h, m, d, device=dev, dtype=F32))
             a3cfg = _a3_cfg(b, h, m, d, npad, _a3_chunks(b, h, npad, 32, 148))
-            check(lib.sml_nystrom_a3_bwd(a3cfg, ptr(ql_b.hi), ptr(qkv.hi), ptr(da3v.f), ptr(a3v_f), ptr(lse3), None, c_i32(npad // m),
-                                         ptr(dql.f), ptr(dqkv.hi), ptr(dqkv.f), stream()), "nystrom_a3_bwd")
+            _prof("a3_bwd", 10.0 * d * b * h * m * npad, (b, h, m, npad),
+                  lambda: check(lib.sml_nystrom_a3_bwd(a3cfg, ptr(ql_b.hi), ptr(qkv.hi), ptr(da3v.f), ptr(a3v_f), ptr(lse3), None,
+                                                       c_i32(npad // m), ptr(dql.f), ptr(dqkv.hi), ptr(dqkv.f), stream()), "nystrom_a3_bwd"))
         else:
             da3 = mm(da3v, v_b.T(), TB(torch.empty(b, h, m, npad, device=dev, dtype=F32)))
             mm(a3.T(), da3v, TB(dv))                                                            # dv = A3^T dA3V
