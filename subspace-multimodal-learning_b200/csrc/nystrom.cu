@@ -452,10 +452,13 @@ __global__ void __launch_bounds__(256) ppeg_dw_kernel(const float* __restrict__ 
 // Measured: the transposed stencil (dx) 549 -> 390 us, the weight gradient 568 -> 526 us, the forward 350 -> 367 us (so the
 // forward stays on the kernel above); ncu: issue 57 %, FMA pipe 38 %, 2.5 instructions per FMA - not memory-bound.
 constexpr int PR_W = 8, PR_H = 4, PRB_W = 16, PRB_H = 16;
-template <bool FLIP>
+// CT = channel count at compile time (512 on the reference path; 0 = run-time): with a constant row pitch every load of a
+// 14-pixel input row is base + immediate, which removes the 64-bit address arithmetic that made up a third of the instructions
+template <bool FLIP, int CT>
 __global__ void __launch_bounds__(256, 2) ppeg_rt_kernel(const float* __restrict__ x, const float* __restrict__ w7,
                                                          const float* __restrict__ bias, float* __restrict__ y, int H, int W,
-                                                         int C, int tiles_x) {
+                                                         int Crt, int tiles_x) {
+  const int C = CT ? CT : Crt;
   const int b = blockIdx.z;
   const int lc = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + lc;
@@ -474,17 +477,23 @@ __global__ void __launch_bounds__(256, 2) ppeg_rt_kernel(const float* __restrict
   for (int r = 0; r < PR_H; ++r)
 #pragma unroll
     for (int u = 0; u < PR_W; ++u) acc[r][u] = bv;
-  const float* xb = x + base + (int64_t)C + c;                     // token 0 of the lattice
+  const bool interior = ox0 >= 3 && ox0 + PR_W + 3 <= W;          // warp-uniform: no column predicate needed
+  const float* xb = x + base + (int64_t)C + c + (int64_t)(ox0 - 3) * C;      // input column ox0 - 3 of lattice row 0
 #pragma unroll
   for (int iy = 0; iy < PR_H + 6; ++iy) {
     const int gy = oy0 - 3 + iy;
     if (gy < 0 || gy >= H) continue;                              // warp-uniform
     const float* rp = xb + (int64_t)gy * W * C;
     float v[PR_W + 6];
+    if (interior) {
 #pragma unroll
-    for (int u = 0; u < PR_W + 6; ++u) {
-      const int gx = ox0 - 3 + u;
-      v[u] = (gx >= 0 && gx < W) ? __ldg(rp + (int64_t)gx * C) : 0.f;
+      for (int u = 0; u < PR_W + 6; ++u) v[u] = __ldg(rp + u * C);
+    } else {
+#pragma unroll
+      for (int u = 0; u < PR_W + 6; ++u) {
+        const int gx = ox0 - 3 + u;
+        v[u] = (gx >= 0 && gx < W) ? __ldg(rp + u * C) : 0.f;
+      }
     }
 #pragma unroll
     for (int r = 0; r < PR_H; ++r) {
@@ -496,20 +505,22 @@ __global__ void __launch_bounds__(256, 2) ppeg_rt_kernel(const float* __restrict
         for (int dj = 0; dj < 7; ++dj) acc[r][u] = fmaf(wr[di * 7 + dj], v[u + dj], acc[r][u]);
     }
   }
-  float* yb = y + base + (int64_t)C + c;
+  float* yb = y + base + (int64_t)C + c + ((int64_t)oy0 * W + ox0) * C;
 #pragma unroll
   for (int r = 0; r < PR_H; ++r) {
     if (oy0 + r >= H) break;
 #pragma unroll
     for (int u = 0; u < PR_W; ++u)
-      if (ox0 + u < W) yb[((int64_t)(oy0 + r) * W + ox0 + u) * C] = acc[r][u];
+      if (ox0 + u < W) yb[(int64_t)r * W * C + u * C] = acc[r][u];
   }
 }
 // weight / bias gradient, same tiling: grid (C/32, groups, B); a block walks its share of the 16 x 16 tiles, every thread keeps
 // the 49 tap sums of its channel; the 8 warps are reduced through shared memory at the end
+template <int CT>
 __global__ void __launch_bounds__(256, 2) ppeg_dw_rt_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                             float* __restrict__ dw_part, float* __restrict__ db_part, int H,
-                                                            int W, int C, int tiles_x, int ntiles) {
+                                                            int W, int Crt, int tiles_x, int ntiles) {
+  const int C = CT ? CT : Crt;
   __shared__ float red[50][33];
   const int b = blockIdx.z, c0 = blockIdx.x * 32;
   const int lc = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -527,23 +538,30 @@ __global__ void __launch_bounds__(256, 2) ppeg_dw_rt_kernel(const float* __restr
       const int oy0 = (tl / tiles_x) * PRB_H + (wp >> 1) * PR_H;
       if (ox0 >= W || oy0 >= H) continue;
       float g[PR_H][PR_W];
+      const float* gp = gb + ((int64_t)oy0 * W + ox0) * C;
 #pragma unroll
       for (int r = 0; r < PR_H; ++r)
 #pragma unroll
         for (int u = 0; u < PR_W; ++u) {
-          g[r][u] = (oy0 + r < H && ox0 + u < W) ? __ldg(gb + ((int64_t)(oy0 + r) * W + ox0 + u) * C) : 0.f;
+          g[r][u] = (oy0 + r < H && ox0 + u < W) ? __ldg(gp + (int64_t)r * W * C + u * C) : 0.f;
           ab += g[r][u];
         }
+      const bool interior = ox0 >= 3 && ox0 + PR_W + 3 <= W;
 #pragma unroll
       for (int iy = 0; iy < PR_H + 6; ++iy) {
         const int gy = oy0 - 3 + iy;
         if (gy < 0 || gy >= H) continue;
-        const float* rp = xb + (int64_t)gy * W * C;
+        const float* rp = xb + ((int64_t)gy * W + ox0 - 3) * C;
         float v[PR_W + 6];
+        if (interior) {
 #pragma unroll
-        for (int u = 0; u < PR_W + 6; ++u) {
-          const int gx = ox0 - 3 + u;
-          v[u] = (gx >= 0 && gx < W) ? __ldg(rp + (int64_t)gx * C) : 0.f;
+          for (int u = 0; u < PR_W + 6; ++u) v[u] = __ldg(rp + u * C);
+        } else {
+#pragma unroll
+          for (int u = 0; u < PR_W + 6; ++u) {
+            const int gx = ox0 - 3 + u;
+            v[u] = (gx >= 0 && gx < W) ? __ldg(rp + u * C) : 0.f;
+          }
         }
 #pragma unroll
         for (int r = 0; r < PR_H; ++r) {
@@ -703,10 +721,15 @@ extern "C" int sml_ppeg_unfold(const float* dwf, float* dw7, float* dw5, float* 
 }
 extern "C" int sml_ppeg_fwd(const float* x, const float* w7, const float* bias, float* y, int32_t B, int32_t H, int32_t W,
                             int32_t C, void* stream) {
-  // forward: the shared-memory kernel (350 us at B = 8 / 128 x 128 x 512 against 367 us for the register-tiled one)
-  const int tx = (W + PT_W - 1) / PT_W, tyc = (H + PT_H - 1) / PT_H;
-  dim3 grid(tx * tyc, (C + PT_C - 1) / PT_C, B);
-  ppeg_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, w7, bias, y, H, W, C, tx);
+  if (C == 512) {                 // constant row pitch: the register-tiled kernel
+    const int tx = (W + PRB_W - 1) / PRB_W, tyc = (H + PRB_H - 1) / PRB_H;
+    dim3 grid(tx * tyc, (C + 31) / 32, B);
+    ppeg_rt_kernel<false, 512><<<grid, 256, 0, as_stream(stream)>>>(x, w7, bias, y, H, W, C, tx);
+  } else {                        // other widths: the shared-memory kernel
+    const int tx = (W + PT_W - 1) / PT_W, tyc = (H + PT_H - 1) / PT_H;
+    dim3 grid(tx * tyc, (C + PT_C - 1) / PT_C, B);
+    ppeg_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, w7, bias, y, H, W, C, tx);
+  }
   SML_LAUNCH_OK("sml_ppeg_fwd");
   return 0;
 }
@@ -719,10 +742,12 @@ extern "C" int sml_ppeg_bwd(const float* x, const float* w7, const float* dy, fl
   cudaStream_t s = as_stream(stream);
   const int tx = (W + PRB_W - 1) / PRB_W, tyc = (H + PRB_H - 1) / PRB_H, nt = tx * tyc;
   dim3 grid(nt, (C + 31) / 32, B);                                              // backward: register-tiled kernels (390 / 526 us against 549 / 568 us)
-  ppeg_rt_kernel<true><<<grid, 256, 0, s>>>(dy, w7, nullptr, dx, H, W, C, tx);  // transposed stencil = flipped taps
+  if (C == 512) ppeg_rt_kernel<true, 512><<<grid, 256, 0, s>>>(dy, w7, nullptr, dx, H, W, C, tx);   // transposed stencil = flipped taps
+  else ppeg_rt_kernel<true, 0><<<grid, 256, 0, s>>>(dy, w7, nullptr, dx, H, W, C, tx);
   SML_LAUNCH_OK("sml_ppeg_bwd(dx)");
   dim3 grid2((C + 31) / 32, nt < PPB_GROUPS ? nt : PPB_GROUPS, B);
-  ppeg_dw_rt_kernel<<<grid2, 256, 0, s>>>(x, dy, dw_part, db_part, H, W, C, tx, nt);
+  if (C == 512) ppeg_dw_rt_kernel<512><<<grid2, 256, 0, s>>>(x, dy, dw_part, db_part, H, W, C, tx, nt);
+  else ppeg_dw_rt_kernel<0><<<grid2, 256, 0, s>>>(x, dy, dw_part, db_part, H, W, C, tx, nt);
   SML_LAUNCH_OK("sml_ppeg_bwd(dw)");
   return 0;
 }
