@@ -176,13 +176,15 @@ __global__ void pinv_init_bwd_scalar_kernel(const float* __restrict__ x, const f
 // with k' = k (fwd) or K-1-k (FLIP: the transposed conv of the backward).  Each thread owns TT consecutive tokens of
 // one channel: the K taps live in registers and every (tap, output) pair is resolved at compile time.
 constexpr int RC_TT = 8;
-template <bool FLIP, int K, typename TS>
-__global__ void __launch_bounds__(128) resconv_kernel(const TS* __restrict__ src, int64_t src_ld,
+// SLD / DLD = the row pitches at compile time (0 = run-time)
+template <bool FLIP, int K, typename TS, int SLD = 0, int DLD = 0>
+__global__ void __launch_bounds__(128) resconv_kernel(const TS* __restrict__ src, int64_t src_ld_rt,
                                                       const float* __restrict__ w, float* __restrict__ dst,
-                                                      int64_t dst_ld, int npad, int hd, int d,
+                                                      int64_t dst_ld_rt, int npad, int hd, int d,
                                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   // thread = 4 adjacent channels (one 128-bit load per token) x RC_TT tokens; requires d % 4 == 0 and 16-byte rows
   constexpr int HALF = K / 2;
+  const int64_t src_ld = SLD ? SLD : src_ld_rt, dst_ld = DLD ? DLD : dst_ld_rt;
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * RC_TT;
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
@@ -653,7 +655,8 @@ extern "C" int sml_nystrom_resconv_fwd(const float* qkv, const float* w, float* 
     const __nv_bfloat16* qb = (const __nv_bfloat16*)qkv_bf16;
     resconv_kernel<false, 33, __nv_bfloat16><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qb + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
   } else if (ksize == 33 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
-    resconv_kernel<false, 33, float><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+    if (hd == 512) resconv_kernel<false, 33, float, 1536, 512><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+    else resconv_kernel<false, 33, float><<<rc_grid4(npad, hd, B, RC_TT), 128, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
   else
     resconv_generic_kernel<false><<<rc_grid(npad, hd, B, 1), 256, 0, as_stream(stream)>>>(qkv + 2 * hd, 3 * hd, w, out, hd, npad, hd, d, ksize);
   SML_LAUNCH_OK("sml_nystrom_resconv_fwd");
