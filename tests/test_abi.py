@@ -72,3 +72,19 @@ def test_bench_reference_arm_does_not_load_the_product():
     assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1
     assert line["config"]["slides_per_step_per_gpu"] == 8 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_a3_chunking_covers_every_tile():
+    """host logic of the fused A3 path (nystrom.py:_a3_chunks / _a3_cfg): every chunk gets at least one key tile, the chunks
+    cover the padded length, and the 64-bit batch stride survives the int32 pair"""
+    import sml_b200
+    from sml_b200.nystrom import _a3_cfg, _a3_chunks
+    for b, h, npad in ((8, 8, 16640), (1, 8, 100864), (2, 8, 1280), (1, 1, 256), (64, 8, 16640)):
+        for tile, slots, rows in ((64, 3 * 148, 4), (32, 148, 1)):
+            n = _a3_chunks(b, h, npad, tile, slots, rows_per_cta=rows)
+            ntot = npad // tile
+            tpc = -(-ntot // n)
+            assert n >= 1 and (n - 1) * tpc < ntot <= n * tpc, (b, h, npad, tile, n)
+    cfg = _a3_cfg(64, 8, 256, 64, 100864 * 16, 3)          # batch stride 3 h d n' > 2^31
+    bs = 100864 * 16 * 3 * 8 * 64
+    assert (cfg[6] & 0xffffffff) | (cfg[7] << 32) == bs

@@ -16,6 +16,8 @@ torch.manual_seed(0)
 qkv = (torch.randn(b, npad, 3, h, d, device=dev) * 0.7).bfloat16()
 ql = (torch.randn(b, h, m, d, device=dev) * 0.5).bfloat16()
 nf, nb = _a3_chunks(b, h, npad, 64, 3 * 148, rows_per_cta=m // 64), _a3_chunks(b, h, npad, 32, 148)
+if len(sys.argv) > 2: nf = int(sys.argv[2])
+if len(sys.argv) > 3: nb = int(sys.argv[3])
 cf, cb = _a3_cfg(b, h, m, d, npad, nf), _a3_cfg(b, h, m, d, npad, nb)
 a3v = torch.empty(b, h, m, d, device=dev); a3v_hi = torch.empty(b, h, m, d, device=dev, dtype=torch.bfloat16)
 lse = torch.empty(b, h, m, device=dev)
