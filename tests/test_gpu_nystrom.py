@@ -289,3 +289,26 @@ def test_nystrom_inference_fused_matches_training_path(m):
         y_inf = mod(x)
     y_tr = mod(x.clone().requires_grad_())
     assert rel_err(y_inf, y_tr) < 2e-2, rel_err(y_inf, y_tr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 13, 9, 96), (1, 50, 50, 512), (2, 17, 33, 512), (1, 128, 128, 512)])
+def test_ppeg_stencil_matches_conv2d(shape):
+    """the folded 7x7 PPEG stencil (mil.py:190-205) on ragged lattices and both kernel families (compile-time 512 channels,
+    run-time channel count): forward, dx, dw, db against F.conv2d"""
+    from sml_b200 import functional as Fn
+    B, H, W, C = shape
+    torch.manual_seed(4)
+    x = torch.randn(B, 1 + H * W, C, device="cuda", requires_grad=True)
+    w7 = (torch.randn(49, C, device="cuda") * 0.1).requires_grad_()
+    bias = torch.randn(C, device="cuda", requires_grad=True)
+    y = Fn.ppeg(x, w7, bias, H, W)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr, br = (t.detach().clone().requires_grad_() for t in (x, w7, bias))
+    img = xr[:, 1:].transpose(1, 2).reshape(B, C, H, W)
+    yr = torch.nn.functional.conv2d(img, wr.t().reshape(C, 1, 7, 7), br, padding=3, groups=C)
+    yr = torch.cat([xr[:, :1], yr.flatten(2).transpose(1, 2)], 1)
+    yr.backward(g)
+    for a, b_, tol in ((y, yr, 1e-5), (x.grad, xr.grad, 1e-5), (w7.grad, wr.grad, 1e-4), (bias.grad, br.grad, 1e-4)):
+        assert rel_err(a, b_) < tol, rel_err(a, b_)
